@@ -1,0 +1,130 @@
+/* xcp.h -- C ABI of libxcp_sm100.so: the B200 (sm_100a) hot path of Tonmoy1321/Multimodal-DeepFake-Detection.
+ *
+ * The reference has no FFI layer: its boundary is the torch.nn.Module API of Xception.py / XceptionLSTMV.py /
+ * XceptionLSTMA.py, and every FLOP is executed by ATen/cuDNN/cuBLAS behind nn.Conv2d / nn.BatchNorm2d /
+ * nn.MaxPool2d / nn.LSTM / nn.Linear.  Each entry point below replaces the library call(s) cited beside it
+ * (file:line in the reference) so that a maintainer can bind it with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless noted.
+ *   - activations: bf16, NHWC, i.e. a row-major [F*H*W, C] matrix, C % 8 == 0, 16-byte aligned.
+ *   - every function takes the CUDA device ordinal and the cudaStream_t (as void*) to launch on, is re-entrant
+ *     and thread-safe (autograd calls backward from another thread), never allocates or frees device memory and
+ *     keeps no reference to its arguments.
+ *   - return value: 0 = ok, < 0 = argument / shape / alignment error, > 0 = cudaError_t.
+ *     xcp_last_error_string() (thread-local) explains the last failure.  Nothing throws, nothing exits.
+ *   - there is no CPU path and no other-architecture path: xcp_check_device() fails on a non-sm_100 device.
+ */
+#ifndef XCP_H
+#define XCP_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* xcp_last_error_string(void);
+int xcp_version(void);
+int xcp_check_device(int device);
+
+/* ---- pointwise / skip 1x1 convolutions, LSTM input projection: tcgen05 + TMEM + TMA GEMMs ------------------
+ * D[M,N] = A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulate.  Replaces nn.Conv2d(k=1) in
+ * SeparableConv2d.pointwise (Xception.py:42,46), Block.skip (Xception.py:55,93), and x_t W_ih^T of nn.LSTM
+ * (XceptionLSTMV.py:18-23).  Also the data gradient (A = dY, B = W^T).
+ * epi: 0 bf16 out | 1 bf16 out + per-channel (sum, sum-sq) partials stats[ceil(M/128)][2][N] for train-mode
+ * BatchNorm (Xception.py:67,73,78) | 2 fp32 out (+ optional bias[N]).  lda/ldb/ldo are row pitches in elements. */
+int xcp_gemm_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N, int K,
+                int epi, float* stats, const float* bias, int device, void* stream);
+/* dW[P,Q] += dY[R,P]^T * X[R,Q] (fp32 accumulate into dW): weight gradient of the layers above. */
+int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, long long ld_x, float* dW, long long ld_dw, int R, int P,
+                   int Q, int device, void* stream);
+/* SIMT cross-check of the two GEMMs above (tests only; never on the product path). */
+int xcp_gemm_ref(const void* A, long long lda, const void* B, long long ldb, float* out, long long ldo, int M, int N, int K,
+                 int mn_major, int device, void* stream);
+/* Dense 3x3 stem conv2 (Xception.py:122,172) and its data gradient as an implicit GEMM; see gemm.cu. */
+int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* stats, int F, int Hg, int Wg, int Cin, int Cout, int Ho,
+                     int Wo, int sign, int device, void* stream);
+
+/* ---- stem conv1 3->32 k3 s2 p0 (Xception.py:118,168): fp32 NCHW in, bf16 NHWC out + BN partials [ceil(M/128)][2][32] */
+int xcp_stem_conv1_fwd(const float* x, const float* w, void* y, float* partials, int F, int H, int W, int device, void* stream);
+int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, int F, int H, int W, int device, void* stream);
+
+/* ---- depthwise 3x3 s1 p1 (SeparableConv2d.conv1, Xception.py:41,45) fused with the preceding ReLU
+ * (Xception.py:61-76) and the producer's BatchNorm affine.  w9 = tap-major weights [9][C] (xcp_pack_dw). */
+int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int H,
+                  int W, int C, int device, void* stream);
+long long xcp_dw3x3_bwd_workspace_floats(int C);
+int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift, int relu, void* dz,
+                  const void* add_full, const void* add_half, float* dw9, float* bnsum, float* workspace, int F, int H, int W,
+                  int C, int device, void* stream);
+
+/* ---- BatchNorm2d (Xception.py:56,67,73,78,119,123,143,147): statistics finalisation (train), affine folding (eval) */
+int xcp_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                    float* mean_out, float* rstd_out, int device, void* stream);
+int xcp_bn_eval_affine(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, float* scale,
+                       float* shift, float* mean_out, float* rstd_out, int C, int device, void* stream);
+/* out = relu?(scale*y + shift) */
+int xcp_bn_act(const void* y, const float* scale, const float* shift, int relu, void* out, long long n, int C, int device,
+               void* stream);
+/* input sampling of the stride-2 skip conv (Xception.py:55,93): out[f,ho,wo,:] = act(x[f,2ho,2wo,:]) */
+int xcp_gather_s2(const void* x, const float* scale, const float* shift, int relu, void* out, int F, int H, int W, int C,
+                  int device, void* stream);
+/* BN + MaxPool2d(3,2,1) (Xception.py:86) + skip BN + residual add (Xception.py:92-98); idx = arg-max taps (uint8) */
+int xcp_pool_add_fwd(const void* y, const float* scale, const float* shift, const void* ys, const float* scale_s,
+                     const float* shift_s, void* out, void* idx, int F, int H, int W, int C, int device, void* stream);
+/* BN + identity residual add (blocks 4-11, Xception.py:96-98) */
+int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const void* skip, void* out, long long n, int C,
+                   int device, void* stream);
+/* bn4 + ReLU + adaptive_avg_pool2d (Xception.py:194-198): feat fp32 [F,C] */
+int xcp_bn_relu_gap(const void* y, const float* scale, const float* shift, float* feat, int F, int HW, int C, int device,
+                    void* stream);
+int xcp_bnbwd_num_parts(void);
+/* two-pass BatchNorm backward with the ReLU / MaxPool / GAP gradient routing folded into its loads; see elementwise.cu */
+int xcp_bn_bwd(int mode, const void* y, const void* G, const void* idx, const float* dfeat, const float* scale,
+               const float* shift, const float* gamma, const float* mean, const float* rstd, int training, const float* presums,
+               float* workspace, float* coef, float* dgamma, float* dbeta, void* dy, int F, int H, int W, int C, int grid_w,
+               int grid_h, int device, void* stream);
+
+/* ---- layout / packing */
+int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int HW, int device, void* stream);
+int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int HW, int device, void* stream);
+int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int device, void* stream);
+int xcp_pack_dw(const float* w, float* w9, int C, int device, void* stream);
+int xcp_unpack_dw_grad(const float* g9, float* gw, int C, int accumulate, int device, void* stream);
+int xcp_pack_conv3x3(const float* w, void* wk, void* wk_t, int O, int I, int device, void* stream);
+int xcp_unpack_conv3x3_grad(const float* gk, float* gw, int O, int I, int device, void* stream);
+/* F.interpolate(size=(S,S), mode="bilinear", align_corners=False) of [planes, n, 1] (XceptionLSTMA.py:45-46) */
+int xcp_bilinear_up(const float* x, float* out, long long planes, int n, int S, int device, void* stream);
+int xcp_cast_f32_bf16(const float* x, void* out, long long n, int device, void* stream);
+
+/* ---- nn.LSTM(2048,H,1,batch_first) recurrence + BPTT (XceptionLSTMV.py:18-23,67) */
+int xcp_lstm_fwd(const float* xproj, const float* b_ih, const float* b_hh, const void* w_hh_t, float* h_out, float* gates,
+                 float* cstate, float* hn, float* cn, int B, int T, int H, int device, void* stream);
+int xcp_lstm_bwd(const float* dout, const float* dhn, const float* dcn, const float* gates, const float* cstate,
+                 const float* hstate, const void* w_hh, void* dgates, void* hprev, float* dbias_ih, float* dbias_hh, int B, int T,
+                 int H, int device, void* stream);
+
+/* ---- classifier head + losses (XceptionLSTMV.py:25-44,68-70; train_audio.py:20; train_visual.py:455-474,532;
+ *      train_au_face.py:423-458,659-674; train_au_patch.py:203-211) */
+int xcp_linear_small_fwd(const float* a, const float* W, const float* bias, const void* mask, float drop_scale, int act,
+                         float* out, int B, int N, int K, int device, void* stream);
+int xcp_linear_small_bwd(const float* delta_raw, const float* out_act, float drop_scale, const float* a, const float* W,
+                         float* dW, float* db, float* din, int B, int N, int K, int device, void* stream);
+int xcp_bce_fwd_bwd(const float* z, const float* y, float smoothing, float* probs, float* loss, float* dz, int B, int device,
+                    void* stream);
+int xcp_arcface_loss(const float* x, const float* w, const long long* labels, float s, float m, int loss_mode,
+                     const float* class_w, float gamma, float* logits, float* loss, float* loss_rows, float* dx, float* dw, int B,
+                     int D, float gscale, int device, void* stream);
+int xcp_fusion_pool_reg(const float* v, const float* a, float* pooled, float* loss_reg, float* dv, float* da, int B, int T, int D,
+                        float lambda_align, float lambda_temp, float gscale, int device, void* stream);
+int xcp_fusion_pool_bwd(const float* dpooled, float* dv, float* da, int B, int T, int D, int device, void* stream);
+
+/* ---- optimizer side: clip_grad_norm_ + Adam / AdamW over a flat fp32 arena */
+int xcp_grad_sumsq(const float* g, long long n, float* out, int zero_first, int device, void* stream);
+int xcp_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int decoupled, int step, const float* sumsq, float max_norm, float grad_scale, int device,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XCP_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of libxcp_sm100.so (the C-ABI boundary declared in include/xcp.h).
+
+Loading is lazy (DataLoader worker processes import the model package but must not touch CUDA,
+SURVEY.md §8b) and LOUD: if the shared object is missing or a call returns non-zero, a RuntimeError
+carrying ``xcp_last_error_string()`` is raised.  There is no CPU / eager fallback anywhere.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxcp_sm100.so")
+
+_T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
+
+# name -> argument type string (see include/xcp.h for the meaning of every argument)
+SIGNATURES = {
+    "xcp_version": "",
+    "xcp_check_device": "i",
+    "xcp_gemm_tn": "plplpliiiippip",
+    "xcp_gemm_wgrad": "plplpliiiip",
+    "xcp_gemm_ref": "plplpliiiiip",
+    "xcp_conv3x3_gemm": "ppppiiiiiiiiip",
+    "xcp_stem_conv1_fwd": "ppppiiiip",
+    "xcp_stem_conv1_wgrad": "pppiiiip",
+    "xcp_dw3x3_fwd": "ppppipiiiiip",
+    "xcp_dw3x3_bwd_workspace_floats": "i",
+    "xcp_dw3x3_bwd": "pppppippppppiiiiip",
+    "xcp_bn_finalize": "piidppppffppppip",
+    "xcp_bn_eval_affine": "ppppfppppiip",
+    "xcp_bn_act": "pppipliip",
+    "xcp_gather_s2": "pppipiiiiip",
+    "xcp_pool_add_fwd": "ppppppppiiiiip",
+    "xcp_bn_add_fwd": "pppppliip",
+    "xcp_bn_relu_gap": "ppppiiiip",
+    "xcp_bnbwd_num_parts": "",
+    "xcp_bn_bwd": "ipppppppppippppppiiiiiiip",
+    "xcp_nchw_to_nhwc": "ppiiiip",
+    "xcp_nhwc_to_nchw": "ppiiiip",
+    "xcp_pack_weight": "pppiiip",
+    "xcp_pack_dw": "ppiip",
+    "xcp_unpack_dw_grad": "ppiiip",
+    "xcp_pack_conv3x3": "pppiiip",
+    "xcp_unpack_conv3x3_grad": "ppiiip",
+    "xcp_bilinear_up": "ppliiip",
+    "xcp_cast_f32_bf16": "pplip",
+    "xcp_lstm_fwd": "pppppppppiiiip",
+    "xcp_lstm_bwd": "pppppppppppiiiip",
+    "xcp_linear_small_fwd": "ppppfipiiiip",
+    "xcp_linear_small_bwd": "ppfpppppiiiip",
+    "xcp_bce_fwd_bwd": "ppfpppiip",
+    "xcp_arcface_loss": "pppffipfpppppiifip",
+    "xcp_fusion_pool_reg": "ppppppiiifffip",
+    "xcp_fusion_pool_bwd": "pppiiiip",
+    "xcp_grad_sumsq": "plpiip",
+    "xcp_adam_step": "pppplfffffiipffip",
+}
+_RET_LONGLONG = {"xcp_dw3x3_bwd_workspace_floats"}
+_NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_dw3x3_bwd_workspace_floats"}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class XcpError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise XcpError(
+                "libxcp_sm100.so is missing at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C multimodal_deepfake_detection_b200/csrc).  There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.xcp_last_error_string.restype = ctypes.c_char_p
+        lib.xcp_last_error_string.argtypes = []
+        for name, sig in SIGNATURES.items():
+            fn = getattr(lib, name)     # AttributeError here == header/library mismatch: fail loudly
+            fn.argtypes = [_T[c] for c in sig]
+            fn.restype = ctypes.c_longlong if name in _RET_LONGLONG else ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name in _NO_STATUS:
+        return rc
+    if rc != 0:
+        msg = lib.xcp_last_error_string()
+        raise XcpError("%s failed (rc=%d): %s" % (name, rc, msg.decode(errors="replace") if msg else "?"))
+    return 0

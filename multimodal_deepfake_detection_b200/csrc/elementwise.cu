@@ -1,0 +1,756 @@
+// Memory-bound glue kernels of the Xception path on NHWC bf16 activations: stem conv1, BatchNorm
+// statistics finalisation (train) / affine folding (eval), BN+ReLU materialisation, stride-2 gather for the
+// skip 1x1 convs, fused BN + MaxPool(3,2,1) + skip-BN + residual add, fused BN + identity residual add,
+// BN + ReLU + global-average-pool, and the backward counterparts (two-pass BatchNorm backward with the
+// max-pool / GAP / ReLU gradient routing folded into its loads), layout converters and weight packing.
+//
+// Reference call sites: Xception.py:118-123,168-174 (stem), :56,67,73,78 (BN), :86 (MaxPool2d(3,2,1)),
+// :92-98 (skip + add), :197 (adaptive_avg_pool2d).  BatchNorm conventions: SURVEY.md App. E.
+#include "common.cuh"
+
+namespace xcp {
+
+// ======================================================================================== stem conv1
+// y[F,H1,W1,32] (bf16 NHWC) = conv3x3 stride 2 pad 0 of x[F,3,H,W] (fp32 NCHW) ; per-block (sum, sumsq).
+__global__ void __launch_bounds__(128)
+stem_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                      float* __restrict__ partials, int F, int H, int W, int H1, int W1) {
+    __shared__ float s_w[27][32];
+    __shared__ float s_t[128][33];
+    for (int i = threadIdx.x; i < 27 * 32; i += 128) {
+        const int oc = i / 27, tap = i % 27;       // w is [oc][ic][kh][kw]
+        s_w[tap][oc] = w[i];
+    }
+    __syncthreads();
+    const long long M = (long long)F * H1 * W1;
+    const long long pix = (long long)blockIdx.x * 128 + threadIdx.x;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    const bool ok = pix < M;
+    if (ok) {
+        const int wo = (int)(pix % W1);
+        const int ho = (int)((pix / W1) % H1);
+        const int f = (int)(pix / ((long long)W1 * H1));
+        const float* xb = x + ((long long)f * 3 * H + 2 * ho) * W + 2 * wo;
+#pragma unroll
+        for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float xv = __ldg(xb + ((long long)ic * H + kh) * W + kw);
+                    const int tap = (ic * 3 + kh) * 3 + kw;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fmaf(xv, s_w[tap][j], acc[j]);
+                }
+        __nv_bfloat16* yp = y + pix * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8[j] = acc[g * 8 + j];
+            *reinterpret_cast<uint4*>(yp + g * 8) = pack8(t8);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s_t[threadIdx.x][j] = acc[j];   // zeros for out-of-range pixels
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int ch = threadIdx.x & 31, st = threadIdx.x >> 5;
+        float s = 0.f;
+        for (int r = 0; r < 128; ++r) {
+            const float v = s_t[r][ch];
+            s += st ? v * v : v;
+        }
+        partials[((long long)blockIdx.x * 2 + st) * 32 + ch] = s;
+    }
+}
+
+// ======================================================================================== BN finalize
+// partials: [nparts][2][C].  Train mode: batch mean / biased var -> scale, shift, saved mean, rstd; running stats
+// updated with momentum and the unbiased variance.  block = 32 channels x 8 part-lanes.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
+                   float* scale, float* shift, float* mean_out, float* rstd_out) {
+    __shared__ double s1[8][32], s2[8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    double a = 0.0, b = 0.0;
+    if (c < C) {
+        for (int pi = ry; pi < nparts; pi += 8) {
+            a += (double)partials[((long long)pi * 2 + 0) * C + c];
+            b += (double)partials[((long long)pi * 2 + 1) * C + c];
+        }
+    }
+    s1[ry][cx] = a; s2[ry][cx] = b;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        for (int r = 1; r < 8; ++r) { a += s1[r][cx]; b += s2[r][cx]; }
+        const double mean = a / count;
+        double var = b / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = gamma[c] * rstd;
+        scale[c] = sc;
+        shift[c] = beta[c] - (float)mean * sc;
+        mean_out[c] = (float)mean;
+        rstd_out[c] = rstd;
+        if (running_mean != nullptr) {
+            const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    }
+}
+
+__global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                      float* scale, float* shift, float* mean_out, float* rstd_out, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float rstd = rsqrtf(rv[c] + eps);
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - rm[c] * sc;
+    if (mean_out) mean_out[c] = rm[c];
+    if (rstd_out) rstd_out[c] = rstd;
+}
+
+// ======================================================================================== elementwise fwd
+XCP_DEVINL void load_affine8(const float* scale, const float* shift, int c0, float (&sc)[8], float (&sh)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(scale + c0), b = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 c = *reinterpret_cast<const float4*>(shift + c0), d = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+    sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
+}
+
+// out = relu?(scale*y + shift)      (n8 = number of 8-channel vectors, C % 8 == 0)
+__global__ void bn_act_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                              int relu, uint4* __restrict__ out, long long n8, int C) {
+    const int ncg = C >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % ncg) * 8;
+        float v[8], sc[8], sh[8];
+        unpack8(ldg_nc_v4(y + i), v);
+        load_affine8(scale, shift, c0, sc, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = fmaf(v[j], sc[j], sh[j]);
+            if (relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        out[i] = pack8(v);
+    }
+}
+
+// out[f,ho,wo,:] = act(x[f,2ho,2wo,:])   (the input sampling of a 1x1 stride-2 conv)
+__global__ void gather_s2_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                 int relu, uint4* __restrict__ out, int F, int H, int W, int C) {
+    const int ncg = C >> 3, Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const long long n8 = (long long)F * Ho * Wo * ncg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % ncg);
+        long long t = i / ncg;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int f = (int)(t / Ho);
+        float v[8];
+        unpack8(ldg_nc_v4(x + (((long long)f * H + 2 * ho) * W + 2 * wo) * ncg + cg), v);
+        if (scale != nullptr) {
+            float sc[8], sh[8];
+            load_affine8(scale, shift, cg * 8, sc, sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        out[i] = pack8(v);
+    }
+}
+
+// out[f,ho,wo,:] = maxpool3x3s2p1( scale*y + shift )[f,ho,wo,:] + (scale_s*ys + shift_s)[f,ho,wo,:]
+// idx (uint8 per element) records the arg-max tap (first maximum in row-major window order) for backward.
+__global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const uint4* __restrict__ ys, const float* __restrict__ scale_s,
+                                    const float* __restrict__ shift_s, uint4* __restrict__ out, uint2* __restrict__ idx, int F,
+                                    int H, int W, int C) {
+    const int ncg = C >> 3, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long n8 = (long long)F * Ho * Wo * ncg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % ncg);
+        long long t = i / ncg;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int f = (int)(t / Ho);
+        float sc[8], sh[8], best[8];
+        int bi[8];
+        load_affine8(scale, shift, cg * 8, sc, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int h = 2 * ho - 1 + kh;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int w = 2 * wo - 1 + kw;
+                if (w < 0 || w >= W) continue;
+                float v[8];
+                unpack8(__ldg(y + (((long long)f * H + h) * W + w) * ncg + cg), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float z = fmaf(v[j], sc[j], sh[j]);
+                    if (z > best[j]) { best[j] = z; bi[j] = kh * 3 + kw; }
+                }
+            }
+        }
+        float s[8];
+        unpack8(ldg_nc_v4(ys + i), s);
+        load_affine8(scale_s, shift_s, cg * 8, sc, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] += fmaf(s[j], sc[j], sh[j]);
+        out[i] = pack8(best);
+        if (idx != nullptr) {
+            uint2 o;
+            o.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+            o.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+            idx[i] = o;
+        }
+    }
+}
+
+// out = scale*y + shift + skip
+__global__ void bn_add_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  const uint4* __restrict__ skip, uint4* __restrict__ out, long long n8, int C) {
+    const int ncg = C >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % ncg) * 8;
+        float v[8], s[8], sc[8], sh[8];
+        unpack8(ldg_nc_v4(y + i), v);
+        unpack8(ldg_nc_v4(skip + i), s);
+        load_affine8(scale, shift, c0, sc, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]) + s[j];
+        out[i] = pack8(v);
+    }
+}
+
+// feat[f,c] = mean_hw relu(scale*y + shift)       grid = (ceil(ncg/32), F), block = (32 cgs, 8 pixel lanes)
+__global__ void __launch_bounds__(256)
+bn_relu_gap_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                   float* __restrict__ feat, int HW, int C) {
+    __shared__ float s_acc[8][32][8];
+    const int ncg = C >> 3;
+    const int cgl = threadIdx.x & 31, lane_p = threadIdx.x >> 5;
+    const int cg = blockIdx.x * 32 + cgl;
+    const int f = blockIdx.y;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (cg < ncg) {
+        float sc[8], sh[8];
+        load_affine8(scale, shift, cg * 8, sc, sh);
+        for (int pidx = lane_p; pidx < HW; pidx += 8) {
+            float v[8];
+            unpack8(ldg_nc_v4(y + ((long long)f * HW + pidx) * ncg + cg), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[lane_p][cgl][j] = acc[j];
+    __syncthreads();
+    if (lane_p == 0 && cg < ncg) {
+        const float inv = 1.f / (float)HW;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = 0.f;
+            for (int r = 0; r < 8; ++r) s += s_acc[r][cgl][j];
+            feat[(long long)f * C + cg * 8 + j] = s * inv;
+        }
+    }
+}
+
+// ======================================================================================== BN backward
+// Source of dz (the gradient wrt the BN output z = scale*y + shift):
+//   0 DIRECT     dz = G
+//   1 RELU       dz = G * [z > 0]                       (x = relu(bn(y)) was consumed, G = dL/dx)
+//   2 POOL       dz[h,w] = sum over the <=4 pooling windows containing (h,w) whose arg-max is (h,w) of G[window]
+//   3 GAP_RELU   dz = dfeat[f,c] / HW * [z > 0]         (GAP over relu(bn(y)))
+enum { SRC_DIRECT = 0, SRC_RELU = 1, SRC_POOL = 2, SRC_GAP_RELU = 3 };
+
+struct BnBwdSrc {
+    int mode;
+    const __nv_bfloat16* G;     // modes 0,1: [F,H,W,C] ; mode 2: [F,Ho,Wo,C]
+    const uint8_t* idx;         // mode 2: [F,Ho,Wo,C]
+    const float* dfeat;         // mode 3: [F,C]
+    const float* scale;         // modes 1,3
+    const float* shift;
+    int F, H, W, C;
+};
+
+XCP_DEVINL void bnbwd_dz8(const BnBwdSrc& s, long long i, int cg, const float (&yv)[8], float (&dz)[8]) {
+    const int ncg = s.C >> 3;
+    if (s.mode == SRC_DIRECT || s.mode == SRC_RELU) {
+        unpack8(ldg_nc_v4(reinterpret_cast<const uint4*>(s.G) + i), dz);
+    } else if (s.mode == SRC_POOL) {
+        long long t = i / ncg;
+        const int w = (int)(t % s.W); t /= s.W;
+        const int h = (int)(t % s.H);
+        const int f = (int)(t / s.H);
+        const int Ho = (s.H - 1) / 2 + 1, Wo = (s.W - 1) / 2 + 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+        const int oh0 = h >> 1, ow0 = w >> 1;          // window o covers inputs 2o-1 .. 2o+1
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int oh = oh0 + a;
+            if (a == 1 && !(h & 1)) continue;          // even h belongs to exactly one window row
+            if (oh >= Ho) continue;
+            const int kh = h - (2 * oh - 1);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int ow = ow0 + b;
+                if (b == 1 && !(w & 1)) continue;
+                if (ow >= Wo) continue;
+                const int kw = w - (2 * ow - 1);
+                const long long o = (((long long)f * Ho + oh) * Wo + ow) * ncg + cg;
+                const uint2 id = __ldg(reinterpret_cast<const uint2*>(s.idx) + o);
+                float g[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(s.G) + o), g);
+                const uint32_t want = (uint32_t)(kh * 3 + kw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t got = ((j < 4 ? id.x : id.y) >> ((j & 3) * 8)) & 0xffu;
+                    if (got == want) dz[j] += g[j];
+                }
+            }
+        }
+    } else {  // SRC_GAP_RELU
+        const long long pix = i / ncg;
+        const int f = (int)(pix / ((long long)s.H * s.W));
+        const float inv = 1.f / (float)(s.H * s.W);
+        const float4 a = *reinterpret_cast<const float4*>(s.dfeat + (long long)f * s.C + cg * 8);
+        const float4 b = *reinterpret_cast<const float4*>(s.dfeat + (long long)f * s.C + cg * 8 + 4);
+        dz[0] = a.x * inv; dz[1] = a.y * inv; dz[2] = a.z * inv; dz[3] = a.w * inv;
+        dz[4] = b.x * inv; dz[5] = b.y * inv; dz[6] = b.z * inv; dz[7] = b.w * inv;
+    }
+    if (s.mode == SRC_RELU || s.mode == SRC_GAP_RELU) {
+        float sc[8], sh[8];
+        load_affine8(s.scale, s.shift, cg * 8, sc, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (!(fmaf(yv[j], sc[j], sh[j]) > 0.f)) dz[j] = 0.f;
+    }
+}
+
+// pass 1: per-channel (sum dz, sum dz*y) -> partials[gridDim.x][2][C]
+__global__ void __launch_bounds__(256)
+bnbwd_reduce_kernel(const uint4* __restrict__ y, const BnBwdSrc s, float* __restrict__ partials, long long n8) {
+    extern __shared__ float s_acc[];   // [2][C]
+    const int C = s.C, ncg = C >> 3;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const long long T = (long long)gridDim.x * blockDim.x;
+    const long long S = T - (T % ncg);                 // stride that keeps a thread on one channel group
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < S) {
+        const int cg = (int)(gid % ncg);
+        float a1[8], a2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+        for (long long i = gid; i < n8; i += S) {
+            float yv[8], dz[8];
+            unpack8(ldg_nc_v4(y + i), yv);
+            bnbwd_dz8(s, i, cg, yv, dz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a1[j] += dz[j]; a2[j] = fmaf(dz[j], yv[j], a2[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&s_acc[cg * 8 + j], a1[j]); atomicAdd(&s_acc[C + cg * 8 + j], a2[j]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partials[(long long)blockIdx.x * 2 * C + i] = s_acc[i];
+}
+
+// pass 1b: fold partials -> coefficients of dy = A*dz + B*y + Cc and the BN parameter gradients (accumulated).
+// presummed != 0: `partials` is already the [2][C] sums (e.g. produced by the depthwise backward kernel).
+__global__ void bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+                                      const float* __restrict__ gamma, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, int training, float* coefA, float* coefB, float* coefC,
+                                      float* dgamma, float* dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int pi = 0; pi < nparts; ++pi) {
+        s1 += (double)partials[(long long)pi * 2 * C + c];
+        s2 += (double)partials[(long long)pi * 2 * C + C + c];
+    }
+    const double m = mean[c], r = rstd[c], g = gamma[c];
+    const double dg = r * (s2 - m * s1);      // sum dz * xhat
+    const double A = g * r;
+    double B = 0.0, Cc = 0.0;
+    if (training) {
+        B = -g * r * r * dg / count;
+        Cc = -B * m - A * s1 / count;
+    }
+    coefA[c] = (float)A; coefB[c] = (float)B; coefC[c] = (float)Cc;
+    if (dgamma != nullptr) dgamma[c] += (float)dg;
+    if (dbeta != nullptr) dbeta[c] += (float)s1;
+}
+
+// pass 2: dy = A*dz + B*y + Cc  (bf16).  conv_grid_w > 0: scatter rows onto a zero-initialised
+// (conv_grid_h x conv_grid_w) "input grid" layout used by the stem implicit-GEMM backward.
+__global__ void __launch_bounds__(256)
+bnbwd_apply_kernel(const uint4* __restrict__ y, const BnBwdSrc s, const float* __restrict__ coefA,
+                   const float* __restrict__ coefB, const float* __restrict__ coefC, uint4* __restrict__ dy, long long n8,
+                   int grid_w, int grid_h) {
+    const int ncg = s.C >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % ncg);
+        float yv[8], dz[8], A[8], B[8], Cc[8];
+        unpack8(ldg_nc_v4(y + i), yv);
+        bnbwd_dz8(s, i, cg, yv, dz);
+        load_affine8(coefA, coefB, cg * 8, A, B);
+        const float4 c0 = *reinterpret_cast<const float4*>(coefC + cg * 8), c1 = *reinterpret_cast<const float4*>(coefC + cg * 8 + 4);
+        Cc[0] = c0.x; Cc[1] = c0.y; Cc[2] = c0.z; Cc[3] = c0.w; Cc[4] = c1.x; Cc[5] = c1.y; Cc[6] = c1.z; Cc[7] = c1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = fmaf(A[j], dz[j], fmaf(B[j], yv[j], Cc[j]));
+        long long o = i;
+        if (grid_w > 0) {
+            long long t = i / ncg;
+            const int w = (int)(t % s.W); t /= s.W;
+            const int h = (int)(t % s.H);
+            const long long f = t / s.H;
+            o = ((f * grid_h + h) * grid_w + w) * ncg + cg;
+        }
+        dy[o] = pack8(dz);
+    }
+}
+
+// ======================================================================================== layout converters
+// NCHW fp32 -> NHWC bf16 via a 32x32 smem transpose over (C, HW) per frame.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int HW) {
+    __shared__ float t[32][33];
+    const int f = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, pp = p0 + threadIdx.x;
+        t[r][threadIdx.x] = (c < C && pp < HW) ? x[((long long)f * C + c) * HW + pp] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int pp = p0 + r, c = c0 + threadIdx.x;
+        if (pp < HW && c < C) out[((long long)f * HW + pp) * C + c] = __float2bfloat16(t[threadIdx.x][r]);
+    }
+}
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int C, int HW) {
+    __shared__ float t[32][33];
+    const int f = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int pp = p0 + r, c = c0 + threadIdx.x;
+        t[r][threadIdx.x] = (c < C && pp < HW) ? __bfloat162float(x[((long long)f * HW + pp) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, pp = p0 + threadIdx.x;
+        if (pp < HW && c < C) out[((long long)f * C + c) * HW + pp] = t[threadIdx.x][r];
+    }
+}
+
+// fp32 [R, Cc] -> bf16 [R, Cc] and (optionally) its transpose bf16 [Cc, R]
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_t,
+                                   int R, int Cc) {
+    __shared__ float t[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int rr = r0 + r, cc = c0 + threadIdx.x;
+        const float v = (rr < R && cc < Cc) ? w[(long long)rr * Cc + cc] : 0.f;
+        t[r][threadIdx.x] = v;
+        if (rr < R && cc < Cc && out != nullptr) out[(long long)rr * Cc + cc] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    if (out_t != nullptr) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            const int cc = c0 + r, rr = r0 + threadIdx.x;
+            if (rr < R && cc < Cc) out_t[(long long)cc * R + rr] = __float2bfloat16(t[threadIdx.x][r]);
+        }
+    }
+}
+
+// depthwise weights [C,1,3,3] fp32 -> tap-major [9][C] fp32 ; and the reverse accumulation for gradients
+__global__ void pack_dw_kernel(const float* __restrict__ w, float* __restrict__ w9, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * C) { const int c = i / 9, k = i % 9; w9[(long long)k * C + c] = w[i]; }
+}
+__global__ void unpack_dw_grad_kernel(const float* __restrict__ g9, float* __restrict__ gw, int C, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * C) {
+        const int c = i / 9, k = i % 9;
+        const float v = g9[(long long)k * C + c];
+        gw[i] = accumulate ? gw[i] + v : v;
+    }
+}
+
+// dense 3x3 weights [O,I,3,3] fp32 -> bf16 [O][tap*I + i]   (K-major "tap-major" packing for the implicit GEMM)
+// and (optionally) bf16 [I][tap*O + o] for the data-gradient implicit GEMM.
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wk, __nv_bfloat16* __restrict__ wk_t,
+                                    int O, int I) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= O * I * 9) return;
+    const int tap = idx % 9, i = (idx / 9) % I, o = idx / (9 * I);
+    const float v = w[idx];
+    wk[(long long)o * (9 * I) + tap * I + i] = __float2bfloat16(v);
+    if (wk_t != nullptr) wk_t[(long long)i * (9 * O) + tap * O + o] = __float2bfloat16(v);
+}
+
+// gradient of pack_conv3x3: gk fp32 [O][tap*I + i]  ->  gw [O,I,3,3] (+=)
+__global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ gk, float* __restrict__ gw, int O, int I) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= O * I * 9) return;
+    const int tap = idx % 9, i = (idx / 9) % I, o = idx / (9 * I);
+    gw[idx] += gk[(long long)o * (9 * I) + tap * I + i];
+}
+
+// Weight gradient of the stem conv1 (3->32, k3 s2 p0; Xception.py:118,168): dW[oc][27] += sum_pix dy[pix][oc] * patch[pix][27].
+// Persistent blocks over 128-pixel chunks; 288 threads x 3 outputs.
+__global__ void __launch_bounds__(288)
+stem_conv1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dW, int F, int H, int W,
+                        int H1, int W1) {
+    __shared__ float s_dy[128][33];
+    __shared__ float s_x[128][28];
+    const long long M = (long long)F * H1 * W1;
+    const long long chunks = (M + 127) / 128;
+    float acc[3] = {0.f, 0.f, 0.f};
+    int oc[3], tp[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) { const int o = threadIdx.x + u * 288; oc[u] = o / 27; tp[u] = o % 27; }
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 128 * 32; i += 288) {
+            const int r = i >> 5, c = i & 31;
+            const long long pix = ch * 128 + r;
+            s_dy[r][c] = pix < M ? __bfloat162float(dy[pix * 32 + c]) : 0.f;
+        }
+        for (int i = threadIdx.x; i < 128 * 27; i += 288) {
+            const int r = i / 27, tap = i % 27;
+            const long long pix = ch * 128 + r;
+            float v = 0.f;
+            if (pix < M) {
+                const int wo = (int)(pix % W1);
+                const int ho = (int)((pix / W1) % H1);
+                const int f = (int)(pix / ((long long)W1 * H1));
+                const int ic = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+                v = x[(((long long)f * 3 + ic) * H + 2 * ho + kh) * W + 2 * wo + kw];
+            }
+            s_x[r][tap] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < 128; ++r) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) acc[u] = fmaf(s_dy[r][oc[u]], s_x[r][tp[u]], acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) atomicAdd(&dW[threadIdx.x + u * 288], acc[u]);
+}
+
+// bilinear (align_corners=False) upsample of [F,C,n,1] fp32 to [F,C,S,S] fp32 (XceptionLSTMA.py:45-46).
+// With input width 1 every output column equals the row value, so only the vertical lerp is computed.
+__global__ void bilinear_up_kernel(const float* __restrict__ x, float* __restrict__ out, long long planes, int n, int S) {
+    const long long total = planes * S * S;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)((i / S) % S);
+        const long long pl = i / ((long long)S * S);
+        float src = ((float)r + 0.5f) * ((float)n / (float)S) - 0.5f;
+        if (src < 0.f) src = 0.f;
+        int i0 = (int)floorf(src);
+        if (i0 > n - 1) i0 = n - 1;
+        const int i1 = min(i0 + 1, n - 1);
+        const float l1 = src - (float)i0, l0 = 1.f - l1;
+        out[i] = l0 * x[pl * n + i0] + l1 * x[pl * n + i1];
+    }
+}
+
+static int ew_grid(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    const long long cap = 8LL * num_sms();
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace xcp
+
+using namespace xcp;
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int xcp_stem_conv1_fwd(const float* x, const float* w, void* y, float* partials, int F, int H, int W, int device,
+                                  void* stream) {
+    XCP_REQUIRE(F > 0 && H >= 3 && W >= 3, "xcp_stem_conv1_fwd: bad shape");
+    XCP_CUDA(cudaSetDevice(device));
+    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
+    const long long M = (long long)F * H1 * W1;
+    stem_conv1_fwd_kernel<<<(int)((M + 127) / 128), 128, 0, ST>>>(x, w, (__nv_bfloat16*)y, partials, F, H, W, H1, W1);
+    return check_cuda(cudaGetLastError(), "stem_conv1_fwd launch");
+}
+
+extern "C" int xcp_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                               float* mean_out, float* rstd_out, int device, void* stream) {
+    XCP_REQUIRE(nparts > 0 && C > 0 && count > 0, "xcp_bn_finalize: bad args");
+    XCP_CUDA(cudaSetDevice(device));
+    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, ST>>>(partials, nparts, C, count, gamma, beta, running_mean, running_var,
+                                                      momentum, eps, scale, shift, mean_out, rstd_out);
+    return check_cuda(cudaGetLastError(), "bn_finalize launch");
+}
+
+extern "C" int xcp_bn_eval_affine(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                  float* scale, float* shift, float* mean_out, float* rstd_out, int C, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, ST>>>(gamma, beta, rm, rv, eps, scale, shift, mean_out, rstd_out, C);
+    return check_cuda(cudaGetLastError(), "bn_eval_affine launch");
+}
+
+extern "C" int xcp_bn_act(const void* y, const float* scale, const float* shift, int relu, void* out, long long n, int C,
+                          int device, void* stream) {
+    XCP_REQUIRE(C % 8 == 0 && n % C == 0, "xcp_bn_act: bad shape");
+    XCP_CUDA(cudaSetDevice(device));
+    bn_act_kernel<<<ew_grid(n / 8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, relu, (uint4*)out, n / 8, C);
+    return check_cuda(cudaGetLastError(), "bn_act launch");
+}
+
+extern "C" int xcp_gather_s2(const void* x, const float* scale, const float* shift, int relu, void* out, int F, int H, int W,
+                             int C, int device, void* stream) {
+    XCP_REQUIRE(C % 8 == 0, "xcp_gather_s2: C %% 8");
+    XCP_CUDA(cudaSetDevice(device));
+    const long long n8 = (long long)F * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    gather_s2_kernel<<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)x, scale, shift, relu, (uint4*)out, F, H, W, C);
+    return check_cuda(cudaGetLastError(), "gather_s2 launch");
+}
+
+extern "C" int xcp_pool_add_fwd(const void* y, const float* scale, const float* shift, const void* ys, const float* scale_s,
+                                const float* shift_s, void* out, void* idx, int F, int H, int W, int C, int device,
+                                void* stream) {
+    XCP_REQUIRE(C % 8 == 0, "xcp_pool_add_fwd: C %% 8");
+    XCP_CUDA(cudaSetDevice(device));
+    const long long n8 = (long long)F * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 8);
+    pool_add_fwd_kernel<<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)ys, scale_s, shift_s,
+                                                          (uint4*)out, (uint2*)idx, F, H, W, C);
+    return check_cuda(cudaGetLastError(), "pool_add_fwd launch");
+}
+
+extern "C" int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const void* skip, void* out, long long n,
+                              int C, int device, void* stream) {
+    XCP_REQUIRE(C % 8 == 0 && n % C == 0, "xcp_bn_add_fwd: bad shape");
+    XCP_CUDA(cudaSetDevice(device));
+    bn_add_fwd_kernel<<<ew_grid(n / 8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)skip, (uint4*)out, n / 8, C);
+    return check_cuda(cudaGetLastError(), "bn_add_fwd launch");
+}
+
+extern "C" int xcp_bn_relu_gap(const void* y, const float* scale, const float* shift, float* feat, int F, int HW, int C,
+                               int device, void* stream) {
+    XCP_REQUIRE(C % 8 == 0, "xcp_bn_relu_gap: C %% 8");
+    XCP_CUDA(cudaSetDevice(device));
+    dim3 grid((C / 8 + 31) / 32, F);
+    bn_relu_gap_kernel<<<grid, 256, 0, ST>>>((const uint4*)y, scale, shift, feat, HW, C);
+    return check_cuda(cudaGetLastError(), "bn_relu_gap launch");
+}
+
+extern "C" int xcp_bnbwd_num_parts(void) { return 2 * 160; }
+
+// Two-pass BatchNorm backward.  mode: 0 direct, 1 relu-masked, 2 through MaxPool(3,2,1) (G, idx at pooled
+// resolution), 3 through GAP+ReLU (dfeat).  Writes dy (bf16) and accumulates dgamma/dbeta.  `presums`
+// non-null skips pass 1 and uses those [2][C] sums (produced by xcp_dw3x3_bwd).
+extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* idx, const float* dfeat, const float* scale,
+                          const float* shift, const float* gamma, const float* mean, const float* rstd, int training,
+                          const float* presums, float* workspace, float* coef, float* dgamma, float* dbeta, void* dy, int F,
+                          int H, int W, int C, int grid_w, int grid_h, int device, void* stream) {
+    XCP_REQUIRE(C % 8 == 0 && mode >= 0 && mode <= 3, "xcp_bn_bwd: bad args");
+    XCP_REQUIRE(coef != nullptr && (presums != nullptr || workspace != nullptr), "xcp_bn_bwd: workspace");
+    XCP_CUDA(cudaSetDevice(device));
+    BnBwdSrc s{mode, (const __nv_bfloat16*)G, (const uint8_t*)idx, dfeat, scale, shift, F, H, W, C};
+    const long long n8 = (long long)F * H * W * (C / 8);
+    const double count = (double)F * H * W;
+    int nparts = 1;
+    const float* sums = presums;
+    if (presums == nullptr) {
+        long long g = (n8 + 255) / 256;
+        nparts = (int)(g < xcp_bnbwd_num_parts() ? g : xcp_bnbwd_num_parts());
+        bnbwd_reduce_kernel<<<nparts, 256, 2 * C * sizeof(float), ST>>>((const uint4*)y, s, workspace, n8);
+        XCP_CUDA(cudaGetLastError());
+        sums = workspace;
+    }
+    bnbwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sums, nparts, C, count, gamma, mean, rstd, training, coef, coef + C,
+                                                           coef + 2 * C, dgamma, dbeta);
+    XCP_CUDA(cudaGetLastError());
+    if (dy != nullptr) {
+        bnbwd_apply_kernel<<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)y, s, coef, coef + C, coef + 2 * C, (uint4*)dy, n8,
+                                                             grid_w, grid_h);
+    }
+    return check_cuda(cudaGetLastError(), "bn_bwd launch");
+}
+
+extern "C" int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int HW, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, F), block(32, 8);
+    nchw_to_nhwc_kernel<<<grid, block, 0, ST>>>(x, (__nv_bfloat16*)out, C, HW);
+    return check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
+}
+
+extern "C" int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int HW, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, F), block(32, 8);
+    nhwc_to_nchw_kernel<<<grid, block, 0, ST>>>((const __nv_bfloat16*)x, out, C, HW);
+    return check_cuda(cudaGetLastError(), "nhwc_to_nchw launch");
+}
+
+extern "C" int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    dim3 grid((Cc + 31) / 32, (R + 31) / 32), block(32, 8);
+    pack_weight_kernel<<<grid, block, 0, ST>>>(w, (__nv_bfloat16*)out, (__nv_bfloat16*)out_t, R, Cc);
+    return check_cuda(cudaGetLastError(), "pack_weight launch");
+}
+
+extern "C" int xcp_pack_dw(const float* w, float* w9, int C, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    pack_dw_kernel<<<(9 * C + 255) / 256, 256, 0, ST>>>(w, w9, C);
+    return check_cuda(cudaGetLastError(), "pack_dw launch");
+}
+
+extern "C" int xcp_unpack_dw_grad(const float* g9, float* gw, int C, int accumulate, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    unpack_dw_grad_kernel<<<(9 * C + 255) / 256, 256, 0, ST>>>(g9, gw, C, accumulate);
+    return check_cuda(cudaGetLastError(), "unpack_dw_grad launch");
+}
+
+extern "C" int xcp_pack_conv3x3(const float* w, void* wk, void* wk_t, int O, int I, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    pack_conv3x3_kernel<<<(O * I * 9 + 255) / 256, 256, 0, ST>>>(w, (__nv_bfloat16*)wk, (__nv_bfloat16*)wk_t, O, I);
+    return check_cuda(cudaGetLastError(), "pack_conv3x3 launch");
+}
+
+extern "C" int xcp_unpack_conv3x3_grad(const float* gk, float* gw, int O, int I, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    unpack_conv3x3_grad_kernel<<<(O * I * 9 + 255) / 256, 256, 0, ST>>>(gk, gw, O, I);
+    return check_cuda(cudaGetLastError(), "unpack_conv3x3_grad launch");
+}
+
+extern "C" int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, int F, int H, int W, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
+    const long long chunks = ((long long)F * H1 * W1 + 127) / 128;
+    long long grid = 2LL * num_sms();
+    if (grid > chunks) grid = chunks;
+    stem_conv1_wgrad_kernel<<<(int)grid, 288, 0, ST>>>(x, (const __nv_bfloat16*)dy, dW, F, H, W, H1, W1);
+    return check_cuda(cudaGetLastError(), "stem_conv1_wgrad launch");
+}
+
+extern "C" int xcp_bilinear_up(const float* x, float* out, long long planes, int n, int S, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    bilinear_up_kernel<<<ew_grid(planes * S * S, 256), 256, 0, ST>>>(x, out, planes, n, S);
+    return check_cuda(cudaGetLastError(), "bilinear_up launch");
+}

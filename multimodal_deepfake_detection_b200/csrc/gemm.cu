@@ -1,0 +1,441 @@
+// tcgen05 / TMEM / TMA bf16 GEMM family for the pointwise (1x1) convolutions, skip convs, LSTM input
+// projection (forward + dgrad: K-major operands) and the weight gradients (MN-major operands, split over
+// the pixel dimension, fp32 RED epilogue).
+//
+// Replaces the cuDNN/cuBLAS calls behind nn.Conv2d(k=1) / nn.Linear that the reference reaches from
+// SeparableConv2d.forward (Xception.py:44-47), Block.forward skip (Xception.py:92-94) and nn.LSTM's
+// input projection (XceptionLSTMV.py:18-23).
+//
+// Structure (one CTA per SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 per instr)
+//   warps 2..5    : epilogue      (tcgen05.ld 32x32b -> regs -> bf16/f32 store, per-channel sum / sum-sq)
+// Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#include "common.cuh"
+
+namespace xcp {
+
+enum { EPI_BF16 = 0, EPI_BF16_STATS = 1, EPI_F32 = 2, EPI_RED_F32 = 3 };
+
+struct GemmParams {
+    int M, N, K;          // output rows, output cols, reduction length (elements)
+    void* out;            // bf16 / f32, row-major [M, ldo]
+    long long ldo;
+    float* stats;         // EPI_BF16_STATS: [num_m_tiles][2][N]
+    const float* bias;    // EPI_F32: optional [N]
+    int num_m_tiles, num_n_tiles, num_k_blocks;
+    int splits, k_blocks_per_split;   // split over the reduction dim (EPI_RED_F32)
+    // implicit-GEMM mode for the dense 3x3 stem conv: K block kb reads A rows shifted by a_row_shift[kb]
+    int conv_taps;        // 0 = plain GEMM
+    int a_row_shift[9];
+    int conv_grid_w, conv_grid_h, conv_out_w, conv_out_h;  // epilogue compaction of the "input grid" rows
+};
+
+constexpr int BLOCK_M = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * 128;
+
+template <int BLOCK_N, int BLOCK_K>
+__host__ __device__ constexpr int b_stage_bytes() { return BLOCK_N * BLOCK_K * 2; }
+
+template <int BLOCK_N, int BLOCK_K, bool STATS>
+__host__ __device__ constexpr int gemm_smem_bytes(int stages) {
+    return 1024 /*align slack*/ + stages * (BLOCK_M * BLOCK_K * 2 + b_stage_bytes<BLOCK_N, BLOCK_K>()) +
+           (STATS ? (4 * 32 * 33 * 4 + 4 * 2 * BLOCK_N * 4) : 0) + 256 /*barriers*/;
+}
+
+// MN_MAJOR=false: A is [M,K] row-major, B is [N,K] row-major (both K-major):      D = A * B^T
+// MN_MAJOR=true : A is [K,M] row-major, B is [K,N] row-major (both MN-major):     D = A^T * B
+// BLOCK_K=64 -> 128B swizzle; BLOCK_K=32 -> 64B swizzle (K-major only; used by the stem implicit GEMM)
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    static_assert(BLOCK_K == 64 || (BLOCK_K == 32 && !MN_MAJOR), "unsupported BLOCK_K");
+    constexpr bool STATS = (EPI == EPI_BF16_STATS);
+    constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t LAYOUT = (BLOCK_K == 64) ? 2u : 4u;       // SWIZZLE_128B : SWIZZLE_64B
+    constexpr uint32_t SBO = 8 * BLOCK_K * 2;                    // bytes between 8-row groups
+    constexpr int UMMA_K = 16;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + STAGES * A_BYTES;
+    uint8_t* after = sB + STAGES * B_BYTES;
+    float* s_tr = reinterpret_cast<float*>(after);                       // [4][32][33]
+    float* s_part = s_tr + (STATS ? 4 * 32 * 33 : 0);                    // [4][2][BLOCK_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + (STATS ? 4 * 2 * BLOCK_N : 0));
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+    const int num_units = tiles_mn * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------ TMA producer
+        int s = 0; uint32_t ph = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+            const int split = u / tiles_mn;
+            const int t = u - split * tiles_mn;
+            const int m_blk = t / p.num_n_tiles, n_blk = t - m_blk * p.num_n_tiles;
+            const int kb0 = split * p.k_blocks_per_split;
+            const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+                if (!MN_MAJOR) {
+                    if (p.conv_taps > 0) {
+                        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], 0, m_blk * BLOCK_M + p.a_row_shift[kb]);
+                    } else {
+                        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BLOCK_K, m_blk * BLOCK_M);
+                    }
+                    tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BLOCK_K, n_blk * BLOCK_N);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < BLOCK_M / 64; ++a)
+                        tma_load_2d(sA + s * A_BYTES + a * (64 * 128), &tmA, &full[s], m_blk * BLOCK_M + a * 64, kb * 64);
+#pragma unroll
+                    for (int a = 0; a < BLOCK_N / 64; ++a)
+                        tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], n_blk * BLOCK_N + a * 64, kb * 64);
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        int s = 0; uint32_t ph = 0; uint32_t iter = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++iter) {
+            const int split = u / tiles_mn;
+            const int kb0 = split * p.k_blocks_per_split;
+            const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+            const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    uint64_t adesc, bdesc;
+                    if (!MN_MAJOR) {
+                        adesc = make_smem_desc(a_base + s * A_BYTES + k * (UMMA_K * 2), 0, SBO, LAYOUT);
+                        bdesc = make_smem_desc(b_base + s * B_BYTES + k * (UMMA_K * 2), 0, SBO, LAYOUT);
+                    } else {
+                        // MN-major, 128B swizzle: atoms of 64 (MN) x 8 (K); LBO = stride between 64-wide MN atoms
+                        // (= 64 K-rows * 128 B), SBO = stride between 8-row K groups (1024 B).
+                        adesc = make_smem_desc(a_base + s * A_BYTES + k * (UMMA_K * 128), 64 * 128, 1024, 2);
+                        bdesc = make_smem_desc(b_base + s * B_BYTES + k * (UMMA_K * 128), 64 * 128, 1024, 2);
+                    }
+                    umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);                       // frees the smem slot when these MMAs retire
+                if (kb == kb1 - 1) umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 2) {
+        // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int q = warp & 3;
+        const int row_in_tile = q * 32 + lane;
+        const int et = threadIdx.x - 64;   // 0..127
+        float* my_tr = s_tr + q * (32 * 33);
+        uint32_t iter = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++iter) {
+            const int split = u / tiles_mn;
+            const int t = u - split * tiles_mn;
+            const int m_blk = t / p.num_n_tiles, n_blk = t - m_blk * p.num_n_tiles;
+            const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
+            mbar_wait(&tmem_full[as], aph);
+            tc_fence_after();
+            const long long grow = (long long)m_blk * BLOCK_M + row_in_tile;
+            // stem implicit GEMM: rows live on the (conv_grid_h x conv_grid_w) input grid; keep only rows whose
+            // (h, w) fall inside the valid output window and compact them.
+            bool row_ok = grow < p.M;
+            long long orow = grow;
+            if (p.conv_taps > 0) {
+                const int gw = p.conv_grid_w, gh = p.conv_grid_h;
+                const long long f = grow / ((long long)gw * gh);
+                const int rem = (int)(grow - f * gw * gh);
+                const int h = rem / gw, w = rem - h * gw;
+                row_ok = row_ok && (h < p.conv_out_h) && (w < p.conv_out_w);
+                orow = (f * p.conv_out_h + h) * p.conv_out_w + w;
+            }
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
+                tmem_ld_wait();
+                const int gcol = n_blk * BLOCK_N + c * 32;
+                if (EPI == EPI_BF16 || EPI == EPI_BF16_STATS) {
+                    __nv_bfloat16* orow_p = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + gcol;
+                    if (row_ok) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (gcol + g * 8 + 8 <= p.N) {
+                                uint4 v;
+                                v.x = pack_bf16(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+                                v.y = pack_bf16(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+                                v.z = pack_bf16(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+                                v.w = pack_bf16(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+                                *reinterpret_cast<uint4*>(orow_p + g * 8) = v;
+                            }
+                        }
+                    }
+                    if (STATS) {
+                        // per-column sum / sum-of-squares over this warp's 32 rows via a padded smem transpose
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) my_tr[lane * 33 + j] = row_ok ? __uint_as_float(r[j]) : 0.f;
+                        __syncwarp();
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) {
+                            const float v = my_tr[l * 33 + lane];
+                            s1 += v;
+                            s2 = fmaf(v, v, s2);
+                        }
+                        s_part[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = s1;
+                        s_part[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = s2;
+                        __syncwarp();
+                    }
+                } else if (EPI == EPI_F32) {
+                    float* orow_p = reinterpret_cast<float*>(p.out) + orow * p.ldo + gcol;
+                    if (row_ok) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            if (gcol + g * 4 + 4 <= p.N) {
+                                float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+                                if (p.bias != nullptr) {
+                                    const float4 b = *reinterpret_cast<const float4*>(p.bias + gcol + g * 4);
+                                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                                }
+                                *reinterpret_cast<float4*>(orow_p + g * 4) = v;
+                            }
+                        }
+                    }
+                } else {  // EPI_RED_F32: accumulate the split-K partial tile into fp32 memory
+                    float* orow_p = reinterpret_cast<float*>(p.out) + orow * p.ldo + gcol;
+                    if (row_ok) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            if (gcol + g * 4 + 4 <= p.N) {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow_p + g * 4),
+                                             "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
+                                             "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                                             : "memory");
+                            }
+                        }
+                    }
+                }
+            }
+            // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (STATS) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = et; c < BLOCK_N; c += 128) {
+                    const int gcol = n_blk * BLOCK_N + c;
+                    if (gcol < p.N) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            s1 += s_part[(qq * 2 + 0) * BLOCK_N + c];
+                            s2 += s_part[(qq * 2 + 1) * BLOCK_N + c];
+                        }
+                        p.stats[((long long)m_blk * 2 + 0) * p.N + gcol] = s1;
+                        p.stats[((long long)m_blk * 2 + 1) * p.N + gcol] = s2;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Debug / cross-check kernel (never used by the product path): plain SIMT GEMM, fp32 accumulate.
+__global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
+                                float* out, long long ldo, int M, int N, int K, int mn_major) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (n >= N || m >= M) return;
+    float acc = 0.f;
+    if (!mn_major) {
+        for (int k = 0; k < K; ++k) acc = fmaf(__bfloat162float(A[m * lda + k]), __bfloat162float(B[n * ldb + k]), acc);
+    } else {
+        for (int k = 0; k < K; ++k) acc = fmaf(__bfloat162float(A[k * lda + m]), __bfloat162float(B[k * ldb + n]), acc);
+    }
+    out[m * ldo + n] = acc;
+}
+
+// ----------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI == EPI_BF16_STATS>(STAGES);
+    static_assert(smem <= 232448, "smem budget");
+    auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K>;
+    static bool attr_set = false;   // per-instantiation; benign race (idempotent)
+    if (!attr_set) {
+        XCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
+    const int grid = units < num_sms() ? units : num_sms();
+    kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+    return check_cuda(cudaGetLastError(), "gemm_kernel launch");
+}
+
+template <int EPI>
+static int dispatch_tn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+    switch (bn) {
+        case 64: return launch_gemm<64, EPI, false, 8, 64>(a, b, p, st);
+        case 128: return launch_gemm<128, EPI, false, 6, 64>(a, b, p, st);
+        default: return launch_gemm<256, EPI, false, 4, 64>(a, b, p, st);
+    }
+}
+
+}  // namespace xcp
+
+using namespace xcp;
+
+static int pick_block_n(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
+
+// D[M,N] = A[M,K] * B[N,K]^T  (bf16 in, fp32 accumulate).  epi: 0 bf16 out, 1 bf16 out + per-column
+// (sum, sum-sq) partials per 128-row tile into stats[ceil(M/128)][2][N], 2 fp32 out (+ optional bias[N]).
+extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo,
+                           int M, int N, int K, int epi, float* stats, const float* bias, int device, void* stream) {
+    XCP_REQUIRE(M > 0 && N > 0 && K > 0, "xcp_gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
+    XCP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "xcp_gemm_tn: K/lda/ldb must be multiples of 8 (16B TMA rows)");
+    XCP_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "xcp_gemm_tn: N/ldo must be multiples of 8");
+    XCP_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)out % 16 == 0), "xcp_gemm_tn: 16B alignment");
+    XCP_REQUIRE(epi >= 0 && epi <= 2, "xcp_gemm_tn: bad epilogue %d", epi);
+    XCP_REQUIRE(epi != EPI_BF16_STATS || stats != nullptr, "xcp_gemm_tn: stats buffer missing");
+    XCP_CUDA(cudaSetDevice(device));
+    const int bn = pick_block_n(N);
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BLOCK_M, 128)) return e;
+    if (int e = make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, bn, 128)) return e;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.stats = stats; p.bias = bias;
+    p.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_tiles = (N + bn - 1) / bn;
+    p.num_k_blocks = (K + 63) / 64;
+    p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (epi) {
+        case EPI_BF16: return dispatch_tn<EPI_BF16>(bn, tmA, tmB, p, st);
+        case EPI_BF16_STATS: return dispatch_tn<EPI_BF16_STATS>(bn, tmA, tmB, p, st);
+        default: return dispatch_tn<EPI_F32>(bn, tmA, tmB, p, st);
+    }
+}
+
+// dW[P,Q] += dY[R,P]^T * X[R,Q]   (weight gradient of Y = X W^T; R = pixels).  fp32 RED accumulation, the
+// reduction dimension is split across CTAs so that small weight matrices still fill the GPU.
+extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, long long ld_x, float* dW, long long ld_dw,
+                              int R, int P, int Q, int device, void* stream) {
+    XCP_REQUIRE(R > 0 && P > 0 && Q > 0, "xcp_gemm_wgrad: empty problem");
+    XCP_REQUIRE(P % 8 == 0 && Q % 8 == 0 && ld_dy % 8 == 0 && ld_x % 8 == 0 && ld_dw % 4 == 0, "xcp_gemm_wgrad: alignment");
+    XCP_CUDA(cudaSetDevice(device));
+    const int bn = pick_block_n(Q);
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_2d(&tmA, dY, (uint64_t)P, (uint64_t)R, (uint64_t)ld_dy * 2, 64, 64, 128)) return e;
+    if (int e = make_tmap_2d(&tmB, X, (uint64_t)Q, (uint64_t)R, (uint64_t)ld_x * 2, 64, 64, 128)) return e;
+    GemmParams p{};
+    p.M = P; p.N = Q; p.K = R; p.out = dW; p.ldo = ld_dw;
+    p.num_m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    p.num_n_tiles = (Q + bn - 1) / bn;
+    p.num_k_blocks = (R + 63) / 64;
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    int splits = (2 * num_sms() + tiles - 1) / tiles;
+    int max_splits = (p.num_k_blocks + 7) / 8;   // at least 8 K-blocks (512 rows) per unit
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.k_blocks_per_split = (p.num_k_blocks + splits - 1) / splits;
+    p.splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bn) {
+        case 64: return launch_gemm<64, EPI_RED_F32, true, 6, 64>(tmA, tmB, p, st);
+        case 128: return launch_gemm<128, EPI_RED_F32, true, 6, 64>(tmA, tmB, p, st);
+        default: return launch_gemm<256, EPI_RED_F32, true, 4, 64>(tmA, tmB, p, st);
+    }
+}
+
+// Dense 3x3 stem convolution (Xception.py:122,172 conv2: 32->64, k3 s1 p0) and its data gradient as an implicit
+// GEMM on tcgen05: activations live as rows of a [F*Hg*Wg, Cin] matrix (the NHWC "input grid"); tap (kh,kw) of
+// the filter is one K block whose A tile is the same TMA box shifted by sign*(kh*Wg + kw) rows.  Rows whose
+// (h, w) fall outside the (Ho x Wo) valid window are computed and dropped by the epilogue (2.7% waste at 149^2).
+//   sign=+1 forward : out[F,Ho,Wo,Cout] compacted, optional BN statistics partials
+//   sign=-1 dgrad   : a = dY on the zero-padded input grid, b = per-tap transposed weights, out on the grid
+extern "C" int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* stats, int F, int Hg, int Wg, int Cin, int Cout,
+                                int Ho, int Wo, int sign, int device, void* stream) {
+    XCP_REQUIRE(Cin == 32 || Cin == 64, "xcp_conv3x3_gemm: Cin must be 32 or 64 (one K block per tap), got %d", Cin);
+    XCP_REQUIRE(Cout % 8 == 0 && Cout <= 64, "xcp_conv3x3_gemm: Cout must be <= 64 and a multiple of 8");
+    XCP_REQUIRE(sign == 1 || sign == -1, "xcp_conv3x3_gemm: sign");
+    XCP_CUDA(cudaSetDevice(device));
+    const long long Mg = (long long)F * Hg * Wg;
+    XCP_REQUIRE(Mg < (1LL << 31) - 65536, "xcp_conv3x3_gemm: grid too large for 32-bit TMA coordinates");
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_2d(&tmA, a, (uint64_t)Cin, (uint64_t)Mg, (uint64_t)Cin * 2, Cin, BLOCK_M, Cin * 2)) return e;
+    if (int e = make_tmap_2d(&tmB, b, (uint64_t)9 * Cin, (uint64_t)Cout, (uint64_t)9 * Cin * 2, Cin, 64, Cin * 2)) return e;
+    GemmParams p{};
+    p.M = (int)Mg; p.N = Cout; p.K = 9 * Cin; p.out = out; p.ldo = Cout; p.stats = stats;
+    p.num_m_tiles = (int)((Mg + BLOCK_M - 1) / BLOCK_M);
+    p.num_n_tiles = 1;
+    p.num_k_blocks = 9;
+    p.splits = 1; p.k_blocks_per_split = 9;
+    p.conv_taps = 9;
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) p.a_row_shift[kh * 3 + kw] = sign * (kh * Wg + kw);
+    p.conv_grid_w = Wg; p.conv_grid_h = Hg; p.conv_out_w = Wo; p.conv_out_h = Ho;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin == 32) {
+        if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, 8, 32>(tmA, tmB, p, st);
+        return launch_gemm<64, EPI_BF16, false, 8, 32>(tmA, tmB, p, st);
+    }
+    if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, 8, 64>(tmA, tmB, p, st);
+    return launch_gemm<64, EPI_BF16, false, 8, 64>(tmA, tmB, p, st);
+}
+
+// Debug cross-check (SIMT).  mn_major=0: out = A[M,K] B[N,K]^T ; 1: out = A[K,M]^T B[K,N].
+extern "C" int xcp_gemm_ref(const void* A, long long lda, const void* B, long long ldb, float* out, long long ldo,
+                            int M, int N, int K, int mn_major, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    dim3 grid((N + 127) / 128, M);
+    gemm_ref_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, out,
+                                                             ldo, M, N, K, mn_major);
+    return check_cuda(cudaGetLastError(), "gemm_ref_kernel launch");
+}

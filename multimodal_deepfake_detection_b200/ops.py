@@ -1,0 +1,393 @@
+"""Thin tensor-level wrappers over the C ABI (include/xcp.h).  PyTorch is used only for device memory
+(the caching allocator owns every buffer) and for the current stream; all arithmetic happens in
+libxcp_sm100.so.  Activations are bf16 NHWC tensors of shape [F, H, W, C]."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+EPI_BF16, EPI_BF16_STATS, EPI_F32 = 0, 1, 2
+SRC_DIRECT, SRC_RELU, SRC_POOL, SRC_GAP_RELU = 0, 1, 2, 3
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.XcpError(f"{name}: expected a CUDA tensor (this package has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.XcpError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.XcpError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def check_device(device: torch.device):
+    _lib.call("xcp_check_device", device.index if device.index is not None else torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------------------------ GEMMs
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """out[M,N] = a[M,K] @ b[N,K]^T.  Returns (out, stats_partials or None)."""
+    _chk(a, BF16, "gemm_tn.a"); _chk(b, BF16, "gemm_tn.b")
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=F32 if epi == EPI_F32 else BF16)
+    stats = torch.empty(((M + 127) // 128, 2, N), device=a.device, dtype=F32) if epi == EPI_BF16_STATS else None
+    _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), a.device.index, _s())
+    return out, stats
+
+
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ld_dw: Optional[int] = None):
+    """dw[P,Q] += dy[R,P]^T @ x[R,Q]  (dw fp32, accumulated in place)."""
+    _chk(dy, BF16, "gemm_wgrad.dy"); _chk(x, BF16, "gemm_wgrad.x")
+    assert dw.dtype == F32
+    R, P = dy.shape
+    Q = x.shape[1]
+    assert x.shape[0] == R
+    _lib.call("xcp_gemm_wgrad", _p(dy), P, _p(x), Q, _p(dw), ld_dw if ld_dw is not None else Q, R, P, Q, dy.device.index, _s())
+
+
+def gemm_ref(a, b, mn_major=False):
+    if not mn_major:
+        M, K = a.shape; N = b.shape[0]
+        out = torch.empty((M, N), device=a.device, dtype=F32)
+        _lib.call("xcp_gemm_ref", _p(a), K, _p(b), K, _p(out), N, M, N, K, 0, a.device.index, _s())
+    else:
+        K, M = a.shape; N = b.shape[1]
+        out = torch.empty((M, N), device=a.device, dtype=F32)
+        _lib.call("xcp_gemm_ref", _p(a), M, _p(b), N, _p(out), N, M, N, K, 1, a.device.index, _s())
+    return out
+
+
+def conv3x3_gemm_fwd(x: torch.Tensor, wk: torch.Tensor, want_stats: bool = True):
+    """Dense 3x3 s1 p0 conv of NHWC x [F,Hg,Wg,Cin] with packed weights wk [Cout, 9*Cin]."""
+    _chk(x, BF16, "conv3x3.x"); _chk(wk, BF16, "conv3x3.wk")
+    F_, Hg, Wg, Cin = x.shape
+    Cout = wk.shape[0]
+    Ho, Wo = Hg - 2, Wg - 2
+    out = torch.empty((F_, Ho, Wo, Cout), device=x.device, dtype=BF16)
+    mt = (F_ * Hg * Wg + 127) // 128
+    stats = torch.empty((mt, 2, Cout), device=x.device, dtype=F32) if want_stats else None
+    _lib.call("xcp_conv3x3_gemm", _p(x), _p(wk), _p(out), _p(stats), F_, Hg, Wg, Cin, Cout, Ho, Wo, 1, x.device.index, _s())
+    return out, stats
+
+
+def conv3x3_gemm_dgrad(dy_grid: torch.Tensor, wk_t: torch.Tensor):
+    """dy_grid [F,Hg,Wg,Cout] (zero outside the valid window) -> dx [F,Hg,Wg,Cin]; wk_t [Cin, 9*Cout]."""
+    F_, Hg, Wg, Cout = dy_grid.shape
+    Cin = wk_t.shape[0]
+    out = torch.empty((F_, Hg, Wg, Cin), device=dy_grid.device, dtype=BF16)
+    _lib.call("xcp_conv3x3_gemm", _p(dy_grid), _p(wk_t), _p(out), _p(None), F_, Hg, Wg, Cout, Cin, Hg, Wg, -1,
+              dy_grid.device.index, _s())
+    return out
+
+
+def conv3x3_wgrad(dy_grid: torch.Tensor, x: torch.Tensor, gk: torch.Tensor):
+    """gk[Cout, 9*Cin] (fp32) += per-tap dy_grid^T @ shifted(x): nine MN-major tcgen05 GEMMs on shifted views."""
+    F_, Hg, Wg, Cout = dy_grid.shape
+    Cin = x.shape[3]
+    R = F_ * Hg * Wg
+    dy2 = dy_grid.view(R, Cout)
+    x2 = x.view(R, Cin)
+    for kh in range(3):
+        for kw in range(3):
+            sh = kh * Wg + kw
+            tap = kh * 3 + kw
+            xv = x2[sh:]
+            _lib.call("xcp_gemm_wgrad", _p(dy2), Cout, _p(xv), Cin, ctypes.c_void_p(gk.data_ptr() + tap * Cin * 4), 9 * Cin,
+                      R - sh, Cout, Cin, x.device.index, _s())
+
+
+# ------------------------------------------------------------------------------------------------ stem / dw
+def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor):
+    _chk(x, F32, "stem_conv1.x"); _chk(w, F32, "stem_conv1.w")
+    F_, _, H, W = x.shape
+    H1, W1 = (H - 3) // 2 + 1, (W - 3) // 2 + 1
+    y = torch.empty((F_, H1, W1, 32), device=x.device, dtype=BF16)
+    parts = torch.empty(((F_ * H1 * W1 + 127) // 128, 2, 32), device=x.device, dtype=F32)
+    _lib.call("xcp_stem_conv1_fwd", _p(x), _p(w), _p(y), _p(parts), F_, H, W, x.device.index, _s())
+    return y, parts
+
+
+def stem_conv1_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
+    F_, _, H, W = x.shape
+    _lib.call("xcp_stem_conv1_wgrad", _p(x), _p(dy), _p(dw), F_, H, W, x.device.index, _s())
+
+
+def dw3x3_fwd(x: torch.Tensor, w9: torch.Tensor, scale=None, shift=None, relu: bool = False, out=None):
+    _chk(x, BF16, "dw3x3.x"); _chk(w9, F32, "dw3x3.w9")
+    F_, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("xcp_dw3x3_fwd", _p(x), _p(w9), _p(scale), _p(shift), int(relu), _p(out), F_, H, W, C, x.device.index, _s())
+    return out
+
+
+def dw3x3_bwd(dD, xin, w9, scale, shift, relu, dw9, add_full=None, add_half=None, want_bnsum=False):
+    _chk(dD, BF16, "dw3x3_bwd.dD"); _chk(xin, BF16, "dw3x3_bwd.xin")
+    F_, H, W, C = xin.shape
+    dz = torch.empty_like(xin)
+    ws = torch.empty((_lib.call("xcp_dw3x3_bwd_workspace_floats", C),), device=xin.device, dtype=F32)
+    bnsum = torch.empty((2, C), device=xin.device, dtype=F32) if want_bnsum else None
+    _lib.call("xcp_dw3x3_bwd", _p(dD), _p(xin), _p(w9), _p(scale), _p(shift), int(relu), _p(dz), _p(add_full), _p(add_half),
+              _p(dw9), _p(bnsum), _p(ws), F_, H, W, C, xin.device.index, _s())
+    return dz, bnsum
+
+
+# ------------------------------------------------------------------------------------------------ BN & friends
+class BNState:
+    """Per-call BatchNorm quantities: folded affine (scale, shift) and saved (mean, rstd)."""
+    __slots__ = ("scale", "shift", "mean", "rstd", "count", "training")
+
+    def __init__(self, C, device):
+        buf = torch.empty((4, C), device=device, dtype=F32)
+        self.scale, self.shift, self.mean, self.rstd = buf[0], buf[1], buf[2], buf[3]
+        self.count = 0.0
+        self.training = True
+
+
+def bn_finalize(parts: torch.Tensor, count: float, gamma, beta, running_mean, running_var, training: bool,
+                momentum: float = BN_MOMENTUM, eps: float = BN_EPS) -> BNState:
+    C = gamma.shape[0]
+    st = BNState(C, gamma.device)
+    st.count = float(count)
+    st.training = training
+    if training:
+        _lib.call("xcp_bn_finalize", _p(parts), parts.shape[0], C, float(count), _p(gamma), _p(beta), _p(running_mean),
+                  _p(running_var), momentum, eps, _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd), gamma.device.index, _s())
+    else:
+        _lib.call("xcp_bn_eval_affine", _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, _p(st.scale), _p(st.shift),
+                  _p(st.mean), _p(st.rstd), C, gamma.device.index, _s())
+    return st
+
+
+def bn_act(y, scale, shift, relu: bool):
+    out = torch.empty_like(y)
+    _lib.call("xcp_bn_act", _p(y), _p(scale), _p(shift), int(relu), _p(out), y.numel(), y.shape[-1], y.device.index, _s())
+    return out
+
+
+def gather_s2(x, scale=None, shift=None, relu=False):
+    F_, H, W, C = x.shape
+    out = torch.empty((F_, (H + 1) // 2, (W + 1) // 2, C), device=x.device, dtype=BF16)
+    _lib.call("xcp_gather_s2", _p(x), _p(scale), _p(shift), int(relu), _p(out), F_, H, W, C, x.device.index, _s())
+    return out
+
+
+def pool_add_fwd(y, scale, shift, ys, scale_s, shift_s, want_idx=True):
+    F_, H, W, C = y.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=BF16)
+    idx = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=torch.uint8) if want_idx else None
+    _lib.call("xcp_pool_add_fwd", _p(y), _p(scale), _p(shift), _p(ys), _p(scale_s), _p(shift_s), _p(out), _p(idx), F_, H, W, C,
+              y.device.index, _s())
+    return out, idx
+
+
+def bn_add_fwd(y, scale, shift, skip):
+    out = torch.empty_like(y)
+    _lib.call("xcp_bn_add_fwd", _p(y), _p(scale), _p(shift), _p(skip), _p(out), y.numel(), y.shape[-1], y.device.index, _s())
+    return out
+
+
+def bn_relu_gap(y, scale, shift):
+    F_, H, W, C = y.shape
+    feat = torch.empty((F_, C), device=y.device, dtype=F32)
+    _lib.call("xcp_bn_relu_gap", _p(y), _p(scale), _p(shift), _p(feat), F_, H * W, C, y.device.index, _s())
+    return feat
+
+
+def bn_bwd(mode: int, y, st: BNState, gamma, dgamma, dbeta, G=None, idx=None, dfeat=None, presums=None, want_dy=True,
+           grid_hw: Optional[Tuple[int, int]] = None):
+    """Backward through z = BN(y) (batch stats if st.training) given the gradient source described by `mode`.
+    Returns dy (bf16, same shape as y, or on the (grid_h, grid_w) padded layout when grid_hw is given)."""
+    F_, H, W, C = y.shape
+    dev = y.device
+    coef = torch.empty((3, C), device=dev, dtype=F32)
+    ws = None
+    if presums is None:
+        ws = torch.empty((_lib.call("xcp_bnbwd_num_parts"), 2, C), device=dev, dtype=F32)
+    dy = None
+    gh = gw = 0
+    if want_dy:
+        if grid_hw is not None:
+            gh, gw = grid_hw
+            dy = torch.zeros((F_, gh, gw, C), device=dev, dtype=BF16)
+        else:
+            dy = torch.empty_like(y)
+    _lib.call("xcp_bn_bwd", mode, _p(y), _p(G), _p(idx), _p(dfeat), _p(st.scale), _p(st.shift), _p(gamma), _p(st.mean),
+              _p(st.rstd), int(st.training), _p(presums), _p(ws), _p(coef), _p(dgamma), _p(dbeta), _p(dy), F_, H, W, C, gw, gh,
+              dev.index, _s())
+    return dy
+
+
+# ------------------------------------------------------------------------------------------------ layout / packing
+def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, F32, "nchw_to_nhwc.x")
+    F_, C, H, W = x.shape
+    out = torch.empty((F_, H, W, C), device=x.device, dtype=BF16)
+    _lib.call("xcp_nchw_to_nhwc", _p(x), _p(out), F_, C, H * W, x.device.index, _s())
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, BF16, "nhwc_to_nchw.x")
+    F_, H, W, C = x.shape
+    out = torch.empty((F_, C, H, W), device=x.device, dtype=F32)
+    _lib.call("xcp_nhwc_to_nchw", _p(x), _p(out), F_, C, H * W, x.device.index, _s())
+    return out
+
+
+def pack_weight(w2d: torch.Tensor, want_t: bool = True):
+    _chk(w2d, F32, "pack_weight.w")
+    R, Cc = w2d.shape
+    out = torch.empty((R, Cc), device=w2d.device, dtype=BF16)
+    out_t = torch.empty((Cc, R), device=w2d.device, dtype=BF16) if want_t else None
+    _lib.call("xcp_pack_weight", _p(w2d), _p(out), _p(out_t), R, Cc, w2d.device.index, _s())
+    return out, out_t
+
+
+def pack_dw(w: torch.Tensor):
+    C = w.shape[0]
+    w9 = torch.empty((9, C), device=w.device, dtype=F32)
+    _lib.call("xcp_pack_dw", _p(w), _p(w9), C, w.device.index, _s())
+    return w9
+
+
+def unpack_dw_grad(g9: torch.Tensor, gw: torch.Tensor, accumulate: bool):
+    _lib.call("xcp_unpack_dw_grad", _p(g9), _p(gw), g9.shape[1], int(accumulate), g9.device.index, _s())
+
+
+def pack_conv3x3(w: torch.Tensor, want_t: bool = True):
+    O, I = w.shape[0], w.shape[1]
+    wk = torch.empty((O, 9 * I), device=w.device, dtype=BF16)
+    wk_t = torch.empty((I, 9 * O), device=w.device, dtype=BF16) if want_t else None
+    _lib.call("xcp_pack_conv3x3", _p(w), _p(wk), _p(wk_t), O, I, w.device.index, _s())
+    return wk, wk_t
+
+
+def unpack_conv3x3_grad(gk: torch.Tensor, gw: torch.Tensor):
+    O, I = gw.shape[0], gw.shape[1]
+    _lib.call("xcp_unpack_conv3x3_grad", _p(gk), _p(gw), O, I, gw.device.index, _s())
+
+
+def bilinear_up(x: torch.Tensor, S: int = 64) -> torch.Tensor:
+    """x: [F, C, n, 1] fp32 -> [F, C, S, S] fp32 (XceptionLSTMA.py:46)."""
+    _chk(x, F32, "bilinear_up.x")
+    F_, C, n, one = x.shape
+    assert one == 1
+    out = torch.empty((F_, C, S, S), device=x.device, dtype=F32)
+    _lib.call("xcp_bilinear_up", _p(x), _p(out), F_ * C, n, S, x.device.index, _s())
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, F32, "cast_bf16.x")
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.call("xcp_cast_f32_bf16", _p(x), _p(out), x.numel(), x.device.index, _s())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ LSTM / head
+def lstm_fwd(xproj, b_ih, b_hh, w_hh_t, B, T, H):
+    dev = xproj.device
+    h_out = torch.empty((B, T, H), device=dev, dtype=F32)
+    gates = torch.empty((B, T, 4 * H), device=dev, dtype=F32)
+    cst = torch.empty((B, T, H), device=dev, dtype=F32)
+    hn = torch.empty((B, H), device=dev, dtype=F32)
+    cn = torch.empty((B, H), device=dev, dtype=F32)
+    _lib.call("xcp_lstm_fwd", _p(xproj), _p(b_ih), _p(b_hh), _p(w_hh_t), _p(h_out), _p(gates), _p(cst), _p(hn), _p(cn), B, T, H,
+              dev.index, _s())
+    return h_out, gates, cst, hn, cn
+
+
+def lstm_bwd(dout, dhn, dcn, gates, cst, hst, w_hh_bf16, dbias_ih, dbias_hh, B, T, H):
+    dev = gates.device
+    dgates = torch.empty((B * T, 4 * H), device=dev, dtype=BF16)
+    hprev = torch.empty((B * T, H), device=dev, dtype=BF16)
+    _lib.call("xcp_lstm_bwd", _p(dout), _p(dhn), _p(dcn), _p(gates), _p(cst), _p(hst), _p(w_hh_bf16), _p(dgates), _p(hprev),
+              _p(dbias_ih), _p(dbias_hh), B, T, H, dev.index, _s())
+    return dgates, hprev
+
+
+def linear_small_fwd(a, W, bias, act: int, mask=None, drop_scale: float = 1.0):
+    B, K = a.shape
+    N = W.shape[0]
+    out = torch.empty((B, N), device=a.device, dtype=F32)
+    _lib.call("xcp_linear_small_fwd", _p(a), _p(W), _p(bias), _p(mask), drop_scale, act, _p(out), B, N, K, a.device.index, _s())
+    return out
+
+
+def linear_small_bwd(delta_raw, out_act, drop_scale, a, W, dW, db, want_din=True):
+    B, K = a.shape
+    N = W.shape[0]
+    din = torch.zeros((B, K), device=a.device, dtype=F32) if want_din else None
+    _lib.call("xcp_linear_small_bwd", _p(delta_raw), _p(out_act), drop_scale, _p(a), _p(W), _p(dW), _p(db), _p(din), B, N, K,
+              a.device.index, _s())
+    return din
+
+
+def bce_fwd_bwd(z, y, smoothing: float = 0.0, want_grad: bool = True):
+    B = z.numel()
+    probs = torch.empty((B, 1), device=z.device, dtype=F32)
+    loss = torch.empty((), device=z.device, dtype=F32)
+    dz = torch.empty((B, 1), device=z.device, dtype=F32) if want_grad else None
+    _lib.call("xcp_bce_fwd_bwd", _p(z), _p(y), smoothing, _p(probs), _p(loss), _p(dz), B, z.device.index, _s())
+    return probs, loss, dz
+
+
+def arcface_loss(x, w, labels, s, m, loss_mode=0, class_w=None, gamma=2.0, dw=None, want_dx=True, gscale=1.0):
+    B, D = x.shape
+    dev = x.device
+    logits = torch.empty((B, 2), device=dev, dtype=F32)
+    loss = torch.zeros((), device=dev, dtype=F32)
+    rows = torch.empty((B,), device=dev, dtype=F32)
+    dx = torch.empty((B, D), device=dev, dtype=F32) if (want_dx and labels is not None) else None
+    _lib.call("xcp_arcface_loss", _p(x), _p(w), _p(labels), s, m, loss_mode, _p(class_w), gamma, _p(logits), _p(loss), _p(rows),
+              _p(dx), _p(dw), B, D, gscale, dev.index, _s())
+    return logits, loss, dx
+
+
+def fusion_pool_reg(v, a, lambda_align, lambda_temp, want_grad=True, gscale=1.0):
+    B, T, D = v.shape
+    dev = v.device
+    pooled = torch.empty((B, 2 * D), device=dev, dtype=F32)
+    loss = torch.empty((), device=dev, dtype=F32)
+    dv = torch.empty_like(v) if want_grad else None
+    da = torch.empty_like(a) if want_grad else None
+    _lib.call("xcp_fusion_pool_reg", _p(v), _p(a), _p(pooled), _p(loss), _p(dv), _p(da), B, T, D, lambda_align, lambda_temp,
+              gscale, dev.index, _s())
+    return pooled, loss, dv, da
+
+
+def fusion_pool_bwd(dpooled, dv, da):
+    B, T, D = dv.shape
+    _lib.call("xcp_fusion_pool_bwd", _p(dpooled), _p(dv), _p(da), B, T, D, dv.device.index, _s())
+
+
+def grad_sumsq(g: torch.Tensor, out: torch.Tensor, zero_first=True):
+    _lib.call("xcp_grad_sumsq", _p(g), g.numel(), _p(out), int(zero_first), g.device.index, _s())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step, sumsq=None, max_norm=0.0, grad_scale=1.0):
+    _lib.call("xcp_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, int(decoupled), step,
+              _p(sumsq), max_norm, grad_scale, p.device.index, _s())

@@ -1,0 +1,422 @@
+"""Kernel-level parity (B200 only): every C-ABI kernel against the single torch fp32 op it replaces,
+on the same seeded inputs, including the awkward shapes of the path (C=728, H=19/10, M % 128 != 0).
+bf16 storage => tolerances are relative to the tensor's max magnitude (written per test)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from multimodal_deepfake_detection_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def setup_module(module):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def rel_err(a, b):
+    a = a.float(); b = b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ GEMMs
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (1000, 128, 128), (300, 256, 256), (2000, 728, 728),
+                                   (1444, 1024, 728), (130, 2048, 1536), (128 * 149 + 5, 64, 128), (77, 8, 8)])
+def test_gemm_tn_bf16_stats(M, N, K):
+    a = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    b = rnd(N, K, seed=2, scale=1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    out, stats = ops.gemm_tn(a, b, ops.EPI_BF16_STATS)
+    assert rel_err(out, ref) < 8e-3          # bf16 rounding of the output only
+    s = stats.sum(0)
+    assert rel_err(s[0], ref.sum(0)) < 2e-3
+    assert rel_err(s[1], (ref * ref).sum(0)) < 2e-3
+    cross = ops.gemm_ref(a, b)
+    assert rel_err(cross, ref) < 1e-4
+    out2, _ = ops.gemm_tn(a, b, ops.EPI_BF16)
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 512, 2048), (300, 2048, 2048), (5, 128, 128)])
+def test_gemm_tn_f32_bias(M, N, K):
+    a = rnd(M, K, seed=3, dtype=torch.bfloat16)
+    b = rnd(N, K, seed=4, scale=1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = rnd(N, seed=5)
+    ref = a.float() @ b.float().t() + bias
+    out, _ = ops.gemm_tn(a, b, ops.EPI_F32, bias=bias)
+    assert rel_err(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("R,P,Q", [(1000, 128, 64), (5000, 728, 728), (300, 512, 2048), (70000, 128, 128), (50, 1024, 728),
+                                   (361 * 16, 2048, 1536)])
+def test_gemm_wgrad(R, P, Q):
+    dy = rnd(R, P, seed=6, dtype=torch.bfloat16)
+    x = rnd(R, Q, seed=7, dtype=torch.bfloat16)
+    ref = dy.float().t() @ x.float()
+    dw = torch.zeros(P, Q, device=DEV)
+    ops.gemm_wgrad(dy, x, dw)
+    assert rel_err(dw, ref) < 1e-4
+    ops.gemm_wgrad(dy, x, dw)               # accumulates
+    assert rel_err(dw, 2 * ref) < 1e-4
+    cross = ops.gemm_ref(dy, x, mn_major=True)
+    assert rel_err(cross, ref) < 1e-4
+
+
+@pytest.mark.parametrize("F_,Hg", [(2, 37), (3, 20), (1, 149)])
+def test_conv3x3_implicit_gemm(F_, Hg):
+    Wg = Hg
+    x = rnd(F_, Hg, Wg, 32, seed=8, dtype=torch.bfloat16)
+    w = rnd(64, 32, 3, 3, seed=9, scale=0.06)
+    wk, wk_t = ops.pack_conv3x3(w)
+    wq = wk.float().view(64, 9, 32).permute(0, 2, 1).reshape(64, 32, 3, 3)   # bf16-rounded weights, [O,I,3,3]
+    assert rel_err(wq, w) < 8e-3
+    x_nchw = x.float().permute(0, 3, 1, 2)
+    ref = F.conv2d(x_nchw, wq)                                               # [F,64,Ho,Wo]
+    out, stats = ops.conv3x3_gemm_fwd(x, wk)
+    assert rel_err(out.float().permute(0, 3, 1, 2), ref) < 8e-3
+    s = stats.sum(0)
+    assert rel_err(s[0], ref.sum((0, 2, 3))) < 2e-3
+    assert rel_err(s[1], (ref * ref).sum((0, 2, 3))) < 2e-3
+    # data gradient: dy on the zero-padded input grid
+    dy = rnd(F_, Hg - 2, Wg - 2, 64, seed=10, dtype=torch.bfloat16)
+    dy_grid = torch.zeros(F_, Hg, Wg, 64, device=DEV, dtype=torch.bfloat16)
+    dy_grid[:, :Hg - 2, :Wg - 2] = dy
+    dx = ops.conv3x3_gemm_dgrad(dy_grid, wk_t)
+    dx_ref = torch.nn.grad.conv2d_input(x_nchw.shape, wq, dy.float().permute(0, 3, 1, 2))
+    assert rel_err(dx.float().permute(0, 3, 1, 2), dx_ref) < 8e-3
+    # weight gradient: nine shifted MN-major GEMMs
+    gk = torch.zeros(64, 9 * 32, device=DEV)
+    ops.conv3x3_wgrad(dy_grid, x, gk)
+    gw = torch.zeros(64, 32, 3, 3, device=DEV)
+    ops.unpack_conv3x3_grad(gk, gw)
+    gw_ref = torch.nn.grad.conv2d_weight(x_nchw, w.shape, dy.float().permute(0, 3, 1, 2))
+    assert rel_err(gw, gw_ref) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ stem conv1
+@pytest.mark.parametrize("F_,H", [(2, 75), (1, 299), (3, 64)])
+def test_stem_conv1(F_, H):
+    x = torch.rand(F_, 3, H, H, device=DEV)
+    w = rnd(32, 3, 3, 3, seed=11, scale=0.3)
+    ref = F.conv2d(x, w, stride=2)
+    y, parts = ops.stem_conv1_fwd(x, w)
+    assert rel_err(y.float().permute(0, 3, 1, 2), ref) < 8e-3
+    s = parts.sum(0)
+    assert rel_err(s[0], ref.sum((0, 2, 3))) < 1e-4
+    assert rel_err(s[1], (ref * ref).sum((0, 2, 3))) < 1e-4
+    dy = rnd(*y.shape, seed=12, dtype=torch.bfloat16)
+    dw = torch.zeros_like(w)
+    ops.stem_conv1_wgrad(x, dy, dw)
+    dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, dy.float().permute(0, 3, 1, 2), stride=2)
+    assert rel_err(dw, dw_ref) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ depthwise
+DW_SHAPES = [(2, 147, 147, 64), (2, 74, 74, 128), (3, 37, 37, 256), (2, 19, 19, 728), (3, 10, 10, 1024), (1, 5, 7, 16),
+             (2, 2, 2, 728), (1, 33, 31, 8)]
+
+
+@pytest.mark.parametrize("shape", DW_SHAPES)
+@pytest.mark.parametrize("affine,relu", [(False, False), (False, True), (True, True), (True, False)])
+def test_dw3x3_fwd_bwd(shape, affine, relu):
+    F_, H, W, C = shape
+    x = rnd(F_, H, W, C, seed=13, dtype=torch.bfloat16)
+    w = rnd(C, 1, 3, 3, seed=14, scale=0.4)
+    w9 = ops.pack_dw(w)
+    scale = (rnd(C, seed=15) * 0.5 + 1.0) if affine else None      # includes some negative / small scales
+    shift = rnd(C, seed=16, scale=0.3) if affine else None
+    xt = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wt = w.clone().requires_grad_(True)
+    a = xt
+    if affine:
+        a = a * scale[None, :, None, None] + shift[None, :, None, None]
+    if relu:
+        a = F.relu(a)
+    ref = F.conv2d(a, wt, padding=1, groups=C)
+    out = ops.dw3x3_fwd(x, w9, scale, shift, relu)
+    assert rel_err(out.float().permute(0, 3, 1, 2), ref) < 8e-3
+    # backward
+    dD = rnd(F_, H, W, C, seed=17, dtype=torch.bfloat16)
+    ref.backward(dD.float().permute(0, 3, 1, 2))
+    dw9 = torch.zeros(9, C, device=DEV)
+    dz, bnsum = ops.dw3x3_bwd(dD, x, w9, scale, shift, relu, dw9, want_bnsum=affine)
+    gw = torch.zeros_like(w)
+    ops.unpack_dw_grad(dw9, gw, False)
+    assert rel_err(gw, wt.grad) < 2e-3
+    # dz is the gradient wrt the pre-activation z (= scale*x+shift, or x): compare through the chain rule
+    dz_ref = xt.grad
+    if affine:
+        sc = scale[None, :, None, None]
+        dz_f = dz.float().permute(0, 3, 1, 2)
+        assert rel_err(dz_f * sc, dz_ref) < 1e-2
+        zsum = dz_f.sum((0, 2, 3))
+        zysum = (dz_f * xt.detach()).sum((0, 2, 3))
+        assert rel_err(bnsum[0], zsum) < 5e-3
+        assert rel_err(bnsum[1], zysum) < 5e-3
+    else:
+        assert rel_err(dz.float().permute(0, 3, 1, 2), dz_ref) < 1e-2
+
+
+def test_dw3x3_bwd_residual_adds():
+    F_, H, W, C = 2, 19, 19, 728
+    x = rnd(F_, H, W, C, seed=18, dtype=torch.bfloat16)
+    w9 = ops.pack_dw(rnd(C, 1, 3, 3, seed=19, scale=0.4))
+    dD = rnd(F_, H, W, C, seed=20, dtype=torch.bfloat16)
+    full = rnd(F_, H, W, C, seed=21, dtype=torch.bfloat16)
+    half = rnd(F_, 10, 10, C, seed=22, dtype=torch.bfloat16)
+    dw9 = torch.zeros(9, C, device=DEV)
+    base, _ = ops.dw3x3_bwd(dD, x, w9, None, None, True, dw9)
+    both, _ = ops.dw3x3_bwd(dD, x, w9, None, None, True, dw9, add_full=full, add_half=half)
+    ref = base.float() + full.float()
+    ref[:, ::2, ::2] += half.float()
+    assert rel_err(both, ref) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ BN & elementwise
+@pytest.mark.parametrize("shape", [(4, 19, 19, 728), (2, 37, 37, 256), (3, 10, 10, 2048), (1, 149, 149, 32)])
+def test_bn_finalize_and_apply(shape):
+    F_, H, W, C = shape
+    y = rnd(F_, H, W, C, seed=23, dtype=torch.bfloat16) * 2 + 0.5
+    yf = y.float().permute(0, 3, 1, 2).contiguous()
+    gamma = rnd(C, seed=24) * 0.2 + 1
+    beta = rnd(C, seed=25, scale=0.2)
+    rm = rnd(C, seed=26, scale=0.1)
+    rv = torch.rand(C, device=DEV) + 0.5
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta); bn.running_mean.copy_(rm); bn.running_var.copy_(rv)
+    bn.train()
+    ref = bn(yf)
+    # partials as a GEMM epilogue would produce them: per 128-row tile sums
+    y2 = y.float().view(-1, C)
+    M = y2.shape[0]
+    mt = (M + 127) // 128
+    pad = torch.zeros(mt * 128, C, device=DEV); pad[:M] = y2
+    parts = torch.stack([pad.view(mt, 128, C).sum(1), (pad * pad).view(mt, 128, C).sum(1)], 1).contiguous()
+    rm2, rv2 = rm.clone(), rv.clone()
+    st = ops.bn_finalize(parts, M, gamma, beta, rm2, rv2, True)
+    assert rel_err(rm2, bn.running_mean) < 1e-5 and rel_err(rv2, bn.running_var) < 1e-5
+    out = ops.bn_act(y, st.scale, st.shift, False)
+    assert rel_err(out.float().permute(0, 3, 1, 2), ref) < 8e-3
+    out = ops.bn_act(y, st.scale, st.shift, True)
+    assert rel_err(out.float().permute(0, 3, 1, 2), F.relu(ref)) < 8e-3
+    bn.eval()
+    st_e = ops.bn_finalize(None, M, gamma, beta, bn.running_mean, bn.running_var, False)
+    out = ops.bn_act(y, st_e.scale, st_e.shift, False)
+    assert rel_err(out.float().permute(0, 3, 1, 2), bn(yf)) < 8e-3
+    # GAP
+    feat = ops.bn_relu_gap(y, st.scale, st.shift)
+    assert rel_err(feat, F.relu(ref).mean((2, 3))) < 1e-3
+    # gather
+    g = ops.gather_s2(y, st.scale, st.shift, True)
+    assert rel_err(g.float().permute(0, 3, 1, 2), F.relu(ref)[:, :, ::2, ::2]) < 8e-3
+    g = ops.gather_s2(y)
+    assert torch.equal(g, y[:, ::2, ::2].contiguous())
+    # bn + add
+    skip = rnd(F_, H, W, C, seed=27, dtype=torch.bfloat16)
+    o = ops.bn_add_fwd(y, st.scale, st.shift, skip)
+    assert rel_err(o.float().permute(0, 3, 1, 2), ref + skip.float().permute(0, 3, 1, 2)) < 8e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 19, 19, 728), (2, 37, 37, 256), (1, 147, 147, 128), (3, 4, 4, 64), (2, 5, 3, 16)])
+def test_pool_add_fwd_and_bn_bwd_pool(shape):
+    F_, H, W, C = shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = rnd(F_, H, W, C, seed=28, dtype=torch.bfloat16)
+    ys = rnd(F_, Ho, Wo, C, seed=29, dtype=torch.bfloat16)
+    gamma = rnd(C, seed=30) * 0.5 + 1
+    gamma[::7] *= -1                                 # negative BN scales must pool correctly
+    beta = rnd(C, seed=31, scale=0.2)
+    gamma_s = rnd(C, seed=32) * 0.2 + 1
+    beta_s = rnd(C, seed=33, scale=0.2)
+
+    def stats_parts(t):
+        t2 = t.float().view(-1, C)
+        return torch.stack([t2.sum(0), (t2 * t2).sum(0)], 0)[None].contiguous(), t2.shape[0]
+
+    p, n = stats_parts(y); st = ops.bn_finalize(p, n, gamma, beta, None, None, True)
+    p, n = stats_parts(ys); st_s = ops.bn_finalize(p, n, gamma_s, beta_s, None, None, True)
+    out, idx = ops.pool_add_fwd(y, st.scale, st.shift, ys, st_s.scale, st_s.shift)
+
+    yt = y.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yst = ys.float().permute(0, 3, 1, 2).requires_grad_(True)
+    g_t = gamma.clone().requires_grad_(True); b_t = beta.clone().requires_grad_(True)
+    z = F.batch_norm(yt, None, None, g_t, b_t, True, 0.1, 1e-5)
+    zs = F.batch_norm(yst, None, None, gamma_s, beta_s, True, 0.1, 1e-5)
+    ref = F.max_pool2d(z, 3, 2, 1) + zs
+    assert rel_err(out.float().permute(0, 3, 1, 2), ref) < 8e-3
+    G = rnd(F_, Ho, Wo, C, seed=34, dtype=torch.bfloat16)
+    ref.backward(G.float().permute(0, 3, 1, 2))
+    dgamma = torch.zeros(C, device=DEV); dbeta = torch.zeros(C, device=DEV)
+    dy = ops.bn_bwd(ops.SRC_POOL, y, st, gamma, dgamma, dbeta, G=G, idx=idx)
+    assert rel_err(dy.float().permute(0, 3, 1, 2), yt.grad) < 2e-2
+    assert rel_err(dgamma, g_t.grad) < 1e-2 and rel_err(dbeta, b_t.grad) < 1e-2
+    # skip branch: direct mode
+    dg2 = torch.zeros(C, device=DEV); db2 = torch.zeros(C, device=DEV)
+    dys = ops.bn_bwd(ops.SRC_DIRECT, ys, st_s, gamma_s, dg2, db2, G=G)
+    assert rel_err(dys.float().permute(0, 3, 1, 2), yst.grad) < 2e-2
+
+
+@pytest.mark.parametrize("mode", ["relu", "gap", "eval_direct"])
+def test_bn_bwd_modes(mode):
+    F_, H, W, C = 3, 10, 10, 2048
+    y = rnd(F_, H, W, C, seed=35, dtype=torch.bfloat16)
+    gamma = rnd(C, seed=36) * 0.2 + 1
+    beta = rnd(C, seed=37, scale=0.2)
+    rm = rnd(C, seed=38, scale=0.1); rv = torch.rand(C, device=DEV) + 0.5
+    y2 = y.float().view(-1, C)
+    parts = torch.stack([y2.sum(0), (y2 * y2).sum(0)], 0)[None].contiguous()
+    training = mode != "eval_direct"
+    st = ops.bn_finalize(parts if training else None, y2.shape[0], gamma, beta, rm.clone(), rv.clone(), training)
+    yt = y.float().permute(0, 3, 1, 2).requires_grad_(True)
+    g_t = gamma.clone().requires_grad_(True); b_t = beta.clone().requires_grad_(True)
+    z = F.batch_norm(yt, rm.clone(), rv.clone(), g_t, b_t, training, 0.1, 1e-5)
+    dgamma = torch.zeros(C, device=DEV); dbeta = torch.zeros(C, device=DEV)
+    if mode == "relu":
+        G = rnd(F_, H, W, C, seed=39, dtype=torch.bfloat16)
+        F.relu(z).backward(G.float().permute(0, 3, 1, 2))
+        dy = ops.bn_bwd(ops.SRC_RELU, y, st, gamma, dgamma, dbeta, G=G)
+    elif mode == "gap":
+        dfeat = rnd(F_, C, seed=40)
+        F.relu(z).mean((2, 3)).backward(dfeat)
+        dy = ops.bn_bwd(ops.SRC_GAP_RELU, y, st, gamma, dgamma, dbeta, dfeat=dfeat)
+    else:
+        G = rnd(F_, H, W, C, seed=41, dtype=torch.bfloat16)
+        z.backward(G.float().permute(0, 3, 1, 2))
+        dy = ops.bn_bwd(ops.SRC_DIRECT, y, st, gamma, dgamma, dbeta, G=G)
+    assert rel_err(dy.float().permute(0, 3, 1, 2), yt.grad) < 2e-2
+    assert rel_err(dgamma, g_t.grad) < 1e-2 and rel_err(dbeta, b_t.grad) < 1e-2
+
+
+def test_layout_and_packing():
+    x = rnd(3, 5, 11, 13, seed=42)
+    n = ops.nchw_to_nhwc(x)
+    assert torch.equal(n, x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    back = ops.nhwc_to_nchw(n)
+    assert torch.equal(back, n.float().permute(0, 3, 1, 2).contiguous())
+    w = rnd(728, 256, seed=43)
+    wb, wt = ops.pack_weight(w)
+    assert torch.equal(wb, w.to(torch.bfloat16)) and torch.equal(wt, w.t().contiguous().to(torch.bfloat16))
+    a = rnd(6, 3, 13, 1, seed=44, scale=20.0)
+    up = ops.bilinear_up(a, 64)
+    ref = F.interpolate(a, size=(64, 64), mode="bilinear", align_corners=False)
+    assert rel_err(up, ref) < 1e-5
+    assert torch.equal(ops.cast_bf16(w), w.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------ LSTM / head
+@pytest.mark.parametrize("B,T,H", [(4, 16, 128), (2, 5, 32), (3, 7, 512)])
+def test_lstm_fwd_bwd(B, T, H):
+    lstm = torch.nn.LSTM(2048, H, 1, batch_first=True).to(DEV)
+    with torch.no_grad():   # the recurrent weights are held in bf16 by the kernel
+        lstm.weight_hh_l0.copy_(lstm.weight_hh_l0.to(torch.bfloat16).float())
+        lstm.weight_ih_l0.copy_(lstm.weight_ih_l0.to(torch.bfloat16).float())
+    x = rnd(B, T, 2048, seed=45, scale=0.5).to(torch.bfloat16).float().requires_grad_(True)
+    ref, (hn_ref, cn_ref) = lstm(x)
+    w_ih_b, _ = ops.pack_weight(lstm.weight_ih_l0.detach(), want_t=False)
+    w_hh_b, w_hh_t = ops.pack_weight(lstm.weight_hh_l0.detach())
+    xproj, _ = ops.gemm_tn(x.detach().view(B * T, 2048).to(torch.bfloat16), w_ih_b, ops.EPI_F32)
+    h, gates, cst, hn, cn = ops.lstm_fwd(xproj, lstm.bias_ih_l0.detach(), lstm.bias_hh_l0.detach(), w_hh_t, B, T, H)
+    assert rel_err(h, ref) < 2e-4 and rel_err(hn, hn_ref[0]) < 2e-4 and rel_err(cn, cn_ref[0]) < 2e-4
+    dout = rnd(B, T, H, seed=46)
+    ref.backward(dout)
+    dbi = torch.zeros(4 * H, device=DEV); dbh = torch.zeros(4 * H, device=DEV)
+    dgates, hprev = ops.lstm_bwd(dout, None, None, gates, cst, h, w_hh_b, dbi, dbh, B, T, H)
+    assert rel_err(dbi, lstm.bias_ih_l0.grad) < 1e-2
+    dwih = torch.zeros(4 * H, 2048, device=DEV)
+    ops.gemm_wgrad(dgates, x.detach().view(B * T, 2048).to(torch.bfloat16), dwih)
+    assert rel_err(dwih, lstm.weight_ih_l0.grad) < 1e-2
+    dwhh = torch.zeros(4 * H, H, device=DEV)
+    ops.gemm_wgrad(dgates, hprev, dwhh)
+    assert rel_err(dwhh, lstm.weight_hh_l0.grad) < 1e-2
+    _, w_ih_t = ops.pack_weight(lstm.weight_ih_l0.detach())
+    dx, _ = ops.gemm_tn(dgates, w_ih_t, ops.EPI_F32)
+    assert rel_err(dx.view(B, T, 2048), x.grad) < 1e-2
+
+
+def test_head_linear_bce():
+    B, K, N = 4, 128, 1024
+    a = rnd(B, K, seed=47).requires_grad_(True)
+    W = rnd(N, K, seed=48, scale=0.1).requires_grad_(True)
+    b = rnd(N, seed=49, scale=0.1).requires_grad_(True)
+    mask = (torch.rand(B, N, device=DEV) > 0.3).to(torch.uint8)
+    ds = 1.0 / 0.7
+    ref = F.relu(F.linear(a, W, b)) * mask.float() * ds
+    out = ops.linear_small_fwd(a.detach(), W.detach(), b.detach(), 1, mask, ds)
+    assert rel_err(out, ref) < 1e-5
+    delta = rnd(B, N, seed=50)
+    ref.backward(delta)
+    dW = torch.zeros_like(W); db = torch.zeros_like(b)
+    din = ops.linear_small_bwd(delta, out, ds, a.detach(), W.detach(), dW, db)
+    assert rel_err(dW, W.grad) < 1e-4 and rel_err(db, b.grad) < 1e-4 and rel_err(din, a.grad) < 1e-4
+    z = rnd(B, 1, seed=51).requires_grad_(True)
+    y = torch.tensor([[1.0], [0.0], [1.0], [0.0]], device=DEV)
+    loss_ref = F.binary_cross_entropy(torch.sigmoid(z), y)
+    loss_ref.backward()
+    probs, loss, dz = ops.bce_fwd_bwd(z.detach(), y)
+    assert rel_err(probs, torch.sigmoid(z)) < 1e-5 and abs(loss.item() - loss_ref.item()) < 1e-5 and rel_err(dz, z.grad) < 1e-4
+    z2 = z.detach().clone().requires_grad_(True)
+    l2 = F.binary_cross_entropy_with_logits(z2, y * 0.9 + 0.05)
+    l2.backward()
+    _, loss_s, dz_s = ops.bce_fwd_bwd(z2.detach(), y, smoothing=0.1)
+    assert abs(loss_s.item() - l2.item()) < 1e-5 and rel_err(dz_s, z2.grad) < 1e-4
+
+
+def test_arcface_and_fusion_against_golden(golden):
+    import numpy as np
+
+    def t(k):
+        return torch.from_numpy(np.asarray(golden[k])).to(DEV)
+
+    lab = t("D_labels")
+    # visual ArcFace (s=30, m=0.5) + CE  (train_visual.py:455-474,532)
+    dw = torch.zeros(2, 32, device=DEV)
+    logits, loss, dx = ops.arcface_loss(t("D2_emb"), t("D2_w"), lab, 30.0, 0.5, 0, dw=dw)
+    assert rel_err(logits, t("D2_logits")) < 1e-4 and abs(loss.item() - float(golden["D2_loss"])) < 1e-4
+    assert rel_err(dx, t("D2_grad_emb")) < 1e-3 and rel_err(dw, t("D2_grad_w")) < 1e-3
+    lg, _, _ = ops.arcface_loss(t("D2_emb"), t("D2_w"), None, 30.0, 0.5)
+    assert rel_err(lg, t("D2_logits_nolabel")) < 1e-4
+    # fusion region (train_au_face.py:659-674), dropout off
+    v, a = t("D_v_tok"), t("D_a_tok")
+    pooled, loss_reg, dv, da = ops.fusion_pool_reg(v, a, 0.2, 0.1)
+    W0, b0, W3, b3 = t("D_embed::0.weight"), t("D_embed::0.bias"), t("D_embed::3.weight"), t("D_embed::3.bias")
+    h = ops.linear_small_fwd(pooled, W0, b0, 1)
+    e = ops.linear_small_fwd(h, W3, b3, 0)
+    darc = torch.zeros(2, 128, device=DEV)
+    logits, loss_cls, de = ops.arcface_loss(e, t("D_arc_w"), lab, 30.0, 0.30, 1, class_w=t("D_class_weights"), gamma=2.0, dw=darc)
+    assert rel_err(logits, t("D_logits")) < 1e-4
+    assert abs((loss_cls + loss_reg).item() - float(golden["D_loss"])) < 1e-4
+    assert rel_err(darc, t("D_grad_arc_w")) < 1e-3
+    dW3 = torch.zeros_like(W3); db3 = torch.zeros_like(b3)
+    dh = ops.linear_small_bwd(de, None, 1.0, h, W3, dW3, db3)
+    dW0 = torch.zeros_like(W0); db0 = torch.zeros_like(b0)
+    dpooled = ops.linear_small_bwd(dh, h, 1.0, pooled, W0, dW0, db0)
+    assert rel_err(dW0, t("D_grad_embed0_w")) < 1e-3
+    ops.fusion_pool_bwd(dpooled, dv, da)
+    assert rel_err(dv, t("D_grad_v_tok")) < 1e-3 and rel_err(da, t("D_grad_a_tok")) < 1e-3
+
+
+def test_adam_and_clip():
+    n = 100003
+    p = rnd(n, seed=52); g = rnd(n, seed=53, scale=0.01)
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=1e-3, weight_decay=1e-4)
+    m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    ss = torch.zeros((), device=DEV)
+    for step in range(1, 4):
+        pt.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([pt], 1.0)
+        opt.step()
+        ops.grad_sumsq(g, ss)
+        ops.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-4, False, step, sumsq=ss, max_norm=1.0)
+        assert rel_err(p, pt.detach()) < 1e-5
