@@ -71,9 +71,9 @@ int xcp_gather_s2(const void* x, const float* scale, const float* shift, int rel
 /* BN + MaxPool2d(3,2,1) (Xception.py:86) + skip BN + residual add (Xception.py:92-98); idx = arg-max taps (uint8) */
 int xcp_pool_add_fwd(const void* y, const float* scale, const float* shift, const void* ys, const float* scale_s,
                      const float* shift_s, void* out, void* idx, int F, int H, int W, int C, int device, void* stream);
-/* BN + identity residual add (blocks 4-11, Xception.py:96-98) */
-int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const void* skip, void* out, long long n, int C,
-                   int device, void* stream);
+/* BN + residual add (blocks 4-11, Xception.py:96-98); scale_s/shift_s != NULL applies the skip BN (stride-1 skip conv) */
+int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const void* skip, const float* scale_s,
+                   const float* shift_s, void* out, long long n, int C, int device, void* stream);
 /* bn4 + ReLU + adaptive_avg_pool2d (Xception.py:194-198): feat fp32 [F,C] */
 int xcp_bn_relu_gap(const void* y, const float* scale, const float* shift, float* feat, int F, int HW, int C, int device,
                     void* stream);
@@ -109,11 +109,13 @@ int xcp_linear_small_fwd(const float* a, const float* W, const float* bias, cons
                          float* out, int B, int N, int K, int device, void* stream);
 int xcp_linear_small_bwd(const float* delta_raw, const float* out_act, float drop_scale, const float* a, const float* W,
                          float* dW, float* db, float* din, int B, int N, int K, int device, void* stream);
+int xcp_sigmoid_fwd(const float* z, float* p, int n, int device, void* stream);
+int xcp_sigmoid_bwd(const float* p, const float* dp, float* dz, int n, int device, void* stream);
 int xcp_bce_fwd_bwd(const float* z, const float* y, float smoothing, float* probs, float* loss, float* dz, int B, int device,
                     void* stream);
 int xcp_arcface_loss(const float* x, const float* w, const long long* labels, float s, float m, int loss_mode,
-                     const float* class_w, float gamma, float* logits, float* loss, float* loss_rows, float* dx, float* dw, int B,
-                     int D, float gscale, int device, void* stream);
+                     const float* class_w, float gamma, const float* dlogits_in, float* logits, float* loss, float* loss_rows,
+                     float* dx, float* dw, int B, int D, float gscale, int device, void* stream);
 int xcp_fusion_pool_reg(const float* v, const float* a, float* pooled, float* loss_reg, float* dv, float* da, int B, int T, int D,
                         float lambda_align, float lambda_temp, float gscale, int device, void* stream);
 int xcp_fusion_pool_bwd(const float* dpooled, float* dv, float* da, int B, int T, int D, int device, void* stream);

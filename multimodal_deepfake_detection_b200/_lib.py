@@ -33,7 +33,7 @@ SIGNATURES = {
     "xcp_bn_act": "pppipliip",
     "xcp_gather_s2": "pppipiiiiip",
     "xcp_pool_add_fwd": "ppppppppiiiiip",
-    "xcp_bn_add_fwd": "pppppliip",
+    "xcp_bn_add_fwd": "pppppppliip",
     "xcp_bn_relu_gap": "ppppiiiip",
     "xcp_bnbwd_num_parts": "",
     "xcp_bn_bwd": "ipppppppppippppppiiiiiiip",
@@ -50,8 +50,10 @@ SIGNATURES = {
     "xcp_lstm_bwd": "pppppppppppiiiip",
     "xcp_linear_small_fwd": "ppppfipiiiip",
     "xcp_linear_small_bwd": "ppfpppppiiiip",
+    "xcp_sigmoid_fwd": "ppiip",
+    "xcp_sigmoid_bwd": "pppiip",
     "xcp_bce_fwd_bwd": "ppfpppiip",
-    "xcp_arcface_loss": "pppffipfpppppiifip",
+    "xcp_arcface_loss": "pppffipfppppppiifip",
     "xcp_fusion_pool_reg": "ppppppiiifffip",
     "xcp_fusion_pool_bwd": "pppiiiip",
     "xcp_grad_sumsq": "plpiip",

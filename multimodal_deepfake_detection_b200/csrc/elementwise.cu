@@ -221,15 +221,21 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
     }
 }
 
-// out = scale*y + shift + skip
+// out = scale*y + shift + (scale_s*skip + shift_s)      (scale_s/shift_s optional: identity skip)
 __global__ void bn_add_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                                  const uint4* __restrict__ skip, uint4* __restrict__ out, long long n8, int C) {
+                                  const uint4* __restrict__ skip, const float* __restrict__ scale_s,
+                                  const float* __restrict__ shift_s, uint4* __restrict__ out, long long n8, int C) {
     const int ncg = C >> 3;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const int c0 = (int)(i % ncg) * 8;
         float v[8], s[8], sc[8], sh[8];
         unpack8(ldg_nc_v4(y + i), v);
         unpack8(ldg_nc_v4(skip + i), s);
+        if (scale_s != nullptr) {
+            load_affine8(scale_s, shift_s, c0, sc, sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = fmaf(s[j], sc[j], sh[j]);
+        }
         load_affine8(scale, shift, c0, sc, sh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]) + s[j];
@@ -643,11 +649,12 @@ extern "C" int xcp_pool_add_fwd(const void* y, const float* scale, const float* 
     return check_cuda(cudaGetLastError(), "pool_add_fwd launch");
 }
 
-extern "C" int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const void* skip, void* out, long long n,
-                              int C, int device, void* stream) {
+extern "C" int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const void* skip, const float* scale_s,
+                              const float* shift_s, void* out, long long n, int C, int device, void* stream) {
     XCP_REQUIRE(C % 8 == 0 && n % C == 0, "xcp_bn_add_fwd: bad shape");
     XCP_CUDA(cudaSetDevice(device));
-    bn_add_fwd_kernel<<<ew_grid(n / 8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)skip, (uint4*)out, n / 8, C);
+    bn_add_fwd_kernel<<<ew_grid(n / 8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)skip, scale_s, shift_s,
+                                                         (uint4*)out, n / 8, C);
     return check_cuda(cudaGetLastError(), "bn_add_fwd launch");
 }
 

@@ -239,8 +239,8 @@ __global__ void bce_fwd_bwd_kernel(const float* __restrict__ z, const float* __r
 // loss_mode 0: CrossEntropy mean ; 1: class-balanced focal (gamma, class weights).  labels < 0 => inference logits only.
 __global__ void __launch_bounds__(256)
 arcface_loss_kernel(const float* __restrict__ x, const float* __restrict__ w, const long long* __restrict__ labels, float s_,
-                    float m_, int loss_mode, const float* __restrict__ class_w, float gamma, float* __restrict__ logits,
-                    float* __restrict__ loss_rows, float* __restrict__ dx, float* __restrict__ dw_partial, int B, int D, float gscale) {
+                    float m_, int loss_mode, const float* __restrict__ class_w, float gamma,
+                    const float* __restrict__ dlogits_in, float* __restrict__ logits, float* __restrict__ loss_rows, float* __restrict__ dx, float* __restrict__ dw_partial, int B, int D, float gscale) {
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -274,8 +274,10 @@ arcface_loss_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     const float p[2] = {e0 / den, e1 / den};
     const float ce_plain = -(lg[y] - mx - logf(den));
     float dl[2];   // dL/dlogits for this row (already including the 1/B mean and gscale)
-    float row_loss;
-    if (loss_mode == 0) {
+    float row_loss = 0.f;
+    if (dlogits_in != nullptr) {   // external criterion: upstream gradient supplied by the caller
+        dl[0] = dlogits_in[b * 2]; dl[1] = dlogits_in[b * 2 + 1];
+    } else if (loss_mode == 0) {
         row_loss = ce_plain;
         dl[0] = (p[0] - (y == 0 ? 1.f : 0.f));
         dl[1] = (p[1] - (y == 1 ? 1.f : 0.f));
@@ -291,9 +293,11 @@ arcface_loss_kernel(const float* __restrict__ x, const float* __restrict__ w, co
         dl[0] = dloss_dce * wy * (p[0] - (y == 0 ? 1.f : 0.f));
         dl[1] = dloss_dce * wy * (p[1] - (y == 1 ? 1.f : 0.f));
     }
-    const float inv = gscale / (float)B;
-    dl[0] *= inv; dl[1] *= inv;
-    if (lane == 0) loss_rows[b] = row_loss / (float)B;
+    if (dlogits_in == nullptr) {
+        const float inv = gscale / (float)B;
+        dl[0] *= inv; dl[1] *= inv;
+    }
+    if (lane == 0 && loss_rows != nullptr) loss_rows[b] = row_loss / (float)B;
     // d cos_c : s * dl_c (* dt_dcos for the label class)
     const float dc0 = s_ * dl[0] * (y == 0 ? dt_dcos : 1.f);
     const float dc1 = s_ * dl[1] * (y == 1 ? dt_dcos : 1.f);
@@ -306,6 +310,16 @@ arcface_loss_kernel(const float* __restrict__ x, const float* __restrict__ w, co
             atomicAdd(&dw_partial[D + k], dc1 * (xv - cosv[1] * c) / nw1);
         }
     }
+}
+
+// p = sigmoid(z) ; dz = dp * p * (1 - p)      (nn.Sigmoid, XceptionLSTMV.py:44,70)
+__global__ void sigmoid_kernel(const float* __restrict__ z, float* __restrict__ p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 1.f / (1.f + expf(-z[i]));
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ dz, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dz[i] = dp[i] * p[i] * (1.f - p[i]);
 }
 
 __global__ void sum_rows_kernel(const float* __restrict__ v, int n, float* __restrict__ out, int accumulate) {
@@ -444,6 +458,18 @@ extern "C" int xcp_linear_small_bwd(const float* delta_raw, const float* out_act
     return check_cuda(cudaGetLastError(), "linear_small_bwd launch");
 }
 
+extern "C" int xcp_sigmoid_fwd(const float* z, float* p, int n, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    sigmoid_kernel<<<(n + 255) / 256, 256, 0, ST>>>(z, p, n);
+    return check_cuda(cudaGetLastError(), "sigmoid launch");
+}
+
+extern "C" int xcp_sigmoid_bwd(const float* p, const float* dp, float* dz, int n, int device, void* stream) {
+    XCP_CUDA(cudaSetDevice(device));
+    sigmoid_bwd_kernel<<<(n + 255) / 256, 256, 0, ST>>>(p, dp, dz, n);
+    return check_cuda(cudaGetLastError(), "sigmoid_bwd launch");
+}
+
 extern "C" int xcp_bce_fwd_bwd(const float* z, const float* y, float smoothing, float* probs, float* loss, float* dz, int B,
                                int device, void* stream) {
     XCP_CUDA(cudaSetDevice(device));
@@ -454,14 +480,14 @@ extern "C" int xcp_bce_fwd_bwd(const float* z, const float* y, float smoothing, 
 // ArcFace logits (+ CE or CB-focal loss and gradients when labels != null).  loss (scalar) is overwritten,
 // dw is accumulated (+=), dx is overwritten.  loss_rows: workspace [B].
 extern "C" int xcp_arcface_loss(const float* x, const float* w, const long long* labels, float s, float m, int loss_mode,
-                                const float* class_w, float gamma, float* logits, float* loss, float* loss_rows, float* dx,
-                                float* dw, int B, int D, float gscale, int device, void* stream) {
+                                const float* class_w, float gamma, const float* dlogits_in, float* logits, float* loss,
+                                float* loss_rows, float* dx, float* dw, int B, int D, float gscale, int device, void* stream) {
     XCP_REQUIRE(B > 0 && D > 0, "xcp_arcface_loss: bad shape");
     XCP_CUDA(cudaSetDevice(device));
-    arcface_loss_kernel<<<(B + 7) / 8, 256, 0, ST>>>(x, w, labels, s, m, loss_mode, class_w, gamma, logits, loss_rows, dx, dw, B,
-                                                     D, gscale);
+    arcface_loss_kernel<<<(B + 7) / 8, 256, 0, ST>>>(x, w, labels, s, m, loss_mode, class_w, gamma, dlogits_in, logits, loss_rows,
+                                                     dx, dw, B, D, gscale);
     XCP_CUDA(cudaGetLastError());
-    if (labels != nullptr && loss != nullptr) sum_rows_kernel<<<1, 256, 0, ST>>>(loss_rows, B, loss, 0);
+    if (labels != nullptr && loss != nullptr && dlogits_in == nullptr) sum_rows_kernel<<<1, 256, 0, ST>>>(loss_rows, B, loss, 0);
     return check_cuda(cudaGetLastError(), "arcface launch");
 }
 

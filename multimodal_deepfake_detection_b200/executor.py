@@ -1,0 +1,340 @@
+"""Plan executor for the Xception backbone on B200: walks the layer graph of the reference
+(Xception.forward, Xception.py:167-201; Block.forward, Xception.py:89-99) and launches the fused sm_100a
+kernels through the C ABI.  The reference's per-op structure is re-cut around HBM traffic:
+
+    DW(prologue: producer's BN affine + ReLU)  ->  PW GEMM (epilogue: BN batch statistics)  ->  BN finalize
+    block tail: BN + MaxPool + skip-BN + add in one pass (strided blocks) / BN + add (identity blocks)
+
+so a BatchNorm output is never materialised except where the graph needs it twice (block inputs).
+Backward mirrors it: two-pass BN backward with the ReLU / max-pool / GAP routing folded into its loads,
+tcgen05 dgrad / wgrad GEMMs, and a depthwise backward that also produces the BN reductions of the layer below.
+
+Everything here is host-side sequencing; no arithmetic is done by torch.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ specs
+class SepSpec:
+    """One [ReLU?] -> SeparableConv2d -> BatchNorm2d unit of a Block (or conv3/bn3, conv4/bn4)."""
+    __slots__ = ("sep", "bn", "cin", "cout", "relu")
+
+    def __init__(self, sep, bn, cin, cout, relu):
+        self.sep, self.bn, self.cin, self.cout, self.relu = sep, bn, cin, cout, relu
+
+
+class BlockSpec:
+    __slots__ = ("units", "stride", "skip", "skipbn", "cin", "cout")
+
+    def __init__(self, units, stride, skip, skipbn, cin, cout):
+        self.units, self.stride, self.skip, self.skipbn, self.cin, self.cout = units, stride, skip, skipbn, cin, cout
+
+
+# ------------------------------------------------------------------------------------------------ packed weights
+class PackCache:
+    """bf16 / re-laid-out copies of the fp32 master parameters, rebuilt when a parameter changes.
+    These are derived caches, never part of state_dict (SURVEY.md §5 checkpoint contract)."""
+
+    def __init__(self):
+        self._c: Dict[int, tuple] = {}
+        self.generation = 0   # bumped by the fused optimizer (raw-pointer updates do not touch _version)
+
+    def _get(self, p: torch.Tensor, kind: str, fn):
+        key = (id(p), kind)
+        tag = (p.data_ptr(), p._version, self.generation, p.device)
+        hit = self._c.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        val = fn(p.detach())
+        self._c[key] = (tag, val)
+        return val
+
+    def pw(self, w: torch.Tensor):
+        """[N,K,1,1] fp32 -> (bf16 [N,K], bf16 [K,N])"""
+        return self._get(w, "pw", lambda t: ops.pack_weight(t.view(t.shape[0], t.shape[1]), True))
+
+    def dw(self, w: torch.Tensor):
+        """[C,1,3,3] fp32 -> fp32 [9,C]"""
+        return self._get(w, "dw", ops.pack_dw)
+
+    def conv3x3(self, w: torch.Tensor):
+        return self._get(w, "c3", lambda t: ops.pack_conv3x3(t, True))
+
+    def linear(self, w: torch.Tensor):
+        """[N,K] fp32 -> (bf16 [N,K], bf16 [K,N])"""
+        return self._get(w, "lin", lambda t: ops.pack_weight(t, True))
+
+
+# ------------------------------------------------------------------------------------------------ gradient sink
+class GradSink:
+    """Flat fp32 gradient arena: one zero-fill per backward, every parameter gradient is a view into it, and
+    (for data parallel) contiguous ranges of it are all-reduced as buckets while backward is still running."""
+
+    def __init__(self, params: List[torch.Tensor], device):
+        self.params = params
+        self.offsets = {}
+        off = 0
+        for p in params:
+            self.offsets[id(p)] = off
+            off += (p.numel() + 3) // 4 * 4      # keep every view 16-byte aligned
+        self.total = off
+        self.flat = torch.zeros((max(off, 4),), device=device, dtype=F32)
+        self.on_ready = None                      # optional callback(lo, hi) for the DDP bucketer
+
+    def view(self, p: torch.Tensor) -> torch.Tensor:
+        o = self.offsets[id(p)]
+        return self.flat[o:o + p.numel()].view(p.shape)
+
+    def done(self, p: torch.Tensor):
+        if self.on_ready is not None:
+            o = self.offsets[id(p)]
+            self.on_ready(o, o + p.numel())
+
+
+# ------------------------------------------------------------------------------------------------ forward pieces
+def _bn_state(bn, parts, count):
+    """BatchNorm2d forward bookkeeping: batch stats + running-stat update in train mode,
+    running stats in eval mode."""
+    training = bn.training or (bn.running_mean is None)
+    if training:
+        rm = bn.running_mean if bn.track_running_stats else None
+        rv = bn.running_var if bn.track_running_stats else None
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        st = ops.bn_finalize(parts, count, bn.weight.detach(), bn.bias.detach(), rm, rv, True, mom, bn.eps)
+    else:
+        st = ops.bn_finalize(None, count, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, False,
+                             0.0, bn.eps)
+    return st
+
+
+def _bn_needs_stats(bn) -> bool:
+    return bn.training or bn.running_mean is None
+
+
+class SepTape:
+    __slots__ = ("spec", "src", "src_st", "src_relu", "d", "y", "st")
+
+
+def sep_forward(cache: PackCache, spec: SepSpec, src: torch.Tensor, src_st, relu: bool, nbt: list) -> SepTape:
+    """src: bf16 NHWC [F,H,W,Cin]; src_st: pending BN state of the producer (or None if src is materialised)."""
+    F_, H, W, C = src.shape
+    w9 = cache.dw(spec.sep.conv1.weight)
+    wb, _ = cache.pw(spec.sep.pointwise.weight)
+    d = ops.dw3x3_fwd(src, w9, src_st.scale if src_st is not None else None, src_st.shift if src_st is not None else None, relu)
+    M = F_ * H * W
+    t = SepTape()
+    t.spec, t.src, t.src_st, t.src_relu, t.d = spec, src, src_st, relu, d
+    if spec.bn is None:
+        y, _ = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16)
+        t.y, t.st = y.view(F_, H, W, spec.cout), None
+        return t
+    need = _bn_needs_stats(spec.bn)
+    y, parts = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16)
+    t.y = y.view(F_, H, W, spec.cout)
+    t.st = _bn_state(spec.bn, parts, M)
+    if need and spec.bn.track_running_stats:
+        nbt.append(spec.bn.num_batches_tracked)
+    return t
+
+
+class BlockTape:
+    __slots__ = ("spec", "inp", "units", "xs", "ys", "st_s", "idx", "out")
+
+
+def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: list, save: bool = True) -> BlockTape:
+    """Block.forward (Xception.py:89-99).  inp: materialised bf16 NHWC block input."""
+    bt = BlockTape()
+    bt.spec, bt.inp, bt.units = spec, inp, []
+    src, src_st = inp, None
+    for u in spec.units:
+        t = sep_forward(cache, u, src, src_st, u.relu, nbt)
+        bt.units.append(t)
+        src, src_st = t.y, t.st
+    last = bt.units[-1]
+    bt.xs = bt.ys = bt.st_s = bt.idx = None
+    F_, H, W, _ = inp.shape
+    if spec.skip is not None:
+        wb, _ = cache.pw(spec.skip.weight)
+        if spec.stride == 2:
+            xs = ops.gather_s2(inp)
+        elif spec.stride == 1:
+            xs = inp
+        else:
+            raise ops._lib.XcpError("Block: only strides 1 and 2 are implemented on the sm_100a path (Xception uses 1, 2)")
+        Fs, Hs, Ws, Cs = xs.shape
+        need = _bn_needs_stats(spec.skipbn)
+        ys, parts = ops.gemm_tn(xs.view(Fs * Hs * Ws, Cs), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16)
+        ys = ys.view(Fs, Hs, Ws, spec.cout)
+        st_s = _bn_state(spec.skipbn, parts, Fs * Hs * Ws)
+        if need and spec.skipbn.track_running_stats:
+            nbt.append(spec.skipbn.num_batches_tracked)
+        bt.xs, bt.ys, bt.st_s = xs, ys, st_s
+        if spec.stride == 2:
+            bt.out, bt.idx = ops.pool_add_fwd(last.y, last.st.scale, last.st.shift, ys, st_s.scale, st_s.shift, want_idx=save)
+        else:
+            bt.out = ops.bn_add_fwd(last.y, last.st.scale, last.st.shift, ys, st_s.scale, st_s.shift)
+    else:
+        if spec.stride != 1:
+            raise ops._lib.XcpError("Block: a strided block without a skip conv cannot occur (Xception.py:54)")
+        bt.out = ops.bn_add_fwd(last.y, last.st.scale, last.st.shift, inp)
+    return bt
+
+
+# ------------------------------------------------------------------------------------------------ backward pieces
+def _pw_backward(cache: PackCache, sink: GradSink, weight: torch.Tensor, dy: torch.Tensor, a: torch.Tensor,
+                 need_dgrad: bool = True):
+    """dy [.., N], a [.., K] (the GEMM's A operand in forward).  Accumulates dW, returns dA (bf16) or None."""
+    N, K = weight.shape[0], weight.shape[1]
+    M = dy.numel() // N
+    ops.gemm_wgrad(dy.view(M, N), a.view(M, K), sink.view(weight).view(N, K))
+    sink.done(weight)
+    if not need_dgrad:
+        return None
+    _, wt = cache.pw(weight)
+    da, _ = ops.gemm_tn(dy.view(M, N), wt, ops.EPI_BF16)
+    return da.view(*a.shape)
+
+
+def _dw_backward(cache: PackCache, sink: GradSink, t: SepTape, dd: torch.Tensor, add_full=None, add_half=None):
+    """Backward of the depthwise conv of unit t.  Returns (dz, bnsum): the gradient wrt the DW's pre-activation
+    source (raw y of the producer if a BN was pending, else the materialised input)."""
+    w = t.spec.sep.conv1.weight
+    w9 = cache.dw(w)
+    C = w.shape[0]
+    dw9 = torch.zeros((9, C), device=dd.device, dtype=F32)
+    aff = t.src_st is not None
+    dz, bnsum = ops.dw3x3_bwd(dd, t.src, w9, t.src_st.scale if aff else None, t.src_st.shift if aff else None, t.src_relu,
+                              dw9, add_full=add_full, add_half=add_half, want_bnsum=aff)
+    ops.unpack_dw_grad(dw9, sink.view(w), True)
+    sink.done(w)
+    return dz, bnsum
+
+
+def _bn_param_grads(sink: GradSink, bn):
+    return sink.view(bn.weight), sink.view(bn.bias)
+
+
+def units_backward(cache: PackCache, sink: GradSink, units: List[SepTape], dy_last: torch.Tensor, add_full=None, add_half=None):
+    """Walk a chain of sep units backwards.  dy_last = gradient wrt the raw PW output of the last unit.
+    Returns the gradient wrt the chain's materialised input."""
+    dy = dy_last
+    for i in range(len(units) - 1, -1, -1):
+        t = units[i]
+        dd = _pw_backward(cache, sink, t.spec.sep.pointwise.weight, dy, t.d)
+        if i == 0:
+            g_in, _ = _dw_backward(cache, sink, t, dd, add_full=add_full, add_half=add_half)
+            return g_in
+        prev = units[i - 1]
+        dz, bnsum = _dw_backward(cache, sink, t, dd)
+        dg, db = _bn_param_grads(sink, prev.spec.bn)
+        dy = ops.bn_bwd(ops.SRC_DIRECT, prev.y, prev.st, prev.spec.bn.weight.detach(), dg, db, G=dz, presums=bnsum)
+        sink.done(prev.spec.bn.weight); sink.done(prev.spec.bn.bias)
+    raise AssertionError
+
+
+def block_backward(cache: PackCache, sink: GradSink, bt: BlockTape, G: torch.Tensor) -> torch.Tensor:
+    """G: gradient wrt the block output (bf16 NHWC).  Returns the gradient wrt the block input."""
+    spec = bt.spec
+    last = bt.units[-1]
+    dg, db = _bn_param_grads(sink, last.spec.bn)
+    add_full = add_half = None
+    if spec.skip is not None:
+        dgs, dbs = _bn_param_grads(sink, spec.skipbn)
+        dys = ops.bn_bwd(ops.SRC_DIRECT, bt.ys, bt.st_s, spec.skipbn.weight.detach(), dgs, dbs, G=G)
+        sink.done(spec.skipbn.weight); sink.done(spec.skipbn.bias)
+        dxs = _pw_backward(cache, sink, spec.skip.weight, dys, bt.xs)
+        if spec.stride == 2:
+            add_half = dxs
+            dy_last = ops.bn_bwd(ops.SRC_POOL, last.y, last.st, last.spec.bn.weight.detach(), dg, db, G=G, idx=bt.idx)
+        else:
+            add_full = dxs
+            dy_last = ops.bn_bwd(ops.SRC_DIRECT, last.y, last.st, last.spec.bn.weight.detach(), dg, db, G=G)
+    else:
+        add_full = G
+        dy_last = ops.bn_bwd(ops.SRC_DIRECT, last.y, last.st, last.spec.bn.weight.detach(), dg, db, G=G)
+    sink.done(last.spec.bn.weight); sink.done(last.spec.bn.bias)
+    return units_backward(cache, sink, bt.units, dy_last, add_full=add_full, add_half=add_half)
+
+
+# ------------------------------------------------------------------------------------------------ whole backbone
+class XceptionTape:
+    __slots__ = ("x", "y1", "st1", "x1", "y2", "st2", "x2", "blocks", "u3", "u4", "feat_shape")
+
+
+def _bump_nbt(nbt: list):
+    if nbt:
+        torch._foreach_add_(nbt, 1)   # integer bookkeeping of num_batches_tracked (not on the compute path)
+
+
+def xception_forward(net, x: torch.Tensor, save: bool = True):
+    """net: Models.Xception.Xception (ours).  x: fp32 NCHW [F,3,H,W] on a B200.  Returns (feat fp32 [F,2048], tape)."""
+    cache: PackCache = net._pack_cache
+    nbt: list = []
+    tp = XceptionTape()
+    F_ = x.shape[0]
+    x = x.contiguous()
+    tp.x = x
+    # stem: conv1 -> bn1 -> relu -> conv2 -> bn2 -> relu                      (Xception.py:168-174)
+    y1, parts1 = ops.stem_conv1_fwd(x, net.conv1.weight.detach())
+    st1 = _bn_state(net.bn1, parts1, y1.numel() // 32)
+    if _bn_needs_stats(net.bn1):
+        nbt.append(net.bn1.num_batches_tracked)
+    x1 = ops.bn_act(y1, st1.scale, st1.shift, True)
+    wk, _ = cache.conv3x3(net.conv2.weight)
+    need2 = _bn_needs_stats(net.bn2)
+    y2, parts2 = ops.conv3x3_gemm_fwd(x1, wk, want_stats=need2)
+    st2 = _bn_state(net.bn2, parts2, y2.numel() // 64)
+    if need2:
+        nbt.append(net.bn2.num_batches_tracked)
+    x2 = ops.bn_act(y2, st2.scale, st2.shift, True)
+    tp.y1, tp.st1, tp.x1, tp.y2, tp.st2, tp.x2 = y1, st1, x1, y2, st2, x2
+    cur = x2
+    tp.blocks = []
+    for spec in net._block_specs:                                             # Xception.py:176-187
+        bt = block_forward(cache, spec, cur, nbt, save)
+        cur = bt.out
+        tp.blocks.append(bt if save else None)
+    # exit flow: conv3 (no ReLU in front) -> bn3 -> relu -> conv4 -> bn4 -> relu -> GAP   (Xception.py:189-198)
+    u3 = sep_forward(cache, net._exit_specs[0], cur, None, False, nbt)
+    u4 = sep_forward(cache, net._exit_specs[1], u3.y, u3.st, True, nbt)
+    feat = ops.bn_relu_gap(u4.y, u4.st.scale, u4.st.shift)
+    tp.u3, tp.u4 = u3, u4
+    _bump_nbt(nbt)
+    return feat, (tp if save else None)
+
+
+def xception_backward(net, tp: XceptionTape, dfeat: torch.Tensor, sink: GradSink):
+    """Backward of xception_forward.  dfeat: fp32 [F,2048].  Parameter gradients go to the sink."""
+    cache: PackCache = net._pack_cache
+    u3, u4 = tp.u3, tp.u4
+    dg, db = _bn_param_grads(sink, net.bn4)
+    dy4 = ops.bn_bwd(ops.SRC_GAP_RELU, u4.y, u4.st, net.bn4.weight.detach(), dg, db, dfeat=dfeat.contiguous())
+    sink.done(net.bn4.weight); sink.done(net.bn4.bias)
+    G = units_backward(cache, sink, [u3, u4], dy4)
+    for bt in reversed(tp.blocks):
+        G = block_backward(cache, sink, bt, G)
+    # stem.  G = dL/dx2 with x2 = relu(bn2(y2)); dy2 is written on the zero-padded conv2 input grid
+    F_, H1, W1, _ = tp.y1.shape
+    dg, db = _bn_param_grads(sink, net.bn2)
+    dy2g = ops.bn_bwd(ops.SRC_RELU, tp.y2, tp.st2, net.bn2.weight.detach(), dg, db, G=G, grid_hw=(H1, W1))
+    sink.done(net.bn2.weight); sink.done(net.bn2.bias)
+    gk = torch.zeros((64, 9 * 32), device=G.device, dtype=F32)
+    ops.conv3x3_wgrad(dy2g, tp.x1, gk)
+    ops.unpack_conv3x3_grad(gk, sink.view(net.conv2.weight))
+    sink.done(net.conv2.weight)
+    _, wk_t = cache.conv3x3(net.conv2.weight)
+    dx1 = ops.conv3x3_gemm_dgrad(dy2g, wk_t)
+    dg, db = _bn_param_grads(sink, net.bn1)
+    dy1 = ops.bn_bwd(ops.SRC_RELU, tp.y1, tp.st1, net.bn1.weight.detach(), dg, db, G=dx1)
+    sink.done(net.bn1.weight); sink.done(net.bn1.bias)
+    ops.stem_conv1_wgrad(tp.x, dy1, sink.view(net.conv1.weight))
+    sink.done(net.conv1.weight)

@@ -1,0 +1,573 @@
+"""Drop-in nn.Module classes for the reference's hot path, executing on hand-written sm_100a kernels.
+
+Same class names, constructor arguments, attribute names, registration order (=> identical seeded init and
+parameters() order) and state_dict keys/shapes/dtypes as the reference:
+
+    SeparableConv2d, Block, Xception, xception      Xception.py:37-47, 50-99, 103-201, 205-213
+    XceptionLSTMV                                   XceptionLSTMV.py:9-70
+    XceptionLSTMA                                   XceptionLSTMA.py:5-59
+    ArcFaceHead, CBFocalLoss, LabelSmoothingBCEWithLogitsLoss
+                                                    train_visual.py:455-474, train_au_face.py:423-458, train_au_patch.py:203-211
+
+The leaf nn.Conv2d / nn.BatchNorm2d / nn.Linear / nn.LSTM objects only *hold* parameters and buffers (so
+checkpoints interchange with the reference); forward never calls them -- it runs the fused plan in executor.py.
+There is no CPU or eager fallback: a CPU tensor or an unsupported configuration raises XcpError.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import executor as ex
+from . import ops
+from ._lib import XcpError
+
+__all__ = ["SeparableConv2d", "Block", "Xception", "xception", "XceptionLSTMV", "XceptionLSTMA", "ArcFaceHead",
+           "CBFocalLoss", "LabelSmoothingBCEWithLogitsLoss", "FusedLSTM", "FusedLinear", "model_urls"]
+
+model_urls = {
+    # same URL as the reference (Xception.py:31-34); only consulted through the local torch hub cache
+    "xception": "http://data.lip6.fr/cadene/pretrainedmodels/xception-43020ad28.pth"
+}
+
+
+def _require_cuda(x: torch.Tensor, who: str):
+    if not x.is_cuda:
+        raise XcpError(f"{who}: input is on {x.device}; this implementation only runs on an sm_100a (B200) device "
+                       f"and has no CPU fallback")
+
+
+def _cache_of(mod: nn.Module) -> ex.PackCache:
+    c = mod.__dict__.get("_pack_cache")
+    if c is None:
+        c = ex.PackCache()
+        mod.__dict__["_pack_cache"] = c
+    return c
+
+
+# ================================================================================================ SeparableConv2d
+class _SepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, w_dw, w_pw):
+        cache = _cache_of(mod)
+        xin = ops.nchw_to_nhwc(x.float().contiguous())
+        spec = ex.SepSpec(mod, None, w_dw.shape[0], w_pw.shape[0], False)
+        t = ex.sep_forward(cache, spec, xin, None, False, [])
+        ctx.mod, ctx.tape = mod, t
+        return ops.nhwc_to_nchw(t.y)
+
+    @staticmethod
+    def backward(ctx, dout):
+        mod, t = ctx.mod, ctx.tape
+        cache = _cache_of(mod)
+        sink = ex.GradSink([mod.conv1.weight, mod.pointwise.weight], dout.device)
+        dy = ops.nchw_to_nhwc(dout.float().contiguous())
+        dd = ex._pw_backward(cache, sink, mod.pointwise.weight, dy, t.d)
+        dz, _ = ex._dw_backward(cache, sink, t, dd)
+        dx = ops.nhwc_to_nchw(dz) if ctx.needs_input_grad[1] else None
+        return None, dx, sink.view(mod.conv1.weight), sink.view(mod.pointwise.weight)
+
+
+class SeparableConv2d(nn.Module):
+    """Depthwise k x k conv followed by a 1x1 conv (Xception.py:37-47)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, padding=0, dilation=1, bias=False):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, in_channels, kernel_size, stride, padding, dilation, groups=in_channels, bias=bias)
+        self.pointwise = nn.Conv2d(in_channels, out_channels, 1, 1, 0, 1, 1, bias=bias)
+
+    def _check_supported(self):
+        c = self.conv1
+        if not (c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1)
+                and c.bias is None and self.pointwise.bias is None and c.in_channels % 8 == 0
+                and self.pointwise.out_channels % 8 == 0):
+            raise XcpError("SeparableConv2d: the sm_100a path implements the configuration every Xception layer uses "
+                           "(k=3, s=1, p=1, d=1, bias=False, channels % 8 == 0); got %r" % (c,))
+
+    def forward(self, x):
+        _require_cuda(x, "SeparableConv2d")
+        self._check_supported()
+        return _SepFn.apply(self, x, self.conv1.weight, self.pointwise.weight)
+
+
+# ================================================================================================ Block
+class _BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        cache = _cache_of(mod)
+        inp = ops.nchw_to_nhwc(x.float().contiguous())
+        nbt: list = []
+        bt = ex.block_forward(cache, mod._spec(), inp, nbt, save=True)
+        ex._bump_nbt(nbt)
+        ctx.mod, ctx.tape, ctx.nparams = mod, bt, len(params)
+        return ops.nhwc_to_nchw(bt.out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        mod, bt = ctx.mod, ctx.tape
+        params = list(mod.parameters())
+        sink = ex.GradSink(params, dout.device)
+        G = ops.nchw_to_nhwc(dout.float().contiguous())
+        gin = ex.block_backward(_cache_of(mod), sink, bt, G)
+        dx = ops.nhwc_to_nchw(gin) if ctx.needs_input_grad[1] else None
+        return (None, dx) + tuple(sink.view(p) for p in params)
+
+
+class Block(nn.Module):
+    """Residual block of separable convs (Xception.py:50-99); same Sequential slot layout as the reference."""
+
+    def __init__(self, in_filters, out_filters, reps, strides=1, start_with_relu=True, grow_first=True):
+        super().__init__()
+        if out_filters != in_filters or strides != 1:
+            self.skip = nn.Conv2d(in_filters, out_filters, 1, stride=strides, bias=False)
+            self.skipbn = nn.BatchNorm2d(out_filters)
+        else:
+            self.skip = None
+        self.relu = nn.ReLU(inplace=True)
+        rep: List[nn.Module] = []
+        filters = in_filters
+        if grow_first:
+            rep += [self.relu, SeparableConv2d(in_filters, out_filters, 3, stride=1, padding=1, bias=False), nn.BatchNorm2d(out_filters)]
+            filters = out_filters
+        for _ in range(reps - 1):
+            rep += [self.relu, SeparableConv2d(filters, filters, 3, stride=1, padding=1, bias=False), nn.BatchNorm2d(filters)]
+        if not grow_first:
+            rep += [self.relu, SeparableConv2d(in_filters, out_filters, 3, stride=1, padding=1, bias=False), nn.BatchNorm2d(out_filters)]
+        if not start_with_relu:
+            rep = rep[1:]
+        else:
+            rep[0] = nn.ReLU(inplace=False)
+        if strides != 1:
+            rep.append(nn.MaxPool2d(3, strides, 1))
+        self.rep = nn.Sequential(*rep)
+        self._in, self._out, self._strides = in_filters, out_filters, strides
+
+    def _spec(self) -> ex.BlockSpec:
+        units = []
+        pending_relu = False
+        mods = list(self.rep)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.ReLU):
+                pending_relu = True
+                i += 1
+            elif isinstance(m, SeparableConv2d):
+                m._check_supported()
+                bn = mods[i + 1]
+                units.append(ex.SepSpec(m, bn, m.conv1.in_channels, m.pointwise.out_channels, pending_relu))
+                pending_relu = False
+                i += 2
+            elif isinstance(m, nn.MaxPool2d):
+                i += 1
+            else:
+                raise XcpError("Block.rep holds an unexpected module %r" % (m,))
+        return ex.BlockSpec(units, self._strides, self.skip, self.skipbn if self.skip is not None else None, self._in, self._out)
+
+    def forward(self, inp):
+        _require_cuda(inp, "Block")
+        return _BlockFn.apply(self, inp, *self.parameters())
+
+
+# ================================================================================================ small linear
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b for classifier-sized layers (B rows processed 32 at a time, warp per output neuron)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x2 = x.reshape(-1, x.shape[-1]).float().contiguous()
+        outs = [ops.linear_small_fwd(x2[i:i + 32], W.detach(), b.detach() if b is not None else None, 0)
+                for i in range(0, x2.shape[0], 32)]
+        ctx.save_for_backward(x2, W)
+        ctx.has_bias, ctx.xshape = b is not None, x.shape
+        return torch.cat(outs, 0).view(*x.shape[:-1], W.shape[0]) if len(outs) > 1 else outs[0].view(*x.shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, W = ctx.saved_tensors
+        d2 = dout.reshape(-1, dout.shape[-1]).float().contiguous()
+        dW = torch.zeros_like(W)
+        db = torch.zeros((W.shape[0],), device=W.device, dtype=W.dtype) if ctx.has_bias else None
+        dins = [ops.linear_small_bwd(d2[i:i + 32], None, 1.0, x2[i:i + 32], W.detach(), dW, db, want_din=ctx.needs_input_grad[0])
+                for i in range(0, x2.shape[0], 32)]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (torch.cat(dins, 0) if len(dins) > 1 else dins[0]).view(ctx.xshape)
+        return dx, dW, db
+
+
+class FusedLinear(nn.Linear):
+    """nn.Linear with the same parameters/keys (Xception.fc, Xception.py:149,199) running on the C-ABI kernels."""
+
+    def forward(self, x):
+        _require_cuda(x, "FusedLinear")
+        return _LinearFn.apply(x, self.weight, self.bias)
+
+
+# ================================================================================================ Xception
+class _XceptionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        save = any(ctx.needs_input_grad[2:])
+        feat, tape = ex.xception_forward(net, x.float(), save=save)
+        ctx.net, ctx.tape = net, tape
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        net = ctx.net
+        params = net._backbone_params()
+        sink = ex.GradSink(params, dfeat.device)
+        hook = net.__dict__.get("_grad_ready_hook")
+        if hook is not None:
+            sink.on_ready = lambda lo, hi: hook(sink, lo, hi)
+        ex.xception_backward(net, ctx.tape, dfeat.float(), sink)
+        ctx.tape = None
+        if hook is not None:
+            hook(sink, -1, -1)     # flush
+        grads = tuple(sink.view(p) if need else None for p, need in zip(params, ctx.needs_input_grad[2:]))
+        return (None, None) + grads
+
+
+class Xception(nn.Module):
+    """Xception backbone (Xception.py:103-201) on the fused sm_100a plan."""
+
+    def __init__(self, num_classes=1000):
+        super().__init__()
+        self.num_classes = num_classes
+        self.conv1 = nn.Conv2d(3, 32, 3, 2, 0, bias=False)
+        self.bn1 = nn.BatchNorm2d(32)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(32, 64, 3, bias=False)
+        self.bn2 = nn.BatchNorm2d(64)
+        self.block1 = Block(64, 128, 2, 2, start_with_relu=False, grow_first=True)
+        self.block2 = Block(128, 256, 2, 2, start_with_relu=True, grow_first=True)
+        self.block3 = Block(256, 728, 2, 2, start_with_relu=True, grow_first=True)
+        self.block4 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block5 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block6 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block7 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block8 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block9 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block10 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block11 = Block(728, 728, 3, 1, start_with_relu=True, grow_first=True)
+        self.block12 = Block(728, 1024, 2, 2, start_with_relu=True, grow_first=False)
+        self.conv3 = SeparableConv2d(1024, 1536, 3, 1, 1)
+        self.bn3 = nn.BatchNorm2d(1536)
+        self.conv4 = SeparableConv2d(1536, 2048, 3, 1, 1)
+        self.bn4 = nn.BatchNorm2d(2048)
+        self.fc = FusedLinear(2048, num_classes)
+        # ------- init weights (Xception.py:155-160) --------
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    # ---- plan plumbing (not part of state_dict)
+    @property
+    def _pack_cache(self) -> ex.PackCache:
+        return _cache_of(self)
+
+    @property
+    def _block_specs(self):
+        return [getattr(self, "block%d" % i)._spec() for i in range(1, 13)]
+
+    @property
+    def _exit_specs(self):
+        return [ex.SepSpec(self.conv3, self.bn3, 1024, 1536, False), ex.SepSpec(self.conv4, self.bn4, 1536, 2048, True)]
+
+    def _backbone_params(self) -> List[nn.Parameter]:
+        """Every parameter except fc.*, in registration order."""
+        fc_ids = {id(p) for p in self.fc.parameters()} if isinstance(self.fc, nn.Module) else set()
+        return [p for p in self.parameters() if id(p) not in fc_ids]
+
+    def features(self, x):
+        """conv1 ... bn4/relu/GAP of Xception.forward (Xception.py:168-198): [F,3,H,W] -> [F,2048]."""
+        _require_cuda(x, "Xception")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise XcpError("Xception: expected an input of shape [F,3,H,W], got %s" % (tuple(x.shape),))
+        return _XceptionFn.apply(self, x, *self._backbone_params())
+
+    def forward(self, x):
+        x = self.features(x)
+        x = self.fc(x)                                                   # Xception.py:199
+        return x
+
+
+def xception(pretrained=False, **kwargs):
+    """Construct Xception (Xception.py:205-213).  ``pretrained=True`` loads the reference's checkpoint from the local
+    torch hub cache ($TORCH_HOME/hub/checkpoints/xception-43020ad28.pth); the reference would download it, this
+    environment has no network, so a missing cache entry keeps the seeded random init and warns."""
+    model = Xception(**kwargs)
+    if pretrained:
+        try:
+            sd = torch.hub.load_state_dict_from_url(model_urls["xception"], progress=False, check_hash=False)
+            model.load_state_dict(sd)
+        except Exception as e:  # URLError offline, or a malformed cache entry
+            warnings.warn("xception(pretrained=True): pretrained weights unavailable (%s: %s); keeping the random "
+                          "initialisation" % (type(e).__name__, e))
+    return model
+
+
+# ================================================================================================ LSTM
+class _LSTMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, w_ih, w_hh, b_ih, b_hh):
+        cache = _cache_of(mod)
+        B, T, I = x.shape
+        H = w_hh.shape[1]
+        xb = x if x.dtype == torch.bfloat16 else ops.cast_bf16(x.float().contiguous())
+        xb = xb.contiguous().view(B * T, I)
+        wih_b, _ = cache.linear(w_ih)
+        _, whh_t = cache.linear(w_hh)
+        xproj, _ = ops.gemm_tn(xb, wih_b, ops.EPI_F32)
+        h, gates, cst, hn, cn = ops.lstm_fwd(xproj, b_ih.detach(), b_hh.detach(), whh_t, B, T, H)
+        ctx.mod, ctx.saved = mod, (xb, gates, cst, h, B, T, H, I)
+        ctx.mark_non_differentiable(cn)
+        return h, hn, cn
+
+    @staticmethod
+    def backward(ctx, dh, dhn, dcn):
+        mod = ctx.mod
+        cache = _cache_of(mod)
+        xb, gates, cst, h, B, T, H, I = ctx.saved
+        w_ih, w_hh, b_ih, b_hh = mod.weight_ih_l0, mod.weight_hh_l0, mod.bias_ih_l0, mod.bias_hh_l0
+        sink = ex.GradSink([w_ih, w_hh, b_ih, b_hh], h.device)
+        whh_b, _ = cache.linear(w_hh)
+        dgates, hprev = ops.lstm_bwd(dh.float().contiguous() if dh is not None else None,
+                                     dhn.float().contiguous() if dhn is not None else None, None, gates, cst, h, whh_b,
+                                     sink.view(b_ih), sink.view(b_hh), B, T, H)
+        ops.gemm_wgrad(dgates, xb, sink.view(w_ih))
+        ops.gemm_wgrad(dgates, hprev, sink.view(w_hh))
+        dx = None
+        if ctx.needs_input_grad[1]:
+            _, wih_t = cache.linear(w_ih)
+            dx, _ = ops.gemm_tn(dgates, wih_t, ops.EPI_F32)
+            dx = dx.view(B, T, I)
+        return None, dx, sink.view(w_ih), sink.view(w_hh), sink.view(b_ih), sink.view(b_hh)
+
+
+class FusedLSTM(nn.LSTM):
+    """nn.LSTM(input, hidden, 1, batch_first=True) with identical parameters / state_dict keys
+    (XceptionLSTMV.py:18-23); forward = one tcgen05 input-projection GEMM + one persistent recurrent kernel."""
+
+    def forward(self, input, hx=None):
+        _require_cuda(input, "FusedLSTM")
+        if hx is not None or self.num_layers != 1 or self.bidirectional or not self.batch_first or self.proj_size != 0:
+            raise XcpError("FusedLSTM: only the reference's configuration is implemented "
+                           "(1 layer, unidirectional, batch_first, zero initial state)")
+        if input.dim() != 3:
+            raise XcpError("FusedLSTM: expected [B,T,%d]" % self.input_size)
+        out, hn, cn = _LSTMFn.apply(self, input, self.weight_ih_l0, self.weight_hh_l0, self.bias_ih_l0, self.bias_hh_l0)
+        return out, (hn.unsqueeze(0), cn.unsqueeze(0))
+
+
+# ================================================================================================ MLP head
+class _HeadFn(torch.autograd.Function):
+    """fc_layers (4 x Linear+ReLU+Dropout(0.3)) + fc_out + sigmoid (XceptionLSTMV.py:25-44,68-70)."""
+
+    @staticmethod
+    def forward(ctx, h_last, training, p_drop, *wb):
+        x = h_last.float().contiguous()
+        B = x.shape[0]
+        if B > 32:
+            raise XcpError("classifier head: at most 32 clips per call (got %d)" % B)
+        acts = [x]
+        scale = 1.0 / (1.0 - p_drop) if (training and p_drop > 0) else 1.0
+        for li in range(4):
+            W, b = wb[2 * li].detach(), wb[2 * li + 1].detach()
+            mask = None
+            if training and p_drop > 0:
+                mask = (torch.rand((B, W.shape[0]), device=x.device) >= p_drop).to(torch.uint8)
+            acts.append(ops.linear_small_fwd(acts[-1], W, b, 1, mask, scale))
+        z = ops.linear_small_fwd(acts[-1], wb[8].detach(), wb[9].detach(), 0)
+        prob = ops.sigmoid_fwd(z)
+        ctx.acts, ctx.prob, ctx.scale, ctx.wb = acts, prob, scale, wb
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        acts, wb, scale = ctx.acts, ctx.wb, ctx.scale
+        sink = ex.GradSink(list(wb), dprob.device)
+        dz = ops.sigmoid_bwd(ctx.prob, dprob.float().contiguous())
+        delta = ops.linear_small_bwd(dz, None, 1.0, acts[4], wb[8].detach(), sink.view(wb[8]), sink.view(wb[9]))
+        for li in range(3, -1, -1):
+            delta = ops.linear_small_bwd(delta, acts[li + 1], scale, acts[li], wb[2 * li].detach(), sink.view(wb[2 * li]),
+                                         sink.view(wb[2 * li + 1]), want_din=(li > 0 or ctx.needs_input_grad[0]))
+        return (delta if ctx.needs_input_grad[0] else None, None, None) + tuple(sink.view(p) for p in wb)
+
+
+class _XceptionLSTMBase(nn.Module):
+    def __init__(self, hidden_dim):
+        super().__init__()
+        self.feature_extractor = xception(pretrained=True)
+        self.feature_extractor.fc = nn.Identity()
+        for param in self.feature_extractor.parameters():
+            param.requires_grad = False                                   # frozen at construction (XceptionLSTMV.py:15-16)
+        self.lstm = FusedLSTM(input_size=2048, hidden_size=hidden_dim, num_layers=1, batch_first=True)
+        self.fc_layers = nn.Sequential(
+            nn.Linear(hidden_dim, 1024), nn.ReLU(), nn.Dropout(0.3),
+            nn.Linear(1024, 1024), nn.ReLU(), nn.Dropout(0.3),
+            nn.Linear(1024, 1024), nn.ReLU(), nn.Dropout(0.3),
+            nn.Linear(1024, 1024), nn.ReLU(), nn.Dropout(0.3),
+        )
+        self.fc_out = nn.Linear(1024, 1)
+        self.sigmoid = nn.Sigmoid()
+
+    def _head_params(self):
+        ps = []
+        for k in (0, 3, 6, 9):
+            ps += [self.fc_layers[k].weight, self.fc_layers[k].bias]
+        return ps + [self.fc_out.weight, self.fc_out.bias]
+
+    def forward(self, features, seq_lengths=None):
+        """lstm -> last step -> fc_layers -> sigmoid(fc_out) (XceptionLSTMV.py:66-70).  The optional second argument
+        exists because train_visual.py's older variants pass seq_lengths; like the shipped class, lengths are not used."""
+        lstm_out, _ = self.lstm(features)
+        last = lstm_out[:, -1, :]
+        drop = self.fc_layers[2]
+        return _HeadFn.apply(last, drop.training, float(drop.p), *self._head_params())
+
+
+class XceptionLSTMV(_XceptionLSTMBase):
+    """Video model (XceptionLSTMV.py:9-70)."""
+
+    def extract_features(self, video_batch, device=None):
+        """(B,T,3,H,W) -> (B,T,2048).  The 2nd positional argument may be a device (shipped signature,
+        XceptionLSTMV.py:46) or a seq_lengths tensor (what train_visual.py:568 passes); tensors are ignored."""
+        if device is not None and not torch.is_tensor(device):
+            self.feature_extractor.to(device)
+            video_batch = video_batch.to(device)
+        b, t, c, h, w = video_batch.shape
+        frames = video_batch.reshape(b * t, c, h, w)
+        feats = self.feature_extractor(frames)
+        return feats.view(b, t, -1)
+
+
+class XceptionLSTMA(_XceptionLSTMBase):
+    """Audio model (XceptionLSTMA.py:5-59): (B,T,3,n_mfcc) -> bilinear 64x64 -> Xception -> LSTM -> head."""
+
+    def extract_features(self, audio_batch, device=None):
+        if device is not None and not torch.is_tensor(device):
+            self.feature_extractor.to(device)
+            audio_batch = audio_batch.to(device)
+        _require_cuda(audio_batch, "XceptionLSTMA")
+        b, t, c, n = audio_batch.shape
+        frames = audio_batch.reshape(b * t, c, n, 1).float().contiguous()
+        frames = ops.bilinear_up(frames, 64)                              # XceptionLSTMA.py:46
+        feats = self.feature_extractor(frames)
+        return feats.view(b, t, feats.shape[-1])
+
+
+# ================================================================================================ heads / losses
+class _ArcFaceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, weight, labels, s, m, loss_mode, class_w, gamma):
+        x = feats.float().contiguous()
+        dw = torch.zeros_like(weight)
+        logits, loss, dx = ops.arcface_loss(x, weight.detach(), labels, s, m, loss_mode, class_w, gamma, dw=dw)
+        ctx.save_for_backward(dx, dw)
+        ctx.mark_non_differentiable(logits)
+        return logits, loss
+
+    @staticmethod
+    def backward(ctx, _dlogits, dloss):
+        dx, dw = ctx.saved_tensors
+        return dx * dloss, dw * dloss, None, None, None, None, None, None
+
+
+class ArcFaceHead(nn.Module):
+    """ArcFace logits (train_visual.py:455-474; train_au_face.py:423-442).  ``forward(features, labels)`` returns the
+    margin logits like the reference.  ``loss(features, labels, ...)`` additionally fuses CrossEntropy / CB-focal and
+    their gradients into the same kernel."""
+
+    def __init__(self, feat_dim, num_classes=2, s=30.0, m=0.5):
+        super().__init__()
+        self.num_classes, self.s, self.m = num_classes, s, m
+        self.weight = nn.Parameter(torch.randn(num_classes, feat_dim))
+        nn.init.xavier_uniform_(self.weight)
+        if num_classes != 2:
+            raise XcpError("ArcFaceHead: the fused kernel implements the reference's binary (real/fake) head")
+
+    def loss(self, features, labels, class_weights=None, gamma=2.0):
+        """(logits, loss): CrossEntropyLoss(ArcFace(features, labels), labels) if class_weights is None, else
+        CBFocalLoss (train_au_face.py:445-458)."""
+        _require_cuda(features, "ArcFaceHead")
+        mode = 0 if class_weights is None else 1
+        return _ArcFaceFn.apply(features, self.weight, labels.long().contiguous(), self.s, self.m, mode, class_weights, gamma)
+
+    def forward(self, features, labels=None):
+        _require_cuda(features, "ArcFaceHead")
+        if labels is None:
+            logits, _, _ = ops.arcface_loss(features.detach().float().contiguous(), self.weight.detach(), None, self.s, self.m)
+            return logits
+        # differentiable logits: route through autograd with an external loss -> use torch-free composite
+        return _ArcLogitsFn.apply(features, self.weight, labels.long().contiguous(), self.s, self.m)
+
+
+class _ArcLogitsFn(torch.autograd.Function):
+    """Margin logits as a differentiable output (for callers that apply their own criterion, train_visual.py:571-572).
+    Backward re-runs the fused kernel once per class column with a one-hot upstream gradient folded in via the
+    linearity of the chain rule: dL/dx = sum_c dL/dlogit_c * dlogit_c/dx."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, labels, s, m):
+        x = feats.float().contiguous()
+        logits, _, _ = ops.arcface_loss(x, weight.detach(), labels, s, m, want_dx=False)
+        ctx.save_for_backward(x, weight, labels)
+        ctx.s, ctx.m = s, m
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, weight, labels = ctx.saved_tensors
+        dx, dw = ops.arcface_logits_bwd(x, weight.detach(), labels, ctx.s, ctx.m, dlogits.float().contiguous())
+        return dx, dw, None, None, None
+
+
+class CBFocalLoss(nn.Module):
+    """Class-balanced focal loss on ArcFace logits (train_au_face.py:445-458).  Weights are computed exactly as the
+    reference does; use ``ArcFaceHead.loss(features, labels, class_weights=cb.class_weights, gamma=cb.gamma)``."""
+
+    def __init__(self, samples_per_cls, beta=0.9999, gamma=2.0):
+        super().__init__()
+        n = [float(v) for v in samples_per_cls]
+        w = [(1.0 - beta) / (1.0 - beta ** v) for v in n]
+        tot = sum(w)
+        w = [v / tot * len(n) for v in w]
+        self.register_buffer("class_weights", torch.tensor(w, dtype=torch.float32))
+        self.gamma = gamma
+
+
+class _BCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, smoothing):
+        z = logits.float().contiguous().view(-1)
+        probs, loss, dz = ops.bce_fwd_bwd(z, targets.float().contiguous().view(-1), smoothing)
+        ctx.save_for_backward(dz)
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dz,) = ctx.saved_tensors
+        return (dz.view(ctx.shape) * dloss), None, None
+
+
+class LabelSmoothingBCEWithLogitsLoss(nn.Module):
+    """train_au_patch.py:203-211 -- BCE-with-logits on targets*(1-s)+0.5*s, loss and gradient in one kernel."""
+
+    def __init__(self, smoothing=0.1):
+        super().__init__()
+        self.smoothing = smoothing
+
+    def forward(self, logits, targets):
+        _require_cuda(logits, "LabelSmoothingBCEWithLogitsLoss")
+        return _BCEFn.apply(logits, targets, float(self.smoothing))

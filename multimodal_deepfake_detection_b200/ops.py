@@ -203,9 +203,10 @@ def pool_add_fwd(y, scale, shift, ys, scale_s, shift_s, want_idx=True):
     return out, idx
 
 
-def bn_add_fwd(y, scale, shift, skip):
+def bn_add_fwd(y, scale, shift, skip, scale_s=None, shift_s=None):
     out = torch.empty_like(y)
-    _lib.call("xcp_bn_add_fwd", _p(y), _p(scale), _p(shift), _p(skip), _p(out), y.numel(), y.shape[-1], y.device.index, _s())
+    _lib.call("xcp_bn_add_fwd", _p(y), _p(scale), _p(shift), _p(skip), _p(scale_s), _p(shift_s), _p(out), y.numel(),
+              y.shape[-1], y.device.index, _s())
     return out
 
 
@@ -346,6 +347,18 @@ def linear_small_bwd(delta_raw, out_act, drop_scale, a, W, dW, db, want_din=True
     return din
 
 
+def sigmoid_fwd(z):
+    p = torch.empty_like(z)
+    _lib.call("xcp_sigmoid_fwd", _p(z), _p(p), z.numel(), z.device.index, _s())
+    return p
+
+
+def sigmoid_bwd(p, dp):
+    dz = torch.empty_like(p)
+    _lib.call("xcp_sigmoid_bwd", _p(p), _p(dp), _p(dz), p.numel(), p.device.index, _s())
+    return dz
+
+
 def bce_fwd_bwd(z, y, smoothing: float = 0.0, want_grad: bool = True):
     B = z.numel()
     probs = torch.empty((B, 1), device=z.device, dtype=F32)
@@ -362,9 +375,21 @@ def arcface_loss(x, w, labels, s, m, loss_mode=0, class_w=None, gamma=2.0, dw=No
     loss = torch.zeros((), device=dev, dtype=F32)
     rows = torch.empty((B,), device=dev, dtype=F32)
     dx = torch.empty((B, D), device=dev, dtype=F32) if (want_dx and labels is not None) else None
-    _lib.call("xcp_arcface_loss", _p(x), _p(w), _p(labels), s, m, loss_mode, _p(class_w), gamma, _p(logits), _p(loss), _p(rows),
-              _p(dx), _p(dw), B, D, gscale, dev.index, _s())
+    _lib.call("xcp_arcface_loss", _p(x), _p(w), _p(labels), s, m, loss_mode, _p(class_w), gamma, _p(None), _p(logits), _p(loss),
+              _p(rows), _p(dx), _p(dw), B, D, gscale, dev.index, _s())
     return logits, loss, dx
+
+
+def arcface_logits_bwd(x, w, labels, s, m, dlogits):
+    """Gradient of the margin logits wrt (x, w) for an upstream dL/dlogits computed by an external criterion."""
+    B, D = x.shape
+    dev = x.device
+    logits = torch.empty((B, 2), device=dev, dtype=F32)
+    dx = torch.empty((B, D), device=dev, dtype=F32)
+    dw = torch.zeros((2, D), device=dev, dtype=F32)
+    _lib.call("xcp_arcface_loss", _p(x), _p(w), _p(labels), s, m, 0, _p(None), 0.0, _p(dlogits), _p(logits), _p(None), _p(None),
+              _p(dx), _p(dw), B, D, 1.0, dev.index, _s())
+    return dx, dw
 
 
 def fusion_pool_reg(v, a, lambda_align, lambda_temp, want_grad=True, gscale=1.0):
