@@ -33,6 +33,8 @@ int xcp_check_device(int device);
  * BatchNorm (Xception.py:67,73,78) | 2 fp32 out (+ optional bias[N]).  lda/ldb/ldo are row pitches in elements. */
 int xcp_gemm_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N, int K,
                 int epi, float* stats, const float* bias, int device, void* stream);
+/* rows of `stats` written by xcp_gemm_tn(epi=1) / xcp_conv3x3_gemm for an M x N problem (<= SM count when N fits one tile) */
+int xcp_gemm_stats_parts(long long M, int N, int device);
 /* dW[P,Q] += dY[R,P]^T * X[R,Q] (fp32 accumulate into dW): weight gradient of the layers above. */
 int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, long long ld_x, float* dW, long long ld_dw, int R, int P,
                    int Q, int device, void* stream);
@@ -43,7 +45,8 @@ int xcp_gemm_ref(const void* A, long long lda, const void* B, long long ldb, flo
 int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* stats, int F, int Hg, int Wg, int Cin, int Cout, int Ho,
                      int Wo, int sign, int device, void* stream);
 
-/* ---- stem conv1 3->32 k3 s2 p0 (Xception.py:118,168): fp32 NCHW in, bf16 NHWC out + BN partials [ceil(M/128)][2][32] */
+/* ---- stem conv1 3->32 k3 s2 p0 (Xception.py:118,168): fp32 NCHW in, bf16 NHWC out + BN partials [xcp_stem_conv1_parts()][2][32] */
+int xcp_stem_conv1_parts(int F, int H, int W, int device);
 int xcp_stem_conv1_fwd(const float* x, const float* w, void* y, float* partials, int F, int H, int W, int device, void* stream);
 int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, int F, int H, int W, int device, void* stream);
 
@@ -51,10 +54,11 @@ int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, int F, int H
  * (Xception.py:61-76) and the producer's BatchNorm affine.  w9 = tap-major weights [9][C] (xcp_pack_dw). */
 int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int H,
                   int W, int C, int device, void* stream);
-long long xcp_dw3x3_bwd_workspace_floats(int C);
+/* backward: dz = mask*conv_transpose(dD) [+ add_full] [+ add_half at even pixels]; dw[C][9] (nn.Conv2d layout) and
+ * bnsum[2][C] = (sum dz, sum dz*x) are accumulated with RED (bnsum only when scale/shift given; caller zero-fills) */
 int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift, int relu, void* dz,
-                  const void* add_full, const void* add_half, float* dw9, float* bnsum, float* workspace, int F, int H, int W,
-                  int C, int device, void* stream);
+                  const void* add_full, const void* add_half, float* dw, float* bnsum, int F, int H, int W, int C, int device,
+                  void* stream);
 
 /* ---- BatchNorm2d (Xception.py:56,67,73,78,119,123,143,147): statistics finalisation (train), affine folding (eval) */
 int xcp_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,

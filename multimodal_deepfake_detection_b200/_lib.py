@@ -20,14 +20,15 @@ SIGNATURES = {
     "xcp_version": "",
     "xcp_check_device": "i",
     "xcp_gemm_tn": "plplpliiiippip",
+    "xcp_gemm_stats_parts": "lii",
     "xcp_gemm_wgrad": "plplpliiiip",
     "xcp_gemm_ref": "plplpliiiiip",
     "xcp_conv3x3_gemm": "ppppiiiiiiiiip",
+    "xcp_stem_conv1_parts": "iiii",
     "xcp_stem_conv1_fwd": "ppppiiiip",
     "xcp_stem_conv1_wgrad": "pppiiiip",
     "xcp_dw3x3_fwd": "ppppipiiiiip",
-    "xcp_dw3x3_bwd_workspace_floats": "i",
-    "xcp_dw3x3_bwd": "pppppippppppiiiiip",
+    "xcp_dw3x3_bwd": "pppppipppppiiiiip",
     "xcp_bn_finalize": "piidppppffppppip",
     "xcp_bn_eval_affine": "ppppfppppiip",
     "xcp_bn_act": "pppipliip",
@@ -59,8 +60,8 @@ SIGNATURES = {
     "xcp_grad_sumsq": "plpiip",
     "xcp_adam_step": "pppplfffffiipffip",
 }
-_RET_LONGLONG = {"xcp_dw3x3_bwd_workspace_floats"}
-_NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_dw3x3_bwd_workspace_floats"}
+_RET_LONGLONG = set()
+_NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp_stem_conv1_parts"}
 
 _lock = threading.Lock()
 _lib = None

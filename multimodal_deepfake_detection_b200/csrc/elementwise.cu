@@ -23,48 +23,53 @@ stem_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     }
     __syncthreads();
     const long long M = (long long)F * H1 * W1;
-    const long long pix = (long long)blockIdx.x * 128 + threadIdx.x;
-    float acc[32];
+    const long long chunks = (M + 127) / 128;
+    float run = 0.f;                               // threads 0..63: running (sum | sumsq) of channel tid & 31
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long pix = ch * 128 + threadIdx.x;
+        float acc[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    const bool ok = pix < M;
-    if (ok) {
-        const int wo = (int)(pix % W1);
-        const int ho = (int)((pix / W1) % H1);
-        const int f = (int)(pix / ((long long)W1 * H1));
-        const float* xb = x + ((long long)f * 3 * H + 2 * ho) * W + 2 * wo;
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        if (pix < M) {
+            const int wo = (int)(pix % W1);
+            const int ho = (int)((pix / W1) % H1);
+            const int f = (int)(pix / ((long long)W1 * H1));
+            const float* xb = x + ((long long)f * 3 * H + 2 * ho) * W + 2 * wo;
 #pragma unroll
-        for (int ic = 0; ic < 3; ++ic)
+            for (int ic = 0; ic < 3; ++ic)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+                for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float xv = __ldg(xb + ((long long)ic * H + kh) * W + kw);
-                    const int tap = (ic * 3 + kh) * 3 + kw;
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float xv = __ldg(xb + ((long long)ic * H + kh) * W + kw);
+                        const int tap = (ic * 3 + kh) * 3 + kw;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = fmaf(xv, s_w[tap][j], acc[j]);
-                }
-        __nv_bfloat16* yp = y + pix * 32;
+                        for (int j = 0; j < 32; ++j) acc[j] = fmaf(xv, s_w[tap][j], acc[j]);
+                    }
+            __nv_bfloat16* yp = y + pix * 32;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            float t8[8];
+            for (int g = 0; g < 4; ++g) {
+                float t8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t8[j] = acc[g * 8 + j];
-            *reinterpret_cast<uint4*>(yp + g * 8) = pack8(t8);
+                for (int j = 0; j < 8; ++j) t8[j] = acc[g * 8 + j];
+                *reinterpret_cast<uint4*>(yp + g * 8) = pack8(t8);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s_t[threadIdx.x][j] = acc[j];   // zeros for out-of-range pixels
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int chn = threadIdx.x & 31, st = threadIdx.x >> 5;
+            float s = 0.f;
+            for (int r = 0; r < 128; ++r) {
+                const float v = s_t[r][chn];
+                s += st ? v * v : v;
+            }
+            run += s;
         }
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s_t[threadIdx.x][j] = acc[j];   // zeros for out-of-range pixels
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        const int ch = threadIdx.x & 31, st = threadIdx.x >> 5;
-        float s = 0.f;
-        for (int r = 0; r < 128; ++r) {
-            const float v = s_t[r][ch];
-            s += st ? v * v : v;
-        }
-        partials[((long long)blockIdx.x * 2 + st) * 32 + ch] = s;
-    }
+    if (threadIdx.x < 64) partials[((long long)blockIdx.x * 2 + (threadIdx.x >> 5)) * 32 + (threadIdx.x & 31)] = run;
 }
 
 // ======================================================================================== BN finalize
@@ -594,13 +599,21 @@ using namespace xcp;
 
 #define ST ((cudaStream_t)stream)
 
+// number of partial rows xcp_stem_conv1_fwd writes ( = its grid size)
+extern "C" int xcp_stem_conv1_parts(int F, int H, int W, int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
+    const long long chunks = ((long long)F * H1 * W1 + 127) / 128;
+    const long long cap = 4LL * num_sms();
+    return (int)(chunks < cap ? chunks : cap);
+}
+
 extern "C" int xcp_stem_conv1_fwd(const float* x, const float* w, void* y, float* partials, int F, int H, int W, int device,
                                   void* stream) {
     XCP_REQUIRE(F > 0 && H >= 3 && W >= 3, "xcp_stem_conv1_fwd: bad shape");
     XCP_CUDA(cudaSetDevice(device));
     const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
-    const long long M = (long long)F * H1 * W1;
-    stem_conv1_fwd_kernel<<<(int)((M + 127) / 128), 128, 0, ST>>>(x, w, (__nv_bfloat16*)y, partials, F, H, W, H1, W1);
+    stem_conv1_fwd_kernel<<<xcp_stem_conv1_parts(F, H, W, device), 128, 0, ST>>>(x, w, (__nv_bfloat16*)y, partials, F, H, W, H1, W1);
     return check_cuda(cudaGetLastError(), "stem_conv1_fwd launch");
 }
 

@@ -22,7 +22,8 @@ struct GemmParams {
     int M, N, K;          // output rows, output cols, reduction length (elements)
     void* out;            // bf16 / f32, row-major [M, ldo]
     long long ldo;
-    float* stats;         // EPI_BF16_STATS: [num_m_tiles][2][N]
+    float* stats;         // EPI_BF16_STATS: [parts][2][N]; parts = gridDim.x if stats_per_cta else num_m_tiles
+    int stats_per_cta;    // single N tile: each CTA accumulates its tiles' sums and writes one partial row
     const float* bias;    // EPI_F32: optional [N]
     int num_m_tiles, num_n_tiles, num_k_blocks;
     int splits, k_blocks_per_split;   // split over the reduction dim (EPI_RED_F32)
@@ -165,6 +166,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int row_in_tile = q * 32 + lane;
         const int et = threadIdx.x - 64;   // 0..127
         float* my_tr = s_tr + q * (32 * 33);
+        float racc[2][(BLOCK_N + 127) / 128];
+#pragma unroll
+        for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) { racc[0][i] = 0.f; racc[1][i] = 0.f; }
         uint32_t iter = 0;
         for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++iter) {
             const int split = u / tiles_mn;
@@ -260,20 +264,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
             if (STATS) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int c = et; c < BLOCK_N; c += 128) {
+#pragma unroll
+                for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) {
+                    const int c = et + i * 128;
                     const int gcol = n_blk * BLOCK_N + c;
-                    if (gcol < p.N) {
+                    if (c < BLOCK_N && gcol < p.N) {
                         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq) {
                             s1 += s_part[(qq * 2 + 0) * BLOCK_N + c];
                             s2 += s_part[(qq * 2 + 1) * BLOCK_N + c];
                         }
-                        p.stats[((long long)m_blk * 2 + 0) * p.N + gcol] = s1;
-                        p.stats[((long long)m_blk * 2 + 1) * p.N + gcol] = s2;
+                        if (p.stats_per_cta) {
+                            racc[0][i] += s1; racc[1][i] += s2;
+                        } else {
+                            p.stats[((long long)m_blk * 2 + 0) * p.N + gcol] = s1;
+                            p.stats[((long long)m_blk * 2 + 1) * p.N + gcol] = s2;
+                        }
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        if (STATS && p.stats_per_cta) {
+#pragma unroll
+            for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) {
+                const int c = et + i * 128;
+                if (c < BLOCK_N && c < p.N) {
+                    p.stats[((long long)blockIdx.x * 2 + 0) * p.N + c] = racc[0][i];
+                    p.stats[((long long)blockIdx.x * 2 + 1) * p.N + c] = racc[1][i];
+                }
             }
         }
     }
@@ -355,12 +375,23 @@ extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long lon
     p.num_n_tiles = (N + bn - 1) / bn;
     p.num_k_blocks = (K + 63) / 64;
     p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
+    p.stats_per_cta = (p.num_n_tiles == 1) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (epi) {
         case EPI_BF16: return dispatch_tn<EPI_BF16>(bn, tmA, tmB, p, st);
         case EPI_BF16_STATS: return dispatch_tn<EPI_BF16_STATS>(bn, tmA, tmB, p, st);
         default: return dispatch_tn<EPI_F32>(bn, tmA, tmB, p, st);
     }
+}
+
+// Number of partial rows xcp_gemm_tn (epi=1) / xcp_conv3x3_gemm write into `stats` for an M x N problem.
+extern "C" int xcp_gemm_stats_parts(long long M, int N, int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    const long long mt = (M + BLOCK_M - 1) / BLOCK_M;
+    const int bn = pick_block_n(N);
+    const int nt = (N + bn - 1) / bn;
+    if (nt > 1) return (int)mt;
+    return (int)(mt < num_sms() ? mt : num_sms());
 }
 
 // dW[P,Q] += dY[R,P]^T * X[R,Q]   (weight gradient of Y = X W^T; R = pixels).  fp32 RED accumulation, the
@@ -421,6 +452,7 @@ extern "C" int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* 
     for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) p.a_row_shift[kh * 3 + kw] = sign * (kh * Wg + kw);
     p.conv_grid_w = Wg; p.conv_grid_h = Hg; p.conv_out_w = Wo; p.conv_out_h = Ho;
+    p.stats_per_cta = 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 32) {
         if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, 8, 32>(tmA, tmB, p, st);

@@ -79,7 +79,7 @@ class GradSink:
     """Flat fp32 gradient arena: one zero-fill per backward, every parameter gradient is a view into it, and
     (for data parallel) contiguous ranges of it are all-reduced as buckets while backward is still running."""
 
-    def __init__(self, params: List[torch.Tensor], device):
+    def __init__(self, params: List[torch.Tensor], device, scratch_floats: int = 0):
         self.params = params
         self.offsets = {}
         off = 0
@@ -87,8 +87,20 @@ class GradSink:
             self.offsets[id(p)] = off
             off += (p.numel() + 3) // 4 * 4      # keep every view 16-byte aligned
         self.total = off
-        self.flat = torch.zeros((max(off, 4),), device=device, dtype=F32)
+        # the tail of the arena is zero-filled scratch for the per-channel BN-backward sums the depthwise backward
+        # accumulates with RED (one memset covers every layer)
+        self._scratch_off = off
+        self._scratch_end = off + scratch_floats
+        self.flat = torch.zeros((max(off + scratch_floats, 4),), device=device, dtype=F32)
         self.on_ready = None                      # optional callback(lo, hi) for the DDP bucketer
+
+    def scratch(self, n: int) -> torch.Tensor:
+        n4 = (n + 3) // 4 * 4
+        if self._scratch_off + n4 > self._scratch_end:
+            return torch.zeros((n,), device=self.flat.device, dtype=F32)
+        o = self._scratch_off
+        self._scratch_off += n4
+        return self.flat[o:o + n]
 
     def view(self, p: torch.Tensor) -> torch.Tensor:
         o = self.offsets[id(p)]
@@ -210,11 +222,10 @@ def _dw_backward(cache: PackCache, sink: GradSink, t: SepTape, dd: torch.Tensor,
     w = t.spec.sep.conv1.weight
     w9 = cache.dw(w)
     C = w.shape[0]
-    dw9 = torch.zeros((9, C), device=dd.device, dtype=F32)
     aff = t.src_st is not None
+    bnsum = sink.scratch(2 * C).view(2, C) if aff else None
     dz, bnsum = ops.dw3x3_bwd(dd, t.src, w9, t.src_st.scale if aff else None, t.src_st.shift if aff else None, t.src_relu,
-                              dw9, add_full=add_full, add_half=add_half, want_bnsum=aff)
-    ops.unpack_dw_grad(dw9, sink.view(w), True)
+                              sink.view(w), add_full=add_full, add_half=add_half, bnsum=bnsum)
     sink.done(w)
     return dz, bnsum
 

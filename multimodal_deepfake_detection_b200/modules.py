@@ -221,7 +221,7 @@ class _XceptionFn(torch.autograd.Function):
     def backward(ctx, dfeat):
         net = ctx.net
         params = net._backbone_params()
-        sink = ex.GradSink(params, dfeat.device)
+        sink = ex.GradSink(params, dfeat.device, scratch_floats=2 * sum(p.numel() for p in params if p.dim() == 1))
         hook = net.__dict__.get("_grad_ready_hook")
         if hook is not None:
             sink.on_ready = lambda lo, hi: hook(sink, lo, hi)

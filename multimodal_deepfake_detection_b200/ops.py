@@ -51,7 +51,9 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optiona
     assert b.shape[1] == K
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=F32 if epi == EPI_F32 else BF16)
-    stats = torch.empty(((M + 127) // 128, 2, N), device=a.device, dtype=F32) if epi == EPI_BF16_STATS else None
+    stats = None
+    if epi == EPI_BF16_STATS:
+        stats = torch.empty((_lib.call("xcp_gemm_stats_parts", M, N, a.device.index), 2, N), device=a.device, dtype=F32)
     _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), a.device.index, _s())
     return out, stats
 
@@ -85,8 +87,9 @@ def conv3x3_gemm_fwd(x: torch.Tensor, wk: torch.Tensor, want_stats: bool = True)
     Cout = wk.shape[0]
     Ho, Wo = Hg - 2, Wg - 2
     out = torch.empty((F_, Ho, Wo, Cout), device=x.device, dtype=BF16)
-    mt = (F_ * Hg * Wg + 127) // 128
-    stats = torch.empty((mt, 2, Cout), device=x.device, dtype=F32) if want_stats else None
+    stats = None
+    if want_stats:
+        stats = torch.empty((_lib.call("xcp_gemm_stats_parts", F_ * Hg * Wg, Cout, x.device.index), 2, Cout), device=x.device, dtype=F32)
     _lib.call("xcp_conv3x3_gemm", _p(x), _p(wk), _p(out), _p(stats), F_, Hg, Wg, Cin, Cout, Ho, Wo, 1, x.device.index, _s())
     return out, stats
 
@@ -123,7 +126,7 @@ def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor):
     F_, _, H, W = x.shape
     H1, W1 = (H - 3) // 2 + 1, (W - 3) // 2 + 1
     y = torch.empty((F_, H1, W1, 32), device=x.device, dtype=BF16)
-    parts = torch.empty(((F_ * H1 * W1 + 127) // 128, 2, 32), device=x.device, dtype=F32)
+    parts = torch.empty((_lib.call("xcp_stem_conv1_parts", F_, H, W, x.device.index), 2, 32), device=x.device, dtype=F32)
     _lib.call("xcp_stem_conv1_fwd", _p(x), _p(w), _p(y), _p(parts), F_, H, W, x.device.index, _s())
     return y, parts
 
@@ -142,14 +145,15 @@ def dw3x3_fwd(x: torch.Tensor, w9: torch.Tensor, scale=None, shift=None, relu: b
     return out
 
 
-def dw3x3_bwd(dD, xin, w9, scale, shift, relu, dw9, add_full=None, add_half=None, want_bnsum=False):
+def dw3x3_bwd(dD, xin, w9, scale, shift, relu, dw, add_full=None, add_half=None, bnsum=None):
+    """dw: fp32 [C,1,3,3] gradient buffer (accumulated); bnsum: zero-filled fp32 [2,C] when scale/shift are given."""
     _chk(dD, BF16, "dw3x3_bwd.dD"); _chk(xin, BF16, "dw3x3_bwd.xin")
     F_, H, W, C = xin.shape
     dz = torch.empty_like(xin)
-    ws = torch.empty((_lib.call("xcp_dw3x3_bwd_workspace_floats", C),), device=xin.device, dtype=F32)
-    bnsum = torch.empty((2, C), device=xin.device, dtype=F32) if want_bnsum else None
+    if scale is not None and bnsum is None:
+        bnsum = torch.zeros((2, C), device=xin.device, dtype=F32)
     _lib.call("xcp_dw3x3_bwd", _p(dD), _p(xin), _p(w9), _p(scale), _p(shift), int(relu), _p(dz), _p(add_full), _p(add_half),
-              _p(dw9), _p(bnsum), _p(ws), F_, H, W, C, xin.device.index, _s())
+              _p(dw), _p(bnsum), F_, H, W, C, xin.device.index, _s())
     return dz, bnsum
 
 

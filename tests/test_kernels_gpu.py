@@ -148,10 +148,8 @@ def test_dw3x3_fwd_bwd(shape, affine, relu):
     # backward
     dD = rnd(F_, H, W, C, seed=17, dtype=torch.bfloat16)
     ref.backward(dD.float().permute(0, 3, 1, 2))
-    dw9 = torch.zeros(9, C, device=DEV)
-    dz, bnsum = ops.dw3x3_bwd(dD, x, w9, scale, shift, relu, dw9, want_bnsum=affine)
     gw = torch.zeros_like(w)
-    ops.unpack_dw_grad(dw9, gw, False)
+    dz, bnsum = ops.dw3x3_bwd(dD, x, w9, scale, shift, relu, gw)
     assert rel_err(gw, wt.grad) < 2e-3
     # dz is the gradient wrt the pre-activation z (= scale*x+shift, or x): compare through the chain rule
     dz_ref = xt.grad
@@ -175,9 +173,9 @@ def test_dw3x3_bwd_residual_adds():
     dD = rnd(F_, H, W, C, seed=20, dtype=torch.bfloat16)
     full = rnd(F_, H, W, C, seed=21, dtype=torch.bfloat16)
     half = rnd(F_, 10, 10, C, seed=22, dtype=torch.bfloat16)
-    dw9 = torch.zeros(9, C, device=DEV)
-    base, _ = ops.dw3x3_bwd(dD, x, w9, None, None, True, dw9)
-    both, _ = ops.dw3x3_bwd(dD, x, w9, None, None, True, dw9, add_full=full, add_half=half)
+    gw = torch.zeros(C, 1, 3, 3, device=DEV)
+    base, _ = ops.dw3x3_bwd(dD, x, w9, None, None, True, gw)
+    both, _ = ops.dw3x3_bwd(dD, x, w9, None, None, True, gw, add_full=full, add_half=half)
     ref = base.float() + full.float()
     ref[:, ::2, ::2] += half.float()
     assert rel_err(both, ref) < 8e-3
@@ -198,7 +196,7 @@ def test_bn_finalize_and_apply(shape):
         bn.weight.copy_(gamma); bn.bias.copy_(beta); bn.running_mean.copy_(rm); bn.running_var.copy_(rv)
     bn.train()
     ref = bn(yf)
-    # partials as a GEMM epilogue would produce them: per 128-row tile sums
+    # partials as a GEMM epilogue could produce them: per 128-row tile sums
     y2 = y.float().view(-1, C)
     M = y2.shape[0]
     mt = (M + 127) // 128

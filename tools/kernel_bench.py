@@ -1,0 +1,96 @@
+"""Per-kernel roofline probe (GPU): times the hot kernels alone at the path's real shapes with CUDA events and
+prints achieved GB/s / TFLOP/s against MEASURED_PEAKS.json.  Inputs are larger than L2 (126 MB) or L2 is
+flushed between iterations.  Usage: python tools/kernel_bench.py [F] [which...]"""
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from multimodal_deepfake_detection_b200 import ops  # noqa: E402
+
+dev = "cuda"
+Fr = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+which = set(sys.argv[2:])
+peaks = {"hbm_gbs": 6450.6, "bf16_tflops": 1658.4}
+if os.path.exists("MEASURED_PEAKS.json"):
+    peaks.update(json.load(open("MEASURED_PEAKS.json")))
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def rnd(*s, dtype=torch.bfloat16):
+    return torch.randn(*s, device=dev).to(dtype)
+
+
+def report(name, ms, gbytes=None, tflop=None):
+    msg = f"{name:48s} {ms*1e3:9.1f} us"
+    if gbytes is not None:
+        bw = gbytes / (ms * 1e-3)
+        msg += f"  {bw:8.1f} GB/s ({bw / peaks['hbm_gbs'] * 100:5.1f}% of measured HBM)"
+    if tflop is not None:
+        tf = tflop / (ms * 1e-3)
+        msg += f"  {tf:8.1f} TFLOP/s ({tf / peaks['bf16_tflops'] * 100:5.1f}% of measured bf16)"
+    print(msg, flush=True)
+
+
+DW = [(147, 64), (147, 128), (74, 128), (74, 256), (37, 256), (37, 728), (19, 728), (10, 1024), (10, 1536)]
+if not which or "dw" in which:
+    for H, C in DW:
+        x = rnd(Fr, H, H, C); w9 = torch.randn(9, C, device=dev)
+        sc = torch.rand(C, device=dev) + 0.5; sh = torch.randn(C, device=dev) * 0.1
+        out = torch.empty_like(x)
+        gb = 2 * x.numel() * 2 / 1e9
+        report(f"dw_fwd affine+relu  {H}x{H}x{C}", timeit(lambda: ops.dw3x3_fwd(x, w9, sc, sh, True, out=out)), gb)
+        report(f"dw_fwd plain        {H}x{H}x{C}", timeit(lambda: ops.dw3x3_fwd(x, w9, None, None, True, out=out)), gb)
+        dD = rnd(Fr, H, H, C); dw9 = torch.zeros(C, 1, 3, 3, device=dev); bns = torch.zeros(2, C, device=dev)
+        gb3 = 3 * x.numel() * 2 / 1e9
+        report(f"dw_bwd affine+relu  {H}x{H}x{C}", timeit(lambda: ops.dw3x3_bwd(dD, x, w9, sc, sh, True, dw9, bnsum=bns)), gb3)
+        del x, out, dD
+
+PW = [(21609, 64, 128), (21609, 128, 128), (5476, 128, 256), (5476, 256, 256), (1369, 256, 728), (1369, 728, 728),
+      (361, 728, 728), (361, 728, 1024), (100, 1024, 1536), (100, 1536, 2048)]
+if not which or "gemm" in which:
+    for pix, K, N in PW:
+        M = pix * Fr
+        a = rnd(M, K); b = rnd(N, K) / math.sqrt(K)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        tf = 2.0 * M * N * K / 1e12
+        gb = (M * K + M * N) * 2 / 1e9
+        report(f"gemm fwd+stats  M={M} K={K} N={N}", timeit(lambda: ops.gemm_tn(a, b, ops.EPI_BF16_STATS, out=out)), gb, tf)
+        report(f"gemm plain      M={M} K={K} N={N}", timeit(lambda: ops.gemm_tn(a, b, ops.EPI_BF16, out=out)), gb, tf)
+        dw = torch.zeros(N, K, device=dev)
+        report(f"gemm wgrad      R={M} P={N} Q={K}", timeit(lambda: ops.gemm_wgrad(out, a, dw)), gb, tf)
+        del a, out
+
+if not which or "ew" in which:
+    for H, C in [(147, 128), (19, 728)]:
+        y = rnd(Fr, H, H, C)
+        sc = torch.rand(C, device=dev) + 0.5; sh = torch.randn(C, device=dev) * 0.1
+        gb = 2 * y.numel() * 2 / 1e9
+        report(f"bn_act              {H}x{H}x{C}", timeit(lambda: ops.bn_act(y, sc, sh, True)), gb)
+        skip = rnd(Fr, H, H, C)
+        report(f"bn_add_fwd          {H}x{H}x{C}", timeit(lambda: ops.bn_add_fwd(y, sc, sh, skip)), gb * 1.5)
+        Ho = (H - 1) // 2 + 1
+        ys = rnd(Fr, Ho, Ho, C)
+        report(f"pool_add_fwd        {H}x{H}x{C}", timeit(lambda: ops.pool_add_fwd(y, sc, sh, ys, sc, sh)), (y.numel() + 2 * ys.numel()) * 2 / 1e9)
+        st = ops.BNState(C, dev); st.scale.copy_(sc); st.shift.copy_(sh); st.mean.zero_(); st.rstd.fill_(1.0)
+        gamma = torch.ones(C, device=dev); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
+        G = rnd(Fr, H, H, C)
+        report(f"bn_bwd direct 2pass {H}x{H}x{C}", timeit(lambda: ops.bn_bwd(ops.SRC_DIRECT, y, st, gamma, dg, db, G=G)), gb * 2.5)
+        del y, skip, ys, G

@@ -58,6 +58,17 @@ for mode in ("eval", "train"):
     print(f"[{mode}] F={Fr} H={H} ours fwd {1e3*(t1-t0):.1f} ms")
     print(f"[{mode}] feat   rel-L2 ours {rel(feat, feat_o):.3e}  max-rel {relmax(feat, feat_o):.3e} | autocast-bf16 oracle {rel(feat_b, feat_o):.3e} {relmax(feat_b, feat_o):.3e}")
     print(f"[{mode}] logits rel-L2 ours {rel(logit, logit_o):.3e} max-rel {relmax(logit, logit_o):.3e} | autocast-bf16 oracle {rel(logit_b, logit_o):.3e}")
+    if not training:
+        # gradient parity with frozen BN statistics (well conditioned: no batch-stat amplification)
+        lo = F.cross_entropy(logit_o * 50, labels); lo.backward()
+        lb = F.cross_entropy(logit_b.float() * 50, labels); lb.backward()
+        l = F.cross_entropy(logit * 50, labels); l.backward()
+        worst = sorted(((rel(p.grad, sdo[k].grad), rel(sdb[k].grad, sdo[k].grad), k) for k, p in net.named_parameters()), reverse=True)
+        import statistics
+        print("   [eval-BN] grad rel-L2 per tensor: median ours %.3e (bf16-oracle %.3e); max ours %.3e (%s)" % (
+            statistics.median(w[0] for w in worst), statistics.median(w[1] for w in worst), worst[0][0], worst[0][2]))
+        for e, eb, k in worst[:8]:
+            print(f"     {k:40s} ours {e:.3e}   bf16-oracle {eb:.3e}")
     if training:
         for k in ("bn1", "block1.skipbn", "block4.rep.2", "block12.rep.5", "bn4"):
             print(f"   running_mean {k}: {rel(net.state_dict()[k + '.running_mean'], ns[k + '.running_mean']):.2e}  running_var: "
