@@ -63,8 +63,27 @@ SIGNATURES = {
 _RET_LONGLONG = set()
 _NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp_stem_conv1_parts"}
 
+# kernels launched per C-ABI call (for bench.py's `gpu_launches`; 0 = host-only query)
+_LAUNCHES = {"xcp_version": 0, "xcp_check_device": 0, "xcp_bnbwd_num_parts": 0, "xcp_gemm_stats_parts": 0,
+             "xcp_stem_conv1_parts": 0, "xcp_bn_bwd": 3, "xcp_arcface_loss": 2}
+_count = 0
+
 _lock = threading.Lock()
 _lib = None
+
+
+def reset_launch_count():
+    global _count
+    _count = 0
+
+
+def launch_count() -> int:
+    return _count
+
+
+def add_launches(n: int):
+    global _count
+    _count += n
 
 
 class XcpError(RuntimeError):
@@ -95,8 +114,10 @@ def load():
 
 
 def call(name: str, *args):
+    global _count
     lib = load()
     rc = getattr(lib, name)(*args)
+    _count += _LAUNCHES.get(name, 1)
     if name in _NO_STATUS:
         return rc
     if rc != 0:

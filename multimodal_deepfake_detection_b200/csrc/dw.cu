@@ -25,6 +25,7 @@ XCP_DEVINL u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"
 XCP_DEVINL u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 XCP_DEVINL u64 bf2_to_f2(uint32_t v) { return pk2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 XCP_DEVINL uint32_t f2_to_bf2(u64 v) { float lo, hi; upk2(v, lo, hi); return pack_bf16(lo, hi); }
+XCP_DEVINL uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 XCP_DEVINL u64 relu2(u64 v) { float lo, hi; upk2(v, lo, hi); return pk2(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
 
 struct DwGeom {
@@ -63,14 +64,16 @@ struct DwFwdParams {
 };
 
 template <bool AFFINE, bool RELU>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(256, 3)
 dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
+    const uint32_t sbase = (raw_addr + 127u) & ~127u;
+    uint8_t* smem = smem_raw + (sbase - raw_addr);
     const DwGeom& g = p.g;
     const int halo_w = g.TW + 2;
-    const uint32_t stage_bytes = (uint32_t)halo_w * (g.TH + 2) * 128u;
+    const uint32_t row_stride = (uint32_t)halo_w * 128u;
+    const uint32_t stage_bytes = row_stride * (uint32_t)(g.TH + 2);
     __shared__ uint64_t full[2];
 
     if (threadIdx.x == 0) {
@@ -95,6 +98,7 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
     const int slice = warp / g.pairs;
     const int r0 = slice * g.rows_per_slice;
     const int r1 = min(r0 + g.rows_per_slice, g.TH);
+    const u64 NEG = pk2(-1e30f, -1e30f);
 
     long long tile = blockIdx.x;
     if (threadIdx.x == 0 && tile < g.num_tiles) issue(tile, 0);
@@ -115,7 +119,7 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
         const bool second = (x0 + 1 < g.TW) && (gx0 + 1 < g.W);
 
         u64 wg[9];
-        u64 sc = 0, sh = 0;
+        u64 sc = 0, shc[4] = {0, 0, 0, 0};
         if (active) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
@@ -125,58 +129,71 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
             if (AFFINE) {
                 const float2 a = *reinterpret_cast<const float2*>(p.scale + c0);
                 const float2 b = *reinterpret_cast<const float2*>(p.shift + c0);
-                sc = pk2(a.x, a.y); sh = pk2(b.x, b.y);
+                sc = pk2(a.x, a.y);
+                const u64 sh = pk2(b.x, b.y);
+                // Out-of-image columns must stay exactly 0 after the affine: with the ReLU fused, a hugely negative
+                // shift does that branch-free (TMA zero-filled the raw value, scale*0 = 0).  Without ReLU the
+                // generic (select) path below is used.
+#pragma unroll
+                for (int dx = 0; dx < 4; ++dx) {
+                    const bool cv = (gx0 - 1 + dx >= 0) && (gx0 - 1 + dx < g.W);
+                    shc[dx] = (cv || !RELU) ? sh : NEG;
+                }
             }
         }
 
         mbar_wait(&full[s], (it >> 1) & 1);
 
         if (active) {
-            const uint8_t* tile_smem = smem + s * stage_bytes + lane * 4;
-            // warp-uniform in-image tests for the four staged columns gx0-1 .. gx0+2
-            bool cv[4];
+            const uint32_t tb = sbase + s * stage_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u;
+            bool cvn[4];
 #pragma unroll
-            for (int dx = 0; dx < 4; ++dx) cv[dx] = (gx0 - 1 + dx >= 0) && (gx0 - 1 + dx < g.W) && (x0 + dx < halo_w);
-            u64 acc[3][2];
+            for (int dx = 0; dx < 4; ++dx) cvn[dx] = (gx0 - 1 + dx >= 0) && (gx0 - 1 + dx < g.W);
+            // load + transform one staged row (halo-tile row index hr) into a 4-column register row
+            auto load_row = [&](int hr, u64 (&w)[4]) {
+                const int gh = th * g.TH + hr - 1;
+                const uint32_t a = tb + (uint32_t)hr * row_stride;
+                if (AFFINE && (gh < 0 || gh >= g.H)) {          // warp-uniform: rows outside the image stay 0
+                    w[0] = 0; w[1] = 0; w[2] = 0; w[3] = 0;
+                    return;
+                }
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { acc[a][0] = 0; acc[a][1] = 0; }
-            __nv_bfloat16* outp = p.out + ((long long)f * g.H * g.W + gx0) * g.C + c0;
+                for (int dx = 0; dx < 4; ++dx) {
+                    u64 z = bf2_to_f2(lds32(a + dx * 128));
+                    if (AFFINE) z = fma2(z, sc, shc[dx]);
+                    if (RELU) z = relu2(z);
+                    if (AFFINE && !RELU && !cvn[dx]) z = 0;
+                    w[dx] = z;
+                }
+            };
+            u64 win[3][4];
+            load_row(r0, win[0]);
+            load_row(r0 + 1, win[1]);
+            __nv_bfloat16* outp = p.out + (((long long)f * g.H + th * g.TH) * g.W + gx0) * g.C + c0;
+            const long long out_row = (long long)g.W * g.C;
+            const int rmax = min(r1, g.H - th * g.TH);       // output rows of this slice that are inside the image
 
-            // One streaming step: input row `ir` is tap row kh=2 of output ir-1 (A0: finished -> store),
-            // kh=1 of output ir (A1) and kh=0 of output ir+1 (A2).
-#define DW_STEP(A0, A1, A2)                                                                              \
-    {                                                                                                    \
-        const int gh = th * g.TH + ir;                                                                   \
-        const bool row_valid = gh >= 0 && gh < g.H;                                                      \
-        u64 v[4];                                                                                        \
-        const uint8_t* rp = tile_smem + ((ir + 1) * halo_w + x0) * 128;                                  \
-        _Pragma("unroll") for (int dx = 0; dx < 4; ++dx) {                                               \
-            v[dx] = 0;                                                                                   \
-            if (row_valid && cv[dx]) {                                                                   \
-                u64 z = bf2_to_f2(*reinterpret_cast<const uint32_t*>(rp + dx * 128));                    \
-                if (AFFINE) z = fma2(z, sc, sh);                                                         \
-                if (RELU) z = relu2(z);                                                                  \
-                v[dx] = z;                                                                               \
-            }                                                                                            \
-        }                                                                                                \
-        _Pragma("unroll") for (int o = 0; o < 2; ++o) {                                                  \
-            A0[o] = fma2(wg[6], v[o], A0[o]); A0[o] = fma2(wg[7], v[o + 1], A0[o]); A0[o] = fma2(wg[8], v[o + 2], A0[o]); \
-            A1[o] = fma2(wg[3], v[o], A1[o]); A1[o] = fma2(wg[4], v[o + 1], A1[o]); A1[o] = fma2(wg[5], v[o + 2], A1[o]); \
-            A2[o] = mul2(wg[0], v[o]);        A2[o] = fma2(wg[1], v[o + 1], A2[o]); A2[o] = fma2(wg[2], v[o + 2], A2[o]); \
-        }                                                                                                \
-        const int orow = ir - 1;                                                                         \
-        const int oh = th * g.TH + orow;                                                                 \
-        if (orow >= r0 && oh < g.H) {                                                                    \
-            __nv_bfloat16* op = outp + (long long)oh * g.W * g.C;                                        \
-            *reinterpret_cast<uint32_t*>(op) = f2_to_bf2(A0[0]);                                         \
-            if (second) *reinterpret_cast<uint32_t*>(op + g.C) = f2_to_bf2(A0[1]);                       \
-        }                                                                                                \
+#define DW_STEP(WA, WB, WC)                                                                               \
+    {                                                                                                     \
+        load_row(o + 2, WC);                                                                              \
+        u64 a0 = mul2(wg[0], WA[0]), a1 = mul2(wg[0], WA[1]);                                             \
+        a0 = fma2(wg[1], WA[1], a0); a1 = fma2(wg[1], WA[2], a1);                                         \
+        a0 = fma2(wg[2], WA[2], a0); a1 = fma2(wg[2], WA[3], a1);                                         \
+        a0 = fma2(wg[3], WB[0], a0); a1 = fma2(wg[3], WB[1], a1);                                         \
+        a0 = fma2(wg[4], WB[1], a0); a1 = fma2(wg[4], WB[2], a1);                                         \
+        a0 = fma2(wg[5], WB[2], a0); a1 = fma2(wg[5], WB[3], a1);                                         \
+        a0 = fma2(wg[6], WC[0], a0); a1 = fma2(wg[6], WC[1], a1);                                         \
+        a0 = fma2(wg[7], WC[1], a0); a1 = fma2(wg[7], WC[2], a1);                                         \
+        a0 = fma2(wg[8], WC[2], a0); a1 = fma2(wg[8], WC[3], a1);                                         \
+        __nv_bfloat16* op = outp + o * out_row;                                                           \
+        *reinterpret_cast<uint32_t*>(op) = f2_to_bf2(a0);                                                 \
+        if (second) *reinterpret_cast<uint32_t*>(op + g.C) = f2_to_bf2(a1);                               \
     }
-            int ir = r0 - 1;
-            while (true) {
-                DW_STEP(acc[0], acc[1], acc[2]); if (++ir > r1) break;
-                DW_STEP(acc[1], acc[2], acc[0]); if (++ir > r1) break;
-                DW_STEP(acc[2], acc[0], acc[1]); if (++ir > r1) break;
+            int o = r0;
+            while (o < rmax) {
+                DW_STEP(win[0], win[1], win[2]); if (++o >= rmax) break;
+                DW_STEP(win[1], win[2], win[0]); if (++o >= rmax) break;
+                DW_STEP(win[2], win[0], win[1]); ++o;
             }
 #undef DW_STEP
         }
@@ -205,16 +222,19 @@ struct DwBwdParams {
     float* bnsum;                 // [2][C]  (sum dz, sum dz*y), accumulated with RED (caller zero-fills); AFFINE only
 };
 
-template <bool AFFINE>
+template <bool AFFINE, bool RELU>
 __global__ void __launch_bounds__(256, 2)
 dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const DwBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
+    const uint32_t sbase = (raw_addr + 127u) & ~127u;
+    uint8_t* smem = smem_raw + (sbase - raw_addr);
     const DwGeom& g = p.g;
     const int halo_w = g.TW + 2;
-    const uint32_t g_bytes = (uint32_t)halo_w * (g.TH + 2) * 128u;
-    const uint32_t x_bytes = (uint32_t)g.TW * g.TH * 128u;
+    const uint32_t row_stride = (uint32_t)halo_w * 128u;
+    const uint32_t g_bytes = row_stride * (uint32_t)(g.TH + 2);
+    const uint32_t x_row = (uint32_t)g.TW * 128u;
+    const uint32_t x_bytes = x_row * (uint32_t)g.TH;
     const uint32_t stage_bytes = g_bytes + x_bytes;
     __shared__ uint64_t full[2];
     __shared__ float s_red[11][64];
@@ -287,69 +307,68 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
         mbar_wait(&full[s], (it >> 1) & 1);
 
         if (active) {
-            const uint8_t* gs = smem + s * stage_bytes + lane * 4;              // dD halo tile
-            const uint8_t* xs = smem + s * stage_bytes + g_bytes + lane * 4;    // forward-input centre tile
-            const bool c3 = x0 + 3 < halo_w;
+            const uint32_t gb = sbase + s * stage_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u;   // dD halo tile
+            const uint32_t xb = gb + g_bytes;                                                          // fwd-input centre tile
+            auto load_g = [&](int hr, u64 (&w)[4]) {
+                const uint32_t a = gb + (uint32_t)hr * row_stride;
+#pragma unroll
+                for (int dx = 0; dx < 4; ++dx) w[dx] = bf2_to_f2(lds32(a + dx * 128));
+            };
             u64 win[3][4];
-            // preload dD rows r0-1 and r0 (halo-tile rows r0, r0+1)
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const uint8_t* rp = gs + ((r0 + a) * halo_w + x0) * 128;
-#pragma unroll
-                for (int dx = 0; dx < 4; ++dx)
-                    win[a][dx] = (dx < 3 || c3) ? bf2_to_f2(*reinterpret_cast<const uint32_t*>(rp + dx * 128)) : 0ull;
-            }
-            // centre row rc: window rows (rc-1, rc, rc+1) = (WA, WB, WC); WC is loaded here
-#define DWB_STEP(WA, WB, WC)                                                                              \
-    {                                                                                                     \
-        const uint8_t* rp = gs + ((rc + 2) * halo_w + x0) * 128;                                          \
-        _Pragma("unroll") for (int dx = 0; dx < 4; ++dx)                                                  \
-            WC[dx] = (dx < 3 || c3) ? bf2_to_f2(*reinterpret_cast<const uint32_t*>(rp + dx * 128)) : 0ull; \
-        const int gh = th * g.TH + rc;                                                                    \
-        if (gh < g.H) {                                                                                   \
-            _Pragma("unroll") for (int o = 0; o < 2; ++o) {                                               \
-                if (o == 0 || second) {                                                                   \
-                    const u64 yv = bf2_to_f2(*reinterpret_cast<const uint32_t*>(xs + (rc * g.TW + x0 + o) * 128)); \
-                    u64 z = AFFINE ? fma2(yv, sc, sh) : yv;                                               \
-                    float zl, zh; upk2(z, zl, zh);                                                        \
-                    const bool pl = p.relu ? zl > 0.f : true, ph = p.relu ? zh > 0.f : true;              \
-                    const u64 av = pk2(pl ? zl : 0.f, ph ? zh : 0.f);                                     \
-                    u64 da = mul2(wg[0], WC[o + 2]);                                                      \
-                    da = fma2(wg[1], WC[o + 1], da); da = fma2(wg[2], WC[o], da);                         \
-                    da = fma2(wg[3], WB[o + 2], da); da = fma2(wg[4], WB[o + 1], da); da = fma2(wg[5], WB[o], da); \
-                    da = fma2(wg[6], WA[o + 2], da); da = fma2(wg[7], WA[o + 1], da); da = fma2(wg[8], WA[o], da); \
-                    dwa[0] = fma2(av, WC[o + 2], dwa[0]); dwa[1] = fma2(av, WC[o + 1], dwa[1]); dwa[2] = fma2(av, WC[o], dwa[2]); \
-                    dwa[3] = fma2(av, WB[o + 2], dwa[3]); dwa[4] = fma2(av, WB[o + 1], dwa[4]); dwa[5] = fma2(av, WB[o], dwa[5]); \
-                    dwa[6] = fma2(av, WA[o + 2], dwa[6]); dwa[7] = fma2(av, WA[o + 1], dwa[7]); dwa[8] = fma2(av, WA[o], dwa[8]); \
-                    float dl, dh; upk2(da, dl, dh);                                                       \
-                    dl = pl ? dl : 0.f; dh = ph ? dh : 0.f;                                               \
-                    const long long pix = (((long long)f * g.H + gh) * g.W + gx0 + o) * g.C + c0;         \
-                    if (p.add_full != nullptr) {                                                          \
-                        const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(p.add_full + pix));   \
-                        dl += bf16_lo(ar); dh += bf16_hi(ar);                                             \
-                    }                                                                                     \
-                    if (p.add_half != nullptr && ((gh | (gx0 + o)) & 1) == 0) {                           \
-                        const int Ho = (g.H + 1) / 2, Wo = (g.W + 1) / 2;                                 \
-                        const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(                      \
-                            p.add_half + (((long long)f * Ho + (gh >> 1)) * Wo + ((gx0 + o) >> 1)) * g.C + c0)); \
-                        dl += bf16_lo(ar); dh += bf16_hi(ar);                                             \
-                    }                                                                                     \
-                    const u64 dzv = pk2(dl, dh);                                                          \
-                    if (AFFINE) { sdz = add2(sdz, dzv); sdzy = fma2(dzv, yv, sdzy); }                     \
-                    *reinterpret_cast<uint32_t*>(p.dz + pix) = pack_bf16(dl, dh);                         \
-                }                                                                                         \
-            }                                                                                             \
-        }                                                                                                 \
+            load_g(r0, win[0]);          // dD row r0-1
+            load_g(r0 + 1, win[1]);      // dD row r0
+            const int gh0 = th * g.TH;
+            const int rmax = min(r1, g.H - gh0);
+            __nv_bfloat16* dzp = p.dz + (((long long)f * g.H + gh0) * g.W + gx0) * g.C + c0;
+            const __nv_bfloat16* afp = p.add_full ? p.add_full + (((long long)f * g.H + gh0) * g.W + gx0) * g.C + c0 : nullptr;
+            const long long row_el = (long long)g.W * g.C;
+
+            // centre row rc: window rows (rc-1, rc, rc+1) = (WA, WB, WC); WC is loaded here.  The neighbour
+            // p + (1-kh, 1-kw) of centre (rc, o) sits in window row 2-kh (WC, WB, WA for kh = 0, 1, 2), staged column o+2-kw.
+#define DWB_PIX(O, WA, WB, WC)                                                                             \
+    {                                                                                                      \
+        const u64 yv = bf2_to_f2(lds32(xb + (uint32_t)rc * x_row + (O) * 128));                            \
+        const u64 z = AFFINE ? fma2(yv, sc, sh) : yv;                                                      \
+        float zl, zh; upk2(z, zl, zh);                                                                     \
+        const bool pl = RELU ? zl > 0.f : true, ph = RELU ? zh > 0.f : true;                               \
+        const u64 av = RELU ? pk2(fmaxf(zl, 0.f), fmaxf(zh, 0.f)) : z;                                     \
+        u64 da = mul2(wg[0], WC[(O) + 2]);                                                                 \
+        da = fma2(wg[1], WC[(O) + 1], da); da = fma2(wg[2], WC[(O)], da);                                  \
+        da = fma2(wg[3], WB[(O) + 2], da); da = fma2(wg[4], WB[(O) + 1], da); da = fma2(wg[5], WB[(O)], da); \
+        da = fma2(wg[6], WA[(O) + 2], da); da = fma2(wg[7], WA[(O) + 1], da); da = fma2(wg[8], WA[(O)], da); \
+        dwa[0] = fma2(av, WC[(O) + 2], dwa[0]); dwa[1] = fma2(av, WC[(O) + 1], dwa[1]); dwa[2] = fma2(av, WC[(O)], dwa[2]); \
+        dwa[3] = fma2(av, WB[(O) + 2], dwa[3]); dwa[4] = fma2(av, WB[(O) + 1], dwa[4]); dwa[5] = fma2(av, WB[(O)], dwa[5]); \
+        dwa[6] = fma2(av, WA[(O) + 2], dwa[6]); dwa[7] = fma2(av, WA[(O) + 1], dwa[7]); dwa[8] = fma2(av, WA[(O)], dwa[8]); \
+        float dl, dh; upk2(da, dl, dh);                                                                    \
+        dl = pl ? dl : 0.f; dh = ph ? dh : 0.f;                                                            \
+        const long long eo = rc * row_el + (O) * g.C;                                                      \
+        if (afp != nullptr) {                                                                              \
+            const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(afp + eo));                        \
+            dl += bf16_lo(ar); dh += bf16_hi(ar);                                                          \
+        }                                                                                                  \
+        if (p.add_half != nullptr && (((gh0 + rc) | (gx0 + (O))) & 1) == 0) {                              \
+            const int Ho = (g.H + 1) / 2, Wo = (g.W + 1) / 2;                                              \
+            const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(                                   \
+                p.add_half + (((long long)f * Ho + ((gh0 + rc) >> 1)) * Wo + ((gx0 + (O)) >> 1)) * g.C + c0)); \
+            dl += bf16_lo(ar); dh += bf16_hi(ar);                                                          \
+        }                                                                                                  \
+        if (AFFINE) { const u64 dzv = pk2(dl, dh); sdz = add2(sdz, dzv); sdzy = fma2(dzv, yv, sdzy); }     \
+        *reinterpret_cast<uint32_t*>(dzp + eo) = pack_bf16(dl, dh);                                        \
     }
-            // Tap/neighbour bookkeeping: neighbour p + (1-kh, 1-kw) of centre (rc, o) sits in window row 2-kh
-            // (WC, WB, WA for kh = 0, 1, 2) and staged column o + 2 - kw.
+#define DWB_STEP(WA, WB, WC)                                                                               \
+    {                                                                                                      \
+        load_g(rc + 2, WC);                                                                                \
+        DWB_PIX(0, WA, WB, WC)                                                                             \
+        if (second) DWB_PIX(1, WA, WB, WC)                                                                 \
+    }
             int rc = r0;
-            while (rc < r1) {
-                DWB_STEP(win[0], win[1], win[2]); if (++rc >= r1) break;
-                DWB_STEP(win[1], win[2], win[0]); if (++rc >= r1) break;
+            while (rc < rmax) {
+                DWB_STEP(win[0], win[1], win[2]); if (++rc >= rmax) break;
+                DWB_STEP(win[1], win[2], win[0]); if (++rc >= rmax) break;
                 DWB_STEP(win[2], win[0], win[1]); ++rc;
             }
 #undef DWB_STEP
+#undef DWB_PIX
         }
         __syncthreads();
     }
@@ -394,13 +413,13 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
     XCP_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "xcp_dw3x3_fwd: bad shape F=%d H=%d W=%d C=%d", F, H, W, C);
     XCP_REQUIRE((scale == nullptr) == (shift == nullptr), "xcp_dw3x3_fwd: scale/shift must both be given or both null");
     XCP_CUDA(cudaSetDevice(device));
-    DwGeom g = make_geom(F, H, W, C, 384, 16);
+    DwGeom g = make_geom(F, H, W, C, 272, 8);
     CUtensorMap tm;
     if (int e = make_dw_tmap(&tm, x, g, 1)) return e;
     DwFwdParams p{g, w9, scale, shift, (__nv_bfloat16*)out};
-    const int smem = 2 * (g.TW + 2) * (g.TH + 2) * 128 + 128;
+    const int smem = 2 * (g.TW + 2) * (g.TH + 2) * 128 + 384;
     const int threads = 32 * g.pairs * g.RS;
-    long long grid = 2LL * num_sms();
+    long long grid = 3LL * num_sms();
     if (grid > g.num_tiles) grid = g.num_tiles;
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FWD(A, R)                                                                                          \
@@ -430,7 +449,7 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     if (int e = make_dw_tmap(&tmX, xin, g, 0)) return e;
     DwBwdParams p{g, w9, scale, shift, relu, (__nv_bfloat16*)dz, (const __nv_bfloat16*)add_full,
                   (const __nv_bfloat16*)add_half, dw, bnsum};
-    const int smem = 2 * ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH) * 128 + 128;
+    const int smem = 2 * ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH) * 128 + 384;
     const int threads = 32 * g.pairs * g.RS;
     const long long sp_tiles = (long long)F * g.n_h * g.n_w;
     long long per_ct = (2LL * num_sms()) / g.c_tiles;
@@ -438,12 +457,13 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     if (per_ct > sp_tiles) per_ct = sp_tiles;
     const int grid = (int)(per_ct * g.c_tiles);
     cudaStream_t st = (cudaStream_t)stream;
-    if (scale != nullptr) {
-        XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        dw3x3_bwd_kernel<true><<<grid, threads, smem, st>>>(tmG, tmX, p);
-    } else {
-        XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        dw3x3_bwd_kernel<false><<<grid, threads, smem, st>>>(tmG, tmX, p);
+#define LAUNCH_BWD(A, R)                                                                                          \
+    {                                                                                                             \
+        XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        dw3x3_bwd_kernel<A, R><<<grid, threads, smem, st>>>(tmG, tmX, p);                                         \
     }
+    if (scale != nullptr) { if (relu) LAUNCH_BWD(true, true) else LAUNCH_BWD(true, false) }
+    else { if (relu) LAUNCH_BWD(false, true) else LAUNCH_BWD(false, false) }
+#undef LAUNCH_BWD
     return check_cuda(cudaGetLastError(), "dw3x3_bwd launch");
 }

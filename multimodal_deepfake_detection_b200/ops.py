@@ -19,6 +19,34 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+class _GemmTimer:
+    """Optional CUDA-event timing of every pointwise-GEMM launch (bench.py roofline): events are recorded on the
+    launching stream right around the kernel, aggregated per problem shape."""
+
+    def __init__(self):
+        self.on = False
+        self.rec = []
+
+    def enable(self, on: bool):
+        self.on = bool(on)
+        if on:
+            self.rec = []
+
+    def collect(self):
+        if not self.rec:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for key, flops, e0, e1 in self.rec:
+            d = out.setdefault(key, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
+        self.rec = []
+        return out
+
+
+GEMM_TIMER = _GemmTimer()
+
+
 def _p(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -54,6 +82,13 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optiona
     stats = None
     if epi == EPI_BF16_STATS:
         stats = torch.empty((_lib.call("xcp_gemm_stats_parts", M, N, a.device.index), 2, N), device=a.device, dtype=F32)
+    if GEMM_TIMER.on and epi == EPI_BF16_STATS:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), a.device.index, _s())
+        e1.record()
+        GEMM_TIMER.rec.append(("M=%d K=%d N=%d" % (M, K, N), 2.0 * M * N * K, e0, e1))
+        return out, stats
     _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), a.device.index, _s())
     return out, stats
 
@@ -239,6 +274,7 @@ def bn_bwd(mode: int, y, st: BNState, gamma, dgamma, dbeta, G=None, idx=None, df
             dy = torch.zeros((F_, gh, gw, C), device=dev, dtype=BF16)
         else:
             dy = torch.empty_like(y)
+    _lib.add_launches(-(1 if presums is not None else 0) - (0 if want_dy else 1))
     _lib.call("xcp_bn_bwd", mode, _p(y), _p(G), _p(idx), _p(dfeat), _p(st.scale), _p(st.shift), _p(gamma), _p(st.mean),
               _p(st.rstd), int(st.training), _p(presums), _p(ws), _p(coef), _p(dgamma), _p(dbeta), _p(dy), F_, H, W, C, gw, gh,
               dev.index, _s())

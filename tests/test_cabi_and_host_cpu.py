@@ -1,0 +1,154 @@
+"""CPU tier: the C-ABI library loads without a GPU and exports exactly what include/xcp.h declares; the Python
+binding table matches the header; the drop-in modules reproduce the reference's state_dict schema and seeded
+init; the product never imports the oracle; CPU inputs fail loudly (no fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from multimodal_deepfake_detection_b200 import _lib  # noqa: E402
+
+
+def _header_decls():
+    src = open(os.path.join(ROOT, "include", "xcp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"(const char\*|long long|int)\s+(xcp_\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.groups()
+        sig = ""
+        args = args.strip()
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                sig += "p" if "*" in a else {"long long": "l", "int": "i", "float": "f", "double": "d"}[
+                    "long long" if a.startswith("long long") else a.split()[0]]
+        out[name] = sig
+    return out
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    if not os.path.isfile(_lib.LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "multimodal_deepfake_detection_b200", "csrc"), "-j", "8"])
+    return ctypes.CDLL(_lib.LIB_PATH)
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    decls = _header_decls()
+    assert len(decls) >= 40
+    for name in decls:
+        assert hasattr(built_lib, name), "libxcp_sm100.so does not export %s" % name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
+    exported = set(re.findall(r" T (xcp_\w+)", out))
+    assert exported == set(decls), (exported ^ set(decls))
+
+
+def test_binding_table_matches_header():
+    decls = _header_decls()
+    decls.pop("xcp_last_error_string")
+    assert decls == _lib.SIGNATURES
+
+
+def test_host_only_calls_work_without_gpu(built_lib):
+    assert _lib.call("xcp_version") >= 100
+    if not torch.cuda.is_available():
+        # a compute call without a device must return an error code and a message, not crash
+        with pytest.raises(_lib.XcpError):
+            _lib.call("xcp_check_device", 0)
+
+
+def test_no_libcuda_or_torch_link_dependency():
+    out = subprocess.check_output(["ldd", _lib.LIB_PATH]).decode()
+    assert "libcuda.so" not in out and "libtorch" not in out and "libc10" not in out
+
+
+def test_sass_is_blackwell_native():
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not out:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "FFMA2"):     # tcgen05.mma, TMA load, tcgen05.ld, packed fp32 FMA
+        assert mnemonic in out, mnemonic
+    assert "HGMMA" not in out
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multimodal_deepfake_detection_b200")
+    offenders = []
+    for d in (pkg, os.path.join(ROOT, "Models"), os.path.join(ROOT, "Dataset")):
+        for base, _, files in os.walk(d):
+            for f in files:
+                if f.endswith(".py"):
+                    txt = open(os.path.join(base, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "xception_oracle" in txt:
+                        offenders.append(os.path.join(base, f))
+    for f in ("train_visual.py", "train_audio.py", "train_au_face.py", "train_au_patch.py", "test_visual.py"):
+        p = os.path.join(ROOT, f)
+        if os.path.exists(p) and re.search(r"^\s*(from|import)\s+oracle\b", open(p).read(), flags=re.M):
+            offenders.append(p)
+    assert not offenders, offenders
+
+
+def test_state_dict_schema_and_seeded_init_match_reference_restatement():
+    from oracle import xception_oracle as O
+    from Models.Xception import Xception
+    from Models.XceptionLSTMV import XceptionLSTMV
+    torch.manual_seed(3)
+    net = Xception(num_classes=2)
+    sd = net.state_dict()
+    shapes = O.xception_param_shapes(2)
+    assert [k for k, _, _ in shapes] == list(sd.keys())
+    assert all(tuple(sd[k].shape) == tuple(s) for k, s, _ in shapes)
+    assert len(sd) == 276
+    assert sd["bn1.num_batches_tracked"].dtype == torch.long
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = XceptionLSTMV(16)
+    keys = list(m.state_dict().keys())
+    assert len(keys) == 288
+    assert keys[-14:] == ["lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
+                          "fc_layers.0.weight", "fc_layers.0.bias", "fc_layers.3.weight", "fc_layers.3.bias",
+                          "fc_layers.6.weight", "fc_layers.6.bias", "fc_layers.9.weight", "fc_layers.9.bias",
+                          "fc_out.weight", "fc_out.bias"]
+    assert not any(p.requires_grad for p in m.feature_extractor.parameters())      # XceptionLSTMV.py:15-16
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 4 * 16 * 2048 + 4 * 16 * 16 + 8 * 16 + \
+        16 * 1024 + 1024 + 3 * (1024 * 1024 + 1024) + 1024 + 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted (GPU box)")
+def test_seeded_init_bit_identical_to_live_reference():
+    from oracle import ref_shim
+    from Models.Xception import Xception
+    ref = ref_shim.load()
+    torch.manual_seed(11); a = Xception(num_classes=5)
+    torch.manual_seed(11); b = ref.Xception(num_classes=5)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert [n for n, _ in a.named_parameters()] == [n for n, _ in b.named_parameters()]
+    assert [n for n, _ in a.named_modules()] == [n for n, _ in b.named_modules()]
+
+
+def test_cpu_inputs_fail_loudly():
+    from multimodal_deepfake_detection_b200 import SeparableConv2d, Xception, XcpError
+    with pytest.raises(XcpError):
+        Xception(num_classes=2)(torch.zeros(1, 3, 75, 75))
+    with pytest.raises(XcpError):
+        SeparableConv2d(8, 8, 3, 1, 1)(torch.zeros(1, 8, 5, 5))
+
+
+def test_block_spec_matches_reference_layout():
+    from multimodal_deepfake_detection_b200 import Block
+    from oracle import xception_oracle as O
+    for (name, cin, cout, reps, stride, swr, gf) in O.BLOCKS:
+        blk = Block(cin, cout, reps, stride, start_with_relu=swr, grow_first=gf)
+        spec = blk._spec()
+        want = O.block_layout(cin, cout, reps, swr, gf)
+        assert [(u.cin, u.cout, u.relu) for u in spec.units] == [(ci, co, r) for (_, _, ci, co, r) in want]
+        keys = [k for k in blk.state_dict() if k.endswith("conv1.weight")]
+        assert keys == ["rep.%d.conv1.weight" % i for (i, _, _, _, _) in want]
