@@ -1,0 +1,27 @@
+"""MFCC loader with the reference's layout (audio_dataloader.py:6-47): `.npy` (120,13) -> (T,3,13) by channel repeat,
+label from the file-name prefix, zero-padding collate -> (B,Tmax,3,13), labels (B,1)."""
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+from .synthetic import SyntheticAudio, collate_audio as collate_fn  # noqa: F401
+
+
+class AudioDataset(Dataset):
+    def __init__(self, folder_path):
+        self.files = sorted(os.path.join(folder_path, f) for f in os.listdir(folder_path) if f.endswith(".npy"))
+
+    def __len__(self):
+        return len(self.files)
+
+    def __getitem__(self, idx):
+        mf = torch.from_numpy(np.load(self.files[idx])).float()              # (T,13)
+        label = 0.0 if os.path.basename(self.files[idx]).lower().startswith("real") else 1.0
+        return mf.unsqueeze(1).repeat(1, 3, 1), torch.tensor([label])
+
+
+def get_audio_dataloader(folder_path, batch_size=8, shuffle=True):
+    ds = AudioDataset(folder_path) if folder_path and os.path.isdir(folder_path) else SyntheticAudio()
+    return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, collate_fn=collate_fn)

@@ -1,0 +1,28 @@
+"""`.npy` face-clip loader with the reference's layout (video_dataloader.py:6-68): files `<label>_*.npy` of uint8
+(T,H,W,3) -> float32 (T,3,H,W)/255; label from the file-name prefix; zero-padding collate."""
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+from .synthetic import SyntheticClips, collate_clips as collate_fn  # noqa: F401
+
+
+class FaceDataset(Dataset):
+    def __init__(self, folder_path):
+        self.files = sorted(os.path.join(folder_path, f) for f in os.listdir(folder_path) if f.endswith(".npy"))
+
+    def __len__(self):
+        return len(self.files)
+
+    def __getitem__(self, idx):
+        arr = np.load(self.files[idx])                                        # (T,H,W,3) uint8
+        label = 0.0 if os.path.basename(self.files[idx]).lower().startswith("real") else 1.0
+        frames = torch.from_numpy(arr).permute(0, 3, 1, 2).float().div_(255.0)
+        return frames, torch.tensor(label, dtype=torch.float32)
+
+
+def get_face_dataloader(folder_path, batch_size=4, shuffle=True, num_workers=0):
+    ds = FaceDataset(folder_path) if folder_path and os.path.isdir(folder_path) else SyntheticClips()
+    return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers, collate_fn=collate_fn, pin_memory=True)

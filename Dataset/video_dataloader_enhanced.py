@@ -1,0 +1,19 @@
+"""`Dataset.video_dataloader_enhanced` as imported by train_visual.py:451 / test_visual.py:466 (absent from the reference;
+signature from the call sites).  Without the LAV-DF / FakeAVCeleb trees it serves synthetic clips."""
+import os
+
+from torch.utils.data import DataLoader
+
+from .synthetic import SyntheticClips, collate_clips_with_lengths as collate_fn  # noqa: F401
+from .video_dataloader import FaceDataset
+
+
+def get_face_dataloader(folder_path=None, mode="lavdf_raw", subset="train", lavdf_json=None, csv_path=None, batch_size=1,
+                        augment_minority=False, shuffle=False, raw_video=True, use_face_detection=True, frame_size=(224, 224),
+                        max_frames=50, synthetic_clips=32):
+    if folder_path and os.path.isdir(folder_path) and any(f.endswith(".npy") for f in os.listdir(folder_path)):
+        ds = FaceDataset(folder_path)
+        ds.samples = [(f, 0 if os.path.basename(f).lower().startswith("real") else 1, None) for f in ds.files]
+    else:
+        ds = SyntheticClips(n=synthetic_clips, frames=min(max_frames, 16), size=frame_size[0], seed=hash(subset) % 1000)
+    return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, collate_fn=collate_fn)

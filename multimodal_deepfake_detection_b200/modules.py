@@ -27,7 +27,8 @@ from . import ops
 from ._lib import XcpError
 
 __all__ = ["SeparableConv2d", "Block", "Xception", "xception", "XceptionLSTMV", "XceptionLSTMA", "ArcFaceHead",
-           "CBFocalLoss", "LabelSmoothingBCEWithLogitsLoss", "FusedLSTM", "FusedLinear", "model_urls"]
+           "CBFocalLoss", "LabelSmoothingBCEWithLogitsLoss", "FusedLSTM", "FusedLinear", "FusionHead", "AUFaceCrossDetector",
+           "model_urls"]
 
 model_urls = {
     # same URL as the reference (Xception.py:31-34); only consulted through the local torch hub cache
@@ -571,3 +572,92 @@ class LabelSmoothingBCEWithLogitsLoss(nn.Module):
     def forward(self, logits, targets):
         _require_cuda(logits, "LabelSmoothingBCEWithLogitsLoss")
         return _BCEFn.apply(logits, targets, float(self.smoothing))
+
+
+# ================================================================================================ fusion head (train_au_face)
+class _FusionHeadFn(torch.autograd.Function):
+    """The fused region of train_au_face.py:659-674: token mean-pooling, concat, embed_head (Linear-ReLU-Dropout-
+    Linear), ArcFace margin logits, CB-focal loss, alignment MSE and temporal smoothness -- loss and every gradient
+    (tokens, embed_head, ArcFace weight) in one pass of C-ABI kernels."""
+
+    @staticmethod
+    def forward(ctx, v_tok, a_tok, labels, W0, b0, W3, b3, arc_w, class_w, cfg):
+        s, m, gamma, la, lt, training, p_drop = cfg
+        v = v_tok.float().contiguous(); a = a_tok.float().contiguous()
+        B = v.shape[0]
+        pooled, loss_reg, dv, da = ops.fusion_pool_reg(v, a, la, lt)
+        scale = 1.0 / (1.0 - p_drop) if (training and p_drop > 0) else 1.0
+        mask = (torch.rand((B, W0.shape[0]), device=v.device) >= p_drop).to(torch.uint8) if scale != 1.0 else None
+        h = ops.linear_small_fwd(pooled, W0.detach(), b0.detach(), 1, mask, scale)
+        e = ops.linear_small_fwd(h, W3.detach(), b3.detach(), 0)
+        darc = torch.zeros_like(arc_w)
+        logits, loss_cls, de = ops.arcface_loss(e, arc_w.detach(), labels, s, m, 1 if class_w is not None else 0, class_w, gamma,
+                                                dw=darc)
+        dW3 = torch.zeros_like(W3); db3 = torch.zeros_like(b3)
+        dh = ops.linear_small_bwd(de, None, 1.0, h, W3.detach(), dW3, db3)
+        dW0 = torch.zeros_like(W0); db0 = torch.zeros_like(b0)
+        dpooled = ops.linear_small_bwd(dh, h, scale, pooled, W0.detach(), dW0, db0)
+        ops.fusion_pool_bwd(dpooled, dv, da)
+        ctx.save_for_backward(dv, da, dW0, db0, dW3, db3, darc)
+        ctx.mark_non_differentiable(logits)
+        return loss_cls + loss_reg, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        dv, da, dW0, db0, dW3, db3, darc = ctx.saved_tensors
+        return (dv * dloss, da * dloss, None, dW0 * dloss, db0 * dloss, dW3 * dloss, db3 * dloss, darc * dloss, None, None)
+
+
+class FusionHead(nn.Module):
+    """embed_head + ArcFace + CB-focal + regularisers of train_au_face.py:598-613,659-674 as one module.
+    Submodule names mirror the script's objects so its checkpoint dict ({"embed", "arcface"}) maps 1:1."""
+
+    def __init__(self, token_dim, samples_per_cls=(1, 1), s=30.0, m=0.30, beta=0.9999, gamma=2.0, lambda_align=0.2,
+                 lambda_temp=0.1, p_drop=0.2):
+        super().__init__()
+        self.embed_head = nn.Sequential(nn.Linear(2 * token_dim, 256), nn.ReLU(inplace=True), nn.Dropout(p_drop), nn.Linear(256, 128))
+        self.arcface = ArcFaceHead(128, 2, s=s, m=m)
+        self.cbfocal = CBFocalLoss(list(samples_per_cls), beta=beta, gamma=gamma)
+        self.lambda_align, self.lambda_temp = lambda_align, lambda_temp
+
+    def forward(self, v_tokens, au_tokens, labels):
+        """-> (loss, logits_arc)"""
+        _require_cuda(v_tokens, "FusionHead")
+        e = self.embed_head
+        cfg = (self.arcface.s, self.arcface.m, self.cbfocal.gamma, self.lambda_align, self.lambda_temp, self.training, float(e[2].p))
+        return _FusionHeadFn.apply(v_tokens, au_tokens, labels.long().contiguous(), e[0].weight, e[0].bias, e[3].weight, e[3].bias,
+                                   self.arcface.weight, self.cbfocal.class_weights, cfg)
+
+    @torch.no_grad()
+    def predict_logits(self, v_tokens, au_tokens):
+        """Inference logits s*cos (labels=None path of ArcFaceHead, train_au_face.py:715-716)."""
+        pooled, _, _, _ = ops.fusion_pool_reg(v_tokens.float().contiguous(), au_tokens.float().contiguous(), 0.0, 0.0, want_grad=False)
+        e = self.embed_head
+        h = ops.linear_small_fwd(pooled, e[0].weight, e[0].bias, 1)
+        emb = ops.linear_small_fwd(h, e[3].weight, e[3].bias, 0)
+        return self.arcface(emb)
+
+
+class AUFaceCrossDetector(nn.Module):
+    """Two-stream detector with the call signature train_au_face.py:594,656 expects (the reference's
+    Models/AUFaceModel.py is absent).  Built from the in-scope hot path only: a face stream
+    (Xception per frame -> FusedLSTM tokens) and an audio/AU stream (bilinear 64x64 -> Xception -> FusedLSTM tokens).
+    forward(videos[B,3,T,H,W], au_patches[B,Ta,3,n]) -> (logits[B,1], v_tokens[B,T,D], au_tokens[B,Ta,D])."""
+
+    def __init__(self, num_aus=17, face_dim=512, au_dim=512, lstm_hidden=256):
+        super().__init__()
+        self.num_aus = num_aus
+        self.face_stream = XceptionLSTMV(lstm_hidden)
+        self.au_stream = XceptionLSTMA(lstm_hidden)
+        self.classifier = FusedLinear(2 * lstm_hidden, 1)
+
+    def forward(self, videos, au_patches, au_mask=None, au_weight=None):
+        _require_cuda(videos, "AUFaceCrossDetector")
+        if videos.dim() == 5 and videos.size(1) == 3:                 # (B,C,T,H,W) -> (B,T,C,H,W), train_au_face.py:643-644
+            videos = videos.permute(0, 2, 1, 3, 4).contiguous()
+        vf = self.face_stream.extract_features(videos)
+        v_tokens = self.face_stream.lstm(vf)[0]
+        af = self.au_stream.extract_features(au_patches)
+        au_tokens = self.au_stream.lstm(af)[0]
+        logits = self.classifier(torch.cat([v_tokens.mean(1), au_tokens.mean(1)], dim=1))
+        return logits, v_tokens, au_tokens
