@@ -48,7 +48,10 @@ int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* stats, int 
 /* ---- stem conv1 3->32 k3 s2 p0 (Xception.py:118,168): fp32 NCHW in, bf16 NHWC out + BN partials [xcp_stem_conv1_parts()][2][32] */
 int xcp_stem_conv1_parts(int F, int H, int W, int device);
 int xcp_stem_conv1_fwd(const float* x, const float* w, void* y, float* partials, int F, int H, int W, int device, void* stream);
-int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, int F, int H, int W, int device, void* stream);
+/* weight gradient: im2col (bf16 [M,32]) + MN-major tcgen05 split-K GEMM; `workspace` = xcp_stem_conv1_wgrad_ws_bytes() bytes */
+long long xcp_stem_conv1_wgrad_ws_bytes(int F, int H, int W);
+int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, void* workspace, int F, int H, int W, int device,
+                         void* stream);
 
 /* ---- depthwise 3x3 s1 p1 (SeparableConv2d.conv1, Xception.py:41,45) fused with the preceding ReLU
  * (Xception.py:61-76) and the producer's BatchNorm affine.  w9 = tap-major weights [9][C] (xcp_pack_dw). */

@@ -26,7 +26,8 @@ SIGNATURES = {
     "xcp_conv3x3_gemm": "ppppiiiiiiiiip",
     "xcp_stem_conv1_parts": "iiii",
     "xcp_stem_conv1_fwd": "ppppiiiip",
-    "xcp_stem_conv1_wgrad": "pppiiiip",
+    "xcp_stem_conv1_wgrad_ws_bytes": "iii",
+    "xcp_stem_conv1_wgrad": "ppppiiiip",
     "xcp_dw3x3_fwd": "ppppipiiiiip",
     "xcp_dw3x3_bwd": "pppppipppppiiiiip",
     "xcp_bn_finalize": "piidppppffppppip",
@@ -60,12 +61,14 @@ SIGNATURES = {
     "xcp_grad_sumsq": "plpiip",
     "xcp_adam_step": "pppplfffffiipffip",
 }
-_RET_LONGLONG = set()
-_NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp_stem_conv1_parts"}
+_RET_LONGLONG = {"xcp_stem_conv1_wgrad_ws_bytes"}
+_NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp_stem_conv1_parts",
+              "xcp_stem_conv1_wgrad_ws_bytes"}
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; 0 = host-only query)
 _LAUNCHES = {"xcp_version": 0, "xcp_check_device": 0, "xcp_bnbwd_num_parts": 0, "xcp_gemm_stats_parts": 0,
-             "xcp_stem_conv1_parts": 0, "xcp_bn_bwd": 3, "xcp_arcface_loss": 2}
+             "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
+             "xcp_arcface_loss": 2}
 _count = 0
 
 _lock = threading.Lock()

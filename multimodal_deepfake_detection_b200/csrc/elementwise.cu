@@ -74,38 +74,52 @@ stem_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 
 // ======================================================================================== BN finalize
 // partials: [nparts][2][C].  Train mode: batch mean / biased var -> scale, shift, saved mean, rstd; running stats
-// updated with momentum and the unbiased variance.  block = 32 channels x 8 part-lanes.
-__global__ void __launch_bounds__(256)
+// updated with momentum and the unbiased variance.  block = 32 channels x 32 part-lanes, so the
+// reduction over (up to ~1400) partial rows is ~nparts/32 independent coalesced loads per thread.
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
                    float* scale, float* shift, float* mean_out, float* rstd_out) {
-    __shared__ double s1[8][32], s2[8][32];
+    __shared__ double s1[32][33], s2[32][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     double a = 0.0, b = 0.0;
     if (c < C) {
-        for (int pi = ry; pi < nparts; pi += 8) {
+        int pi = ry;
+        for (; pi + 96 < nparts; pi += 128) {
+            const float a0 = partials[((long long)pi * 2 + 0) * C + c], b0 = partials[((long long)pi * 2 + 1) * C + c];
+            const float a1 = partials[((long long)(pi + 32) * 2 + 0) * C + c], b1 = partials[((long long)(pi + 32) * 2 + 1) * C + c];
+            const float a2 = partials[((long long)(pi + 64) * 2 + 0) * C + c], b2 = partials[((long long)(pi + 64) * 2 + 1) * C + c];
+            const float a3 = partials[((long long)(pi + 96) * 2 + 0) * C + c], b3 = partials[((long long)(pi + 96) * 2 + 1) * C + c];
+            a += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+            b += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+        }
+        for (; pi < nparts; pi += 32) {
             a += (double)partials[((long long)pi * 2 + 0) * C + c];
             b += (double)partials[((long long)pi * 2 + 1) * C + c];
         }
     }
     s1[ry][cx] = a; s2[ry][cx] = b;
     __syncthreads();
-    if (ry == 0 && c < C) {
-        for (int r = 1; r < 8; ++r) { a += s1[r][cx]; b += s2[r][cx]; }
+    // transpose-reduce: warp w sums channel w's 32 lane partials
+    a = s1[cx][ry]; b = s2[cx][ry];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    const int cc = blockIdx.x * 32 + ry;
+    if (cx == 0 && cc < C) {
         const double mean = a / count;
         double var = b / count - mean * mean;
         if (var < 0.0) var = 0.0;
         const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float sc = gamma[c] * rstd;
-        scale[c] = sc;
-        shift[c] = beta[c] - (float)mean * sc;
-        mean_out[c] = (float)mean;
-        rstd_out[c] = rstd;
+        const float sc = gamma[cc] * rstd;
+        scale[cc] = sc;
+        shift[cc] = beta[cc] - (float)mean * sc;
+        mean_out[cc] = (float)mean;
+        rstd_out[cc] = rstd;
         if (running_mean != nullptr) {
             const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
-            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            running_mean[cc] = (1.f - momentum) * running_mean[cc] + momentum * (float)mean;
+            running_var[cc] = (1.f - momentum) * running_var[cc] + momentum * (float)unbiased;
         }
     }
 }
@@ -387,18 +401,37 @@ bnbwd_reduce_kernel(const uint4* __restrict__ y, const BnBwdSrc s, float* __rest
 }
 
 // pass 1b: fold partials -> coefficients of dy = A*dz + B*y + Cc and the BN parameter gradients (accumulated).
-// presummed != 0: `partials` is already the [2][C] sums (e.g. produced by the depthwise backward kernel).
-__global__ void bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
-                                      const float* __restrict__ gamma, const float* __restrict__ mean,
-                                      const float* __restrict__ rstd, int training, float* coefA, float* coefB, float* coefC,
-                                      float* dgamma, float* dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// nparts == 1: `partials` is already the [2][C] sums (e.g. produced by the depthwise backward kernel).
+// block = 32 channels x 8 part-lanes.
+__global__ void __launch_bounds__(256)
+bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+                      const float* __restrict__ gamma, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, int training, float* coefA, float* coefB, float* coefC,
+                      float* dgamma, float* dbeta) {
+    __shared__ double sh1[8][32], sh2[8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
     double s1 = 0.0, s2 = 0.0;
-    for (int pi = 0; pi < nparts; ++pi) {
-        s1 += (double)partials[(long long)pi * 2 * C + c];
-        s2 += (double)partials[(long long)pi * 2 * C + C + c];
+    if (c < C) {
+        int pi = ry;
+        for (; pi + 24 < nparts; pi += 32) {
+            const float a0 = partials[(long long)pi * 2 * C + c], b0 = partials[(long long)pi * 2 * C + C + c];
+            const float a1 = partials[(long long)(pi + 8) * 2 * C + c], b1 = partials[(long long)(pi + 8) * 2 * C + C + c];
+            const float a2 = partials[(long long)(pi + 16) * 2 * C + c], b2 = partials[(long long)(pi + 16) * 2 * C + C + c];
+            const float a3 = partials[(long long)(pi + 24) * 2 * C + c], b3 = partials[(long long)(pi + 24) * 2 * C + C + c];
+            s1 += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+            s2 += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+        }
+        for (; pi < nparts; pi += 8) {
+            s1 += (double)partials[(long long)pi * 2 * C + c];
+            s2 += (double)partials[(long long)pi * 2 * C + C + c];
+        }
     }
+    sh1[ry][cx] = s1; sh2[ry][cx] = s2;
+    __syncthreads();
+    if (ry != 0 || c >= C) return;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) { s1 += sh1[r][cx]; s2 += sh2[r][cx]; }
     const double m = mean[c], r = rstd[c], g = gamma[c];
     const double dg = r * (s2 - m * s1);      // sum dz * xhat
     const double A = g * r;
@@ -527,47 +560,38 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ gk, float* 
 }
 
 // Weight gradient of the stem conv1 (3->32, k3 s2 p0; Xception.py:118,168): dW[oc][27] += sum_pix dy[pix][oc] * patch[pix][27].
-// Persistent blocks over 128-pixel chunks; 288 threads x 3 outputs.
-__global__ void __launch_bounds__(288)
-stem_conv1_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dW, int F, int H, int W,
-                        int H1, int W1) {
-    __shared__ float s_dy[128][33];
-    __shared__ float s_x[128][28];
+// Done on the tensor cores: the 27-tap input patches are materialised once as a bf16 [M, 32] matrix (taps 27..31
+// zero) and the reduction over the M = F*H1*W1 pixels is the MN-major split-K tcgen05 GEMM of gemm.cu
+// (xcp_gemm_wgrad, P = Q = 32), followed by a 864-element scatter-add into the nn.Conv2d layout.
+__global__ void __launch_bounds__(256)
+stem_conv1_im2col_kernel(const float* __restrict__ x, uint4* __restrict__ patches, int F, int H, int W, int H1, int W1) {
     const long long M = (long long)F * H1 * W1;
-    const long long chunks = (M + 127) / 128;
-    float acc[3] = {0.f, 0.f, 0.f};
-    int oc[3], tp[3];
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < M; pix += (long long)gridDim.x * blockDim.x) {
+        const int wo = (int)(pix % W1);
+        const int ho = (int)((pix / W1) % H1);
+        const int f = (int)(pix / ((long long)W1 * H1));
+        const float* xb = x + ((long long)f * 3 * H + 2 * ho) * W + 2 * wo;
+        float v[32];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) { const int o = threadIdx.x + u * 288; oc[u] = o / 27; tp[u] = o % 27; }
-    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 128 * 32; i += 288) {
-            const int r = i >> 5, c = i & 31;
-            const long long pix = ch * 128 + r;
-            s_dy[r][c] = pix < M ? __bfloat162float(dy[pix * 32 + c]) : 0.f;
-        }
-        for (int i = threadIdx.x; i < 128 * 27; i += 288) {
-            const int r = i / 27, tap = i % 27;
-            const long long pix = ch * 128 + r;
-            float v = 0.f;
-            if (pix < M) {
-                const int wo = (int)(pix % W1);
-                const int ho = (int)((pix / W1) % H1);
-                const int f = (int)(pix / ((long long)W1 * H1));
-                const int ic = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-                v = x[(((long long)f * 3 + ic) * H + 2 * ho + kh) * W + 2 * wo + kw];
-            }
-            s_x[r][tap] = v;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int r = 0; r < 128; ++r) {
+        for (int ic = 0; ic < 3; ++ic)
 #pragma unroll
-            for (int u = 0; u < 3; ++u) acc[u] = fmaf(s_dy[r][oc[u]], s_x[r][tp[u]], acc[u]);
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) v[(ic * 3 + kh) * 3 + kw] = __ldg(xb + ((long long)ic * H + kh) * W + kw);
+#pragma unroll
+        for (int j = 27; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8[j] = v[g * 8 + j];
+            patches[pix * 4 + g] = pack8(t8);
         }
     }
-#pragma unroll
-    for (int u = 0; u < 3; ++u) atomicAdd(&dW[threadIdx.x + u * 288], acc[u]);
+}
+__global__ void stem_conv1_wgrad_scatter_kernel(const float* __restrict__ gk, float* __restrict__ dW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 32 * 27) dW[i] += gk[(i / 27) * 32 + (i % 27)];
 }
 
 // bilinear (align_corners=False) upsample of [F,C,n,1] fp32 to [F,C,S,S] fp32 (XceptionLSTMA.py:45-46).
@@ -622,7 +646,7 @@ extern "C" int xcp_bn_finalize(const float* partials, int nparts, int C, double 
                                float* mean_out, float* rstd_out, int device, void* stream) {
     XCP_REQUIRE(nparts > 0 && C > 0 && count > 0, "xcp_bn_finalize: bad args");
     XCP_CUDA(cudaSetDevice(device));
-    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, ST>>>(partials, nparts, C, count, gamma, beta, running_mean, running_var,
+    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST>>>(partials, nparts, C, count, gamma, beta, running_mean, running_var,
                                                       momentum, eps, scale, shift, mean_out, rstd_out);
     return check_cuda(cudaGetLastError(), "bn_finalize launch");
 }
@@ -704,7 +728,7 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
         XCP_CUDA(cudaGetLastError());
         sums = workspace;
     }
-    bnbwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sums, nparts, C, count, gamma, mean, rstd, training, coef, coef + C,
+    bnbwd_finalize_kernel<<<(C + 31) / 32, 256, 0, ST>>>(sums, nparts, C, count, gamma, mean, rstd, training, coef, coef + C,
                                                            coef + 2 * C, dgamma, dbeta);
     XCP_CUDA(cudaGetLastError());
     if (dy != nullptr) {
@@ -759,13 +783,29 @@ extern "C" int xcp_unpack_conv3x3_grad(const float* gk, float* gw, int O, int I,
     return check_cuda(cudaGetLastError(), "unpack_conv3x3_grad launch");
 }
 
-extern "C" int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, int F, int H, int W, int device, void* stream) {
+extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, long long ld_x, float* dW, long long ld_dw,
+                              int R, int P, int Q, int device, void* stream);
+
+// bytes of device scratch xcp_stem_conv1_wgrad needs (im2col patches bf16 [M,32] + fp32 [32,32] accumulator)
+extern "C" long long xcp_stem_conv1_wgrad_ws_bytes(int F, int H, int W) {
+    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
+    return (long long)F * H1 * W1 * 64 + 32 * 32 * 4;
+}
+
+extern "C" int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, void* workspace, int F, int H, int W, int device,
+                                    void* stream) {
+    XCP_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 16) == 0, "xcp_stem_conv1_wgrad: workspace missing / unaligned");
     XCP_CUDA(cudaSetDevice(device));
     const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
-    const long long chunks = ((long long)F * H1 * W1 + 127) / 128;
-    long long grid = 2LL * num_sms();
-    if (grid > chunks) grid = chunks;
-    stem_conv1_wgrad_kernel<<<(int)grid, 288, 0, ST>>>(x, (const __nv_bfloat16*)dy, dW, F, H, W, H1, W1);
+    const long long M = (long long)F * H1 * W1;
+    XCP_REQUIRE(M < (1LL << 31), "xcp_stem_conv1_wgrad: too many pixels for 32-bit TMA coordinates");
+    float* gk = reinterpret_cast<float*>(workspace);
+    uint4* patches = reinterpret_cast<uint4*>(reinterpret_cast<char*>(workspace) + 32 * 32 * 4);
+    XCP_CUDA(cudaMemsetAsync(gk, 0, 32 * 32 * 4, ST));
+    stem_conv1_im2col_kernel<<<ew_grid(M, 256), 256, 0, ST>>>(x, patches, F, H, W, H1, W1);
+    XCP_CUDA(cudaGetLastError());
+    if (int e = xcp_gemm_wgrad(dy, 32, patches, 32, gk, 32, (int)M, 32, 32, device, stream)) return e;
+    stem_conv1_wgrad_scatter_kernel<<<4, 256, 0, ST>>>(gk, dW);
     return check_cuda(cudaGetLastError(), "stem_conv1_wgrad launch");
 }
 

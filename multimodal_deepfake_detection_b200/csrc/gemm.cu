@@ -12,6 +12,13 @@
 //   warps 2..5    : epilogue      (tcgen05.ld 32x32b -> regs -> bf16/f32 store, per-channel sum / sum-sq)
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
+//
+// CTA2 = true runs the same pipeline on CTA pairs (2-CTA clusters, tcgen05 cta_group::2): the pair owns a
+// 256 x BLOCK_N output tile, each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues
+// M=256 MMAs that read both CTAs' shared memory, and each CTA's epilogue drains its own 128 TMEM lanes.  Per SM
+// and per K block that is 16 KB (A) + BLOCK_N/2 x 128 B (B) of L2->SM traffic instead of 16 KB + BLOCK_N x 128 B:
+// the first ncu pass showed the 1-CTA 128x256 tiles were limited by exactly that operand traffic (tensor pipe
+// 34-39 % active, DRAM traffic = algorithmic bytes), and the smaller stage also buys a 6-deep ring.
 #include "common.cuh"
 
 namespace xcp {
@@ -40,22 +47,24 @@ constexpr int A_STAGE_BYTES = BLOCK_M * 128;
 template <int BLOCK_N, int BLOCK_K>
 __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_N * BLOCK_K * 2; }
 
-template <int BLOCK_N, int BLOCK_K, bool STATS>
+template <int BLOCK_N, int BLOCK_K, bool STATS, bool CTA2>
 __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
-    return 1024 /*align slack*/ + stages * (BLOCK_M * BLOCK_K * 2 + b_stage_bytes<BLOCK_N, BLOCK_K>()) +
+    return 1024 /*align slack*/ + stages * (BLOCK_M * BLOCK_K * 2 + b_stage_bytes<BLOCK_N, BLOCK_K>() / (CTA2 ? 2 : 1)) +
            (STATS ? (4 * 32 * 33 * 4 + 4 * 2 * BLOCK_N * 4) : 0) + 256 /*barriers*/;
 }
 
 // MN_MAJOR=false: A is [M,K] row-major, B is [N,K] row-major (both K-major):      D = A * B^T
 // MN_MAJOR=true : A is [K,M] row-major, B is [K,N] row-major (both MN-major):     D = A^T * B
 // BLOCK_K=64 -> 128B swizzle; BLOCK_K=32 -> 64B swizzle (K-major only; used by the stem implicit GEMM)
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K>
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     static_assert(BLOCK_K == 64 || (BLOCK_K == 32 && !MN_MAJOR), "unsupported BLOCK_K");
+    static_assert(!CTA2 || (BLOCK_K == 64 && BLOCK_N >= 128), "CTA-pair mode: BLOCK_K 64, BLOCK_N 128/256");
     constexpr bool STATS = (EPI == EPI_BF16_STATS);
+    constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;         // B rows (N) staged by this CTA
     constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     constexpr uint32_t LAYOUT = (BLOCK_K == 64) ? 2u : 4u;       // SWIZZLE_128B : SWIZZLE_64B
     constexpr uint32_t SBO = 8 * BLOCK_K * 2;                    // bytes between 8-row groups
     constexpr int UMMA_K = 16;
@@ -79,58 +88,77 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;        // rank in the CTA pair; 0 = leader (issues the MMAs)
+    const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // tile-scheduler slot (a CTA or a CTA pair)
+    const int num_workers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 8 : 4); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+    if (CTA2) cluster_sync_all();                               // peer barriers are initialised before anything signals them
+    if (warp == 1) { if (CTA2) tmem_alloc_cg2(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+    const int tiles_mn = p.num_m_tiles * p.num_n_tiles;        // num_m_tiles counts 256-row tiles in CTA-pair mode
     const int num_units = tiles_mn * p.splits;
+    const int m_row0_mul = CTA2 ? 2 * BLOCK_M : BLOCK_M;
 
     if (warp == 0 && lane == 0) {
-        // ------------------------------------------------ TMA producer
+        // ------------------------------------------------ TMA producer (one per CTA; in pair mode both signal the leader)
         int s = 0; uint32_t ph = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const uint32_t full0_leader = CTA2 ? mapa_cluster(smem_u32(&full[0]), 0) : 0u;   // leader's full[0] (barriers are 8 B apart)
+        for (int u = worker; u < num_units; u += num_workers) {
             const int split = u / tiles_mn;
             const int t = u - split * tiles_mn;
             const int m_blk = t / p.num_n_tiles, n_blk = t - m_blk * p.num_n_tiles;
+            const int m0 = m_blk * m_row0_mul + (int)rank * BLOCK_M;        // first A row (K-major) / M column (MN-major)
+            const int n0 = n_blk * BLOCK_N + (int)rank * B_ROWS;
             const int kb0 = split * p.k_blocks_per_split;
             const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+                if (!CTA2) mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+                else if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
                 if (!MN_MAJOR) {
-                    if (p.conv_taps > 0) {
-                        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], 0, m_blk * BLOCK_M + p.a_row_shift[kb]);
+                    if (CTA2) {
+                        tma_load_2d_cg2(sA + s * A_BYTES, &tmA, (full0_leader + 8u * (uint32_t)s), kb * BLOCK_K, m0);
+                        tma_load_2d_cg2(sB + s * B_BYTES, &tmB, (full0_leader + 8u * (uint32_t)s), kb * BLOCK_K, n0);
                     } else {
-                        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BLOCK_K, m_blk * BLOCK_M);
+                        if (p.conv_taps > 0) {
+                            tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], 0, m0 + p.a_row_shift[kb]);
+                        } else {
+                            tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BLOCK_K, m0);
+                        }
+                        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BLOCK_K, n0);
                     }
-                    tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BLOCK_K, n_blk * BLOCK_N);
                 } else {
 #pragma unroll
-                    for (int a = 0; a < BLOCK_M / 64; ++a)
-                        tma_load_2d(sA + s * A_BYTES + a * (64 * 128), &tmA, &full[s], m_blk * BLOCK_M + a * 64, kb * 64);
+                    for (int a = 0; a < BLOCK_M / 64; ++a) {
+                        if (CTA2) tma_load_2d_cg2(sA + s * A_BYTES + a * (64 * 128), &tmA, (full0_leader + 8u * (uint32_t)s), m0 + a * 64, kb * 64);
+                        else tma_load_2d(sA + s * A_BYTES + a * (64 * 128), &tmA, &full[s], m0 + a * 64, kb * 64);
+                    }
 #pragma unroll
-                    for (int a = 0; a < BLOCK_N / 64; ++a)
-                        tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], n_blk * BLOCK_N + a * 64, kb * 64);
+                    for (int a = 0; a < B_ROWS / 64; ++a) {
+                        if (CTA2) tma_load_2d_cg2(sB + s * B_BYTES + a * (64 * 128), &tmB, (full0_leader + 8u * (uint32_t)s), n0 + a * 64, kb * 64);
+                        else tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], n0 + a * 64, kb * 64);
+                    }
                 }
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ------------------------------------------------ MMA issuer (leader CTA only in pair mode)
+        constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         int s = 0; uint32_t ph = 0; uint32_t iter = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++iter) {
+        for (int u = worker; u < num_units; u += num_workers, ++iter) {
             const int split = u / tiles_mn;
             const int kb0 = split * p.k_blocks_per_split;
             const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
@@ -153,10 +181,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         adesc = make_smem_desc(a_base + s * A_BYTES + k * (UMMA_K * 128), 64 * 128, 1024, 2);
                         bdesc = make_smem_desc(b_base + s * B_BYTES + k * (UMMA_K * 128), 64 * 128, 1024, 2);
                     }
-                    umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    if (CTA2) umma_bf16_cg2(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&empty[s]);                       // frees the smem slot when these MMAs retire
-                if (kb == kb1 - 1) umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+                // frees the smem slot (in both CTAs) when these MMAs retire; last K block: accumulator ready
+                if (CTA2) {
+                    umma_commit_cg2(&empty[s], 3);
+                    if (kb == kb1 - 1) umma_commit_cg2(&tmem_full[as], 3);
+                } else {
+                    umma_commit(&empty[s]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+                }
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -170,10 +205,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) { racc[0][i] = 0.f; racc[1][i] = 0.f; }
         uint32_t iter = 0;
-        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++iter) {
+        const uint32_t tmem_empty_leader[2] = {CTA2 ? mapa_cluster(smem_u32(&tmem_empty[0]), 0) : 0u,
+                                               CTA2 ? mapa_cluster(smem_u32(&tmem_empty[1]), 0) : 0u};
+        for (int u = worker; u < num_units; u += num_workers, ++iter) {
             const int split = u / tiles_mn;
             const int t = u - split * tiles_mn;
-            const int m_blk = t / p.num_n_tiles, n_blk = t - m_blk * p.num_n_tiles;
+            const int n_blk = t % p.num_n_tiles;
+            const int m_blk = (t / p.num_n_tiles) * (CTA2 ? 2 : 1) + (int)rank;     // 128-row block of this CTA
             const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
@@ -261,7 +299,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) { if (CTA2) mbar_arrive_cluster(tmem_empty_leader[as]); else mbar_arrive(&tmem_empty[as]); }
             if (STATS) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
@@ -277,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                         if (p.stats_per_cta) {
                             racc[0][i] += s1; racc[1][i] += s2;
-                        } else {
+                        } else if ((long long)m_blk * BLOCK_M < p.M) {   // (pair mode: the odd tail block has no rows)
                             p.stats[((long long)m_blk * 2 + 0) * p.N + gcol] = s1;
                             p.stats[((long long)m_blk * 2 + 1) * p.N + gcol] = s2;
                         }
@@ -300,9 +338,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();          // the peer may still be reading this CTA's smem / signalling its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CTA2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -323,29 +362,87 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __n
 }
 
 // ----------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K>
+// Persistent grid size: one CTA (or CTA pair) per SM (pair), capped by the number of work units.
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2>
+static int gemm_grid(int units) {
+    if (!CTA2) return units < num_sms() ? units : num_sms();
+    static int max_clusters[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (max_clusters[dev] == 0) {
+        constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI == EPI_BF16_STATS, CTA2>(STAGES);
+        auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() & ~1); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+        if (n > num_sms() / 2) n = num_sms() / 2;
+        max_clusters[dev] = n;
+    }
+    const int c = units < max_clusters[dev] ? units : max_clusters[dev];
+    return 2 * c;
+}
+
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2 = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI == EPI_BF16_STATS>(STAGES);
+    constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI == EPI_BF16_STATS, CTA2>(STAGES);
     static_assert(smem <= 232448, "smem budget");
-    auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K>;
+    auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>;
     static bool attr_set = false;   // per-instantiation; benign race (idempotent)
     if (!attr_set) {
         XCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
-    const int grid = units < num_sms() ? units : num_sms();
-    kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
-    return check_cuda(cudaGetLastError(), "gemm_kernel launch");
+    const int grid = gemm_grid<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>(units);
+    if (!CTA2) {
+        kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+        return check_cuda(cudaGetLastError(), "gemm_kernel launch");
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p), "gemm_kernel (CTA pair) launch");
+}
+
+// K-major ("TN") problem plan shared by the launcher and xcp_gemm_stats_parts.
+struct TnPlan { int bn; bool cta2; int num_m_tiles, num_n_tiles; };
+static TnPlan plan_tn(long long M, int N) {
+    TnPlan pl;
+    pl.bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    pl.cta2 = pl.bn >= 128 && M > BLOCK_M;
+    const int tile_m = pl.cta2 ? 2 * BLOCK_M : BLOCK_M;
+    pl.num_m_tiles = (int)((M + tile_m - 1) / tile_m);
+    pl.num_n_tiles = (N + pl.bn - 1) / pl.bn;
+    return pl;
 }
 
 template <int EPI>
-static int dispatch_tn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
-    switch (bn) {
-        case 64: return launch_gemm<64, EPI, false, 8, 64>(a, b, p, st);
-        case 128: return launch_gemm<128, EPI, false, 6, 64>(a, b, p, st);
-        default: return launch_gemm<256, EPI, false, 4, 64>(a, b, p, st);
+static int dispatch_tn(const TnPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+    if (pl.bn == 64) return launch_gemm<64, EPI, false, 8, 64>(a, b, p, st);
+    if (pl.bn == 128) {
+        if (pl.cta2) return launch_gemm<128, EPI, false, 8, 64, true>(a, b, p, st);
+        return launch_gemm<128, EPI, false, 6, 64>(a, b, p, st);
     }
+    if (pl.cta2) return launch_gemm<256, EPI, false, 6, 64, true>(a, b, p, st);
+    return launch_gemm<256, EPI, false, 4, 64>(a, b, p, st);
+}
+
+// persistent grid of a K-major launch (= number of per-CTA statistics rows when N fits one tile)
+template <int EPI>
+static int grid_tn(const TnPlan& pl, int units) {
+    if (pl.bn == 64) return gemm_grid<64, EPI, false, 8, 64, false>(units);
+    if (pl.bn == 128) return pl.cta2 ? gemm_grid<128, EPI, false, 8, 64, true>(units) : gemm_grid<128, EPI, false, 6, 64, false>(units);
+    return pl.cta2 ? gemm_grid<256, EPI, false, 6, 64, true>(units) : gemm_grid<256, EPI, false, 4, 64, false>(units);
 }
 
 }  // namespace xcp
@@ -365,33 +462,31 @@ extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long lon
     XCP_REQUIRE(epi >= 0 && epi <= 2, "xcp_gemm_tn: bad epilogue %d", epi);
     XCP_REQUIRE(epi != EPI_BF16_STATS || stats != nullptr, "xcp_gemm_tn: stats buffer missing");
     XCP_CUDA(cudaSetDevice(device));
-    const int bn = pick_block_n(N);
+    const TnPlan pl = plan_tn(M, N);
     CUtensorMap tmA, tmB;
     if (int e = make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BLOCK_M, 128)) return e;
-    if (int e = make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, bn, 128)) return e;
+    if (int e = make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, pl.cta2 ? pl.bn / 2 : pl.bn, 128)) return e;
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.stats = stats; p.bias = bias;
-    p.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    p.num_n_tiles = (N + bn - 1) / bn;
+    p.num_m_tiles = pl.num_m_tiles;
+    p.num_n_tiles = pl.num_n_tiles;
     p.num_k_blocks = (K + 63) / 64;
     p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
     p.stats_per_cta = (p.num_n_tiles == 1) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (epi) {
-        case EPI_BF16: return dispatch_tn<EPI_BF16>(bn, tmA, tmB, p, st);
-        case EPI_BF16_STATS: return dispatch_tn<EPI_BF16_STATS>(bn, tmA, tmB, p, st);
-        default: return dispatch_tn<EPI_F32>(bn, tmA, tmB, p, st);
+        case EPI_BF16: return dispatch_tn<EPI_BF16>(pl, tmA, tmB, p, st);
+        case EPI_BF16_STATS: return dispatch_tn<EPI_BF16_STATS>(pl, tmA, tmB, p, st);
+        default: return dispatch_tn<EPI_F32>(pl, tmA, tmB, p, st);
     }
 }
 
-// Number of partial rows xcp_gemm_tn (epi=1) / xcp_conv3x3_gemm write into `stats` for an M x N problem.
+// Number of partial rows xcp_gemm_tn (epi=1) writes into `stats` for an M x N problem.
 extern "C" int xcp_gemm_stats_parts(long long M, int N, int device) {
     if (cudaSetDevice(device) != cudaSuccess) return -1;
-    const long long mt = (M + BLOCK_M - 1) / BLOCK_M;
-    const int bn = pick_block_n(N);
-    const int nt = (N + bn - 1) / bn;
-    if (nt > 1) return (int)mt;
-    return (int)(mt < num_sms() ? mt : num_sms());
+    const TnPlan pl = plan_tn(M, N);
+    if (pl.num_n_tiles > 1) return (int)((M + BLOCK_M - 1) / BLOCK_M);
+    return grid_tn<EPI_BF16_STATS>(pl, pl.num_m_tiles);
 }
 
 // dW[P,Q] += dY[R,P]^T * X[R,Q]   (weight gradient of Y = X W^T; R = pixels).  fp32 RED accumulation, the
@@ -402,16 +497,19 @@ extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, lo
     XCP_REQUIRE(P % 8 == 0 && Q % 8 == 0 && ld_dy % 8 == 0 && ld_x % 8 == 0 && ld_dw % 4 == 0, "xcp_gemm_wgrad: alignment");
     XCP_CUDA(cudaSetDevice(device));
     const int bn = pick_block_n(Q);
+    const bool cta2 = bn >= 128 && P > BLOCK_M;        // CTA pairs own 256 x bn tiles of dW (halves the operand traffic per SM)
     CUtensorMap tmA, tmB;
     if (int e = make_tmap_2d(&tmA, dY, (uint64_t)P, (uint64_t)R, (uint64_t)ld_dy * 2, 64, 64, 128)) return e;
     if (int e = make_tmap_2d(&tmB, X, (uint64_t)Q, (uint64_t)R, (uint64_t)ld_x * 2, 64, 64, 128)) return e;
     GemmParams p{};
     p.M = P; p.N = Q; p.K = R; p.out = dW; p.ldo = ld_dw;
-    p.num_m_tiles = (P + BLOCK_M - 1) / BLOCK_M;
+    const int tile_m = cta2 ? 2 * BLOCK_M : BLOCK_M;
+    p.num_m_tiles = (P + tile_m - 1) / tile_m;
     p.num_n_tiles = (Q + bn - 1) / bn;
     p.num_k_blocks = (R + 63) / 64;
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    int splits = (2 * num_sms() + tiles - 1) / tiles;
+    const int workers = cta2 ? num_sms() / 2 : num_sms();
+    int splits = (2 * workers) / tiles;          // floor: at most two full waves of units
     int max_splits = (p.num_k_blocks + 7) / 8;   // at least 8 K-blocks (512 rows) per unit
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -420,8 +518,12 @@ extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, lo
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
         case 64: return launch_gemm<64, EPI_RED_F32, true, 6, 64>(tmA, tmB, p, st);
-        case 128: return launch_gemm<128, EPI_RED_F32, true, 6, 64>(tmA, tmB, p, st);
-        default: return launch_gemm<256, EPI_RED_F32, true, 4, 64>(tmA, tmB, p, st);
+        case 128:
+            if (cta2) return launch_gemm<128, EPI_RED_F32, true, 8, 64, true>(tmA, tmB, p, st);
+            return launch_gemm<128, EPI_RED_F32, true, 6, 64>(tmA, tmB, p, st);
+        default:
+            if (cta2) return launch_gemm<256, EPI_RED_F32, true, 6, 64, true>(tmA, tmB, p, st);
+            return launch_gemm<256, EPI_RED_F32, true, 4, 64>(tmA, tmB, p, st);
     }
 }
 

@@ -126,33 +126,66 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 }
 
 // ============================================================================================ small-batch Linear
-// out[b][n] = act( sum_k a[b][k] W[n][k] + bias[n] ) * dropmask ; warp per output neuron, B <= 32 rows.
-// act: 0 none, 1 relu.  mask (optional, uint8 [B][N], 1 = keep) scaled by drop_scale = 1/(1-p).
+// out[b][n] = act( sum_k a[b][k] W[n][k] + bias[n] ) * dropmask ; warp per output neuron, B <= 32 rows processed in
+// chunks of 8.  act: 0 none, 1 relu.  mask (optional, uint8 [B][N], 1 = keep) scaled by drop_scale = 1/(1-p).
+// Weight-bandwidth bound (fp32 masters, 4 MB per 1024x1024 layer): every lane issues its float4 weight loads for
+// 8 K-chunks back to back before the FMAs so a warp keeps 4 KB in flight; the activations come from L1.
 constexpr int MAXB = 32;
+constexpr int LIN_BCH = 8;
 __global__ void __launch_bounds__(256)
 linear_small_fwd_kernel(const float* __restrict__ a, const float* __restrict__ W, const float* __restrict__ bias,
                         const uint8_t* __restrict__ mask, float drop_scale, int act, float* __restrict__ out, int B, int N, int K) {
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
-    float acc[MAXB];
+    const float* wrow = W + (long long)n * K;
+    for (int b0 = 0; b0 < B; b0 += LIN_BCH) {
+        float acc[LIN_BCH];
 #pragma unroll
-    for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-        const float wv = W[(long long)n * K + k];
+        for (int b = 0; b < LIN_BCH; ++b) acc[b] = 0.f;
+        if ((K & 3) == 0) {
+            const int K4 = K >> 2;
+            for (int c0 = 0; c0 < K4; c0 += 8 * 32) {
+                float4 wv[8];
 #pragma unroll
-        for (int b = 0; b < MAXB; ++b)
-            if (b < B) acc[b] = fmaf(wv, a[(long long)b * K + k], acc[b]);
-    }
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j * 32 + lane;
+                    wv[j] = c < K4 ? __ldg(reinterpret_cast<const float4*>(wrow) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
-    for (int b = 0; b < MAXB; ++b) {
-        if (b < B) {
-            float v = warp_sum(acc[b]);
-            if (lane == 0) {
-                v += bias ? bias[n] : 0.f;
-                if (act == 1) v = fmaxf(v, 0.f);
-                if (mask) v = mask[(long long)b * N + n] ? v * drop_scale : 0.f;
-                out[(long long)b * N + n] = v;
+                for (int b = 0; b < LIN_BCH; ++b) {
+                    if (b0 + b < B) {
+                        const float4* ar = reinterpret_cast<const float4*>(a + (long long)(b0 + b) * K);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = c0 + j * 32 + lane;
+                            if (c < K4) {
+                                const float4 av = ar[c];
+                                acc[b] = fmaf(wv[j].x, av.x, acc[b]); acc[b] = fmaf(wv[j].y, av.y, acc[b]);
+                                acc[b] = fmaf(wv[j].z, av.z, acc[b]); acc[b] = fmaf(wv[j].w, av.w, acc[b]);
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) {
+                const float wv = wrow[k];
+#pragma unroll
+                for (int b = 0; b < LIN_BCH; ++b)
+                    if (b0 + b < B) acc[b] = fmaf(wv, a[(long long)(b0 + b) * K + k], acc[b]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < LIN_BCH; ++b) {
+            if (b0 + b < B) {
+                float v = warp_sum(acc[b]);
+                if (lane == 0) {
+                    v += bias ? bias[n] : 0.f;
+                    if (act == 1) v = fmaxf(v, 0.f);
+                    if (mask) v = mask[(long long)(b0 + b) * N + n] ? v * drop_scale : 0.f;
+                    out[(long long)(b0 + b) * N + n] = v;
+                }
             }
         }
     }
@@ -160,46 +193,75 @@ linear_small_fwd_kernel(const float* __restrict__ a, const float* __restrict__ W
 
 // Backward of the layer above.  delta_raw = dL/d(out) ; out_act = saved layer output (null for a linear output);
 // effective delta = delta_raw * (out_act > 0 ? drop_scale : 0).  dW += delta^T a ; db += sum_b delta ;
-// din[b][k] += sum_n delta[b][n] W[n][k]   (din must be zero-initialised; CTA partials -> global RED).
+// din[b][k] += sum_n delta[b][n] W[n][k]   (din must be zero-initialised).
+// A CTA owns LIN_NS output neurons x a 4*KT-wide column chunk (blockIdx.y): thread = (row group, float4 column), the
+// row of W and of dW is streamed once with 16-byte accesses while din partials stay in registers; one vector RED
+// per (b, float4 column) at the end.  K % 4 == 0.
+constexpr int LIN_NS = 16;
+template <int KT>
 __global__ void __launch_bounds__(256)
 linear_small_bwd_kernel(const float* __restrict__ delta_raw, const float* __restrict__ out_act, float drop_scale,
                         const float* __restrict__ a, const float* __restrict__ W, float* __restrict__ dW, float* __restrict__ db,
                         float* __restrict__ din, int B, int N, int K) {
-    extern __shared__ float s_din[];   // [B][K]
-    for (int i = threadIdx.x; i < B * K; i += blockDim.x) s_din[i] = 0.f;
-    __syncthreads();
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (n < N) {
-        float d[MAXB];
-        float dbs = 0.f;
-#pragma unroll
-        for (int b = 0; b < MAXB; ++b) {
-            d[b] = 0.f;
-            if (b < B) {
-                float v = delta_raw[(long long)b * N + n];
-                if (out_act) v = out_act[(long long)b * N + n] > 0.f ? v * drop_scale : 0.f;
-                d[b] = v;
-                dbs += v;
+    constexpr int RG = 256 / KT;
+    const int kc = threadIdx.x % KT, rg = threadIdx.x / KT;
+    const int K4 = K >> 2;
+    const int c4 = blockIdx.y * KT + kc;                  // float4 column
+    const bool col_ok = c4 < K4;
+    const int n0 = blockIdx.x * LIN_NS;
+    __shared__ float s_d[LIN_NS][LIN_BCH];
+    for (int b0 = 0; b0 < B; b0 += LIN_BCH) {
+        __syncthreads();
+        if (threadIdx.x < LIN_NS * LIN_BCH) {
+            const int nn = threadIdx.x / LIN_BCH, b = threadIdx.x % LIN_BCH;
+            float v = 0.f;
+            if (n0 + nn < N && b0 + b < B) {
+                v = delta_raw[(long long)(b0 + b) * N + n0 + nn];
+                if (out_act) v = out_act[(long long)(b0 + b) * N + n0 + nn] > 0.f ? v * drop_scale : 0.f;
             }
+            s_d[nn][b] = v;
         }
-        if (lane == 0 && db) db[n] += dbs;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = W[(long long)n * K + k];
-            float g = 0.f;
+        __syncthreads();
+        if (db != nullptr && blockIdx.y == 0 && threadIdx.x < LIN_NS && n0 + threadIdx.x < N) {
+            float t = 0.f;
 #pragma unroll
-            for (int b = 0; b < MAXB; ++b) {
-                if (b < B) {
-                    g = fmaf(d[b], a[(long long)b * K + k], g);
-                    if (din) atomicAdd(&s_din[b * K + k], d[b] * wv);
+            for (int b = 0; b < LIN_BCH; ++b) t += s_d[threadIdx.x][b];
+            db[n0 + threadIdx.x] += t;
+        }
+        if (!col_ok) continue;
+        float4 av[LIN_BCH], acc[LIN_BCH];
+#pragma unroll
+        for (int b = 0; b < LIN_BCH; ++b) {
+            av[b] = (b0 + b < B) ? reinterpret_cast<const float4*>(a + (long long)(b0 + b) * K)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll 4
+        for (int nn = rg; nn < LIN_NS; nn += RG) {
+            const int n = n0 + nn;
+            if (n >= N) break;
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (long long)n * K) + c4);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dW) g = reinterpret_cast<const float4*>(dW + (long long)n * K)[c4];
+#pragma unroll
+            for (int b = 0; b < LIN_BCH; ++b) {
+                const float d = s_d[nn][b];
+                g.x = fmaf(d, av[b].x, g.x); g.y = fmaf(d, av[b].y, g.y); g.z = fmaf(d, av[b].z, g.z); g.w = fmaf(d, av[b].w, g.w);
+                acc[b].x = fmaf(d, wv.x, acc[b].x); acc[b].y = fmaf(d, wv.y, acc[b].y);
+                acc[b].z = fmaf(d, wv.z, acc[b].z); acc[b].w = fmaf(d, wv.w, acc[b].w);
+            }
+            if (dW) reinterpret_cast<float4*>(dW + (long long)n * K)[c4] = g;
+        }
+        if (din != nullptr) {
+#pragma unroll
+            for (int b = 0; b < LIN_BCH; ++b) {
+                if (b0 + b < B) {
+                    float* dp = din + (long long)(b0 + b) * K + c4 * 4;
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(acc[b].x), "f"(acc[b].y),
+                                 "f"(acc[b].z), "f"(acc[b].w) : "memory");
                 }
             }
-            if (dW) dW[(long long)n * K + k] += g;
         }
     }
-    __syncthreads();
-    if (din)
-        for (int i = threadIdx.x; i < B * K; i += blockDim.x) atomicAdd(&din[i], s_din[i]);
 }
 
 // p = sigmoid(z), loss = BCE mean (log clamped at -100 like nn.BCELoss), dz = dL/dz = (p - y)/B * gscale.
@@ -450,11 +512,14 @@ extern "C" int xcp_linear_small_fwd(const float* a, const float* W, const float*
 extern "C" int xcp_linear_small_bwd(const float* delta_raw, const float* out_act, float drop_scale, const float* a, const float* W,
                                     float* dW, float* db, float* din, int B, int N, int K, int device, void* stream) {
     XCP_REQUIRE(B > 0 && B <= MAXB, "xcp_linear_small_bwd: batch %d exceeds %d rows", B, MAXB);
-    const size_t smem = (size_t)B * K * sizeof(float);
-    XCP_REQUIRE(smem <= 200 * 1024, "xcp_linear_small_bwd: B*K too large");
+    XCP_REQUIRE(K % 4 == 0, "xcp_linear_small_bwd: K must be a multiple of 4 (got %d)", K);
     XCP_CUDA(cudaSetDevice(device));
-    XCP_CUDA(cudaFuncSetAttribute(linear_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    linear_small_bwd_kernel<<<(N + 7) / 8, 256, smem, ST>>>(delta_raw, out_act, drop_scale, a, W, dW, db, din, B, N, K);
+    const int K4 = K / 4;
+    const int nb = (N + LIN_NS - 1) / LIN_NS;
+    if (K4 <= 32) linear_small_bwd_kernel<32><<<dim3(nb, 1), 256, 0, ST>>>(delta_raw, out_act, drop_scale, a, W, dW, db, din, B, N, K);
+    else if (K4 <= 64) linear_small_bwd_kernel<64><<<dim3(nb, 1), 256, 0, ST>>>(delta_raw, out_act, drop_scale, a, W, dW, db, din, B, N, K);
+    else if (K4 <= 128) linear_small_bwd_kernel<128><<<dim3(nb, 1), 256, 0, ST>>>(delta_raw, out_act, drop_scale, a, W, dW, db, din, B, N, K);
+    else linear_small_bwd_kernel<256><<<dim3(nb, (K4 + 255) / 256), 256, 0, ST>>>(delta_raw, out_act, drop_scale, a, W, dW, db, din, B, N, K);
     return check_cuda(cudaGetLastError(), "linear_small_bwd launch");
 }
 

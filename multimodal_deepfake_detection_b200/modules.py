@@ -330,7 +330,9 @@ class _LSTMFn(torch.autograd.Function):
         _, whh_t = cache.linear(w_hh)
         xproj, _ = ops.gemm_tn(xb, wih_b, ops.EPI_F32)
         h, gates, cst, hn, cn = ops.lstm_fwd(xproj, b_ih.detach(), b_hh.detach(), whh_t, B, T, H)
-        ctx.mod, ctx.saved = mod, (xb, gates, cst, h, B, T, H, I)
+        # (detached alias: keeping the Function's own output in ctx would create a reference cycle output -> grad_fn -> ctx
+        #  that only the cyclic GC frees, pinning the previous step's autograd graph and its AccumulateGrad streams)
+        ctx.mod, ctx.saved = mod, (xb, gates, cst, h.detach(), B, T, H, I)
         ctx.mark_non_differentiable(cn)
         return h, hn, cn
 
@@ -390,7 +392,7 @@ class _HeadFn(torch.autograd.Function):
             acts.append(ops.linear_small_fwd(acts[-1], W, b, 1, mask, scale))
         z = ops.linear_small_fwd(acts[-1], wb[8].detach(), wb[9].detach(), 0)
         prob = ops.sigmoid_fwd(z)
-        ctx.acts, ctx.prob, ctx.scale, ctx.wb = acts, prob, scale, wb
+        ctx.acts, ctx.prob, ctx.scale, ctx.wb = acts, prob.detach(), scale, wb     # detached: no output -> grad_fn -> ctx cycle
         return prob
 
     @staticmethod

@@ -168,7 +168,8 @@ def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor):
 
 def stem_conv1_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
     F_, _, H, W = x.shape
-    _lib.call("xcp_stem_conv1_wgrad", _p(x), _p(dy), _p(dw), F_, H, W, x.device.index, _s())
+    ws = torch.empty((_lib.call("xcp_stem_conv1_wgrad_ws_bytes", F_, H, W),), device=x.device, dtype=torch.uint8)
+    _lib.call("xcp_stem_conv1_wgrad", _p(x), _p(dy), _p(dw), _p(ws), F_, H, W, x.device.index, _s())
 
 
 def dw3x3_fwd(x: torch.Tensor, w9: torch.Tensor, scale=None, shift=None, relu: bool = False, out=None):

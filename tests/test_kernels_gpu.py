@@ -118,7 +118,11 @@ def test_stem_conv1(F_, H):
     dw = torch.zeros_like(w)
     ops.stem_conv1_wgrad(x, dy, dw)
     dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, dy.float().permute(0, 3, 1, 2), stride=2)
-    assert rel_err(dw, dw_ref) < 1e-4
+    # the 27-tap patches are staged in bf16 for the tensor-core reduction (2^-9 per element, random sign): same
+    # operand precision as torch's bf16-autocast conv backward; far inside the 1e-2 per-tensor gradient tolerance
+    assert rel_err(dw, dw_ref) < 5e-3
+    dw_bf = torch.nn.grad.conv2d_weight(x.bfloat16().float(), w.shape, dy.float().permute(0, 3, 1, 2), stride=2)
+    assert rel_err(dw, dw_bf) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------------ depthwise
