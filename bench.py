@@ -154,7 +154,7 @@ def run_ours(args):
     import torch.distributed as dist
     import torch.nn.functional as F
 
-    from multimodal_deepfake_detection_b200 import XceptionLSTMV, _lib, ops
+    from multimodal_deepfake_detection_b200 import FusedAdam, XceptionLSTMV, _lib, ops
     from multimodal_deepfake_detection_b200.ddp import GradBucketer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -180,7 +180,7 @@ def run_ours(args):
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
     bucketer = GradBucketer(model, backbone=model.feature_extractor) if world > 1 else None
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, capturable=True)      # train_visual.py:533
+    opt = FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4)      # Adam(lr=1e-5, weight_decay=1e-4), train_visual.py:533
     g = torch.Generator().manual_seed(1000 * rank)
     host_clips = [torch.rand(B, T_FRAMES, 3, HW, HW, generator=g).pin_memory() for _ in range(2)]
     host_y = [torch.randint(0, 2, (B, 1), generator=g).float().pin_memory() for _ in range(2)]
@@ -278,9 +278,18 @@ def run_ours(args):
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     h2d = host_clips[0].numel() * 4 + host_y[0].numel() * 4
 
-    if rank != 0:
+    def finish():
+        # Leave without tearing the NCCL communicator down: destroy_process_group() can block on communicators that
+        # were captured into the CUDA graph (seen at N=2: the JSON line printed, then the ranks never exited).
+        sys.stdout.flush(); sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     peaks = _peaks()
     # ---- roofline of the dominant kernel family: the middle-flow pointwise GEMM (M = F*361, K = N = 728) forward
@@ -304,7 +313,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "XceptionLSTMV(128) train step, backbone unfrozen, train-mode BN, BCE, Adam(1e-5, wd 1e-4)",
+        "config": {"workload": "XceptionLSTMV(128) train step, backbone unfrozen, train-mode BN, BCE, fused Adam(1e-5, wd 1e-4)",
                    "clips_per_gpu": B, "global_batch": B * world, "frames_per_clip": T_FRAMES, "frame": "3x299x299",
                    "parallelism": "dp%d" % world, "launch": mode, "l2": "per-step working set (~%.0f GB of activations) >> 126 MB L2" % (B * 16 * 0.117)},
         "clocks": clocks,
@@ -316,8 +325,7 @@ def run_ours(args):
         "loss": last.get("loss"),
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

@@ -60,15 +60,19 @@ int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale, const floa
 /* backward: dz = mask*conv_transpose(dD) [+ add_full] [+ add_half at even pixels]; dw[C][9] (nn.Conv2d layout) and
  * bnsum[2][C] = (sum dz, sum dz*x) are accumulated with RED (bnsum only when scale/shift given; caller zero-fills) */
 int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift, int relu, void* dz,
-                  const void* add_full, const void* add_half, float* dw, float* bnsum, int F, int H, int W, int C, int device,
-                  void* stream);
+                  const void* add_full, const void* add_half, float* dw, float* bnsum, int F, int H, int W, int C, int c_real,
+                  int device, void* stream);
 
+/* Channel padding: activations whose channel count is not a multiple of 64 (728 in the middle flow) are stored with a
+ * physical pitch C rounded up to 64 (768) so every pixel row is whole 128-byte lines for TMA; the pad channels are kept
+ * exactly zero (zero-padded packed weights, zero BN scale/shift).  Functions that touch per-channel PARAMETER arrays
+ * take c_real = the logical channel count (the length of gamma / beta / running stats / dw rows); C is the pitch. */
 /* ---- BatchNorm2d (Xception.py:56,67,73,78,119,123,143,147): statistics finalisation (train), affine folding (eval) */
-int xcp_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
+int xcp_bn_finalize(const float* partials, int nparts, int C, int c_real, double count, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                     float* mean_out, float* rstd_out, int device, void* stream);
 int xcp_bn_eval_affine(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, float* scale,
-                       float* shift, float* mean_out, float* rstd_out, int C, int device, void* stream);
+                       float* shift, float* mean_out, float* rstd_out, int C, int c_real, int device, void* stream);
 /* out = relu?(scale*y + shift) */
 int xcp_bn_act(const void* y, const float* scale, const float* shift, int relu, void* out, long long n, int C, int device,
                void* stream);
@@ -88,14 +92,15 @@ int xcp_bnbwd_num_parts(void);
 /* two-pass BatchNorm backward with the ReLU / MaxPool / GAP gradient routing folded into its loads; see elementwise.cu */
 int xcp_bn_bwd(int mode, const void* y, const void* G, const void* idx, const float* dfeat, const float* scale,
                const float* shift, const float* gamma, const float* mean, const float* rstd, int training, const float* presums,
-               float* workspace, float* coef, float* dgamma, float* dbeta, void* dy, int F, int H, int W, int C, int grid_w,
-               int grid_h, int device, void* stream);
+               float* workspace, float* coef, float* dgamma, float* dbeta, void* dy, int F, int H, int W, int C, int c_real,
+               int grid_w, int grid_h, int device, void* stream);
 
 /* ---- layout / packing */
-int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int HW, int device, void* stream);
-int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int HW, int device, void* stream);
-int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int device, void* stream);
-int xcp_pack_dw(const float* w, float* w9, int C, int device, void* stream);
+int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int Cp, int HW, int device, void* stream);   /* Cp = NHWC pitch */
+int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int Cp, int HW, int device, void* stream);
+/* fp32 [R,Cc] -> bf16 [Rp,Cp] (zero padded) and optionally its transpose bf16 [Cp,Rp] */
+int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int Rp, int Cp, int device, void* stream);
+int xcp_pack_dw(const float* w, float* w9, int C, int Cp, int device, void* stream);                      /* w9 = [9][Cp] */
 int xcp_unpack_dw_grad(const float* g9, float* gw, int C, int accumulate, int device, void* stream);
 int xcp_pack_conv3x3(const float* w, void* wk, void* wk_t, int O, int I, int device, void* stream);
 int xcp_unpack_conv3x3_grad(const float* gk, float* gw, int O, int I, int device, void* stream);
@@ -132,6 +137,14 @@ int xcp_grad_sumsq(const float* g, long long n, float* out, int zero_first, int 
 int xcp_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int decoupled, int step, const float* sumsq, float max_norm, float grad_scale, int device,
                   void* stream);
+/* multi-tensor form: `table` = n_tensors x {float* p; const float* g; float* m; float* v; long long n; int* step} in device
+ * memory (each tensor's own device-side step counter is incremented by the call, so the launch is CUDA-graph capturable and
+ * keeps torch.optim.Adam's per-parameter step semantics), `chunks` = n_chunks x {int tensor, int chunk} (8192-element chunks);
+ * max_norm > 0 clips by the global norm first (sumsq_ws: device float scratch).  Replaces the per-tensor loop of
+ * torch.optim.Adam.step / clip_grad_norm_ (train_visual.py:533,574-577; train_au_face.py:616-619,678-693). */
+int xcp_adam_multi(const void* table, int n_tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int decoupled, float* sumsq_ws, float max_norm, float grad_scale, int device,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,5 +7,6 @@ from .modules import (ArcFaceHead, AUFaceCrossDetector, Block, CBFocalLoss, Fuse
                       LabelSmoothingBCEWithLogitsLoss,
                       SeparableConv2d, Xception, XceptionLSTMA, XceptionLSTMV, model_urls, xception)
 from ._lib import XcpError, LIB_PATH  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
 __version__ = "0.1.0"

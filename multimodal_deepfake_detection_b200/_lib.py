@@ -29,20 +29,20 @@ SIGNATURES = {
     "xcp_stem_conv1_wgrad_ws_bytes": "iii",
     "xcp_stem_conv1_wgrad": "ppppiiiip",
     "xcp_dw3x3_fwd": "ppppipiiiiip",
-    "xcp_dw3x3_bwd": "pppppipppppiiiiip",
-    "xcp_bn_finalize": "piidppppffppppip",
-    "xcp_bn_eval_affine": "ppppfppppiip",
+    "xcp_dw3x3_bwd": "pppppipppppiiiiiip",
+    "xcp_bn_finalize": "piiidppppffppppip",
+    "xcp_bn_eval_affine": "ppppfppppiiip",
     "xcp_bn_act": "pppipliip",
     "xcp_gather_s2": "pppipiiiiip",
     "xcp_pool_add_fwd": "ppppppppiiiiip",
     "xcp_bn_add_fwd": "pppppppliip",
     "xcp_bn_relu_gap": "ppppiiiip",
     "xcp_bnbwd_num_parts": "",
-    "xcp_bn_bwd": "ipppppppppippppppiiiiiiip",
-    "xcp_nchw_to_nhwc": "ppiiiip",
-    "xcp_nhwc_to_nchw": "ppiiiip",
-    "xcp_pack_weight": "pppiiip",
-    "xcp_pack_dw": "ppiip",
+    "xcp_bn_bwd": "ipppppppppippppppiiiiiiiip",
+    "xcp_nchw_to_nhwc": "ppiiiiip",
+    "xcp_nhwc_to_nchw": "ppiiiiip",
+    "xcp_pack_weight": "pppiiiiip",
+    "xcp_pack_dw": "ppiiip",
     "xcp_unpack_dw_grad": "ppiiip",
     "xcp_pack_conv3x3": "pppiiip",
     "xcp_unpack_conv3x3_grad": "ppiiip",
@@ -60,6 +60,7 @@ SIGNATURES = {
     "xcp_fusion_pool_bwd": "pppiiiip",
     "xcp_grad_sumsq": "plpiip",
     "xcp_adam_step": "pppplfffffiipffip",
+    "xcp_adam_multi": "pipifffffipffip",
 }
 _RET_LONGLONG = {"xcp_stem_conv1_wgrad_ws_bytes"}
 _NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp_stem_conv1_parts",
@@ -68,7 +69,7 @@ _NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; 0 = host-only query)
 _LAUNCHES = {"xcp_version": 0, "xcp_check_device": 0, "xcp_bnbwd_num_parts": 0, "xcp_gemm_stats_parts": 0,
              "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
-             "xcp_arcface_loss": 2}
+             "xcp_arcface_loss": 2, "xcp_adam_multi": 2}
 _count = 0
 
 _lock = threading.Lock()

@@ -141,6 +141,18 @@ XCP_DEVINL void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x (4 x 256 bit = 32 fp32 columns): the mma-style fragment.  Thread t receives, for column block j = 0..3,
+// r[4j+0..1] = TMEM lane (base + t/4),     columns 8j + 2(t%4) + {0,1}
+// r[4j+2..3] = TMEM lane (base + t/4 + 8), columns 8j + 2(t%4) + {0,1}
+XCP_DEVINL void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 // ------------------------------------------------------------------ CTA-pair (cta_group::2) variants
 // Two CTAs of a 2-CTA cluster (same TPC) execute one M=256 MMA: each provides its own 128 rows of A and half
 // of B's N rows, and receives its 128 rows of D in its own TMEM.  Only the leader (cluster rank 0) issues MMAs; TMA
@@ -230,6 +242,14 @@ XCP_DEVINL uint4 ldg_nc_v4(const void* p) {
                  : "l"(p));
     return r;
 }
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): two fp32 lanes in one 64-bit register
+typedef unsigned long long u64;
+
+XCP_DEVINL u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+XCP_DEVINL void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+XCP_DEVINL u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+XCP_DEVINL u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+XCP_DEVINL u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 XCP_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

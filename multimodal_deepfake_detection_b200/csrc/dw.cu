@@ -16,13 +16,6 @@
 
 namespace xcp {
 
-typedef unsigned long long u64;
-
-XCP_DEVINL u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-XCP_DEVINL void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-XCP_DEVINL u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-XCP_DEVINL u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-XCP_DEVINL u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 XCP_DEVINL u64 bf2_to_f2(uint32_t v) { return pk2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 XCP_DEVINL uint32_t f2_to_bf2(u64 v) { float lo, hi; upk2(v, lo, hi); return pack_bf16(lo, hi); }
 XCP_DEVINL uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
@@ -220,6 +213,7 @@ struct DwBwdParams {
     const __nv_bfloat16* add_half;   // optional: [F,ceil(H/2),ceil(W/2),C] gradient of the stride-2 skip gather
     float* dw;                    // [C][9]  (the nn.Conv2d weight-gradient layout), accumulated with RED
     float* bnsum;                 // [2][C]  (sum dz, sum dz*y), accumulated with RED (caller zero-fills); AFFINE only
+    int c_real;                   // logical channel count (<= C, the physical pitch): dw has c_real rows
 };
 
 template <bool AFFINE, bool RELU>
@@ -391,7 +385,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
         const int k = i / 64, c = ct * 64 + (i % 64);
         if (c >= g.C) continue;
         const float v = s_red[k][i % 64];
-        if (k < 9) atomicAdd(&p.dw[(long long)c * 9 + k], v);
+        if (k < 9) { if (c < p.c_real) atomicAdd(&p.dw[(long long)c * 9 + k], v); }
         else if (AFFINE) atomicAdd(&p.bnsum[(long long)(k - 9) * g.C + c], v);
     }
 }
@@ -438,8 +432,8 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
 // scale/shift are given (the caller zero-fills bnsum).
 extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift,
                              int relu, void* dz, const void* add_full, const void* add_half, float* dw, float* bnsum,
-                             int F, int H, int W, int C, int device, void* stream) {
-    XCP_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "xcp_dw3x3_bwd: bad shape");
+                             int F, int H, int W, int C, int c_real, int device, void* stream) {
+    XCP_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && c_real > 0 && c_real <= C, "xcp_dw3x3_bwd: bad shape");
     XCP_REQUIRE((scale == nullptr) == (shift == nullptr), "xcp_dw3x3_bwd: scale/shift");
     XCP_REQUIRE(dw != nullptr && (scale == nullptr || bnsum != nullptr), "xcp_dw3x3_bwd: dw / bnsum missing");
     XCP_CUDA(cudaSetDevice(device));
@@ -448,7 +442,7 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     if (int e = make_dw_tmap(&tmG, dD, g, 1)) return e;
     if (int e = make_dw_tmap(&tmX, xin, g, 0)) return e;
     DwBwdParams p{g, w9, scale, shift, relu, (__nv_bfloat16*)dz, (const __nv_bfloat16*)add_full,
-                  (const __nv_bfloat16*)add_half, dw, bnsum};
+                  (const __nv_bfloat16*)add_half, dw, bnsum, c_real};
     const int smem = 2 * ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH) * 128 + 384;
     const int threads = 32 * g.pairs * g.RS;
     const long long sp_tiles = (long long)F * g.n_h * g.n_w;

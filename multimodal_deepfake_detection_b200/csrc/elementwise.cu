@@ -77,7 +77,7 @@ stem_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 // updated with momentum and the unbiased variance.  block = 32 channels x 32 part-lanes, so the
 // reduction over (up to ~1400) partial rows is ~nparts/32 independent coalesced loads per thread.
 __global__ void __launch_bounds__(1024)
-bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, const float* __restrict__ gamma,
+bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, int C_real, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
                    float* scale, float* shift, float* mean_out, float* rstd_out) {
     __shared__ double s1[32][33], s2[32][33];
@@ -106,7 +106,10 @@ bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
     const int cc = blockIdx.x * 32 + ry;
-    if (cx == 0 && cc < C) {
+    if (cx == 0 && cc >= C_real && cc < C) {       // zero-padded channels (physical width > logical): stay exactly 0
+        scale[cc] = 0.f; shift[cc] = 0.f; mean_out[cc] = 0.f; rstd_out[cc] = 0.f;
+    }
+    if (cx == 0 && cc < C_real) {
         const double mean = a / count;
         double var = b / count - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -125,9 +128,15 @@ bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double
 }
 
 __global__ void bn_eval_affine_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
-                                      float* scale, float* shift, float* mean_out, float* rstd_out, int C) {
+                                      float* scale, float* shift, float* mean_out, float* rstd_out, int C, int C_real) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
+    if (c >= C_real) {
+        scale[c] = 0.f; shift[c] = 0.f;
+        if (mean_out) mean_out[c] = 0.f;
+        if (rstd_out) rstd_out[c] = 0.f;
+        return;
+    }
     const float rstd = rsqrtf(rv[c] + eps);
     const float sc = gamma[c] * rstd;
     scale[c] = sc;
@@ -404,7 +413,7 @@ bnbwd_reduce_kernel(const uint4* __restrict__ y, const BnBwdSrc s, float* __rest
 // nparts == 1: `partials` is already the [2][C] sums (e.g. produced by the depthwise backward kernel).
 // block = 32 channels x 8 part-lanes.
 __global__ void __launch_bounds__(256)
-bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, int C_real, double count,
                       const float* __restrict__ gamma, const float* __restrict__ mean,
                       const float* __restrict__ rstd, int training, float* coefA, float* coefB, float* coefC,
                       float* dgamma, float* dbeta) {
@@ -430,6 +439,7 @@ bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, dou
     sh1[ry][cx] = s1; sh2[ry][cx] = s2;
     __syncthreads();
     if (ry != 0 || c >= C) return;
+    if (c >= C_real) { coefA[c] = 0.f; coefB[c] = 0.f; coefC[c] = 0.f; return; }     // zero-padded channels
 #pragma unroll
     for (int r = 1; r < 8; ++r) { s1 += sh1[r][cx]; s2 += sh2[r][cx]; }
     const double m = mean[c], r = rstd[c], g = gamma[c];
@@ -476,7 +486,8 @@ bnbwd_apply_kernel(const uint4* __restrict__ y, const BnBwdSrc s, const float* _
 
 // ======================================================================================== layout converters
 // NCHW fp32 -> NHWC bf16 via a 32x32 smem transpose over (C, HW) per frame.
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int HW) {
+// Cp >= C is the physical (padded) channel pitch of the NHWC tensor; pad channels are written as zeros / ignored.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int Cp, int HW) {
     __shared__ float t[32][33];
     const int f = blockIdx.z;
     const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -487,16 +498,16 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int pp = p0 + r, c = c0 + threadIdx.x;
-        if (pp < HW && c < C) out[((long long)f * HW + pp) * C + c] = __float2bfloat16(t[threadIdx.x][r]);
+        if (pp < HW && c < Cp) out[((long long)f * HW + pp) * Cp + c] = __float2bfloat16(t[threadIdx.x][r]);
     }
 }
-__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int C, int HW) {
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int C, int Cp, int HW) {
     __shared__ float t[32][33];
     const int f = blockIdx.z;
     const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int pp = p0 + r, c = c0 + threadIdx.x;
-        t[r][threadIdx.x] = (c < C && pp < HW) ? __bfloat162float(x[((long long)f * HW + pp) * C + c]) : 0.f;
+        t[r][threadIdx.x] = (c < C && pp < HW) ? __bfloat162float(x[((long long)f * HW + pp) * Cp + c]) : 0.f;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -505,30 +516,30 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
     }
 }
 
-// fp32 [R, Cc] -> bf16 [R, Cc] and (optionally) its transpose bf16 [Cc, R]
+// fp32 [R, Cc] -> bf16 [Rp, Cp] (zero padded) and (optionally) its transpose bf16 [Cp, Rp]
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_t,
-                                   int R, int Cc) {
+                                   int R, int Cc, int Rp, int Cp) {
     __shared__ float t[32][33];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int rr = r0 + r, cc = c0 + threadIdx.x;
         const float v = (rr < R && cc < Cc) ? w[(long long)rr * Cc + cc] : 0.f;
         t[r][threadIdx.x] = v;
-        if (rr < R && cc < Cc && out != nullptr) out[(long long)rr * Cc + cc] = __float2bfloat16(v);
+        if (rr < Rp && cc < Cp && out != nullptr) out[(long long)rr * Cp + cc] = __float2bfloat16(v);
     }
     __syncthreads();
     if (out_t != nullptr) {
         for (int r = threadIdx.y; r < 32; r += blockDim.y) {
             const int cc = c0 + r, rr = r0 + threadIdx.x;
-            if (rr < R && cc < Cc) out_t[(long long)cc * R + rr] = __float2bfloat16(t[threadIdx.x][r]);
+            if (rr < Rp && cc < Cp) out_t[(long long)cc * Rp + rr] = __float2bfloat16(t[threadIdx.x][r]);
         }
     }
 }
 
 // depthwise weights [C,1,3,3] fp32 -> tap-major [9][C] fp32 ; and the reverse accumulation for gradients
-__global__ void pack_dw_kernel(const float* __restrict__ w, float* __restrict__ w9, int C) {
+__global__ void pack_dw_kernel(const float* __restrict__ w, float* __restrict__ w9, int C, int Cp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 9 * C) { const int c = i / 9, k = i % 9; w9[(long long)k * C + c] = w[i]; }
+    if (i < 9 * Cp) { const int c = i / 9, k = i % 9; w9[(long long)k * Cp + c] = c < C ? w[i] : 0.f; }
 }
 __global__ void unpack_dw_grad_kernel(const float* __restrict__ g9, float* __restrict__ gw, int C, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -641,20 +652,22 @@ extern "C" int xcp_stem_conv1_fwd(const float* x, const float* w, void* y, float
     return check_cuda(cudaGetLastError(), "stem_conv1_fwd launch");
 }
 
-extern "C" int xcp_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta,
+extern "C" int xcp_bn_finalize(const float* partials, int nparts, int C, int c_real, double count, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                                float* mean_out, float* rstd_out, int device, void* stream) {
-    XCP_REQUIRE(nparts > 0 && C > 0 && count > 0, "xcp_bn_finalize: bad args");
+    XCP_REQUIRE(nparts > 0 && C > 0 && count > 0 && c_real > 0 && c_real <= C, "xcp_bn_finalize: bad args");
     XCP_CUDA(cudaSetDevice(device));
-    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST>>>(partials, nparts, C, count, gamma, beta, running_mean, running_var,
+    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST>>>(partials, nparts, C, c_real, count, gamma, beta, running_mean, running_var,
                                                       momentum, eps, scale, shift, mean_out, rstd_out);
     return check_cuda(cudaGetLastError(), "bn_finalize launch");
 }
 
 extern "C" int xcp_bn_eval_affine(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
-                                  float* scale, float* shift, float* mean_out, float* rstd_out, int C, int device, void* stream) {
+                                  float* scale, float* shift, float* mean_out, float* rstd_out, int C, int c_real, int device,
+                                  void* stream) {
+    XCP_REQUIRE(c_real > 0 && c_real <= C, "xcp_bn_eval_affine: bad args");
     XCP_CUDA(cudaSetDevice(device));
-    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, ST>>>(gamma, beta, rm, rv, eps, scale, shift, mean_out, rstd_out, C);
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, ST>>>(gamma, beta, rm, rv, eps, scale, shift, mean_out, rstd_out, C, c_real);
     return check_cuda(cudaGetLastError(), "bn_eval_affine launch");
 }
 
@@ -712,8 +725,8 @@ extern "C" int xcp_bnbwd_num_parts(void) { return 2 * 160; }
 extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* idx, const float* dfeat, const float* scale,
                           const float* shift, const float* gamma, const float* mean, const float* rstd, int training,
                           const float* presums, float* workspace, float* coef, float* dgamma, float* dbeta, void* dy, int F,
-                          int H, int W, int C, int grid_w, int grid_h, int device, void* stream) {
-    XCP_REQUIRE(C % 8 == 0 && mode >= 0 && mode <= 3, "xcp_bn_bwd: bad args");
+                          int H, int W, int C, int c_real, int grid_w, int grid_h, int device, void* stream) {
+    XCP_REQUIRE(C % 8 == 0 && mode >= 0 && mode <= 3 && c_real > 0 && c_real <= C, "xcp_bn_bwd: bad args");
     XCP_REQUIRE(coef != nullptr && (presums != nullptr || workspace != nullptr), "xcp_bn_bwd: workspace");
     XCP_CUDA(cudaSetDevice(device));
     BnBwdSrc s{mode, (const __nv_bfloat16*)G, (const uint8_t*)idx, dfeat, scale, shift, F, H, W, C};
@@ -728,7 +741,7 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
         XCP_CUDA(cudaGetLastError());
         sums = workspace;
     }
-    bnbwd_finalize_kernel<<<(C + 31) / 32, 256, 0, ST>>>(sums, nparts, C, count, gamma, mean, rstd, training, coef, coef + C,
+    bnbwd_finalize_kernel<<<(C + 31) / 32, 256, 0, ST>>>(sums, nparts, C, c_real, count, gamma, mean, rstd, training, coef, coef + C,
                                                            coef + 2 * C, dgamma, dbeta);
     XCP_CUDA(cudaGetLastError());
     if (dy != nullptr) {
@@ -738,30 +751,34 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
     return check_cuda(cudaGetLastError(), "bn_bwd launch");
 }
 
-extern "C" int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int HW, int device, void* stream) {
+extern "C" int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int Cp, int HW, int device, void* stream) {
+    XCP_REQUIRE(Cp >= C, "xcp_nchw_to_nhwc: channel pitch < channels");
     XCP_CUDA(cudaSetDevice(device));
-    dim3 grid((HW + 31) / 32, (C + 31) / 32, F), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, ST>>>(x, (__nv_bfloat16*)out, C, HW);
+    dim3 grid((HW + 31) / 32, (Cp + 31) / 32, F), block(32, 8);
+    nchw_to_nhwc_kernel<<<grid, block, 0, ST>>>(x, (__nv_bfloat16*)out, C, Cp, HW);
     return check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
 }
 
-extern "C" int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int HW, int device, void* stream) {
+extern "C" int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int Cp, int HW, int device, void* stream) {
+    XCP_REQUIRE(Cp >= C, "xcp_nhwc_to_nchw: channel pitch < channels");
     XCP_CUDA(cudaSetDevice(device));
     dim3 grid((HW + 31) / 32, (C + 31) / 32, F), block(32, 8);
-    nhwc_to_nchw_kernel<<<grid, block, 0, ST>>>((const __nv_bfloat16*)x, out, C, HW);
+    nhwc_to_nchw_kernel<<<grid, block, 0, ST>>>((const __nv_bfloat16*)x, out, C, Cp, HW);
     return check_cuda(cudaGetLastError(), "nhwc_to_nchw launch");
 }
 
-extern "C" int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int device, void* stream) {
+extern "C" int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int Rp, int Cp, int device, void* stream) {
+    XCP_REQUIRE(Rp >= R && Cp >= Cc, "xcp_pack_weight: padded dims smaller than the matrix");
     XCP_CUDA(cudaSetDevice(device));
-    dim3 grid((Cc + 31) / 32, (R + 31) / 32), block(32, 8);
-    pack_weight_kernel<<<grid, block, 0, ST>>>(w, (__nv_bfloat16*)out, (__nv_bfloat16*)out_t, R, Cc);
+    dim3 grid((Cp + 31) / 32, (Rp + 31) / 32), block(32, 8);
+    pack_weight_kernel<<<grid, block, 0, ST>>>(w, (__nv_bfloat16*)out, (__nv_bfloat16*)out_t, R, Cc, Rp, Cp);
     return check_cuda(cudaGetLastError(), "pack_weight launch");
 }
 
-extern "C" int xcp_pack_dw(const float* w, float* w9, int C, int device, void* stream) {
+extern "C" int xcp_pack_dw(const float* w, float* w9, int C, int Cp, int device, void* stream) {
+    XCP_REQUIRE(Cp >= C, "xcp_pack_dw: channel pitch < channels");
     XCP_CUDA(cudaSetDevice(device));
-    pack_dw_kernel<<<(9 * C + 255) / 256, 256, 0, ST>>>(w, w9, C);
+    pack_dw_kernel<<<(9 * Cp + 255) / 256, 256, 0, ST>>>(w, w9, C, Cp);
     return check_cuda(cudaGetLastError(), "pack_dw launch");
 }
 

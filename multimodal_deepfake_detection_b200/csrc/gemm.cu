@@ -50,7 +50,7 @@ __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_N * BLOCK_K * 2
 template <int BLOCK_N, int BLOCK_K, bool STATS, bool CTA2>
 __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
     return 1024 /*align slack*/ + stages * (BLOCK_M * BLOCK_K * 2 + b_stage_bytes<BLOCK_N, BLOCK_K>() / (CTA2 ? 2 : 1)) +
-           (STATS ? (4 * 32 * 33 * 4 + 4 * 2 * BLOCK_N * 4) : 0) + 256 /*barriers*/;
+           (STATS ? (4 * 32 * 36 * 4 + 4 * 2 * BLOCK_N * 4) : 0) + 256 /*barriers*/;
 }
 
 // MN_MAJOR=false: A is [M,K] row-major, B is [N,K] row-major (both K-major):      D = A * B^T
@@ -76,8 +76,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * A_BYTES;
     uint8_t* after = sB + STAGES * B_BYTES;
-    float* s_tr = reinterpret_cast<float*>(after);                       // [4][32][33]
-    float* s_part = s_tr + (STATS ? 4 * 32 * 33 : 0);                    // [4][2][BLOCK_N]
+    float* s_tr = reinterpret_cast<float*>(after);                       // [4][32][36]  (144-byte rows: conflict-free v4 stores)
+    float* s_part = s_tr + (STATS ? 4 * 32 * 36 : 0);                    // [4][2][BLOCK_N]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + (STATS ? 4 * 2 * BLOCK_N : 0));
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
@@ -200,7 +200,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int q = warp & 3;
         const int row_in_tile = q * 32 + lane;
         const int et = threadIdx.x - 64;   // 0..127
-        float* my_tr = s_tr + q * (32 * 33);
+        float* my_tr = s_tr + q * (32 * 36);
         float racc[2][(BLOCK_N + 127) / 128];
 #pragma unroll
         for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) { racc[0][i] = 0.f; racc[1][i] = 0.f; }
@@ -249,20 +249,79 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             }
                         }
                     }
-                    if (STATS) {
-                        // per-column sum / sum-of-squares over this warp's 32 rows via a padded smem transpose
+                    if (STATS && p.conv_taps == 0) {
+                        // Per-column sum / sum-of-squares over this warp's 32 rows.  The accumulator chunk is read a second
+                        // time from TMEM in the mma-fragment shape (16x256b: a thread holds 4 rows x 4 column pairs), reduced
+                        // over its 4 rows with packed f32x2 math and then across the 8 lanes that share its columns by
+                        // recursive halving (14 shuffles).  The shared-memory crossbar carries the UMMA operand reads
+                        // (~96 of 128 B/clk), so the epilogue must stay off it: the first version transposed through smem
+                        // (8 KB per chunk) and cost 30 % of the kernel.  Rows past M are exact zeros (TMA zero fill).
+                        uint32_t fa[16], fb[16];
+                        const uint32_t tcol = tmem_base + as * BLOCK_N + c * 32;
+                        tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32) << 16), fa);
+                        tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32 + 16) << 16), fb);
+                        tmem_ld_wait();
+                        u64 s1[4], s2[4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) my_tr[lane * 33 + j] = row_ok ? __uint_as_float(r[j]) : 0.f;
-                        __syncwarp();
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                        for (int l = 0; l < 32; ++l) {
-                            const float v = my_tr[l * 33 + lane];
-                            s1 += v;
-                            s2 = fmaf(v, v, s2);
+                        for (int j = 0; j < 4; ++j) {
+                            const u64 v0 = pk2(__uint_as_float(fa[4 * j + 0]), __uint_as_float(fa[4 * j + 1]));
+                            const u64 v1 = pk2(__uint_as_float(fa[4 * j + 2]), __uint_as_float(fa[4 * j + 3]));
+                            const u64 v2 = pk2(__uint_as_float(fb[4 * j + 0]), __uint_as_float(fb[4 * j + 1]));
+                            const u64 v3 = pk2(__uint_as_float(fb[4 * j + 2]), __uint_as_float(fb[4 * j + 3]));
+                            s1[j] = add2(add2(v0, v1), add2(v2, v3));
+                            s2[j] = fma2(v0, v0, fma2(v1, v1, fma2(v2, v2, mul2(v3, v3))));
                         }
-                        s_part[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = s1;
-                        s_part[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = s2;
+                        // lanes t, t^4, t^8, t^16 hold partial sums of the same 8 columns: halve the live set each round
+                        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                        u64 k1[2], k2[2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {                         // round 1 (xor 16): keep column blocks {2*b4, 2*b4+1}
+                            const u64 snd1 = b4 ? s1[j] : s1[j + 2], snd2 = b4 ? s2[j] : s2[j + 2];
+                            const u64 kp1 = b4 ? s1[j + 2] : s1[j], kp2 = b4 ? s2[j + 2] : s2[j];
+                            k1[j] = add2(kp1, __shfl_xor_sync(0xffffffffu, snd1, 16));
+                            k2[j] = add2(kp2, __shfl_xor_sync(0xffffffffu, snd2, 16));
+                        }
+                        const u64 snd1 = b3 ? k1[0] : k1[1], snd2 = b3 ? k2[0] : k2[1];      // round 2 (xor 8): keep block 2*b4 + b3
+                        const u64 m1 = add2(b3 ? k1[1] : k1[0], __shfl_xor_sync(0xffffffffu, snd1, 8));
+                        const u64 m2 = add2(b3 ? k2[1] : k2[0], __shfl_xor_sync(0xffffffffu, snd2, 8));
+                        float m1l, m1h, m2l, m2h;
+                        upk2(m1, m1l, m1h); upk2(m2, m2l, m2h);
+                        const float t1 = (b2 ? m1h : m1l) + __shfl_xor_sync(0xffffffffu, b2 ? m1l : m1h, 4);   // round 3 (xor 4)
+                        const float t2 = (b2 ? m2h : m2l) + __shfl_xor_sync(0xffffffffu, b2 ? m2l : m2h, 4);
+                        const int col = 8 * ((b4 ? 2 : 0) + (b3 ? 1 : 0)) + 2 * (lane & 3) + (b2 ? 1 : 0);
+                        s_part[(q * 2 + 0) * BLOCK_N + c * 32 + col] = t1;
+                        s_part[(q * 2 + 1) * BLOCK_N + c * 32 + col] = t2;
+                    } else if (STATS) {
+                        // stem implicit GEMM (rows outside the valid window must be masked): padded smem transpose -- each
+                        // lane stores its row as 8 x 16 B, then lane (h, cp) = (lane/16, lane%16) sums the column pair
+                        // (2cp, 2cp+1) over rows 16h..16h+15; one xor-16 shuffle joins the two halves.
+                        if (!row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = 0u;
+                        }
+                        const uint32_t tr_w = smem_u32(my_tr) + (uint32_t)lane * 144u;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tr_w + g * 16), "r"(r[g * 4 + 0]),
+                                         "r"(r[g * 4 + 1]), "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3]) : "memory");
+                        __syncwarp();
+                        const uint32_t tr_r = smem_u32(my_tr) + (uint32_t)(lane >> 4) * (16u * 144u) + (uint32_t)(lane & 15) * 8u;
+                        u64 s1 = 0ull, s2 = 0ull;
+#pragma unroll
+                        for (int l = 0; l < 16; ++l) {
+                            u64 v;
+                            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(tr_r + l * 144));
+                            s1 = add2(s1, v);
+                            s2 = fma2(v, v, s2);
+                        }
+                        float a0, a1, b0, b1;
+                        upk2(s1, a0, a1); upk2(s2, b0, b1);
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+                        b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+                        if (lane < 16) {
+                            *reinterpret_cast<float2*>(&s_part[(q * 2 + 0) * BLOCK_N + c * 32 + lane * 2]) = make_float2(a0, a1);
+                            *reinterpret_cast<float2*>(&s_part[(q * 2 + 1) * BLOCK_N + c * 32 + lane * 2]) = make_float2(b0, b1);
+                        }
                         __syncwarp();
                     }
                 } else if (EPI == EPI_F32) {

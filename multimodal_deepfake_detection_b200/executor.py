@@ -40,6 +40,15 @@ class BlockSpec:
 
 
 # ------------------------------------------------------------------------------------------------ packed weights
+# Bumped by optimizers that update parameters through raw pointers (optim.FusedAdam): Tensor._version does not move,
+# so every PackCache entry carries this epoch in its tag.
+PARAM_EPOCH = [0]
+
+
+def bump_param_epoch():
+    PARAM_EPOCH[0] += 1
+
+
 class PackCache:
     """bf16 / re-laid-out copies of the fp32 master parameters, rebuilt when a parameter changes.
     These are derived caches, never part of state_dict (SURVEY.md §5 checkpoint contract)."""
@@ -50,7 +59,7 @@ class PackCache:
 
     def _get(self, p: torch.Tensor, kind: str, fn):
         key = (id(p), kind)
-        tag = (p.data_ptr(), p._version, self.generation, p.device)
+        tag = (p.data_ptr(), p._version, self.generation, PARAM_EPOCH[0], p.device)
         hit = self._c.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -59,12 +68,12 @@ class PackCache:
         return val
 
     def pw(self, w: torch.Tensor):
-        """[N,K,1,1] fp32 -> (bf16 [N,K], bf16 [K,N])"""
-        return self._get(w, "pw", lambda t: ops.pack_weight(t.view(t.shape[0], t.shape[1]), True))
+        """[N,K,1,1] fp32 -> (bf16 [Np,Kp], bf16 [Kp,Np]), zero-padded to the physical channel pitches (ops.phys)"""
+        return self._get(w, "pw", lambda t: ops.pack_weight(t.view(t.shape[0], t.shape[1]), True, pad=True))
 
     def dw(self, w: torch.Tensor):
-        """[C,1,3,3] fp32 -> fp32 [9,C]"""
-        return self._get(w, "dw", ops.pack_dw)
+        """[C,1,3,3] fp32 -> fp32 [9,Cp] (zero pad channels)"""
+        return self._get(w, "dw", lambda t: ops.pack_dw(t, pad=True))
 
     def conv3x3(self, w: torch.Tensor):
         return self._get(w, "c3", lambda t: ops.pack_conv3x3(t, True))
@@ -115,7 +124,7 @@ class GradSink:
 # ------------------------------------------------------------------------------------------------ forward pieces
 def _bn_state(bn, parts, count):
     """BatchNorm2d forward bookkeeping: batch stats + running-stat update in train mode,
-    running stats in eval mode."""
+    running stats in eval mode.  The state vectors have the physical channel pitch (pad channels: scale = shift = 0)."""
     training = bn.training or (bn.running_mean is None)
     if training:
         rm = bn.running_mean if bn.track_running_stats else None
@@ -124,7 +133,7 @@ def _bn_state(bn, parts, count):
         st = ops.bn_finalize(parts, count, bn.weight.detach(), bn.bias.detach(), rm, rv, True, mom, bn.eps)
     else:
         st = ops.bn_finalize(None, count, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, False,
-                             0.0, bn.eps)
+                             0.0, bn.eps, C=ops.phys(bn.weight.shape[0]))
     return st
 
 
@@ -137,7 +146,7 @@ class SepTape:
 
 
 def sep_forward(cache: PackCache, spec: SepSpec, src: torch.Tensor, src_st, relu: bool, nbt: list) -> SepTape:
-    """src: bf16 NHWC [F,H,W,Cin]; src_st: pending BN state of the producer (or None if src is materialised)."""
+    """src: bf16 NHWC [F,H,W,phys(Cin)]; src_st: pending BN state of the producer (or None if src is materialised)."""
     F_, H, W, C = src.shape
     w9 = cache.dw(spec.sep.conv1.weight)
     wb, _ = cache.pw(spec.sep.pointwise.weight)
@@ -147,11 +156,11 @@ def sep_forward(cache: PackCache, spec: SepSpec, src: torch.Tensor, src_st, relu
     t.spec, t.src, t.src_st, t.src_relu, t.d = spec, src, src_st, relu, d
     if spec.bn is None:
         y, _ = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16)
-        t.y, t.st = y.view(F_, H, W, spec.cout), None
+        t.y, t.st = y.view(F_, H, W, y.shape[1]), None
         return t
     need = _bn_needs_stats(spec.bn)
     y, parts = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16)
-    t.y = y.view(F_, H, W, spec.cout)
+    t.y = y.view(F_, H, W, y.shape[1])
     t.st = _bn_state(spec.bn, parts, M)
     if need and spec.bn.track_running_stats:
         nbt.append(spec.bn.num_batches_tracked)
@@ -185,7 +194,7 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
         Fs, Hs, Ws, Cs = xs.shape
         need = _bn_needs_stats(spec.skipbn)
         ys, parts = ops.gemm_tn(xs.view(Fs * Hs * Ws, Cs), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16)
-        ys = ys.view(Fs, Hs, Ws, spec.cout)
+        ys = ys.view(Fs, Hs, Ws, ys.shape[1])
         st_s = _bn_state(spec.skipbn, parts, Fs * Hs * Ws)
         if need and spec.skipbn.track_running_stats:
             nbt.append(spec.skipbn.num_batches_tracked)
@@ -204,15 +213,17 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
 # ------------------------------------------------------------------------------------------------ backward pieces
 def _pw_backward(cache: PackCache, sink: GradSink, weight: torch.Tensor, dy: torch.Tensor, a: torch.Tensor,
                  need_dgrad: bool = True):
-    """dy [.., N], a [.., K] (the GEMM's A operand in forward).  Accumulates dW, returns dA (bf16) or None."""
+    """dy [.., Np], a [.., Kp] (the GEMM's A operand in forward; physical channel pitches).  Accumulates dW [N,K],
+    returns dA (bf16) or None."""
     N, K = weight.shape[0], weight.shape[1]
-    M = dy.numel() // N
-    ops.gemm_wgrad(dy.view(M, N), a.view(M, K), sink.view(weight).view(N, K))
+    Np, Kp = dy.shape[-1], a.shape[-1]
+    M = dy.numel() // Np
+    ops.gemm_wgrad(dy.view(M, Np), a.view(M, Kp), sink.view(weight).view(N, K))
     sink.done(weight)
     if not need_dgrad:
         return None
     _, wt = cache.pw(weight)
-    da, _ = ops.gemm_tn(dy.view(M, N), wt, ops.EPI_BF16)
+    da, _ = ops.gemm_tn(dy.view(M, Np), wt, ops.EPI_BF16)
     return da.view(*a.shape)
 
 
@@ -221,7 +232,7 @@ def _dw_backward(cache: PackCache, sink: GradSink, t: SepTape, dd: torch.Tensor,
     source (raw y of the producer if a BN was pending, else the materialised input)."""
     w = t.spec.sep.conv1.weight
     w9 = cache.dw(w)
-    C = w.shape[0]
+    C = t.src.shape[-1]                 # physical pitch
     aff = t.src_st is not None
     bnsum = sink.scratch(2 * C).view(2, C) if aff else None
     dz, bnsum = ops.dw3x3_bwd(dd, t.src, w9, t.src_st.scale if aff else None, t.src_st.shift if aff else None, t.src_relu,

@@ -55,21 +55,21 @@ class _SepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, w_dw, w_pw):
         cache = _cache_of(mod)
-        xin = ops.nchw_to_nhwc(x.float().contiguous())
+        xin = ops.nchw_to_nhwc(x.float().contiguous(), pad=True)
         spec = ex.SepSpec(mod, None, w_dw.shape[0], w_pw.shape[0], False)
         t = ex.sep_forward(cache, spec, xin, None, False, [])
         ctx.mod, ctx.tape = mod, t
-        return ops.nhwc_to_nchw(t.y)
+        return ops.nhwc_to_nchw(t.y, w_pw.shape[0])
 
     @staticmethod
     def backward(ctx, dout):
         mod, t = ctx.mod, ctx.tape
         cache = _cache_of(mod)
         sink = ex.GradSink([mod.conv1.weight, mod.pointwise.weight], dout.device)
-        dy = ops.nchw_to_nhwc(dout.float().contiguous())
+        dy = ops.nchw_to_nhwc(dout.float().contiguous(), pad=True)
         dd = ex._pw_backward(cache, sink, mod.pointwise.weight, dy, t.d)
         dz, _ = ex._dw_backward(cache, sink, t, dd)
-        dx = ops.nhwc_to_nchw(dz) if ctx.needs_input_grad[1] else None
+        dx = ops.nhwc_to_nchw(dz, mod.conv1.weight.shape[0]) if ctx.needs_input_grad[1] else None
         return None, dx, sink.view(mod.conv1.weight), sink.view(mod.pointwise.weight)
 
 
@@ -100,21 +100,21 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, *params):
         cache = _cache_of(mod)
-        inp = ops.nchw_to_nhwc(x.float().contiguous())
+        inp = ops.nchw_to_nhwc(x.float().contiguous(), pad=True)
         nbt: list = []
         bt = ex.block_forward(cache, mod._spec(), inp, nbt, save=True)
         ex._bump_nbt(nbt)
         ctx.mod, ctx.tape, ctx.nparams = mod, bt, len(params)
-        return ops.nhwc_to_nchw(bt.out)
+        return ops.nhwc_to_nchw(bt.out, mod._out)
 
     @staticmethod
     def backward(ctx, dout):
         mod, bt = ctx.mod, ctx.tape
         params = list(mod.parameters())
         sink = ex.GradSink(params, dout.device)
-        G = ops.nchw_to_nhwc(dout.float().contiguous())
+        G = ops.nchw_to_nhwc(dout.float().contiguous(), pad=True)
         gin = ex.block_backward(_cache_of(mod), sink, bt, G)
-        dx = ops.nhwc_to_nchw(gin) if ctx.needs_input_grad[1] else None
+        dx = ops.nhwc_to_nchw(gin, mod._in) if ctx.needs_input_grad[1] else None
         return (None, dx) + tuple(sink.view(p) for p in params)
 
 
@@ -222,7 +222,7 @@ class _XceptionFn(torch.autograd.Function):
     def backward(ctx, dfeat):
         net = ctx.net
         params = net._backbone_params()
-        sink = ex.GradSink(params, dfeat.device, scratch_floats=2 * sum(p.numel() for p in params if p.dim() == 1))
+        sink = ex.GradSink(params, dfeat.device, scratch_floats=2 * sum(ops.phys(p.numel()) + 4 for p in params if p.dim() == 1))
         hook = net.__dict__.get("_grad_ready_hook")
         if hook is not None:
             sink.on_ready = lambda lo, hi: hook(sink, lo, hi)

@@ -19,6 +19,13 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+def phys(C: int) -> int:
+    """Physical channel pitch of an NHWC activation with C logical channels: widths above 64 are rounded up to a
+    multiple of 64 (728 -> 768) so that every pixel row is whole 128-byte lines (TMA boxes, 16-byte vectors); the
+    pad channels are kept exactly zero (include/xcp.h, "Channel padding")."""
+    return C if C <= 64 else (C + 63) // 64 * 64
+
+
 class _GemmTimer:
     """Optional CUDA-event timing of every pointwise-GEMM launch (bench.py roofline): events are recorded on the
     launching stream right around the kernel, aggregated per problem shape."""
@@ -97,10 +104,12 @@ def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ld_dw: Optio
     """dw[P,Q] += dy[R,P]^T @ x[R,Q]  (dw fp32, accumulated in place)."""
     _chk(dy, BF16, "gemm_wgrad.dy"); _chk(x, BF16, "gemm_wgrad.x")
     assert dw.dtype == F32
-    R, P = dy.shape
-    Q = x.shape[1]
+    R = dy.shape[0]
     assert x.shape[0] == R
-    _lib.call("xcp_gemm_wgrad", _p(dy), P, _p(x), Q, _p(dw), ld_dw if ld_dw is not None else Q, R, P, Q, dy.device.index, _s())
+    P, Q = (dw.shape[0], dw.shape[1]) if dw.dim() == 2 else (dy.shape[1], x.shape[1])   # logical (the operands may be channel-padded)
+    assert P <= dy.shape[1] and Q <= x.shape[1]
+    _lib.call("xcp_gemm_wgrad", _p(dy), dy.shape[1], _p(x), x.shape[1], _p(dw), ld_dw if ld_dw is not None else Q, R, P, Q,
+              dy.device.index, _s())
 
 
 def gemm_ref(a, b, mn_major=False):
@@ -182,14 +191,14 @@ def dw3x3_fwd(x: torch.Tensor, w9: torch.Tensor, scale=None, shift=None, relu: b
 
 
 def dw3x3_bwd(dD, xin, w9, scale, shift, relu, dw, add_full=None, add_half=None, bnsum=None):
-    """dw: fp32 [C,1,3,3] gradient buffer (accumulated); bnsum: zero-filled fp32 [2,C] when scale/shift are given."""
+    """dw: fp32 [C_real,1,3,3] gradient buffer (accumulated); bnsum: zero-filled fp32 [2,C] when scale/shift are given."""
     _chk(dD, BF16, "dw3x3_bwd.dD"); _chk(xin, BF16, "dw3x3_bwd.xin")
     F_, H, W, C = xin.shape
     dz = torch.empty_like(xin)
     if scale is not None and bnsum is None:
         bnsum = torch.zeros((2, C), device=xin.device, dtype=F32)
     _lib.call("xcp_dw3x3_bwd", _p(dD), _p(xin), _p(w9), _p(scale), _p(shift), int(relu), _p(dz), _p(add_full), _p(add_half),
-              _p(dw), _p(bnsum), F_, H, W, C, xin.device.index, _s())
+              _p(dw), _p(bnsum), F_, H, W, C, dw.shape[0], xin.device.index, _s())
     return dz, bnsum
 
 
@@ -206,17 +215,20 @@ class BNState:
 
 
 def bn_finalize(parts: torch.Tensor, count: float, gamma, beta, running_mean, running_var, training: bool,
-                momentum: float = BN_MOMENTUM, eps: float = BN_EPS) -> BNState:
-    C = gamma.shape[0]
+                momentum: float = BN_MOMENTUM, eps: float = BN_EPS, C: Optional[int] = None) -> BNState:
+    """C = physical channel pitch of the activation (default: the width of `parts`, else len(gamma))."""
+    Cr = gamma.shape[0]
+    if C is None:
+        C = parts.shape[-1] if parts is not None else Cr
     st = BNState(C, gamma.device)
     st.count = float(count)
     st.training = training
     if training:
-        _lib.call("xcp_bn_finalize", _p(parts), parts.shape[0], C, float(count), _p(gamma), _p(beta), _p(running_mean),
+        _lib.call("xcp_bn_finalize", _p(parts), parts.shape[0], C, Cr, float(count), _p(gamma), _p(beta), _p(running_mean),
                   _p(running_var), momentum, eps, _p(st.scale), _p(st.shift), _p(st.mean), _p(st.rstd), gamma.device.index, _s())
     else:
         _lib.call("xcp_bn_eval_affine", _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, _p(st.scale), _p(st.shift),
-                  _p(st.mean), _p(st.rstd), C, gamma.device.index, _s())
+                  _p(st.mean), _p(st.rstd), C, Cr, gamma.device.index, _s())
     return st
 
 
@@ -277,41 +289,48 @@ def bn_bwd(mode: int, y, st: BNState, gamma, dgamma, dbeta, G=None, idx=None, df
             dy = torch.empty_like(y)
     _lib.add_launches(-(1 if presums is not None else 0) - (0 if want_dy else 1))
     _lib.call("xcp_bn_bwd", mode, _p(y), _p(G), _p(idx), _p(dfeat), _p(st.scale), _p(st.shift), _p(gamma), _p(st.mean),
-              _p(st.rstd), int(st.training), _p(presums), _p(ws), _p(coef), _p(dgamma), _p(dbeta), _p(dy), F_, H, W, C, gw, gh,
-              dev.index, _s())
+              _p(st.rstd), int(st.training), _p(presums), _p(ws), _p(coef), _p(dgamma), _p(dbeta), _p(dy), F_, H, W, C,
+              gamma.shape[0], gw, gh, dev.index, _s())
     return dy
 
 
 # ------------------------------------------------------------------------------------------------ layout / packing
-def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+def nchw_to_nhwc(x: torch.Tensor, pad: bool = False) -> torch.Tensor:
+    """fp32 NCHW -> bf16 NHWC; pad=True stores the channels with the physical pitch phys(C) (zero pad channels)."""
     _chk(x, F32, "nchw_to_nhwc.x")
     F_, C, H, W = x.shape
-    out = torch.empty((F_, H, W, C), device=x.device, dtype=BF16)
-    _lib.call("xcp_nchw_to_nhwc", _p(x), _p(out), F_, C, H * W, x.device.index, _s())
+    Cp = phys(C) if pad else C
+    out = torch.empty((F_, H, W, Cp), device=x.device, dtype=BF16)
+    _lib.call("xcp_nchw_to_nhwc", _p(x), _p(out), F_, C, Cp, H * W, x.device.index, _s())
     return out
 
 
-def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+def nhwc_to_nchw(x: torch.Tensor, C: Optional[int] = None) -> torch.Tensor:
+    """bf16 NHWC (channel pitch x.shape[3]) -> fp32 NCHW with the first C channels (default all)."""
     _chk(x, BF16, "nhwc_to_nchw.x")
-    F_, H, W, C = x.shape
+    F_, H, W, Cp = x.shape
+    C = Cp if C is None else C
     out = torch.empty((F_, C, H, W), device=x.device, dtype=F32)
-    _lib.call("xcp_nhwc_to_nchw", _p(x), _p(out), F_, C, H * W, x.device.index, _s())
+    _lib.call("xcp_nhwc_to_nchw", _p(x), _p(out), F_, C, Cp, H * W, x.device.index, _s())
     return out
 
 
-def pack_weight(w2d: torch.Tensor, want_t: bool = True):
+def pack_weight(w2d: torch.Tensor, want_t: bool = True, pad: bool = False):
+    """fp32 [R,Cc] -> bf16 [Rp,Cp] (+ transpose [Cp,Rp]); pad=True zero-pads both dims to phys()."""
     _chk(w2d, F32, "pack_weight.w")
     R, Cc = w2d.shape
-    out = torch.empty((R, Cc), device=w2d.device, dtype=BF16)
-    out_t = torch.empty((Cc, R), device=w2d.device, dtype=BF16) if want_t else None
-    _lib.call("xcp_pack_weight", _p(w2d), _p(out), _p(out_t), R, Cc, w2d.device.index, _s())
+    Rp, Cp = (phys(R), phys(Cc)) if pad else (R, Cc)
+    out = torch.empty((Rp, Cp), device=w2d.device, dtype=BF16)
+    out_t = torch.empty((Cp, Rp), device=w2d.device, dtype=BF16) if want_t else None
+    _lib.call("xcp_pack_weight", _p(w2d), _p(out), _p(out_t), R, Cc, Rp, Cp, w2d.device.index, _s())
     return out, out_t
 
 
-def pack_dw(w: torch.Tensor):
+def pack_dw(w: torch.Tensor, pad: bool = False):
     C = w.shape[0]
-    w9 = torch.empty((9, C), device=w.device, dtype=F32)
-    _lib.call("xcp_pack_dw", _p(w), _p(w9), C, w.device.index, _s())
+    Cp = phys(C) if pad else C
+    w9 = torch.empty((9, Cp), device=w.device, dtype=F32)
+    _lib.call("xcp_pack_dw", _p(w), _p(w9), C, Cp, w.device.index, _s())
     return w9
 
 

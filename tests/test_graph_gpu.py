@@ -46,7 +46,8 @@ def test_graphed_step_tracks_eager_steps():
     m_e = _model(7)
     m_g = copy.deepcopy(m_e)
     opt_e = torch.optim.Adam(m_e.parameters(), lr=1e-4, capturable=True)
-    opt_g = torch.optim.Adam(m_g.parameters(), lr=1e-4, capturable=True)
+    from multimodal_deepfake_detection_b200 import FusedAdam
+    opt_g = FusedAdam(m_g.parameters(), lr=1e-4)          # one multi-tensor launch, device-side step counter: capturable
     step_e, step_g = _make_step(m_e, opt_e), _make_step(m_g, opt_g)
     # the capture warm-up executes real steps: give both models the same history
     warm = batches[0]

@@ -65,7 +65,9 @@ if not which or "dw" in which:
 
 PW = [(21609, 64, 128), (21609, 128, 128), (5476, 128, 256), (5476, 256, 256), (1369, 256, 728), (1369, 728, 728),
       (361, 728, 728), (361, 728, 1024), (100, 1024, 1536), (100, 1536, 2048)]
-if not which or "gemm" in which:
+if "gemm768" in which:      # alignment probe: 728-wide rows are 1456 B (not 128 B aligned); 768-wide are 1536 B
+    PW = [(1369, 728, 728), (1369, 768, 768), (361, 728, 728), (361, 768, 768), (361, 768, 1024), (361, 1024, 1024)]
+if not which or "gemm" in which or "gemm768" in which:
     for pix, K, N in PW:
         M = pix * Fr
         a = rnd(M, K); b = rnd(N, K) / math.sqrt(K)
