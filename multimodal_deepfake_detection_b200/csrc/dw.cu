@@ -6,13 +6,19 @@
 // element is fetched once by TMA into a shared-memory halo tile (OOB zero fill = the conv's zero padding) and
 // every output element is written once.
 //
-// Mapping (v2, chosen after the first ncu pass showed the v1 kernels issue- and latency-bound, not DRAM-bound):
-//   tile   = (TH x TW pixels) x 64 channels of one frame, 2-deep TMA ring per persistent CTA
-//   warp   = one pair of adjacent pixel columns (x one row slice)      -> border tests are warp-uniform branches
-//   lane   = one pair of adjacent channels, held as a packed f32x2     -> all math is FFMA2 (fma.rn.f32x2)
+// Mapping (v3).  ncu on v2 (warp = 2 pixel columns) showed the kernels instruction-issue bound, not DRAM bound:
+// 28 (forward) / 43 (backward) lane-instructions per element at ~60 % issue-slot utilisation (profiles/r1j), because a
+// 2-column warp loads and transforms 4 staged columns per 2 outputs and pays the address / predicate / loop overhead
+// every 4 elements.  v3:
+//   tile   = (TH x TW pixels) x 64 channels of one frame, TW a multiple of 4, 2-deep TMA ring per persistent CTA
+//   warp   = a STRIP of 4 adjacent pixel columns x one row slice  -> 6 staged columns per 4 outputs (1.5x instead of 2x)
+//   lane   = one pair of adjacent channels, held as a packed f32x2   -> all math is FFMA2 (fma.rn.f32x2)
 // so one warp instruction touches 32 lanes x 4 B = one pixel's 128 contiguous bytes in shared and global memory.
-// The warp streams down its columns with a 3-row register window (forward: partial sums; backward: dD values).
+// The warp streams down its strip with a 3-row x 6-column register window; border handling is warp-uniform (tiles
+// overhang the image, the overhang is TMA zero fill on the way in and a uniform predicate on the way out).
 #include "common.cuh"
+#include <type_traits>
+#include <stdlib.h>
 
 namespace xcp {
 
@@ -21,32 +27,64 @@ XCP_DEVINL uint32_t f2_to_bf2(u64 v) { float lo, hi; upk2(v, lo, hi); return pac
 XCP_DEVINL uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 XCP_DEVINL u64 relu2(u64 v) { float lo, hi; upk2(v, lo, hi); return pk2(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
 
+constexpr int SW = 4;            // output columns per warp strip
+constexpr int LW = SW + 2;       // staged columns a strip reads
+
 struct DwGeom {
     int F, H, W, C;
-    int TH, TW, n_h, n_w, c_tiles;   // tiling
-    int pairs, RS, rows_per_slice;   // warps per tile = pairs * RS
-    long long num_tiles;
+    int TH, TW, n_h, n_w, c_tiles;   // tiling (TW = SW * strips)
+    int strips, RS, rows_per_slice;  // compute warps per tile = strips * RS
+    int sp_tiles;                    // spatial tiles = F * n_h * n_w (one CTA keeps ONE channel tile for its whole life)
+    int stages;                      // depth of the TMA ring
 };
 
+// Pick the tile shape that minimises the estimated lane-instructions per useful output element (staged-column and
+// warm-up-row redundancy of the register window, tile overhang past the image) with a mild penalty for halo re-reads
+// and for CTAs with few warps.  max_halo_pixels bounds the staged tile (shared memory per stage).
 static DwGeom make_geom(int F, int H, int W, int C, int max_halo_pixels, int max_warps) {
-    DwGeom g{};
-    g.F = F; g.H = H; g.W = W; g.C = C;
-    g.n_w = (W + 2 * max_warps - 1) / (2 * max_warps);
-    g.TW = (W + g.n_w - 1) / g.n_w;
-    int th_max = max_halo_pixels / (g.TW + 2) - 2;
-    if (th_max < 1) th_max = 1;
-    g.n_h = (H + th_max - 1) / th_max;
-    g.TH = (H + g.n_h - 1) / g.n_h;
-    g.c_tiles = (C + 63) / 64;
-    g.pairs = (g.TW + 1) / 2;
-    g.RS = max_warps / g.pairs;
-    if (g.RS < 1) g.RS = 1;
-    if (g.RS > g.TH) g.RS = g.TH;
-    g.rows_per_slice = (g.TH + g.RS - 1) / g.RS;
-    g.RS = (g.TH + g.rows_per_slice - 1) / g.rows_per_slice;
-    g.num_tiles = (long long)F * g.n_h * g.n_w * g.c_tiles;
-    return g;
+    DwGeom best{};
+    double best_cost = 1e30;
+    for (int ns = 1; ns <= max_warps; ++ns) {
+        if (ns > 1 && SW * (ns - 1) >= W) break;          // already wider than the image
+        DwGeom g{};
+        g.F = F; g.H = H; g.W = W; g.C = C;
+        g.strips = ns;
+        g.TW = SW * ns;
+        g.n_w = (W + g.TW - 1) / g.TW;
+        const int th_max = max_halo_pixels / (g.TW + 2) - 2;
+        if (th_max < 1) continue;
+        g.n_h = (H + th_max - 1) / th_max;
+        g.TH = (H + g.n_h - 1) / g.n_h;
+        g.RS = max_warps / ns;
+        if (g.RS < 1) g.RS = 1;
+        if (g.RS > g.TH) g.RS = g.TH;
+        g.rows_per_slice = (g.TH + g.RS - 1) / g.RS;
+        g.RS = (g.TH + g.rows_per_slice - 1) / g.rows_per_slice;
+        g.c_tiles = (C + 63) / 64;
+        g.sp_tiles = F * g.n_h * g.n_w;
+        const double rps = g.rows_per_slice;
+        const double col_waste = (double)g.n_w * g.TW / W;
+        const double row_waste = (double)g.n_h * g.RS * rps / H;
+        const double instr = 3.0 * ((double)LW / SW) * (rps + 2.0) / rps + 6.5;
+        const double halo = (double)(g.TW + 2) * (g.TH + 2) / ((double)g.TW * g.TH);
+        const int warps = ns * g.RS;
+        const double cost = instr * col_waste * row_waste * (1.0 + 0.25 * (halo - 1.0)) *
+                            (1.0 + 0.3 * (double)(max_warps - warps) / max_warps);
+        if (cost < best_cost) { best_cost = cost; best = g; }
+    }
+    return best;
 }
+
+// Ring protocol shared by both kernels.  Warps 0..NW-1 compute, warp NW is the TMA producer (one elected lane):
+//   producer : wait empty[s] -> arm full[s] with the stage's byte count -> issue the TMA box(es)
+//   consumer : wait full[s]  -> compute from the staged tile -> (warp) arrive on empty[s]
+// so a fast warp never waits for a slow one at a CTA-wide barrier (the v2/v3.0 kernels spent 1.5 issue-slots per issued
+// instruction stalled at __syncthreads, profiles/r1l) and the prefetch runs `stages - 1` tiles ahead.
+struct DwRing {
+    uint64_t* full;
+    uint64_t* empty;
+    int stages;
+};
 
 struct DwFwdParams {
     DwGeom g;
@@ -56,141 +94,153 @@ struct DwFwdParams {
     __nv_bfloat16* out;   // [F,H,W,C]
 };
 
-template <bool AFFINE, bool RELU>
-__global__ void __launch_bounds__(256, 3)
+constexpr int DW_MAX_STAGES = 4;
+
+template <bool AFFINE, bool RELU, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t sbase = (raw_addr + 127u) & ~127u;
     uint8_t* smem = smem_raw + (sbase - raw_addr);
-    const DwGeom& g = p.g;
-    const int halo_w = g.TW + 2;
-    const uint32_t row_stride = (uint32_t)halo_w * 128u;
-    const uint32_t stage_bytes = row_stride * (uint32_t)(g.TH + 2);
-    __shared__ uint64_t full[2];
+    const int gH = p.g.H, gW = p.g.W, gC = p.g.C, TH = p.g.TH, TW = p.g.TW;
+    const int n_h = p.g.n_h, n_w = p.g.n_w, c_tiles = p.g.c_tiles;
+    const int sp_tiles = p.g.sp_tiles, stages = p.g.stages;
+    const uint32_t row_stride = (uint32_t)(TW + 2) * 128u;
+    const uint32_t stage_bytes = row_stride * (uint32_t)(TH + 2);
+    __shared__ uint64_t full[DW_MAX_STAGES], empty[DW_MAX_STAGES];
+    const int NW = p.g.strips * p.g.RS;                 // compute warps
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); }
         fence_barrier_init();
         tma_prefetch_desc(&tmX);
     }
     __syncthreads();
 
-    auto issue = [&](long long tile, int s) {
-        long long t = tile;
-        const int ct = (int)(t % g.c_tiles); t /= g.c_tiles;
-        const int tw = (int)(t % g.n_w); t /= g.n_w;
-        const int th = (int)(t % g.n_h); t /= g.n_h;
-        mbar_arrive_expect_tx(&full[s], stage_bytes);
-        tma_load_4d(smem + s * stage_bytes, &tmX, &full[s], ct * 64, tw * g.TW - 1, th * g.TH - 1, (int)t);
-    };
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = (warp % g.pairs) * 2;          // first of the warp's two tile-local columns
-    const int slice = warp / g.pairs;
-    const int r0 = slice * g.rows_per_slice;
-    const int r1 = min(r0 + g.rows_per_slice, g.TH);
-    const u64 NEG = pk2(-1e30f, -1e30f);
+    const int ct = blockIdx.x % c_tiles;                 // host guarantees gridDim.x % c_tiles == 0
+    const int sp_stride = gridDim.x / c_tiles;
+    const int sp0 = blockIdx.x / c_tiles;
 
-    long long tile = blockIdx.x;
-    if (threadIdx.x == 0 && tile < g.num_tiles) issue(tile, 0);
-
-    for (int it = 0; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        const long long next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < g.num_tiles) issue(next, s ^ 1);
-
-        long long t = tile;
-        const int ct = (int)(t % g.c_tiles); t /= g.c_tiles;
-        const int tw = (int)(t % g.n_w); t /= g.n_w;
-        const int th = (int)(t % g.n_h); t /= g.n_h;
-        const int f = (int)t;
-        const int c0 = ct * 64 + lane * 2;
-        const int gx0 = tw * g.TW + x0;
-        const bool active = slice < g.RS && c0 < g.C && gx0 < g.W;      // gx0 < W is warp-uniform, c0 < C per lane
-        const bool second = (x0 + 1 < g.TW) && (gx0 + 1 < g.W);
-
-        u64 wg[9];
-        u64 sc = 0, shc[4] = {0, 0, 0, 0};
-        if (active) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const float2 a = *reinterpret_cast<const float2*>(p.w9 + (long long)k * g.C + c0);
-                wg[k] = pk2(a.x, a.y);
-            }
-            if (AFFINE) {
-                const float2 a = *reinterpret_cast<const float2*>(p.scale + c0);
-                const float2 b = *reinterpret_cast<const float2*>(p.shift + c0);
-                sc = pk2(a.x, a.y);
-                const u64 sh = pk2(b.x, b.y);
-                // Out-of-image columns must stay exactly 0 after the affine: with the ReLU fused, a hugely negative
-                // shift does that branch-free (TMA zero-filled the raw value, scale*0 = 0).  Without ReLU the
-                // generic (select) path below is used.
-#pragma unroll
-                for (int dx = 0; dx < 4; ++dx) {
-                    const bool cv = (gx0 - 1 + dx >= 0) && (gx0 - 1 + dx < g.W);
-                    shc[dx] = (cv || !RELU) ? sh : NEG;
-                }
+    if (warp == NW) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int sp = sp0; sp < sp_tiles; sp += sp_stride) {
+                const int tw = sp % n_w; const int t2 = sp / n_w;
+                const int th = t2 % n_h; const int f = t2 / n_h;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                tma_load_4d(smem + s * stage_bytes, &tmX, &full[s], ct * 64, tw * TW - 1, th * TH - 1, f);
+                if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
-
-        mbar_wait(&full[s], (it >> 1) & 1);
-
-        if (active) {
-            const uint32_t tb = sbase + s * stage_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u;
-            bool cvn[4];
-#pragma unroll
-            for (int dx = 0; dx < 4; ++dx) cvn[dx] = (gx0 - 1 + dx >= 0) && (gx0 - 1 + dx < g.W);
-            // load + transform one staged row (halo-tile row index hr) into a 4-column register row
-            auto load_row = [&](int hr, u64 (&w)[4]) {
-                const int gh = th * g.TH + hr - 1;
-                const uint32_t a = tb + (uint32_t)hr * row_stride;
-                if (AFFINE && (gh < 0 || gh >= g.H)) {          // warp-uniform: rows outside the image stay 0
-                    w[0] = 0; w[1] = 0; w[2] = 0; w[3] = 0;
-                    return;
-                }
-#pragma unroll
-                for (int dx = 0; dx < 4; ++dx) {
-                    u64 z = bf2_to_f2(lds32(a + dx * 128));
-                    if (AFFINE) z = fma2(z, sc, shc[dx]);
-                    if (RELU) z = relu2(z);
-                    if (AFFINE && !RELU && !cvn[dx]) z = 0;
-                    w[dx] = z;
-                }
-            };
-            u64 win[3][4];
-            load_row(r0, win[0]);
-            load_row(r0 + 1, win[1]);
-            __nv_bfloat16* outp = p.out + (((long long)f * g.H + th * g.TH) * g.W + gx0) * g.C + c0;
-            const long long out_row = (long long)g.W * g.C;
-            const int rmax = min(r1, g.H - th * g.TH);       // output rows of this slice that are inside the image
-
-#define DW_STEP(WA, WB, WC)                                                                               \
-    {                                                                                                     \
-        load_row(o + 2, WC);                                                                              \
-        u64 a0 = mul2(wg[0], WA[0]), a1 = mul2(wg[0], WA[1]);                                             \
-        a0 = fma2(wg[1], WA[1], a0); a1 = fma2(wg[1], WA[2], a1);                                         \
-        a0 = fma2(wg[2], WA[2], a0); a1 = fma2(wg[2], WA[3], a1);                                         \
-        a0 = fma2(wg[3], WB[0], a0); a1 = fma2(wg[3], WB[1], a1);                                         \
-        a0 = fma2(wg[4], WB[1], a0); a1 = fma2(wg[4], WB[2], a1);                                         \
-        a0 = fma2(wg[5], WB[2], a0); a1 = fma2(wg[5], WB[3], a1);                                         \
-        a0 = fma2(wg[6], WC[0], a0); a1 = fma2(wg[6], WC[1], a1);                                         \
-        a0 = fma2(wg[7], WC[1], a0); a1 = fma2(wg[7], WC[2], a1);                                         \
-        a0 = fma2(wg[8], WC[2], a0); a1 = fma2(wg[8], WC[3], a1);                                         \
-        __nv_bfloat16* op = outp + o * out_row;                                                           \
-        *reinterpret_cast<uint32_t*>(op) = f2_to_bf2(a0);                                                 \
-        if (second) *reinterpret_cast<uint32_t*>(op + g.C) = f2_to_bf2(a1);                               \
+        return;
     }
-            int o = r0;
-            while (o < rmax) {
-                DW_STEP(win[0], win[1], win[2]); if (++o >= rmax) break;
-                DW_STEP(win[1], win[2], win[0]); if (++o >= rmax) break;
-                DW_STEP(win[2], win[0], win[1]); ++o;
-            }
-#undef DW_STEP
+
+    // ---------------------------------------------------------------------- compute warps
+    const int x0 = (warp % p.g.strips) * SW;       // first of the warp's tile-local columns
+    const int slice = warp / p.g.strips;
+    const int r0 = slice * p.g.rows_per_slice;
+    const int r1 = min(r0 + p.g.rows_per_slice, TH);
+    const int c0 = ct * 64 + lane * 2;
+    const bool lane_ok = c0 < gC;
+    const long long pix_b = (long long)gC * 2;      // bytes per pixel / per image row in global memory
+    const long long row_b = (long long)gW * pix_b;
+
+    // the CTA's channel tile never changes: weights and the fused affine live in registers for the whole kernel
+    u64 wg[9];
+    u64 sc = 0, sh = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wg[k] = 0;
+    if (lane_ok) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float2 a = *reinterpret_cast<const float2*>(p.w9 + (long long)k * gC + c0);
+            wg[k] = pk2(a.x, a.y);
         }
-        __syncthreads();   // everyone is done with stage s before it is refilled
+        if (AFFINE) {
+            const float2 a = *reinterpret_cast<const float2*>(p.scale + c0);
+            const float2 b = *reinterpret_cast<const float2*>(p.shift + c0);
+            sc = pk2(a.x, a.y);
+            sh = pk2(b.x, b.y);
+        }
+    }
+
+    int s = 0; uint32_t ph = 0;
+    for (int sp = sp0; sp < sp_tiles; sp += sp_stride) {
+        const int tw = sp % n_w; const int t2 = sp / n_w;
+        const int th = t2 % n_h; const int f = t2 / n_h;
+        const int gx0 = tw * TW + x0;
+        const int gh0 = th * TH;
+        const bool active = lane_ok && gx0 < gW;                    // gx0 < W is warp-uniform, c0 < C per lane
+        const int ncols = min(SW, gW - gx0);                        // valid output columns of this strip (warp-uniform)
+
+        mbar_wait(&full[s], ph);
+
+        if (active) {
+            const uint32_t tb = sbase + s * stage_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u + (uint32_t)r0 * row_stride;
+            char* op = reinterpret_cast<char*>(p.out) + ((long long)f * gH + gh0 + r0) * row_b + (long long)gx0 * pix_b +
+                       (long long)c0 * 2;
+            const int rmax = min(r1, gH - gh0);              // output rows of this slice that are inside the image
+            // EDGE = the strip's 6 staged columns reach outside the image (TMA zero-filled them): after the fused
+            // affine they must be forced back to exactly 0 (the conv's zero padding applies to the activated input).
+            // Interior strips -- the vast majority -- run the select-free instantiation.
+            auto run = [&](auto edge_tag) {
+                constexpr bool EDGE = decltype(edge_tag)::value;
+                bool cvn[LW];
+#pragma unroll
+                for (int dx = 0; dx < LW; ++dx) cvn[dx] = (gx0 - 1 + dx >= 0) && (gx0 - 1 + dx < gW);
+                // load + transform one staged row (a = its shared-memory address, gh = its image row) into registers
+                auto load_row = [&](uint32_t a, int gh, u64 (&w)[LW]) {
+                    // rows outside the image must stay exactly 0 after the fused affine: scale = shift = 0 for them
+                    // (branch-free, so the loads of the next row still overlap the FMAs of this one)
+                    const bool row_in = (gh >= 0) && (gh < gH);
+                    const u64 scr = (AFFINE && !row_in) ? 0ull : sc;
+                    const u64 shr = (AFFINE && !row_in) ? 0ull : sh;
+#pragma unroll
+                    for (int dx = 0; dx < LW; ++dx) {
+                        u64 z = bf2_to_f2(lds32(a + dx * 128));
+                        if (AFFINE) z = fma2(z, scr, shr);
+                        if (RELU) z = relu2(z);
+                        if (AFFINE && EDGE && !cvn[dx]) z = 0;
+                        w[dx] = z;
+                    }
+                };
+                u64 win[3][LW];
+                uint32_t a = tb;
+                int gh = gh0 + r0 - 1;
+                load_row(a, gh, win[0]); a += row_stride; ++gh;
+                load_row(a, gh, win[1]); a += row_stride; ++gh;
+                char* o_ptr = op;
+
+#define DW_STEP(WA, WB, WC)                                                                                 \
+    {                                                                                                       \
+        load_row(a, gh, WC); a += row_stride; ++gh;                                                         \
+        _Pragma("unroll") for (int px = 0; px < SW; ++px) {                                                 \
+            u64 a0 = mul2(wg[0], WA[px]);                                                                   \
+            a0 = fma2(wg[1], WA[px + 1], a0); a0 = fma2(wg[2], WA[px + 2], a0);                             \
+            a0 = fma2(wg[3], WB[px], a0); a0 = fma2(wg[4], WB[px + 1], a0); a0 = fma2(wg[5], WB[px + 2], a0); \
+            a0 = fma2(wg[6], WC[px], a0); a0 = fma2(wg[7], WC[px + 1], a0); a0 = fma2(wg[8], WC[px + 2], a0); \
+            if (!EDGE || px < ncols) *reinterpret_cast<uint32_t*>(o_ptr + px * pix_b) = f2_to_bf2(a0);      \
+        }                                                                                                   \
+        o_ptr += row_b;                                                                                     \
+    }
+                int o = r0;
+                while (o < rmax) {
+                    DW_STEP(win[0], win[1], win[2]); if (++o >= rmax) break;
+                    DW_STEP(win[1], win[2], win[0]); if (++o >= rmax) break;
+                    DW_STEP(win[2], win[0], win[1]); ++o;
+                }
+#undef DW_STEP
+            };
+            if (gx0 >= 1 && gx0 + SW < gW) run(std::false_type{});
+            else run(std::true_type{});
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);     // this warp is done with stage s
+        if (++s == stages) { s = 0; ph ^= 1; }
     }
 }
 
@@ -199,7 +249,7 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
 //     da[p]        = sum_{kh,kw} w[kh][kw] * dD[p + (1-kh, 1-kw)]
 //     dw[kh][kw]  += a[p] * dD[p + (1-kh, 1-kw)]
 // Both need the same 3x3 neighbourhood of dD (TMA halo tile, zero fill = correct padding) and only the centre value
-// of the forward input (second TMA tile, no halo).  The warp keeps a 3-row x 4-column window of dD in registers.
+// of the forward input (second TMA tile, no halo).  The warp keeps a 3-row x 6-column window of dD in registers.
 // The kernel also applies the ReLU mask / BN-affine chain rule, accumulates the per-channel sums the BatchNorm
 // backward of the producer needs (sum dz, sum dz*y), and can add the residual-branch gradient(s).
 struct DwBwdParams {
@@ -207,35 +257,35 @@ struct DwBwdParams {
     const float* w9;              // [9][C]
     const float* scale;           // AFFINE only
     const float* shift;
-    int relu;
     __nv_bfloat16* dz;            // out: grad wrt the pre-activation (z if AFFINE, x otherwise) [F,H,W,C]
-    const __nv_bfloat16* add_full;   // optional: same-shape gradient to add (identity skip), after masking
-    const __nv_bfloat16* add_half;   // optional: [F,ceil(H/2),ceil(W/2),C] gradient of the stride-2 skip gather
+    const __nv_bfloat16* add_full;   // ADDM & 1: same-shape gradient to add (identity skip), after masking
+    const __nv_bfloat16* add_half;   // ADDM & 2: [F,ceil(H/2),ceil(W/2),C] gradient of the stride-2 skip gather
     float* dw;                    // [C][9]  (the nn.Conv2d weight-gradient layout), accumulated with RED
     float* bnsum;                 // [2][C]  (sum dz, sum dz*y), accumulated with RED (caller zero-fills); AFFINE only
     int c_real;                   // logical channel count (<= C, the physical pitch): dw has c_real rows
 };
 
-template <bool AFFINE, bool RELU>
+template <bool AFFINE, bool RELU, int ADDM>
 __global__ void __launch_bounds__(256, 2)
 dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const DwBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t sbase = (raw_addr + 127u) & ~127u;
     uint8_t* smem = smem_raw + (sbase - raw_addr);
-    const DwGeom& g = p.g;
-    const int halo_w = g.TW + 2;
-    const uint32_t row_stride = (uint32_t)halo_w * 128u;
-    const uint32_t g_bytes = row_stride * (uint32_t)(g.TH + 2);
-    const uint32_t x_row = (uint32_t)g.TW * 128u;
-    const uint32_t x_bytes = x_row * (uint32_t)g.TH;
+    const int gH = p.g.H, gW = p.g.W, gC = p.g.C, TH = p.g.TH, TW = p.g.TW;
+    const int n_h = p.g.n_h, n_w = p.g.n_w, c_tiles = p.g.c_tiles;
+    const int sp_tiles = p.g.sp_tiles, stages = p.g.stages;
+    const uint32_t row_stride = (uint32_t)(TW + 2) * 128u;
+    const uint32_t g_bytes = row_stride * (uint32_t)(TH + 2);
+    const uint32_t x_row = (uint32_t)TW * 128u;
+    const uint32_t x_bytes = x_row * (uint32_t)TH;
     const uint32_t stage_bytes = g_bytes + x_bytes;
-    __shared__ uint64_t full[2];
+    __shared__ uint64_t full[DW_MAX_STAGES], empty[DW_MAX_STAGES];
     __shared__ float s_red[11][64];
+    const int NW = p.g.strips * p.g.RS;
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); }
         fence_barrier_init();
         tma_prefetch_desc(&tmG);
         tma_prefetch_desc(&tmX);
@@ -244,131 +294,144 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
     __syncthreads();
 
     // A CTA owns one channel tile for its whole life so the weight / BN partial sums stay in registers.
-    const int ct = blockIdx.x % g.c_tiles;
-    const long long sp_tiles = (long long)g.F * g.n_h * g.n_w;
-    const int sp_stride = gridDim.x / g.c_tiles;          // host guarantees gridDim.x % c_tiles == 0
-    long long sp = blockIdx.x / g.c_tiles;
-
-    auto issue = [&](long long sp_tile, int s) {
-        long long t = sp_tile;
-        const int tw = (int)(t % g.n_w); t /= g.n_w;
-        const int th = (int)(t % g.n_h); t /= g.n_h;
-        mbar_arrive_expect_tx(&full[s], stage_bytes);
-        tma_load_4d(smem + s * stage_bytes, &tmG, &full[s], ct * 64, tw * g.TW - 1, th * g.TH - 1, (int)t);
-        tma_load_4d(smem + s * stage_bytes + g_bytes, &tmX, &full[s], ct * 64, tw * g.TW, th * g.TH, (int)t);
-    };
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = (warp % g.pairs) * 2;
-    const int slice = warp / g.pairs;
-    const int r0 = slice * g.rows_per_slice;
-    const int r1 = min(r0 + g.rows_per_slice, g.TH);
+    const int ct = blockIdx.x % c_tiles;                 // host guarantees gridDim.x % c_tiles == 0
+    const int sp_stride = gridDim.x / c_tiles;
+    const int sp0 = blockIdx.x / c_tiles;
+
+    const int x0 = (warp % p.g.strips) * SW;
+    const int slice = warp / p.g.strips;
+    const int r0 = slice * p.g.rows_per_slice;
+    const int r1 = min(r0 + p.g.rows_per_slice, TH);
     const int c0 = ct * 64 + lane * 2;
-    const bool lane_active = slice < g.RS && c0 < g.C;
+    const bool lane_ok = warp < NW && c0 < gC;
+    const long long pix_b = (long long)gC * 2;
+    const long long row_b = (long long)gW * pix_b;
+    const int Ho = (gH + 1) / 2, Wo = (gW + 1) / 2;
 
     u64 wg[9], dwa[9];
     u64 sdz = 0, sdzy = 0, sc = pk2(1.f, 1.f), sh = 0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) { wg[k] = 0; dwa[k] = 0; }
-    if (lane_active) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float2 a = *reinterpret_cast<const float2*>(p.w9 + (long long)k * g.C + c0);
-            wg[k] = pk2(a.x, a.y);
+
+    if (warp == NW) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int sp = sp0; sp < sp_tiles; sp += sp_stride) {
+                const int tw = sp % n_w; const int t2 = sp / n_w;
+                const int th = t2 % n_h; const int f = t2 / n_h;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                tma_load_4d(smem + s * stage_bytes, &tmG, &full[s], ct * 64, tw * TW - 1, th * TH - 1, f);
+                tma_load_4d(smem + s * stage_bytes + g_bytes, &tmX, &full[s], ct * 64, tw * TW, th * TH, f);
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
         }
-        if (AFFINE) {
-            const float2 a = *reinterpret_cast<const float2*>(p.scale + c0);
-            const float2 b = *reinterpret_cast<const float2*>(p.shift + c0);
-            sc = pk2(a.x, a.y); sh = pk2(b.x, b.y);
-        }
-    }
-
-    if (threadIdx.x == 0 && sp < sp_tiles) issue(sp, 0);
-
-    for (int it = 0; sp < sp_tiles; sp += sp_stride, ++it) {
-        const int s = it & 1;
-        const long long next = sp + sp_stride;
-        if (threadIdx.x == 0 && next < sp_tiles) issue(next, s ^ 1);
-
-        long long t = sp;
-        const int tw = (int)(t % g.n_w); t /= g.n_w;
-        const int th = (int)(t % g.n_h); t /= g.n_h;
-        const int f = (int)t;
-        const int gx0 = tw * g.TW + x0;
-        const bool active = lane_active && gx0 < g.W;
-        const bool second = (x0 + 1 < g.TW) && (gx0 + 1 < g.W);
-
-        mbar_wait(&full[s], (it >> 1) & 1);
-
-        if (active) {
-            const uint32_t gb = sbase + s * stage_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u;   // dD halo tile
-            const uint32_t xb = gb + g_bytes;                                                          // fwd-input centre tile
-            auto load_g = [&](int hr, u64 (&w)[4]) {
-                const uint32_t a = gb + (uint32_t)hr * row_stride;
+    } else {
+        // ------------------------------------------------------------------ compute warps
+        if (lane_ok) {
 #pragma unroll
-                for (int dx = 0; dx < 4; ++dx) w[dx] = bf2_to_f2(lds32(a + dx * 128));
-            };
-            u64 win[3][4];
-            load_g(r0, win[0]);          // dD row r0-1
-            load_g(r0 + 1, win[1]);      // dD row r0
-            const int gh0 = th * g.TH;
-            const int rmax = min(r1, g.H - gh0);
-            __nv_bfloat16* dzp = p.dz + (((long long)f * g.H + gh0) * g.W + gx0) * g.C + c0;
-            const __nv_bfloat16* afp = p.add_full ? p.add_full + (((long long)f * g.H + gh0) * g.W + gx0) * g.C + c0 : nullptr;
-            const long long row_el = (long long)g.W * g.C;
+            for (int k = 0; k < 9; ++k) {
+                const float2 a = *reinterpret_cast<const float2*>(p.w9 + (long long)k * gC + c0);
+                wg[k] = pk2(a.x, a.y);
+            }
+            if (AFFINE) {
+                const float2 a = *reinterpret_cast<const float2*>(p.scale + c0);
+                const float2 b = *reinterpret_cast<const float2*>(p.shift + c0);
+                sc = pk2(a.x, a.y); sh = pk2(b.x, b.y);
+            }
+        }
+        int s = 0; uint32_t ph = 0;
+        for (int sp = sp0; sp < sp_tiles; sp += sp_stride) {
+            const int tw = sp % n_w; const int t2 = sp / n_w;
+            const int th = t2 % n_h; const int f = t2 / n_h;
+            const int gx0 = tw * TW + x0;                 // always even (TW and x0 are multiples of 4)
+            const int gh0 = th * TH;
+            const bool active = lane_ok && gx0 < gW;
+            const int ncols = min(SW, gW - gx0);
 
-            // centre row rc: window rows (rc-1, rc, rc+1) = (WA, WB, WC); WC is loaded here.  The neighbour
-            // p + (1-kh, 1-kw) of centre (rc, o) sits in window row 2-kh (WC, WB, WA for kh = 0, 1, 2), staged column o+2-kw.
-#define DWB_PIX(O, WA, WB, WC)                                                                             \
-    {                                                                                                      \
-        const u64 yv = bf2_to_f2(lds32(xb + (uint32_t)rc * x_row + (O) * 128));                            \
-        const u64 z = AFFINE ? fma2(yv, sc, sh) : yv;                                                      \
-        float zl, zh; upk2(z, zl, zh);                                                                     \
-        const bool pl = RELU ? zl > 0.f : true, ph = RELU ? zh > 0.f : true;                               \
-        const u64 av = RELU ? pk2(fmaxf(zl, 0.f), fmaxf(zh, 0.f)) : z;                                     \
-        u64 da = mul2(wg[0], WC[(O) + 2]);                                                                 \
-        da = fma2(wg[1], WC[(O) + 1], da); da = fma2(wg[2], WC[(O)], da);                                  \
-        da = fma2(wg[3], WB[(O) + 2], da); da = fma2(wg[4], WB[(O) + 1], da); da = fma2(wg[5], WB[(O)], da); \
-        da = fma2(wg[6], WA[(O) + 2], da); da = fma2(wg[7], WA[(O) + 1], da); da = fma2(wg[8], WA[(O)], da); \
-        dwa[0] = fma2(av, WC[(O) + 2], dwa[0]); dwa[1] = fma2(av, WC[(O) + 1], dwa[1]); dwa[2] = fma2(av, WC[(O)], dwa[2]); \
-        dwa[3] = fma2(av, WB[(O) + 2], dwa[3]); dwa[4] = fma2(av, WB[(O) + 1], dwa[4]); dwa[5] = fma2(av, WB[(O)], dwa[5]); \
-        dwa[6] = fma2(av, WA[(O) + 2], dwa[6]); dwa[7] = fma2(av, WA[(O) + 1], dwa[7]); dwa[8] = fma2(av, WA[(O)], dwa[8]); \
-        float dl, dh; upk2(da, dl, dh);                                                                    \
-        dl = pl ? dl : 0.f; dh = ph ? dh : 0.f;                                                            \
-        const long long eo = rc * row_el + (O) * g.C;                                                      \
-        if (afp != nullptr) {                                                                              \
-            const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(afp + eo));                        \
-            dl += bf16_lo(ar); dh += bf16_hi(ar);                                                          \
-        }                                                                                                  \
-        if (p.add_half != nullptr && (((gh0 + rc) | (gx0 + (O))) & 1) == 0) {                              \
-            const int Ho = (g.H + 1) / 2, Wo = (g.W + 1) / 2;                                              \
-            const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(                                   \
-                p.add_half + (((long long)f * Ho + ((gh0 + rc) >> 1)) * Wo + ((gx0 + (O)) >> 1)) * g.C + c0)); \
-            dl += bf16_lo(ar); dh += bf16_hi(ar);                                                          \
-        }                                                                                                  \
-        if (AFFINE) { const u64 dzv = pk2(dl, dh); sdz = add2(sdz, dzv); sdzy = fma2(dzv, yv, sdzy); }     \
-        *reinterpret_cast<uint32_t*>(dzp + eo) = pack_bf16(dl, dh);                                        \
-    }
+            mbar_wait(&full[s], ph);
+
+            if (active) {
+                const uint32_t gb = sbase + s * stage_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u + (uint32_t)r0 * row_stride;
+                const uint32_t xb = sbase + s * stage_bytes + g_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u + (uint32_t)r0 * x_row;
+                const int rmax = min(r1, gH - gh0);
+                const long long e0 = ((long long)f * gH + gh0 + r0) * row_b + (long long)gx0 * pix_b + (long long)c0 * 2;
+                auto run = [&](auto edge_tag) {
+                    constexpr bool EDGE = decltype(edge_tag)::value;      // partial strip: ncols < SW
+                    auto load_g = [&](uint32_t a, u64 (&w)[LW]) {
+#pragma unroll
+                        for (int dx = 0; dx < LW; ++dx) w[dx] = bf2_to_f2(lds32(a + dx * 128));
+                    };
+                    u64 win[3][LW];
+                    uint32_t ga = gb, xa = xb;
+                    load_g(ga, win[0]); ga += row_stride;        // dD row r0-1
+                    load_g(ga, win[1]); ga += row_stride;        // dD row r0
+                    char* dzp = reinterpret_cast<char*>(p.dz) + e0;
+                    const char* afp = (ADDM & 1) ? reinterpret_cast<const char*>(p.add_full) + e0 : nullptr;
+                    // stride-2 skip gradient: lives at the even (row, column) pixels; gx0 is even, so columns px = 0, 2
+                    const char* hfp = nullptr;
+                    const long long hrow_b = (long long)Wo * pix_b;
+                    if (ADDM & 2) hfp = reinterpret_cast<const char*>(p.add_half) + ((long long)f * Ho * Wo + (gx0 >> 1)) * pix_b + (long long)c0 * 2;
+                    int gh = gh0 + r0;
+
+                    // centre row: window rows (rc-1, rc, rc+1) = (WA, WB, WC); WC is loaded here.  The neighbour
+                    // p + (1-kh, 1-kw) of centre (rc, px) sits in window row 2-kh (WC, WB, WA for kh = 0, 1, 2), staged column px+2-kw.
 #define DWB_STEP(WA, WB, WC)                                                                               \
     {                                                                                                      \
-        load_g(rc + 2, WC);                                                                                \
-        DWB_PIX(0, WA, WB, WC)                                                                             \
-        if (second) DWB_PIX(1, WA, WB, WC)                                                                 \
+        load_g(ga, WC); ga += row_stride;                                                                  \
+        const char* hrow = nullptr;                                                                        \
+        if ((ADDM & 2) && (gh & 1) == 0) hrow = hfp + (long long)(gh >> 1) * hrow_b;                       \
+        _Pragma("unroll") for (int px = 0; px < SW; ++px) {                                                \
+            if (!EDGE || px < ncols) {                                                                     \
+                const u64 yv = bf2_to_f2(lds32(xa + px * 128));                                            \
+                const u64 z = AFFINE ? fma2(yv, sc, sh) : yv;                                              \
+                float zl, zh; upk2(z, zl, zh);                                                             \
+                const u64 av = RELU ? pk2(fmaxf(zl, 0.f), fmaxf(zh, 0.f)) : z;                             \
+                u64 da = mul2(wg[0], WC[px + 2]);                                                          \
+                da = fma2(wg[1], WC[px + 1], da); da = fma2(wg[2], WC[px], da);                            \
+                da = fma2(wg[3], WB[px + 2], da); da = fma2(wg[4], WB[px + 1], da); da = fma2(wg[5], WB[px], da); \
+                da = fma2(wg[6], WA[px + 2], da); da = fma2(wg[7], WA[px + 1], da); da = fma2(wg[8], WA[px], da); \
+                dwa[0] = fma2(av, WC[px + 2], dwa[0]); dwa[1] = fma2(av, WC[px + 1], dwa[1]); dwa[2] = fma2(av, WC[px], dwa[2]); \
+                dwa[3] = fma2(av, WB[px + 2], dwa[3]); dwa[4] = fma2(av, WB[px + 1], dwa[4]); dwa[5] = fma2(av, WB[px], dwa[5]); \
+                dwa[6] = fma2(av, WA[px + 2], dwa[6]); dwa[7] = fma2(av, WA[px + 1], dwa[7]); dwa[8] = fma2(av, WA[px], dwa[8]); \
+                float dl, dh; upk2(da, dl, dh);                                                            \
+                if (RELU) { dl = zl > 0.f ? dl : 0.f; dh = zh > 0.f ? dh : 0.f; }                          \
+                if (ADDM & 1) {                                                                            \
+                    const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(afp + px * pix_b));        \
+                    dl += bf16_lo(ar); dh += bf16_hi(ar);                                                  \
+                }                                                                                          \
+                if ((ADDM & 2) && (px & 1) == 0 && hrow != nullptr) {                                      \
+                    const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(hrow + (px >> 1) * pix_b)); \
+                    dl += bf16_lo(ar); dh += bf16_hi(ar);                                                  \
+                }                                                                                          \
+                if (AFFINE) { const u64 dzv = pk2(dl, dh); sdz = add2(sdz, dzv); sdzy = fma2(dzv, yv, sdzy); } \
+                *reinterpret_cast<uint32_t*>(dzp + px * pix_b) = pack_bf16(dl, dh);                        \
+            }                                                                                              \
+        }                                                                                                  \
+        xa += x_row; dzp += row_b; ++gh;                                                                   \
+        if (ADDM & 1) afp += row_b;                                                                        \
     }
-            int rc = r0;
-            while (rc < rmax) {
-                DWB_STEP(win[0], win[1], win[2]); if (++rc >= rmax) break;
-                DWB_STEP(win[1], win[2], win[0]); if (++rc >= rmax) break;
-                DWB_STEP(win[2], win[0], win[1]); ++rc;
-            }
+                    int rc = r0;
+                    while (rc < rmax) {
+                        DWB_STEP(win[0], win[1], win[2]); if (++rc >= rmax) break;
+                        DWB_STEP(win[1], win[2], win[0]); if (++rc >= rmax) break;
+                        DWB_STEP(win[2], win[0], win[1]); ++rc;
+                    }
 #undef DWB_STEP
-#undef DWB_PIX
+                };
+                if (ncols == SW) run(std::false_type{});
+                else run(std::true_type{});
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == stages) { s = 0; ph ^= 1; }
         }
-        __syncthreads();
     }
 
     // CTA reduction (shared-memory atomics, once per CTA lifetime) then one RED per (tap, channel) to global.
-    if (lane_active) {
+    if (lane_ok) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             float lo, hi; upk2(dwa[k], lo, hi);
@@ -383,10 +446,10 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
     __syncthreads();
     for (int i = threadIdx.x; i < 11 * 64; i += blockDim.x) {
         const int k = i / 64, c = ct * 64 + (i % 64);
-        if (c >= g.C) continue;
+        if (c >= gC) continue;
         const float v = s_red[k][i % 64];
         if (k < 9) { if (c < p.c_real) atomicAdd(&p.dw[(long long)c * 9 + k], v); }
-        else if (AFFINE) atomicAdd(&p.bnsum[(long long)(k - 9) * g.C + c], v);
+        else if (AFFINE) atomicAdd(&p.bnsum[(long long)(k - 9) * gC + c], v);
     }
 }
 
@@ -395,6 +458,14 @@ static int make_dw_tmap(CUtensorMap* m, const void* base, const DwGeom& g, int h
     const uint64_t strides[3] = {(uint64_t)g.C * 2, (uint64_t)g.W * g.C * 2, (uint64_t)g.H * g.W * g.C * 2};
     const uint32_t box[4] = {64, (uint32_t)(g.TW + 2 * halo), (uint32_t)(g.TH + 2 * halo), 1};
     return make_tmap_4d(m, base, dims, strides, box, 0);
+}
+
+// persistent grid: `ctas_per_sm` resident CTAs per SM, rounded down to a multiple of the channel tiles (>= c_tiles)
+static int dw_grid(const DwGeom& g, int ctas_per_sm) {
+    long long per_ct = ((long long)ctas_per_sm * num_sms()) / g.c_tiles;
+    if (per_ct < 1) per_ct = 1;
+    if (per_ct > g.sp_tiles) per_ct = g.sp_tiles;
+    return (int)(per_ct * g.c_tiles);
 }
 
 }  // namespace xcp
@@ -406,20 +477,32 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
                              int F, int H, int W, int C, int device, void* stream) {
     XCP_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "xcp_dw3x3_fwd: bad shape F=%d H=%d W=%d C=%d", F, H, W, C);
     XCP_REQUIRE((scale == nullptr) == (shift == nullptr), "xcp_dw3x3_fwd: scale/shift must both be given or both null");
+    XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_fwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
-    DwGeom g = make_geom(F, H, W, C, 272, 8);
+    // resident CTAs per SM: 2 (<= 128 registers per thread, spill-free, deep ring) measured 10-20 % faster than 3 (80
+    // registers, spills) on every Xception shape (gpurun r1m)
+    const int minb = 2;
+    DwGeom g = make_geom(F, H, W, C, minb == 3 ? 272 : 400, 7);
+    const int stage_bytes = (g.TW + 2) * (g.TH + 2) * 128;
+    g.stages = ((minb == 3 ? 73 : 110) * 1024) / stage_bytes;
+    if (g.stages > DW_MAX_STAGES) g.stages = DW_MAX_STAGES;
+    if (g.stages < 2) g.stages = 2;
     CUtensorMap tm;
     if (int e = make_dw_tmap(&tm, x, g, 1)) return e;
     DwFwdParams p{g, w9, scale, shift, (__nv_bfloat16*)out};
-    const int smem = 2 * (g.TW + 2) * (g.TH + 2) * 128 + 384;
-    const int threads = 32 * g.pairs * g.RS;
-    long long grid = 3LL * num_sms();
-    if (grid > g.num_tiles) grid = g.num_tiles;
+    const int smem = g.stages * stage_bytes + 256;
+    const int threads = 32 * (g.strips * g.RS + 1);
+    const int grid = dw_grid(g, minb);
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_FWD(A, R)                                                                                          \
-    {                                                                                                             \
-        XCP_CUDA(cudaFuncSetAttribute(dw3x3_fwd_kernel<A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        dw3x3_fwd_kernel<A, R><<<(int)grid, threads, smem, st>>>(tm, p);                                          \
+#define LAUNCH_FWD(A, R)                                                                                                 \
+    {                                                                                                                    \
+        if (minb == 3) {                                                                                                 \
+            XCP_CUDA(cudaFuncSetAttribute(dw3x3_fwd_kernel<A, R, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            dw3x3_fwd_kernel<A, R, 3><<<grid, threads, smem, st>>>(tm, p);                                               \
+        } else {                                                                                                         \
+            XCP_CUDA(cudaFuncSetAttribute(dw3x3_fwd_kernel<A, R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            dw3x3_fwd_kernel<A, R, 2><<<grid, threads, smem, st>>>(tm, p);                                               \
+        }                                                                                                                \
     }
     if (scale != nullptr) { if (relu) LAUNCH_FWD(true, true) else LAUNCH_FWD(true, false) }
     else { if (relu) LAUNCH_FWD(false, true) else LAUNCH_FWD(false, false) }
@@ -428,7 +511,7 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
 }
 
 // Backward of xcp_dw3x3_fwd.  dz = mask * conv_transpose(dD) [+ add_full] [+ add_half at even pixels];
-// dw[C][9] += weight gradient (nn.Conv2d layout); bnsum[2][C] += (sum dz, sum dz*x) per channel when
+// dw[c_real][9] += weight gradient (nn.Conv2d layout); bnsum[2][C] += (sum dz, sum dz*x) per channel when
 // scale/shift are given (the caller zero-fills bnsum).
 extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift,
                              int relu, void* dz, const void* add_full, const void* add_half, float* dw, float* bnsum,
@@ -436,28 +519,36 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     XCP_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && c_real > 0 && c_real <= C, "xcp_dw3x3_bwd: bad shape");
     XCP_REQUIRE((scale == nullptr) == (shift == nullptr), "xcp_dw3x3_bwd: scale/shift");
     XCP_REQUIRE(dw != nullptr && (scale == nullptr || bnsum != nullptr), "xcp_dw3x3_bwd: dw / bnsum missing");
+    XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_bwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
-    DwGeom g = make_geom(F, H, W, C, 240, 8);
+    DwGeom g = make_geom(F, H, W, C, 200, 7);
+    const int stage_bytes = ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH) * 128;
+    g.stages = (108 * 1024) / stage_bytes;                       // two resident CTAs per SM
+    if (g.stages > DW_MAX_STAGES) g.stages = DW_MAX_STAGES;
+    if (g.stages < 2) g.stages = 2;
     CUtensorMap tmG, tmX;
     if (int e = make_dw_tmap(&tmG, dD, g, 1)) return e;
     if (int e = make_dw_tmap(&tmX, xin, g, 0)) return e;
-    DwBwdParams p{g, w9, scale, shift, relu, (__nv_bfloat16*)dz, (const __nv_bfloat16*)add_full,
+    DwBwdParams p{g, w9, scale, shift, (__nv_bfloat16*)dz, (const __nv_bfloat16*)add_full,
                   (const __nv_bfloat16*)add_half, dw, bnsum, c_real};
-    const int smem = 2 * ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH) * 128 + 384;
-    const int threads = 32 * g.pairs * g.RS;
-    const long long sp_tiles = (long long)F * g.n_h * g.n_w;
-    long long per_ct = (2LL * num_sms()) / g.c_tiles;
-    if (per_ct < 1) per_ct = 1;
-    if (per_ct > sp_tiles) per_ct = sp_tiles;
-    const int grid = (int)(per_ct * g.c_tiles);
+    const int smem = g.stages * stage_bytes + 256;
+    const int threads = 32 * (g.strips * g.RS + 1);
+    const int grid = dw_grid(g, 2);
+    const int addm = (add_full != nullptr ? 1 : 0) | (add_half != nullptr ? 2 : 0);
+    const int variant = ((scale != nullptr) ? 8 : 0) | (relu ? 4 : 0) | addm;
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_BWD(A, R)                                                                                          \
-    {                                                                                                             \
-        XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        dw3x3_bwd_kernel<A, R><<<grid, threads, smem, st>>>(tmG, tmX, p);                                         \
+#define LAUNCH_BWD(A, R, M)                                                                                          \
+    case ((A ? 8 : 0) | (R ? 4 : 0) | M): {                                                                          \
+        XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<A, R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        dw3x3_bwd_kernel<A, R, M><<<grid, threads, smem, st>>>(tmG, tmX, p);                                         \
+    } break;
+    switch (variant) {
+        LAUNCH_BWD(false, false, 0) LAUNCH_BWD(false, false, 1) LAUNCH_BWD(false, false, 2) LAUNCH_BWD(false, false, 3)
+        LAUNCH_BWD(false, true, 0) LAUNCH_BWD(false, true, 1) LAUNCH_BWD(false, true, 2) LAUNCH_BWD(false, true, 3)
+        LAUNCH_BWD(true, false, 0) LAUNCH_BWD(true, false, 1) LAUNCH_BWD(true, false, 2) LAUNCH_BWD(true, false, 3)
+        LAUNCH_BWD(true, true, 0) LAUNCH_BWD(true, true, 1) LAUNCH_BWD(true, true, 2) LAUNCH_BWD(true, true, 3)
+        default: break;
     }
-    if (scale != nullptr) { if (relu) LAUNCH_BWD(true, true) else LAUNCH_BWD(true, false) }
-    else { if (relu) LAUNCH_BWD(false, true) else LAUNCH_BWD(false, false) }
 #undef LAUNCH_BWD
     return check_cuda(cudaGetLastError(), "dw3x3_bwd launch");
 }

@@ -380,8 +380,21 @@ XCP_DEVINL void bnbwd_dz8(const BnBwdSrc& s, long long i, int cg, const float (&
     }
 }
 
-// pass 1: per-channel (sum dz, sum dz*y) -> partials[gridDim.x][2][C]
-__global__ void __launch_bounds__(256)
+// ReLU mask of modes 1,3 applied to an already loaded dz vector
+XCP_DEVINL void bnbwd_mask8(const BnBwdSrc& s, int cg, const float (&yv)[8], float (&dz)[8]) {
+    float sc[8], sh[8];
+    load_affine8(s.scale, s.shift, cg * 8, sc, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (!(fmaf(yv[j], sc[j], sh[j]) > 0.f)) dz[j] = 0.f;
+}
+
+// pass 1: per-channel (sum dz, sum dz*y) -> partials[gridDim.x][2][C].
+// A thread stays on one channel group (stride S is a multiple of ncg) and keeps BNBWD_U independent 16-byte loads of y
+// (and of G in the direct / ReLU modes) in flight: the first version had one load pair per thread outstanding and
+// reached 47 % of the DRAM peak with the issue slots 18 % busy (ncu, profiles/r1j), i.e. it was latency bound.
+constexpr int BNBWD_U = 4;
+__global__ void __launch_bounds__(256, 2)
 bnbwd_reduce_kernel(const uint4* __restrict__ y, const BnBwdSrc s, float* __restrict__ partials, long long n8) {
     extern __shared__ float s_acc[];   // [2][C]
     const int C = s.C, ncg = C >> 3;
@@ -395,7 +408,32 @@ bnbwd_reduce_kernel(const uint4* __restrict__ y, const BnBwdSrc s, float* __rest
         float a1[8], a2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
-        for (long long i = gid; i < n8; i += S) {
+        const bool paired = (s.mode == SRC_DIRECT || s.mode == SRC_RELU);      // G has y's shape and index
+        const uint4* Gv = reinterpret_cast<const uint4*>(s.G);
+        long long i = gid;
+        for (; i + (BNBWD_U - 1) * S < n8; i += BNBWD_U * S) {
+            uint4 yr[BNBWD_U], gr[BNBWD_U];
+#pragma unroll
+            for (int u = 0; u < BNBWD_U; ++u) yr[u] = ldg_nc_v4(y + i + u * S);
+            if (paired) {
+#pragma unroll
+                for (int u = 0; u < BNBWD_U; ++u) gr[u] = ldg_nc_v4(Gv + i + u * S);
+            }
+#pragma unroll
+            for (int u = 0; u < BNBWD_U; ++u) {
+                float yv[8], dz[8];
+                unpack8(yr[u], yv);
+                if (paired) {
+                    unpack8(gr[u], dz);
+                    if (s.mode == SRC_RELU) bnbwd_mask8(s, cg, yv, dz);
+                } else {
+                    bnbwd_dz8(s, i + u * S, cg, yv, dz);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a1[j] += dz[j]; a2[j] = fmaf(dz[j], yv[j], a2[j]); }
+            }
+        }
+        for (; i < n8; i += S) {
             float yv[8], dz[8];
             unpack8(ldg_nc_v4(y + i), yv);
             bnbwd_dz8(s, i, cg, yv, dz);
@@ -457,19 +495,25 @@ bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, int
 
 // pass 2: dy = A*dz + B*y + Cc  (bf16).  conv_grid_w > 0: scatter rows onto a zero-initialised
 // (conv_grid_h x conv_grid_w) "input grid" layout used by the stem implicit-GEMM backward.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bnbwd_apply_kernel(const uint4* __restrict__ y, const BnBwdSrc s, const float* __restrict__ coefA,
                    const float* __restrict__ coefB, const float* __restrict__ coefC, uint4* __restrict__ dy, long long n8,
                    int grid_w, int grid_h) {
     const int ncg = s.C >> 3;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i % ncg);
-        float yv[8], dz[8], A[8], B[8], Cc[8];
-        unpack8(ldg_nc_v4(y + i), yv);
-        bnbwd_dz8(s, i, cg, yv, dz);
-        load_affine8(coefA, coefB, cg * 8, A, B);
+    const long long T = (long long)gridDim.x * blockDim.x;
+    const long long S = T - (T % ncg);                 // a thread stays on one channel group: coefficients live in registers
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= S) return;
+    const int cg = (int)(gid % ncg);
+    float A[8], B[8], Cc[8];
+    load_affine8(coefA, coefB, cg * 8, A, B);
+    {
         const float4 c0 = *reinterpret_cast<const float4*>(coefC + cg * 8), c1 = *reinterpret_cast<const float4*>(coefC + cg * 8 + 4);
         Cc[0] = c0.x; Cc[1] = c0.y; Cc[2] = c0.z; Cc[3] = c0.w; Cc[4] = c1.x; Cc[5] = c1.y; Cc[6] = c1.z; Cc[7] = c1.w;
+    }
+    const bool paired = (s.mode == SRC_DIRECT || s.mode == SRC_RELU);
+    const uint4* Gv = reinterpret_cast<const uint4*>(s.G);
+    auto emit = [&](long long i, const float (&yv)[8], float (&dz)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dz[j] = fmaf(A[j], dz[j], fmaf(B[j], yv[j], Cc[j]));
         long long o = i;
@@ -481,6 +525,34 @@ bnbwd_apply_kernel(const uint4* __restrict__ y, const BnBwdSrc s, const float* _
             o = ((f * grid_h + h) * grid_w + w) * ncg + cg;
         }
         dy[o] = pack8(dz);
+    };
+    long long i = gid;
+    for (; i + (BNBWD_U - 1) * S < n8; i += BNBWD_U * S) {
+        uint4 yr[BNBWD_U], gr[BNBWD_U];
+#pragma unroll
+        for (int u = 0; u < BNBWD_U; ++u) yr[u] = ldg_nc_v4(y + i + u * S);
+        if (paired) {
+#pragma unroll
+            for (int u = 0; u < BNBWD_U; ++u) gr[u] = ldg_nc_v4(Gv + i + u * S);
+        }
+#pragma unroll
+        for (int u = 0; u < BNBWD_U; ++u) {
+            float yv[8], dz[8];
+            unpack8(yr[u], yv);
+            if (paired) {
+                unpack8(gr[u], dz);
+                if (s.mode == SRC_RELU) bnbwd_mask8(s, cg, yv, dz);
+            } else {
+                bnbwd_dz8(s, i + u * S, cg, yv, dz);
+            }
+            emit(i + u * S, yv, dz);
+        }
+    }
+    for (; i < n8; i += S) {
+        float yv[8], dz[8];
+        unpack8(ldg_nc_v4(y + i), yv);
+        bnbwd_dz8(s, i, cg, yv, dz);
+        emit(i, yv, dz);
     }
 }
 
@@ -717,7 +789,7 @@ extern "C" int xcp_bn_relu_gap(const void* y, const float* scale, const float* s
     return check_cuda(cudaGetLastError(), "bn_relu_gap launch");
 }
 
-extern "C" int xcp_bnbwd_num_parts(void) { return 2 * 160; }
+extern "C" int xcp_bnbwd_num_parts(void) { return 2 * 148; }     // resident CTAs of bnbwd_reduce_kernel on a B200 (2 per SM)
 
 // Two-pass BatchNorm backward.  mode: 0 direct, 1 relu-masked, 2 through MaxPool(3,2,1) (G, idx at pooled
 // resolution), 3 through GAP+ReLU (dfeat).  Writes dy (bf16) and accumulates dgamma/dbeta.  `presums`
@@ -737,6 +809,7 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
     if (presums == nullptr) {
         long long g = (n8 + 255) / 256;
         nparts = (int)(g < xcp_bnbwd_num_parts() ? g : xcp_bnbwd_num_parts());
+        if ((long long)nparts * 256 < C / 8) nparts = (C / 8 + 255) / 256;      // at least one thread per channel group
         bnbwd_reduce_kernel<<<nparts, 256, 2 * C * sizeof(float), ST>>>((const uint4*)y, s, workspace, n8);
         XCP_CUDA(cudaGetLastError());
         sums = workspace;
@@ -745,8 +818,11 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
                                                            coef + 2 * C, dgamma, dbeta);
     XCP_CUDA(cudaGetLastError());
     if (dy != nullptr) {
-        bnbwd_apply_kernel<<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)y, s, coef, coef + C, coef + 2 * C, (uint4*)dy, n8,
-                                                             grid_w, grid_h);
+        // grid-stride with a channel-group preserving stride: the grid must hold at least one thread per channel group
+        long long ga_ = ((n8 + BNBWD_U - 1) / BNBWD_U + 255) / 256;
+        int ga = (int)(ga_ < 2LL * num_sms() ? (ga_ > 0 ? ga_ : 1) : 2LL * num_sms());      // persistent: 2 resident CTAs per SM
+        if ((long long)ga * 256 < C / 8) ga = (C / 8 + 255) / 256;
+        bnbwd_apply_kernel<<<ga, 256, 0, ST>>>((const uint4*)y, s, coef, coef + C, coef + 2 * C, (uint4*)dy, n8, grid_w, grid_h);
     }
     return check_cuda(cudaGetLastError(), "bn_bwd launch");
 }

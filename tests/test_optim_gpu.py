@@ -18,8 +18,10 @@ def test_fused_adam_matches_torch(decoupled, max_norm):
     dev = torch.device("cuda", 0)
     ours = [torch.nn.Parameter(t.clone()) for t in _params(dev)]
     ref = [torch.nn.Parameter(t.clone()) for t in _params(dev)]
-    o = FusedAdam(ours, lr=1e-2, weight_decay=1e-2, decoupled=decoupled, max_norm=max_norm)
-    r = (torch.optim.AdamW if decoupled else torch.optim.Adam)(ref, lr=1e-2, weight_decay=1e-2)
+    # eps = 1e-4 keeps the update a smooth function of the gradient: with the default 1e-8 the first steps are
+    # lr * g / (|g| + eps), which amplifies the last-bit difference between fmaf(wd, p, g) and wd * p + g wherever g ~ 0
+    o = FusedAdam(ours, lr=1e-2, eps=1e-4, weight_decay=1e-2, decoupled=decoupled, max_norm=max_norm)
+    r = (torch.optim.AdamW if decoupled else torch.optim.Adam)(ref, lr=1e-2, eps=1e-4, weight_decay=1e-2)
     g = torch.Generator().manual_seed(5)
     for step in range(5):
         for a, b in zip(ours, ref):
@@ -42,7 +44,7 @@ def test_fused_adam_matches_torch(decoupled, max_norm):
     assert float(sd["state"][1]["step"]) == 5.0
     assert not any(k.startswith("_xcp") for k in sd["param_groups"][0])
     ours2 = [torch.nn.Parameter(t.detach().clone()) for t in ours]
-    o2 = FusedAdam(ours2, lr=1e-2, weight_decay=1e-2, decoupled=decoupled, max_norm=max_norm)
+    o2 = FusedAdam(ours2, lr=1e-2, eps=1e-4, weight_decay=1e-2, decoupled=decoupled, max_norm=max_norm)
     o2.load_state_dict(sd)
     for a, a2, b in zip(ours, ours2, ref):
         gr = torch.randn(a.shape, generator=g).to(dev)
