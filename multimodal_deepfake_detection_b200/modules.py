@@ -377,7 +377,7 @@ class _HeadFn(torch.autograd.Function):
     """fc_layers (4 x Linear+ReLU+Dropout(0.3)) + fc_out + sigmoid (XceptionLSTMV.py:25-44,68-70)."""
 
     @staticmethod
-    def forward(ctx, h_last, training, p_drop, *wb):
+    def forward(ctx, h_last, training, p_drop, want_logits, *wb):
         x = h_last.float().contiguous()
         B = x.shape[0]
         if B > 32:
@@ -391,6 +391,9 @@ class _HeadFn(torch.autograd.Function):
                 mask = (torch.rand((B, W.shape[0]), device=x.device) >= p_drop).to(torch.uint8)
             acts.append(ops.linear_small_fwd(acts[-1], W, b, 1, mask, scale))
         z = ops.linear_small_fwd(acts[-1], wb[8].detach(), wb[9].detach(), 0)
+        if want_logits:                          # fc_out without the sigmoid (criteria that take logits, train_au_patch.py:203-214)
+            ctx.acts, ctx.prob, ctx.scale, ctx.wb = acts, None, scale, wb
+            return z
         prob = ops.sigmoid_fwd(z)
         ctx.acts, ctx.prob, ctx.scale, ctx.wb = acts, prob.detach(), scale, wb     # detached: no output -> grad_fn -> ctx cycle
         return prob
@@ -399,12 +402,12 @@ class _HeadFn(torch.autograd.Function):
     def backward(ctx, dprob):
         acts, wb, scale = ctx.acts, ctx.wb, ctx.scale
         sink = ex.GradSink(list(wb), dprob.device)
-        dz = ops.sigmoid_bwd(ctx.prob, dprob.float().contiguous())
+        dz = dprob.float().contiguous() if ctx.prob is None else ops.sigmoid_bwd(ctx.prob, dprob.float().contiguous())
         delta = ops.linear_small_bwd(dz, None, 1.0, acts[4], wb[8].detach(), sink.view(wb[8]), sink.view(wb[9]))
         for li in range(3, -1, -1):
             delta = ops.linear_small_bwd(delta, acts[li + 1], scale, acts[li], wb[2 * li].detach(), sink.view(wb[2 * li]),
                                          sink.view(wb[2 * li + 1]), want_din=(li > 0 or ctx.needs_input_grad[0]))
-        return (delta if ctx.needs_input_grad[0] else None, None, None) + tuple(sink.view(p) for p in wb)
+        return (delta if ctx.needs_input_grad[0] else None, None, None, None) + tuple(sink.view(p) for p in wb)
 
 
 class _XceptionLSTMBase(nn.Module):
@@ -436,7 +439,14 @@ class _XceptionLSTMBase(nn.Module):
         lstm_out, _ = self.lstm(features)
         last = lstm_out[:, -1, :]
         drop = self.fc_layers[2]
-        return _HeadFn.apply(last, drop.training, float(drop.p), *self._head_params())
+        return _HeadFn.apply(last, drop.training, float(drop.p), False, *self._head_params())
+
+    def forward_logits(self, features):
+        """Same path as forward() without the final sigmoid: fc_out logits (B,1) for logit-space criteria such as
+        LabelSmoothingBCEWithLogitsLoss (train_au_patch.py:203-214)."""
+        lstm_out, _ = self.lstm(features)
+        drop = self.fc_layers[2]
+        return _HeadFn.apply(lstm_out[:, -1, :], drop.training, float(drop.p), True, *self._head_params())
 
 
 class XceptionLSTMV(_XceptionLSTMBase):

@@ -152,3 +152,27 @@ def test_block_spec_matches_reference_layout():
         assert [(u.cin, u.cout, u.relu) for u in spec.units] == [(ci, co, r) for (_, _, ci, co, r) in want]
         keys = [k for k in blk.state_dict() if k.endswith("conv1.weight")]
         assert keys == ["rep.%d.conv1.weight" % i for (i, _, _, _, _) in want]
+
+
+def test_loop_metrics_match_sklearn():
+    """binary_metrics / youden_threshold (loops.py) reproduce the sklearn calls of train_visual.py:476-487."""
+    np = pytest.importorskip("numpy")
+    skm = pytest.importorskip("sklearn.metrics")
+    from multimodal_deepfake_detection_b200.loops import binary_metrics, youden_threshold
+    rng = np.random.default_rng(0)
+    for n, ties in [(200, True), (57, False), (1000, True)]:
+        y = rng.integers(0, 2, n)
+        p = np.clip(y * 0.3 + rng.random(n) * 0.8, 0, 1)
+        if ties:
+            p = np.round(p, 2)
+        m = binary_metrics(y, p)
+        fpr, tpr, thr = skm.roc_curve(y, p)
+        assert abs(m["AUC"] - skm.roc_auc_score(y, p)) < 1e-9
+        assert abs(m["AP"] - skm.average_precision_score(y, p)) < 1e-9
+        fnr = 1 - tpr
+        k = np.nanargmin(np.abs(fpr - fnr))
+        assert abs(m["EER"] - (fpr[k] + fnr[k]) / 2) < 1e-9
+        assert abs(m["pAUC"] - skm.auc(fpr[fpr <= 0.1], tpr[fpr <= 0.1]) / 0.1) < 1e-9
+        t, f_, t_ = youden_threshold(y, p)
+        assert abs((t_ - f_) - np.max(tpr - fpr)) < 1e-12
+    assert binary_metrics([1, 1, 1], [0.2, 0.3, 0.9])["EER"] == 1.0      # single-class sentinel of the reference
