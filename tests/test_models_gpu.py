@@ -304,3 +304,41 @@ def test_short_training_curve_tracks_oracle():
     # the first steps must coincide; later the two bf16/fp32 trajectories separate chaotically (both over-fit the batch)
     assert np.abs(ours[:5] - ref[:5]).max() < 2e-2, (ours[:5].tolist(), ref[:5].tolist())
     assert ours[-5:].mean() < 0.1 and ref[-5:].mean() < 0.1, (ours[-5:].tolist(), ref[-5:].tolist())
+
+
+def test_200_step_training_curve_within_tolerance():
+    """north_star: "a 200-step training-loss curve within tolerance".  200 steps of the reference's first-phase protocol
+    (backbone frozen as constructed, train-mode BN, Adam on LSTM + head; train_visual.py:551-553,558) on two alternating
+    batches, our bf16 path with the fused optimizer against the fp32 oracle driven by torch.optim.Adam.
+    Tolerance: |loss_ours - loss_oracle| <= 2e-2 at every one of the 200 steps, <= 5e-3 on average."""
+    from multimodal_deepfake_detection_b200 import FusedAdam
+    m, full = _lstm_models(64, XceptionLSTMV)
+    g = torch.Generator().manual_seed(11)
+    batches = [(torch.rand(4, 3, 3, 107, 107, generator=g).to(DEV), torch.randint(0, 2, (4, 1), generator=g).float().to(DEV))
+               for _ in range(2)]
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.eval()
+    fo = _leaf(full)
+    trainable = [k for k in fo if not k.startswith("feature_extractor") and fo[k].requires_grad]
+    opt_o = torch.optim.Adam([fo[k] for k in trainable], lr=1e-4, weight_decay=1e-4)
+    opt = FusedAdam([p for p in m.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+    ours, ref = [], []
+    for step in range(200):
+        clips, y = batches[step & 1]
+        opt_o.zero_grad(); ns = {}
+        lo = F.binary_cross_entropy(O.xception_lstm_forward(fo, clips, training=True, new_stats=ns), y); lo.backward(); opt_o.step()
+        for k, v in ns.items():
+            fo[k] = v
+        opt.zero_grad(set_to_none=True)
+        l = F.binary_cross_entropy(m(m.extract_features(clips, torch.device(DEV))), y); l.backward(); opt.step()
+        ours.append(l.detach()); ref.append(lo.detach())
+    ours, ref = torch.stack(ours).cpu().numpy(), torch.stack(ref).cpu().numpy()
+    d = np.abs(ours - ref)
+    assert d.max() < 2e-2 and d.mean() < 5e-3, (float(d.max()), float(d.mean()), ours[::25].tolist(), ref[::25].tolist())
+    assert ours[-10:].mean() < ours[:10].mean()          # and it actually trains
+    # running statistics of the (train-mode) frozen BatchNorms moved alike over the 200 steps
+    cur = m.state_dict()
+    for k in ("feature_extractor.bn1.running_mean", "feature_extractor.block8.rep.5.running_var", "feature_extractor.bn4.running_var"):
+        assert rel(cur[k], fo[k]) < 2e-2, k
