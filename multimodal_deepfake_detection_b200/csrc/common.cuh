@@ -63,12 +63,13 @@ XCP_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (clean launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (clean launch failure) instead of hanging the GPU.  try_wait suspends the warp in
+// hardware for a bounded time per call, so the retry loop is cheap; the bound is an iteration count (no clock reads in
+// the loop: waiting warps share issue slots with working ones).
 XCP_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) {  // ~4 s
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) {    // seconds
             printf("xcp: mbarrier timeout block %d thread %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, parity);
             __trap();
         }

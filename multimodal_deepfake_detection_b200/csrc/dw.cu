@@ -123,6 +123,73 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
     const int sp_stride = gridDim.x / c_tiles;
     const int sp0 = blockIdx.x / c_tiles;
 
+    // ---------------------------------------------------------------------- compute warps
+    const int x0 = (warp % p.g.strips) * SW;       // first of the warp's tile-local columns
+    const int slice = warp / p.g.strips;
+    const int r0 = slice * p.g.rows_per_slice;
+    const int r1 = min(r0 + p.g.rows_per_slice, TH);
+    const int c0 = ct * 64 + lane * 2;
+    const bool lane_ok = c0 < gC;
+    const long long pix_b = (long long)gC * 2;      // bytes per pixel / per image row in global memory
+    const long long row_b = (long long)gW * pix_b;
+
+    // the CTA's channel tile never changes: weights and the fused affine live in registers for the whole kernel
+    //
+    // FOLD (BN affine + ReLU in front of the conv, 22 of the 34 depthwise layers):  relu(s*y + b) = |s| * max(sgn*y, sgn*t) + b
+    // with t = -b/s, sgn = sign(s).  The scale is folded into the taps (w'_k = w_k * s) and
+    // the shift becomes the constant b * sum_k w_k the accumulator starts from, so the activation costs one FMNMX per
+    // staged element instead of FMNMX + FMA -- the ncu pass on v3.1 showed this instantiation math-pipe throttled
+    // (42 FFMA2 = 84 FMA-pipe cycles per row step).  Zero padding: an out-of-image tap must contribute 0 = w'_k * t + b * w_k,
+    // i.e. out-of-image staged values are replaced by t (border strips / rows only; warp-uniform).
+    constexpr bool FOLD = AFFINE && RELU;
+    u64 wg[9];
+    u64 sc = 0, sh = 0, tpair = 0, cst = 0;
+    uint32_t yoob = 0;
+    bool pos0 = true, pos1 = true;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wg[k] = 0;
+    if (lane_ok) {
+        float2 wv[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wv[k] = *reinterpret_cast<const float2*>(p.w9 + (long long)k * gC + c0);
+        if (AFFINE) {
+            const float2 a = *reinterpret_cast<const float2*>(p.scale + c0);
+            const float2 b = *reinterpret_cast<const float2*>(p.shift + c0);
+            sc = pk2(a.x, a.y);
+            sh = pk2(b.x, b.y);
+            if (FOLD) {
+                float s0 = a.x, s1 = a.y, t0 = 0.f, t1 = 0.f;
+                // s == 0: constant activation relu(b); a vanishing scale of the right sign reproduces it (and its zero padding)
+                if (s0 == 0.f) s0 = (b.x == 0.f) ? 0.f : 1e-30f;
+                if (s1 == 0.f) s1 = (b.y == 0.f) ? 0.f : 1e-30f;
+                if (s0 != 0.f) t0 = -b.x / s0;
+                if (s1 != 0.f) t1 = -b.y / s1;
+                pos0 = s0 >= 0.f; pos1 = s1 >= 0.f;
+                // negative scale: s * min(y, t) = |s| * max(-y, -t); the staged value gets its sign bit flipped on unpack
+                tpair = pk2(pos0 ? t0 : -t0, pos1 ? t1 : -t1);
+                // bf16 stand-in for out-of-image pixels: rounded away from the kept side so that max(sgn*y_oob, sgn*t) = sgn*t
+                auto oob = [](float t, bool pos) -> uint32_t {
+                    uint32_t b = __float_as_uint(t) >> 16;
+                    const float v = __uint_as_float(b << 16);
+                    if (pos ? (v > t) : (v < t)) b += 1;            // truncation moved it the wrong way: one bf16 ulp outwards
+                    return b & 0xffffu;
+                };
+                yoob = oob(t0, pos0) | (oob(t1, pos1) << 16);
+                float w0 = 0.f, w1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { w0 += wv[k].x; w1 += wv[k].y; wv[k].x *= fabsf(s0); wv[k].y *= fabsf(s1); }
+                cst = pk2(b.x * w0, b.y * w1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wg[k] = pk2(wv[k].x, wv[k].y);
+    }
+
+    // block-uniform: does any channel of this tile have a negative BN scale?  (gamma is initialised to 1 and is almost always
+    // positive; the sign-free instantiation saves one instruction per staged element)
+    const bool any_neg = FOLD ? (__syncthreads_or((warp < NW && lane_ok && !(pos0 && pos1)) ? 1 : 0) != 0) : false;
+    const uint32_t sg0 = pos0 ? 0u : 0x80000000u, sg1 = pos1 ? 0u : 0x80000000u;
+
     if (warp == NW) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
@@ -139,35 +206,6 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
         return;
     }
 
-    // ---------------------------------------------------------------------- compute warps
-    const int x0 = (warp % p.g.strips) * SW;       // first of the warp's tile-local columns
-    const int slice = warp / p.g.strips;
-    const int r0 = slice * p.g.rows_per_slice;
-    const int r1 = min(r0 + p.g.rows_per_slice, TH);
-    const int c0 = ct * 64 + lane * 2;
-    const bool lane_ok = c0 < gC;
-    const long long pix_b = (long long)gC * 2;      // bytes per pixel / per image row in global memory
-    const long long row_b = (long long)gW * pix_b;
-
-    // the CTA's channel tile never changes: weights and the fused affine live in registers for the whole kernel
-    u64 wg[9];
-    u64 sc = 0, sh = 0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) wg[k] = 0;
-    if (lane_ok) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float2 a = *reinterpret_cast<const float2*>(p.w9 + (long long)k * gC + c0);
-            wg[k] = pk2(a.x, a.y);
-        }
-        if (AFFINE) {
-            const float2 a = *reinterpret_cast<const float2*>(p.scale + c0);
-            const float2 b = *reinterpret_cast<const float2*>(p.shift + c0);
-            sc = pk2(a.x, a.y);
-            sh = pk2(b.x, b.y);
-        }
-    }
-
     int s = 0; uint32_t ph = 0;
     for (int sp = sp0; sp < sp_tiles; sp += sp_stride) {
         const int tw = sp % n_w; const int t2 = sp / n_w;
@@ -179,14 +217,79 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
 
         mbar_wait(&full[s], ph);
 
-        if (active) {
+        if (gx0 < gW) {                 // warp-uniform; per-lane channel validity (lane_ok) is applied to the math only
             const uint32_t tb = sbase + s * stage_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u + (uint32_t)r0 * row_stride;
             char* op = reinterpret_cast<char*>(p.out) + ((long long)f * gH + gh0 + r0) * row_b + (long long)gx0 * pix_b +
                        (long long)c0 * 2;
             const int rmax = min(r1, gH - gh0);              // output rows of this slice that are inside the image
-            // EDGE = the strip's 6 staged columns reach outside the image (TMA zero-filled them): after the fused
-            // affine they must be forced back to exactly 0 (the conv's zero padding applies to the activated input).
-            // Interior strips -- the vast majority -- run the select-free instantiation.
+            if (FOLD && rmax > r0) {
+                // Halo fix-up.  Staged pixels outside the image were zero-filled by TMA, but the folded activation needs them
+                // to read as "t" (they must contribute exactly w'_k * t + b * w_k = 0).  Each warp patches the part of the
+                // halo tile IT reads (<= 1 row above, 1 row below, 1 column left, <= 4 columns right; border tiles only) with
+                // the bf16 value y_oob chosen so that max(sgn*y_oob, sgn*t) == sgn*t.  Neighbouring warps may patch the same
+                // pixel with the same value.  After this the row loop has no border logic at all.
+                const int nrows = rmax - r0 + 2;                                  // staged rows this warp reads
+                if (gh0 + r0 == 0) {
+#pragma unroll
+                    for (int dx = 0; dx < LW; ++dx) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tb + dx * 128), "r"(yoob) : "memory");
+                }
+                if (gh0 + rmax == gH) {
+                    const uint32_t a = tb + (uint32_t)(nrows - 1) * row_stride;
+#pragma unroll
+                    for (int dx = 0; dx < LW; ++dx) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + dx * 128), "r"(yoob) : "memory");
+                }
+                if (gx0 == 0) {
+                    for (int r = 0; r < nrows; ++r) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tb + (uint32_t)r * row_stride), "r"(yoob) : "memory");
+                }
+                if (gx0 + SW >= gW) {
+                    const int dx0 = gW - gx0 + 1;                                 // first staged column outside the image
+                    for (int r = 0; r < nrows; ++r)
+                        for (int dx = dx0; dx < LW; ++dx)
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(tb + (uint32_t)r * row_stride + dx * 128), "r"(yoob) : "memory");
+                }
+                __syncwarp();
+                auto run = [&](auto signed_tag) {
+                    if (!lane_ok) return;
+                    constexpr bool SIGNED = decltype(signed_tag)::value;
+                    float t0, t1; upk2(tpair, t0, t1);
+                    auto load_row = [&](uint32_t a, u64 (&w)[LW]) {
+#pragma unroll
+                        for (int dx = 0; dx < LW; ++dx) {
+                            const uint32_t v = lds32(a + dx * 128);
+                            uint32_t ul = v << 16, uh = v & 0xffff0000u;
+                            if (SIGNED) { ul ^= sg0; uh ^= sg1; }
+                            w[dx] = pk2(fmaxf(__uint_as_float(ul), t0), fmaxf(__uint_as_float(uh), t1));
+                        }
+                    };
+                    u64 win[3][LW];
+                    uint32_t a = tb;
+                    load_row(a, win[0]); a += row_stride;
+                    load_row(a, win[1]); a += row_stride;
+                    char* o_ptr = op;
+#define DW_STEP(WA, WB, WC)                                                                                 \
+    {                                                                                                       \
+        load_row(a, WC); a += row_stride;                                                                   \
+        _Pragma("unroll") for (int px = 0; px < SW; ++px) {                                                 \
+            u64 a0 = fma2(wg[0], WA[px], cst);                                                              \
+            a0 = fma2(wg[1], WA[px + 1], a0); a0 = fma2(wg[2], WA[px + 2], a0);                             \
+            a0 = fma2(wg[3], WB[px], a0); a0 = fma2(wg[4], WB[px + 1], a0); a0 = fma2(wg[5], WB[px + 2], a0); \
+            a0 = fma2(wg[6], WC[px], a0); a0 = fma2(wg[7], WC[px + 1], a0); a0 = fma2(wg[8], WC[px + 2], a0); \
+            if (px < ncols) *reinterpret_cast<uint32_t*>(o_ptr + px * pix_b) = f2_to_bf2(a0);               \
+        }                                                                                                   \
+        o_ptr += row_b;                                                                                     \
+    }
+                    int o = r0;
+                    while (o < rmax) {
+                        DW_STEP(win[0], win[1], win[2]); if (++o >= rmax) break;
+                        DW_STEP(win[1], win[2], win[0]); if (++o >= rmax) break;
+                        DW_STEP(win[2], win[0], win[1]); ++o;
+                    }
+#undef DW_STEP
+                };
+                if (!any_neg) run(std::false_type{}); else run(std::true_type{});
+            } else if (!FOLD && lane_ok) {
+            // EDGE = the strip's 6 staged columns reach outside the image (TMA zero-filled them): after a fused affine
+            // they must be forced back to exactly 0 (the conv's zero padding applies to the activated input).
             auto run = [&](auto edge_tag) {
                 constexpr bool EDGE = decltype(edge_tag)::value;
                 bool cvn[LW];
@@ -194,8 +297,7 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
                 for (int dx = 0; dx < LW; ++dx) cvn[dx] = (gx0 - 1 + dx >= 0) && (gx0 - 1 + dx < gW);
                 // load + transform one staged row (a = its shared-memory address, gh = its image row) into registers
                 auto load_row = [&](uint32_t a, int gh, u64 (&w)[LW]) {
-                    // rows outside the image must stay exactly 0 after the fused affine: scale = shift = 0 for them
-                    // (branch-free, so the loads of the next row still overlap the FMAs of this one)
+                    // rows outside the image must stay exactly 0 after the fused affine: scale = shift = 0
                     const bool row_in = (gh >= 0) && (gh < gH);
                     const u64 scr = (AFFINE && !row_in) ? 0ull : sc;
                     const u64 shr = (AFFINE && !row_in) ? 0ull : sh;
@@ -223,7 +325,7 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
             a0 = fma2(wg[1], WA[px + 1], a0); a0 = fma2(wg[2], WA[px + 2], a0);                             \
             a0 = fma2(wg[3], WB[px], a0); a0 = fma2(wg[4], WB[px + 1], a0); a0 = fma2(wg[5], WB[px + 2], a0); \
             a0 = fma2(wg[6], WC[px], a0); a0 = fma2(wg[7], WC[px + 1], a0); a0 = fma2(wg[8], WC[px + 2], a0); \
-            if (!EDGE || px < ncols) *reinterpret_cast<uint32_t*>(o_ptr + px * pix_b) = f2_to_bf2(a0);      \
+            if (px < ncols) *reinterpret_cast<uint32_t*>(o_ptr + px * pix_b) = f2_to_bf2(a0);               \
         }                                                                                                   \
         o_ptr += row_b;                                                                                     \
     }
@@ -235,8 +337,9 @@ dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
                 }
 #undef DW_STEP
             };
-            if (gx0 >= 1 && gx0 + SW < gW) run(std::false_type{});
+            if (!AFFINE || (gx0 >= 1 && gx0 + SW < gW)) run(std::false_type{});
             else run(std::true_type{});
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);     // this warp is done with stage s

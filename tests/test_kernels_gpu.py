@@ -126,7 +126,7 @@ def test_stem_conv1(F_, H):
 
 
 # ------------------------------------------------------------------------------------------------ depthwise
-DW_SHAPES = [(2, 147, 147, 64), (2, 74, 74, 128), (3, 37, 37, 256), (2, 19, 19, 728), (3, 10, 10, 1024), (1, 5, 7, 16),
+DW_SHAPES = [(2, 147, 147, 64), (2, 74, 74, 128), (3, 37, 37, 256), (2, 19, 19, 728), (3, 10, 10, 1024), (1, 5, 7, 16), (9, 37, 37, 728),
              (2, 2, 2, 728), (1, 33, 31, 8)]
 
 
@@ -139,6 +139,8 @@ def test_dw3x3_fwd_bwd(shape, affine, relu):
     w9 = ops.pack_dw(w)
     scale = (rnd(C, seed=15) * 0.5 + 1.0) if affine else None      # includes some negative / small scales
     shift = rnd(C, seed=16, scale=0.3) if affine else None
+    if affine:      # corner cases of the folded BN affine: negative scale, zero scale with +/- shift, zero-padded channel (0, 0)
+        scale[0], scale[1], shift[1], scale[2], shift[2], scale[3], shift[3] = -0.7, 0.0, 0.3, 0.0, -0.3, 0.0, 0.0
     xt = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     wt = w.clone().requires_grad_(True)
     a = xt
