@@ -288,6 +288,18 @@ def run_ours(args):
             torch.cuda.synchronize()
             os._exit(0)
 
+    # ---- inference (the "infer frames/sec" half of the metric): eval-mode forward of the same clips, BN folded from the
+    # running statistics, no saved activations (test_visual.py:609-624 protocol), device-resident inputs
+    model.eval()
+    def infer(i):
+        with torch.no_grad():
+            return model(model.extract_features(dev_clips, dev))
+    for i in range(3):
+        infer(i)
+    ms_inf = timed(infer, args.steps)
+    infer_fps = world * B * T_FRAMES * args.steps / (ms_inf * 1e-3)
+    model.train()
+
     if rank != 0:
         finish()
         return
@@ -320,6 +332,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / max(args.steps, 1)},
         "gpu_launches": launches,
+        "infer": {"value": infer_fps, "unit": "frames/s", "ms_per_pass": ms_inf / max(args.steps, 1),
+                  "what": "XceptionLSTMV eval-mode forward (BN folded, no_grad), %d clips x %d frames per GPU per pass" % (B, T_FRAMES)},
         "roofline": roof,
         "cpu_baseline": cpu,
         "loss": last.get("loss"),
@@ -333,7 +347,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step")
+    ap.add_argument("--clips", type=int, default=16, help="clips per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager per-kernel launches instead of CUDA-graph replays")
