@@ -9,7 +9,8 @@
 // Structure (one CTA per SM, persistent over tiles):
 //   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 per instr)
-//   warps 2..5    : epilogue      (tcgen05.ld 32x32b -> regs -> bf16/f32 store, per-channel sum / sum-sq)
+//   warps 2..9    : epilogue      (tcgen05.ld 32x32b -> regs -> bf16/f32 store; per-channel sum / sum-sq from a second
+//                                   16x256b read of the accumulator, kept in registers across the CTA's tiles)
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 //
@@ -26,6 +27,8 @@ namespace xcp {
 enum { EPI_BF16 = 0, EPI_BF16_STATS = 1, EPI_F32 = 2, EPI_RED_F32 = 3 };
 
 struct GemmParams {
+    CUtensorMap tmC;      // EPI_BF16 / EPI_BF16_STATS with tma_store: the bf16 output as [M rows, N cols], box 32 x 32, 64B swizzle
+    int tma_store;
     int M, N, K;          // output rows, output cols, reduction length (elements)
     void* out;            // bf16 / f32, row-major [M, ldo]
     long long ldo;
@@ -41,16 +44,30 @@ struct GemmParams {
 };
 
 constexpr int BLOCK_M = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
 constexpr int A_STAGE_BYTES = BLOCK_M * 128;
 
 template <int BLOCK_N, int BLOCK_K>
 __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_N * BLOCK_K * 2; }
 
-template <int BLOCK_N, int BLOCK_K, bool STATS, bool CTA2>
+constexpr int STORE_STAGE_BYTES = 8 * 2 * 2048;   // TMA-store epilogue: 8 warps x 2 buffers x (32 rows x 64 B)
+template <int BLOCK_N, int BLOCK_K, int EPI, bool CTA2>
+__host__ __device__ constexpr int gemm_fixed_smem() {
+    return 1024 /*align slack*/ + 256 /*barriers*/ +
+           (EPI == EPI_BF16_STATS ? ((BLOCK_N == 64 ? 8 * 32 * 36 * 4 : 0) + 4 * 2 * BLOCK_N * 4) : 0) +
+           ((EPI == EPI_BF16 || EPI == EPI_BF16_STATS) ? STORE_STAGE_BYTES : 0);
+}
+template <int BLOCK_N, int BLOCK_K, bool CTA2>
+__host__ __device__ constexpr int gemm_stage_bytes() { return BLOCK_M * BLOCK_K * 2 + b_stage_bytes<BLOCK_N, BLOCK_K>() / (CTA2 ? 2 : 1); }
+template <int BLOCK_N, int BLOCK_K, int EPI, bool CTA2>
 __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
-    return 1024 /*align slack*/ + stages * (BLOCK_M * BLOCK_K * 2 + b_stage_bytes<BLOCK_N, BLOCK_K>() / (CTA2 ? 2 : 1)) +
-           (STATS ? (4 * 32 * 36 * 4 + 4 * 2 * BLOCK_N * 4) : 0) + 256 /*barriers*/;
+    return gemm_fixed_smem<BLOCK_N, BLOCK_K, EPI, CTA2>() + stages * gemm_stage_bytes<BLOCK_N, BLOCK_K, CTA2>();
+}
+// deepest TMA ring that fits the 227 KB of an SM next to the epilogue's scratch (at most 8 stages)
+template <int BLOCK_N, int BLOCK_K, int EPI, bool CTA2>
+__host__ __device__ constexpr int fit_stages() {
+    const int s = (232448 - gemm_fixed_smem<BLOCK_N, BLOCK_K, EPI, CTA2>()) / gemm_stage_bytes<BLOCK_N, BLOCK_K, CTA2>();
+    return s > 8 ? 8 : s;
 }
 
 // MN_MAJOR=false: A is [M,K] row-major, B is [N,K] row-major (both K-major):      D = A * B^T
@@ -58,7 +75,7 @@ __host__ __device__ constexpr int gemm_smem_bytes(int stages) {
 // BLOCK_K=64 -> 128B swizzle; BLOCK_K=32 -> 64B swizzle (K-major only; used by the stem implicit GEMM)
 template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
     static_assert(BLOCK_K == 64 || (BLOCK_K == 32 && !MN_MAJOR), "unsupported BLOCK_K");
     static_assert(!CTA2 || (BLOCK_K == 64 && BLOCK_N >= 128), "CTA-pair mode: BLOCK_K 64, BLOCK_N 128/256");
     constexpr bool STATS = (EPI == EPI_BF16_STATS);
@@ -76,9 +93,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * A_BYTES;
     uint8_t* after = sB + STAGES * B_BYTES;
-    float* s_tr = reinterpret_cast<float*>(after);                       // [4][32][36]  (144-byte rows: conflict-free v4 stores)
-    float* s_part = s_tr + (STATS ? 4 * 32 * 36 : 0);                    // [4][2][BLOCK_N]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + (STATS ? 4 * 2 * BLOCK_N : 0));
+    float* s_tr = reinterpret_cast<float*>(after);                       // [8][32][36]  (144-byte rows: conflict-free v4 stores); BLOCK_N == 64 only
+    float* s_part = s_tr + ((STATS && BLOCK_N == 64) ? 8 * 32 * 36 : 0);                    // [4][2][BLOCK_N]
+    uint8_t* s_store = reinterpret_cast<uint8_t*>(s_part + (STATS ? 4 * 2 * BLOCK_N : 0));      // [8 warps][2][32 rows x 64 B], 64B-swizzled
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_store + ((EPI == EPI_BF16 || EPI == EPI_BF16_STATS) ? STORE_STAGE_BYTES : 0));
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
@@ -94,7 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 8 : 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 16 : 8); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -196,15 +214,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp >= 2) {
-        // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        // ------------------------------------------------ epilogue: 8 warps.  Warp w drains TMEM lane quarter w % 4 (the
+        // hardware restriction) and column half (w - 2) / 4 of the tile, so two warps work on every 32-row slab: the
+        // HBM-bound entry-flow GEMMs (K = 64..256: one to four K blocks per tile) are limited by how fast the epilogue
+        // turns accumulators into bf16 rows, not by the MMAs.
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NC = BLOCK_N / 32;                       // 32-column chunks per tile
+        constexpr int NCW = NC >= 2 ? NC / 2 : 1;              // chunks per warp
+        const int c_lo = NC >= 2 ? half * NCW : 0;
+        const int c_hi = NC >= 2 ? c_lo + NCW : (half == 0 ? 1 : 0);
         const int row_in_tile = q * 32 + lane;
-        const int et = threadIdx.x - 64;   // 0..127
-        float* my_tr = s_tr + q * (32 * 36);
-        float racc[2][(BLOCK_N + 127) / 128];
+        const int et = threadIdx.x - 64;   // 0..255
+        float* my_tr = s_tr + (warp - 2) * (32 * 36);          // BLOCK_N == 64 only (stem implicit GEMM)
+        // statistics modes: REG  = one N tile per CTA (stats_per_cta) -> per-thread register accumulators over ALL tiles of the
+        //                          CTA in the mma-fragment layout, one cross-lane reduction at the very end;
+        //                   TILE = several N tiles -> per-tile reduction (recursive halving) and per-tile partial rows;
+        //                   CONV = stem implicit GEMM (row masks) -> shared-memory transpose per chunk.
+        const bool reg_stats = STATS && p.stats_per_cta && p.conv_taps == 0;
+        u64 acc1[NCW][4], acc2[NCW][4];
 #pragma unroll
-        for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) { racc[0][i] = 0.f; racc[1][i] = 0.f; }
-        uint32_t iter = 0;
+        for (int i = 0; i < NCW; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc1[i][j] = 0ull; acc2[i][j] = 0ull; }
+        float racc1 = 0.f, racc2 = 0.f;                        // CONV mode: column `et` of the (single, 64-wide) N tile
+        uint32_t iter = 0, n_store = 0;
         const uint32_t tmem_empty_leader[2] = {CTA2 ? mapa_cluster(smem_u32(&tmem_empty[0]), 0) : 0u,
                                                CTA2 ? mapa_cluster(smem_u32(&tmem_empty[1]), 0) : 0u};
         for (int u = worker; u < num_units; u += num_workers, ++iter) {
@@ -228,13 +262,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 row_ok = row_ok && (h < p.conv_out_h) && (w < p.conv_out_w);
                 orow = (f * p.conv_out_h + h) * p.conv_out_w + w;
             }
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+#pragma unroll
+            for (int ci = 0; ci < NCW; ++ci) {
+                const int c = c_lo + ci;
+                if (c >= c_hi) break;
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
+                uint32_t fa[16], fb[16];
+                if (STATS && p.conv_taps == 0) {
+                    // The accumulator chunk is read a second time in the mma-fragment shape (16x256b: a thread holds
+                    // 4 rows x 4 column pairs) for the column statistics.  The shared-memory crossbar carries the UMMA
+                    // operand reads (~96 of 128 B/clk), so the epilogue must stay off it: the first version transposed
+                    // through smem (8 KB per chunk) and cost 30 % of the kernel.  Rows past M are exact zeros (TMA fill).
+                    const uint32_t tcol = tmem_base + as * BLOCK_N + c * 32;
+                    tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32) << 16), fa);
+                    tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32 + 16) << 16), fb);
+                }
                 tmem_ld_wait();
                 const int gcol = n_blk * BLOCK_N + c * 32;
                 if (EPI == EPI_BF16 || EPI == EPI_BF16_STATS) {
+                    if (p.tma_store) {
+                        // bf16 rows -> 64B-swizzled staging tile (conflict-free 16 B stores) -> one bulk tensor store of the
+                        // 32 x 32 box: full-line coalesced writes issued by the TMA unit instead of 32 row-scattered 16 B
+                        // pieces per warp instruction; rows / columns past M / N are clipped by the tensor map.
+                        const uint32_t stg = smem_u32(s_store) + (uint32_t)(((warp - 2) * 2 + (int)(n_store & 1)) * 2048);
+                        if (n_store >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint32_t a = stg + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) * 16);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                                         "r"(pack_bf16(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]))),
+                                         "r"(pack_bf16(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]))),
+                                         "r"(pack_bf16(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]))),
+                                         "r"(pack_bf16(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]))) : "memory");
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&p.tmC),
+                                         "r"(stg), "r"(gcol), "r"(m_blk * BLOCK_M + q * 32) : "memory");
+                            tma_store_commit();
+                        }
+                        ++n_store;
+                    } else {
                     __nv_bfloat16* orow_p = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + gcol;
                     if (row_ok) {
 #pragma unroll
@@ -249,18 +319,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             }
                         }
                     }
+                    }
                     if (STATS && p.conv_taps == 0) {
-                        // Per-column sum / sum-of-squares over this warp's 32 rows.  The accumulator chunk is read a second
-                        // time from TMEM in the mma-fragment shape (16x256b: a thread holds 4 rows x 4 column pairs), reduced
-                        // over its 4 rows with packed f32x2 math and then across the 8 lanes that share its columns by
-                        // recursive halving (14 shuffles).  The shared-memory crossbar carries the UMMA operand reads
-                        // (~96 of 128 B/clk), so the epilogue must stay off it: the first version transposed through smem
-                        // (8 KB per chunk) and cost 30 % of the kernel.  Rows past M are exact zeros (TMA zero fill).
-                        uint32_t fa[16], fb[16];
-                        const uint32_t tcol = tmem_base + as * BLOCK_N + c * 32;
-                        tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32) << 16), fa);
-                        tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32 + 16) << 16), fb);
-                        tmem_ld_wait();
                         u64 s1[4], s2[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -271,58 +331,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             s1[j] = add2(add2(v0, v1), add2(v2, v3));
                             s2[j] = fma2(v0, v0, fma2(v1, v1, fma2(v2, v2, mul2(v3, v3))));
                         }
-                        // lanes t, t^4, t^8, t^16 hold partial sums of the same 8 columns: halve the live set each round
-                        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-                        u64 k1[2], k2[2];
+                        if (reg_stats) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {                         // round 1 (xor 16): keep column blocks {2*b4, 2*b4+1}
-                            const u64 snd1 = b4 ? s1[j] : s1[j + 2], snd2 = b4 ? s2[j] : s2[j + 2];
-                            const u64 kp1 = b4 ? s1[j + 2] : s1[j], kp2 = b4 ? s2[j + 2] : s2[j];
-                            k1[j] = add2(kp1, __shfl_xor_sync(0xffffffffu, snd1, 16));
-                            k2[j] = add2(kp2, __shfl_xor_sync(0xffffffffu, snd2, 16));
+                            for (int j = 0; j < 4; ++j) { acc1[ci][j] = add2(acc1[ci][j], s1[j]); acc2[ci][j] = add2(acc2[ci][j], s2[j]); }
+                        } else {
+                            // lanes t, t^4, t^8, t^16 hold partial sums of the same 8 columns: halve the live set each round
+                            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                            u64 k1[2], k2[2];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {                         // round 1 (xor 16): keep column blocks {2*b4, 2*b4+1}
+                                const u64 snd1 = b4 ? s1[j] : s1[j + 2], snd2 = b4 ? s2[j] : s2[j + 2];
+                                const u64 kp1 = b4 ? s1[j + 2] : s1[j], kp2 = b4 ? s2[j + 2] : s2[j];
+                                k1[j] = add2(kp1, __shfl_xor_sync(0xffffffffu, snd1, 16));
+                                k2[j] = add2(kp2, __shfl_xor_sync(0xffffffffu, snd2, 16));
+                            }
+                            const u64 snd1 = b3 ? k1[0] : k1[1], snd2 = b3 ? k2[0] : k2[1];      // round 2 (xor 8): keep block 2*b4 + b3
+                            const u64 m1 = add2(b3 ? k1[1] : k1[0], __shfl_xor_sync(0xffffffffu, snd1, 8));
+                            const u64 m2 = add2(b3 ? k2[1] : k2[0], __shfl_xor_sync(0xffffffffu, snd2, 8));
+                            float m1l, m1h, m2l, m2h;
+                            upk2(m1, m1l, m1h); upk2(m2, m2l, m2h);
+                            const float t1 = (b2 ? m1h : m1l) + __shfl_xor_sync(0xffffffffu, b2 ? m1l : m1h, 4);   // round 3 (xor 4)
+                            const float t2 = (b2 ? m2h : m2l) + __shfl_xor_sync(0xffffffffu, b2 ? m2l : m2h, 4);
+                            const int col = 8 * ((b4 ? 2 : 0) + (b3 ? 1 : 0)) + 2 * (lane & 3) + (b2 ? 1 : 0);
+                            s_part[(q * 2 + 0) * BLOCK_N + c * 32 + col] = t1;
+                            s_part[(q * 2 + 1) * BLOCK_N + c * 32 + col] = t2;
                         }
-                        const u64 snd1 = b3 ? k1[0] : k1[1], snd2 = b3 ? k2[0] : k2[1];      // round 2 (xor 8): keep block 2*b4 + b3
-                        const u64 m1 = add2(b3 ? k1[1] : k1[0], __shfl_xor_sync(0xffffffffu, snd1, 8));
-                        const u64 m2 = add2(b3 ? k2[1] : k2[0], __shfl_xor_sync(0xffffffffu, snd2, 8));
-                        float m1l, m1h, m2l, m2h;
-                        upk2(m1, m1l, m1h); upk2(m2, m2l, m2h);
-                        const float t1 = (b2 ? m1h : m1l) + __shfl_xor_sync(0xffffffffu, b2 ? m1l : m1h, 4);   // round 3 (xor 4)
-                        const float t2 = (b2 ? m2h : m2l) + __shfl_xor_sync(0xffffffffu, b2 ? m2l : m2h, 4);
-                        const int col = 8 * ((b4 ? 2 : 0) + (b3 ? 1 : 0)) + 2 * (lane & 3) + (b2 ? 1 : 0);
-                        s_part[(q * 2 + 0) * BLOCK_N + c * 32 + col] = t1;
-                        s_part[(q * 2 + 1) * BLOCK_N + c * 32 + col] = t2;
                     } else if (STATS) {
                         // stem implicit GEMM (rows outside the valid window must be masked): padded smem transpose -- each
                         // lane stores its row as 8 x 16 B, then lane (h, cp) = (lane/16, lane%16) sums the column pair
                         // (2cp, 2cp+1) over rows 16h..16h+15; one xor-16 shuffle joins the two halves.
-                        if (!row_ok) {
+                        if (BLOCK_N == 64) {
+                            if (!row_ok) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) r[j] = 0u;
-                        }
-                        const uint32_t tr_w = smem_u32(my_tr) + (uint32_t)lane * 144u;
+                                for (int j = 0; j < 32; ++j) r[j] = 0u;
+                            }
+                            const uint32_t tr_w = smem_u32(my_tr) + (uint32_t)lane * 144u;
 #pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tr_w + g * 16), "r"(r[g * 4 + 0]),
-                                         "r"(r[g * 4 + 1]), "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3]) : "memory");
-                        __syncwarp();
-                        const uint32_t tr_r = smem_u32(my_tr) + (uint32_t)(lane >> 4) * (16u * 144u) + (uint32_t)(lane & 15) * 8u;
-                        u64 s1 = 0ull, s2 = 0ull;
+                            for (int g = 0; g < 8; ++g)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tr_w + g * 16), "r"(r[g * 4 + 0]),
+                                             "r"(r[g * 4 + 1]), "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3]) : "memory");
+                            __syncwarp();
+                            const uint32_t tr_r = smem_u32(my_tr) + (uint32_t)(lane >> 4) * (16u * 144u) + (uint32_t)(lane & 15) * 8u;
+                            u64 s1 = 0ull, s2 = 0ull;
 #pragma unroll
-                        for (int l = 0; l < 16; ++l) {
-                            u64 v;
-                            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(tr_r + l * 144));
-                            s1 = add2(s1, v);
-                            s2 = fma2(v, v, s2);
+                            for (int l = 0; l < 16; ++l) {
+                                u64 v;
+                                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(tr_r + l * 144));
+                                s1 = add2(s1, v);
+                                s2 = fma2(v, v, s2);
+                            }
+                            float a0, a1, b0, b1;
+                            upk2(s1, a0, a1); upk2(s2, b0, b1);
+                            a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+                            b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+                            if (lane < 16) {
+                                *reinterpret_cast<float2*>(&s_part[(q * 2 + 0) * BLOCK_N + c * 32 + lane * 2]) = make_float2(a0, a1);
+                                *reinterpret_cast<float2*>(&s_part[(q * 2 + 1) * BLOCK_N + c * 32 + lane * 2]) = make_float2(b0, b1);
+                            }
+                            __syncwarp();
                         }
-                        float a0, a1, b0, b1;
-                        upk2(s1, a0, a1); upk2(s2, b0, b1);
-                        a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-                        b0 += __shfl_xor_sync(0xffffffffu, b0, 16); b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
-                        if (lane < 16) {
-                            *reinterpret_cast<float2*>(&s_part[(q * 2 + 0) * BLOCK_N + c * 32 + lane * 2]) = make_float2(a0, a1);
-                            *reinterpret_cast<float2*>(&s_part[(q * 2 + 1) * BLOCK_N + c * 32 + lane * 2]) = make_float2(b0, b1);
-                        }
-                        __syncwarp();
                     }
                 } else if (EPI == EPI_F32) {
                     float* orow_p = reinterpret_cast<float*>(p.out) + orow * p.ldo + gcol;
@@ -359,11 +426,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (CTA2) mbar_arrive_cluster(tmem_empty_leader[as]); else mbar_arrive(&tmem_empty[as]); }
-            if (STATS) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-                for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) {
-                    const int c = et + i * 128;
+            if (STATS && !reg_stats) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {
+                    const int c = et;
                     const int gcol = n_blk * BLOCK_N + c;
                     if (c < BLOCK_N && gcol < p.N) {
                         float s1 = 0.f, s2 = 0.f;
@@ -373,24 +439,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             s2 += s_part[(qq * 2 + 1) * BLOCK_N + c];
                         }
                         if (p.stats_per_cta) {
-                            racc[0][i] += s1; racc[1][i] += s2;
+                            racc1 += s1; racc2 += s2;
                         } else if ((long long)m_blk * BLOCK_M < p.M) {   // (pair mode: the odd tail block has no rows)
                             p.stats[((long long)m_blk * 2 + 0) * p.N + gcol] = s1;
                             p.stats[((long long)m_blk * 2 + 1) * p.N + gcol] = s2;
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
+        if ((EPI == EPI_BF16 || EPI == EPI_BF16_STATS) && p.tma_store && lane == 0) tma_store_wait_read<0>();
         if (STATS && p.stats_per_cta) {
+            if (reg_stats) {
+                // one cross-lane reduction for the whole kernel: full butterfly over the 8 lanes that share a column set
+                // (xor 4, 8, 16), lanes 0..3 of each warp publish their 8 column pairs per chunk, then the 4 lane quarters
+                // are summed through shared memory
 #pragma unroll
-            for (int i = 0; i < (BLOCK_N + 127) / 128; ++i) {
-                const int c = et + i * 128;
-                if (c < BLOCK_N && c < p.N) {
-                    p.stats[((long long)blockIdx.x * 2 + 0) * p.N + c] = racc[0][i];
-                    p.stats[((long long)blockIdx.x * 2 + 1) * p.N + c] = racc[1][i];
+                for (int ci = 0; ci < NCW; ++ci) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        u64 a = acc1[ci][j], b = acc2[ci][j];
+#pragma unroll
+                        for (int o = 4; o <= 16; o <<= 1) { a = add2(a, __shfl_xor_sync(0xffffffffu, a, o)); b = add2(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+                        const int c = c_lo + ci;
+                        if (lane < 4 && c < c_hi) {
+                            float a0, a1, b0, b1;
+                            upk2(a, a0, a1); upk2(b, b0, b1);
+                            const int col = c * 32 + 8 * j + 2 * lane;
+                            *reinterpret_cast<float2*>(&s_part[(q * 2 + 0) * BLOCK_N + col]) = make_float2(a0, a1);
+                            *reinterpret_cast<float2*>(&s_part[(q * 2 + 1) * BLOCK_N + col]) = make_float2(b0, b1);
+                        }
+                    }
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et < BLOCK_N) {
+                    racc1 = 0.f; racc2 = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) { racc1 += s_part[(qq * 2 + 0) * BLOCK_N + et]; racc2 += s_part[(qq * 2 + 1) * BLOCK_N + et]; }
+                }
+            }
+            if (et < BLOCK_N && et < p.N) {
+                p.stats[((long long)blockIdx.x * 2 + 0) * p.N + et] = racc1;
+                p.stats[((long long)blockIdx.x * 2 + 1) * p.N + et] = racc2;
             }
         }
     }
@@ -430,7 +521,7 @@ static int gemm_grid(int units) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (max_clusters[dev] == 0) {
-        constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI == EPI_BF16_STATS, CTA2>(STAGES);
+        constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI, CTA2>(STAGES);
         auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaLaunchConfig_t cfg = {};
@@ -450,7 +541,7 @@ static int gemm_grid(int units) {
 
 template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2 = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI == EPI_BF16_STATS, CTA2>(STAGES);
+    constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI, CTA2>(STAGES);
     static_assert(smem <= 232448, "smem budget");
     auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>;
     static bool attr_set = false;   // per-instantiation; benign race (idempotent)
@@ -487,21 +578,21 @@ static TnPlan plan_tn(long long M, int N) {
 
 template <int EPI>
 static int dispatch_tn(const TnPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
-    if (pl.bn == 64) return launch_gemm<64, EPI, false, 8, 64>(a, b, p, st);
+    if (pl.bn == 64) return launch_gemm<64, EPI, false, fit_stages<64, 64, EPI, false>(), 64>(a, b, p, st);
     if (pl.bn == 128) {
-        if (pl.cta2) return launch_gemm<128, EPI, false, 8, 64, true>(a, b, p, st);
-        return launch_gemm<128, EPI, false, 6, 64>(a, b, p, st);
+        if (pl.cta2) return launch_gemm<128, EPI, false, fit_stages<128, 64, EPI, true>(), 64, true>(a, b, p, st);
+        return launch_gemm<128, EPI, false, fit_stages<128, 64, EPI, false>(), 64>(a, b, p, st);
     }
-    if (pl.cta2) return launch_gemm<256, EPI, false, 6, 64, true>(a, b, p, st);
-    return launch_gemm<256, EPI, false, 4, 64>(a, b, p, st);
+    if (pl.cta2) return launch_gemm<256, EPI, false, fit_stages<256, 64, EPI, true>(), 64, true>(a, b, p, st);
+    return launch_gemm<256, EPI, false, fit_stages<256, 64, EPI, false>(), 64>(a, b, p, st);
 }
 
 // persistent grid of a K-major launch (= number of per-CTA statistics rows when N fits one tile)
 template <int EPI>
 static int grid_tn(const TnPlan& pl, int units) {
-    if (pl.bn == 64) return gemm_grid<64, EPI, false, 8, 64, false>(units);
-    if (pl.bn == 128) return pl.cta2 ? gemm_grid<128, EPI, false, 8, 64, true>(units) : gemm_grid<128, EPI, false, 6, 64, false>(units);
-    return pl.cta2 ? gemm_grid<256, EPI, false, 6, 64, true>(units) : gemm_grid<256, EPI, false, 4, 64, false>(units);
+    if (pl.bn == 64) return gemm_grid<64, EPI, false, fit_stages<64, 64, EPI, false>(), 64, false>(units);
+    if (pl.bn == 128) return pl.cta2 ? gemm_grid<128, EPI, false, fit_stages<128, 64, EPI, true>(), 64, true>(units) : gemm_grid<128, EPI, false, fit_stages<128, 64, EPI, false>(), 64, false>(units);
+    return pl.cta2 ? gemm_grid<256, EPI, false, fit_stages<256, 64, EPI, true>(), 64, true>(units) : gemm_grid<256, EPI, false, fit_stages<256, 64, EPI, false>(), 64, false>(units);
 }
 
 }  // namespace xcp
@@ -532,6 +623,10 @@ extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long lon
     p.num_k_blocks = (K + 63) / 64;
     p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
     p.stats_per_cta = (p.num_n_tiles == 1) ? 1 : 0;
+    if (epi != EPI_F32) {
+        if (int e = make_tmap_2d(&p.tmC, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 32, 32, 64)) return e;
+        p.tma_store = 1;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     switch (epi) {
         case EPI_BF16: return dispatch_tn<EPI_BF16>(pl, tmA, tmB, p, st);
@@ -576,13 +671,13 @@ extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, lo
     p.splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
-        case 64: return launch_gemm<64, EPI_RED_F32, true, 6, 64>(tmA, tmB, p, st);
+        case 64: return launch_gemm<64, EPI_RED_F32, true, fit_stages<64, 64, EPI_RED_F32, false>(), 64>(tmA, tmB, p, st);
         case 128:
-            if (cta2) return launch_gemm<128, EPI_RED_F32, true, 8, 64, true>(tmA, tmB, p, st);
-            return launch_gemm<128, EPI_RED_F32, true, 6, 64>(tmA, tmB, p, st);
+            if (cta2) return launch_gemm<128, EPI_RED_F32, true, fit_stages<128, 64, EPI_RED_F32, true>(), 64, true>(tmA, tmB, p, st);
+            return launch_gemm<128, EPI_RED_F32, true, fit_stages<128, 64, EPI_RED_F32, false>(), 64>(tmA, tmB, p, st);
         default:
-            if (cta2) return launch_gemm<256, EPI_RED_F32, true, 6, 64, true>(tmA, tmB, p, st);
-            return launch_gemm<256, EPI_RED_F32, true, 4, 64>(tmA, tmB, p, st);
+            if (cta2) return launch_gemm<256, EPI_RED_F32, true, fit_stages<256, 64, EPI_RED_F32, true>(), 64, true>(tmA, tmB, p, st);
+            return launch_gemm<256, EPI_RED_F32, true, fit_stages<256, 64, EPI_RED_F32, false>(), 64>(tmA, tmB, p, st);
     }
 }
 
@@ -616,11 +711,11 @@ extern "C" int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* 
     p.stats_per_cta = 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 32) {
-        if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, 8, 32>(tmA, tmB, p, st);
-        return launch_gemm<64, EPI_BF16, false, 8, 32>(tmA, tmB, p, st);
+        if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, fit_stages<64, 32, EPI_BF16_STATS, false>(), 32>(tmA, tmB, p, st);
+        return launch_gemm<64, EPI_BF16, false, fit_stages<64, 32, EPI_BF16, false>(), 32>(tmA, tmB, p, st);
     }
-    if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, 8, 64>(tmA, tmB, p, st);
-    return launch_gemm<64, EPI_BF16, false, 8, 64>(tmA, tmB, p, st);
+    if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, fit_stages<64, 64, EPI_BF16_STATS, false>(), 64>(tmA, tmB, p, st);
+    return launch_gemm<64, EPI_BF16, false, fit_stages<64, 64, EPI_BF16, false>(), 64>(tmA, tmB, p, st);
 }
 
 // Debug cross-check (SIMT).  mn_major=0: out = A[M,K] B[N,K]^T ; 1: out = A[K,M]^T B[K,N].
