@@ -370,7 +370,8 @@ struct DwBwdParams {
 
 template <bool AFFINE, bool RELU, int ADDM>
 __global__ void __launch_bounds__(256, 2)
-dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const DwBwdParams p) {
+dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmF, const DwBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t sbase = (raw_addr + 127u) & ~127u;
@@ -382,7 +383,10 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
     const uint32_t g_bytes = row_stride * (uint32_t)(TH + 2);
     const uint32_t x_row = (uint32_t)TW * 128u;
     const uint32_t x_bytes = x_row * (uint32_t)TH;
-    const uint32_t stage_bytes = g_bytes + x_bytes;
+    // stage = [dD halo tile][forward-input centre tile][identity-skip gradient centre tile (ADDM & 1)]: the residual gradient is
+    // staged by TMA like the other operands -- read with per-pixel __ldg it made the block-entry layers 2.6x slower than the
+    // others (190 vs 73 us at 19x19x768, profiles/r1x)
+    const uint32_t stage_bytes = g_bytes + x_bytes * ((ADDM & 1) ? 2u : 1u);
     __shared__ uint64_t full[DW_MAX_STAGES], empty[DW_MAX_STAGES];
     __shared__ float s_red[11][64];
     const int NW = p.g.strips * p.g.RS;
@@ -392,6 +396,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
         fence_barrier_init();
         tma_prefetch_desc(&tmG);
         tma_prefetch_desc(&tmX);
+        if (ADDM & 1) tma_prefetch_desc(&tmF);
     }
     for (int i = threadIdx.x; i < 11 * 64; i += blockDim.x) (&s_red[0][0])[i] = 0.f;
     __syncthreads();
@@ -428,6 +433,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
                 mbar_arrive_expect_tx(&full[s], stage_bytes);
                 tma_load_4d(smem + s * stage_bytes, &tmG, &full[s], ct * 64, tw * TW - 1, th * TH - 1, f);
                 tma_load_4d(smem + s * stage_bytes + g_bytes, &tmX, &full[s], ct * 64, tw * TW, th * TH, f);
+                if (ADDM & 1) tma_load_4d(smem + s * stage_bytes + g_bytes + x_bytes, &tmF, &full[s], ct * 64, tw * TW, th * TH, f);
                 if (++s == stages) { s = 0; ph ^= 1; }
             }
         }
@@ -472,7 +478,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
                     load_g(ga, win[0]); ga += row_stride;        // dD row r0-1
                     load_g(ga, win[1]); ga += row_stride;        // dD row r0
                     char* dzp = reinterpret_cast<char*>(p.dz) + e0;
-                    const char* afp = (ADDM & 1) ? reinterpret_cast<const char*>(p.add_full) + e0 : nullptr;
+                    uint32_t fa = xb + x_bytes;                  // identity-skip gradient, centre tile (ADDM & 1)
                     // stride-2 skip gradient: lives at the even (row, column) pixels; gx0 is even, so columns px = 0, 2
                     const char* hfp = nullptr;
                     const long long hrow_b = (long long)Wo * pix_b;
@@ -502,7 +508,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
                 float dl, dh; upk2(da, dl, dh);                                                            \
                 if (RELU) { dl = zl > 0.f ? dl : 0.f; dh = zh > 0.f ? dh : 0.f; }                          \
                 if (ADDM & 1) {                                                                            \
-                    const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(afp + px * pix_b));        \
+                    const uint32_t ar = lds32(fa + px * 128);                                              \
                     dl += bf16_lo(ar); dh += bf16_hi(ar);                                                  \
                 }                                                                                          \
                 if ((ADDM & 2) && (px & 1) == 0 && hrow != nullptr) {                                      \
@@ -514,7 +520,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
             }                                                                                              \
         }                                                                                                  \
         xa += x_row; dzp += row_b; ++gh;                                                                   \
-        if (ADDM & 1) afp += row_b;                                                                        \
+        if (ADDM & 1) fa += x_row;                                                                         \
     }
                     int rc = r0;
                     while (rc < rmax) {
@@ -624,14 +630,15 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     XCP_REQUIRE(dw != nullptr && (scale == nullptr || bnsum != nullptr), "xcp_dw3x3_bwd: dw / bnsum missing");
     XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_bwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
-    DwGeom g = make_geom(F, H, W, C, 200, 7);
-    const int stage_bytes = ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH) * 128;
+    DwGeom g = make_geom(F, H, W, C, add_full != nullptr ? 170 : 200, 7);
+    const int stage_bytes = ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH * (add_full != nullptr ? 2 : 1)) * 128;
     g.stages = (108 * 1024) / stage_bytes;                       // two resident CTAs per SM
     if (g.stages > DW_MAX_STAGES) g.stages = DW_MAX_STAGES;
     if (g.stages < 2) g.stages = 2;
-    CUtensorMap tmG, tmX;
+    CUtensorMap tmG, tmX, tmF;
     if (int e = make_dw_tmap(&tmG, dD, g, 1)) return e;
     if (int e = make_dw_tmap(&tmX, xin, g, 0)) return e;
+    if (int e = make_dw_tmap(&tmF, add_full != nullptr ? add_full : xin, g, 0)) return e;
     DwBwdParams p{g, w9, scale, shift, (__nv_bfloat16*)dz, (const __nv_bfloat16*)add_full,
                   (const __nv_bfloat16*)add_half, dw, bnsum, c_real};
     const int smem = g.stages * stage_bytes + 256;
@@ -643,7 +650,7 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
 #define LAUNCH_BWD(A, R, M)                                                                                          \
     case ((A ? 8 : 0) | (R ? 4 : 0) | M): {                                                                          \
         XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<A, R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        dw3x3_bwd_kernel<A, R, M><<<grid, threads, smem, st>>>(tmG, tmX, p);                                         \
+        dw3x3_bwd_kernel<A, R, M><<<grid, threads, smem, st>>>(tmG, tmX, tmF, p);                                         \
     } break;
     switch (variant) {
         LAUNCH_BWD(false, false, 0) LAUNCH_BWD(false, false, 1) LAUNCH_BWD(false, false, 2) LAUNCH_BWD(false, false, 3)

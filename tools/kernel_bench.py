@@ -61,6 +61,8 @@ if not which or "dw" in which:
         dD = rnd(Fr, H, H, C); dw9 = torch.zeros(C, 1, 3, 3, device=dev); bns = torch.zeros(2, C, device=dev)
         gb3 = 3 * x.numel() * 2 / 1e9
         report(f"dw_bwd affine+relu  {H}x{H}x{C}", timeit(lambda: ops.dw3x3_bwd(dD, x, w9, sc, sh, True, dw9, bnsum=bns)), gb3)
+        if H == 19:
+            report(f"dw_bwd relu+add_full {H}x{H}x{C}", timeit(lambda: ops.dw3x3_bwd(dD, x, w9, None, None, True, dw9, add_full=dD)), gb3 * 4 / 3)
         del x, out, dD
 
 PW = [(21609, 64, 128), (21609, 128, 128), (5476, 128, 256), (5476, 256, 256), (1369, 256, 728), (1369, 728, 728),
@@ -95,4 +97,7 @@ if not which or "ew" in which:
         gamma = torch.ones(C, device=dev); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
         G = rnd(Fr, H, H, C)
         report(f"bn_bwd direct 2pass {H}x{H}x{C}", timeit(lambda: ops.bn_bwd(ops.SRC_DIRECT, y, st, gamma, dg, db, G=G)), gb * 2.5)
-        del y, skip, ys, G
+        Gp = rnd(Fr, Ho, Ho, C)
+        _, idx = ops.pool_add_fwd(y, sc, sh, ys, sc, sh, want_idx=True)
+        report(f"bn_bwd pool 2pass   {H}x{H}x{C}", timeit(lambda: ops.bn_bwd(ops.SRC_POOL, y, st, gamma, dg, db, G=Gp, idx=idx)), gb * 2.5)
+        del y, skip, ys, G, Gp, idx
