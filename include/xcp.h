@@ -44,6 +44,11 @@ int xcp_gemm_ref(const void* A, long long lda, const void* B, long long ldb, flo
 /* Dense 3x3 stem conv2 (Xception.py:122,172) and its data gradient as an implicit GEMM; see gemm.cu. */
 int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* stats, int F, int Hg, int Wg, int Cin, int Cout, int Ho,
                      int Wo, int sign, int device, void* stream);
+/* weight gradient of the same conv in one launch: gk[Cout][tap*Cin + i] (fp32, tap-major packing, accumulated) from
+ * dy_grid [F,Hg,Wg,Cout] (zero outside the valid window) and the conv input x [F,Hg,Wg,Cin]  (conv2 backward of
+ * Xception.py:122,172) */
+int xcp_conv3x3_wgrad(const void* dy_grid, const void* x, float* gk, int F, int Hg, int Wg, int Cin, int Cout, int device,
+                      void* stream);
 
 /* ---- stem conv1 3->32 k3 s2 p0 (Xception.py:118,168): fp32 NCHW in, bf16 NHWC out + BN partials [xcp_stem_conv1_parts()][2][32] */
 int xcp_stem_conv1_parts(int F, int H, int W, int device);

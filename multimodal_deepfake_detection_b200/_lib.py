@@ -24,6 +24,7 @@ SIGNATURES = {
     "xcp_gemm_wgrad": "plplpliiiip",
     "xcp_gemm_ref": "plplpliiiiip",
     "xcp_conv3x3_gemm": "ppppiiiiiiiiip",
+    "xcp_conv3x3_wgrad": "pppiiiiiip",
     "xcp_stem_conv1_parts": "iiii",
     "xcp_stem_conv1_fwd": "ppppiiiip",
     "xcp_stem_conv1_wgrad_ws_bytes": "iii",

@@ -40,6 +40,11 @@ struct GemmParams {
     // implicit-GEMM mode for the dense 3x3 stem conv: K block kb reads A rows shifted by a_row_shift[kb]
     int conv_taps;        // 0 = plain GEMM
     int a_row_shift[9];
+    // weight gradient of the dense 3x3 conv (MN-major): N tile n_blk = filter tap; its B operand is the same activation
+    // matrix read n-tile-independently at column 0 but shifted by a_row_shift[n_blk] rows, its output lands at column
+    // n_blk * wg_tap_cols.  Taps are the fastest-varying unit index, so the 9 CTAs of a K split stream the same rows of
+    // both operands through L2 together and DRAM sees them once (9 separate GEMMs re-read dY nine times).
+    int wg_taps, wg_tap_cols;
     int conv_grid_w, conv_grid_h, conv_out_w, conv_out_h;  // epilogue compaction of the "input grid" rows
 };
 
@@ -165,6 +170,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int a = 0; a < B_ROWS / 64; ++a) {
                         if (CTA2) tma_load_2d_cg2(sB + s * B_BYTES + a * (64 * 128), &tmB, (full0_leader + 8u * (uint32_t)s), n0 + a * 64, kb * 64);
+                        else if (p.wg_taps > 0) tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], a * 64, kb * 64 + p.a_row_shift[n_blk]);
                         else tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], n0 + a * 64, kb * 64);
                     }
                 }
@@ -279,7 +285,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32 + 16) << 16), fb);
                 }
                 tmem_ld_wait();
-                const int gcol = n_blk * BLOCK_N + c * 32;
+                const int gcol = (p.wg_taps > 0 ? n_blk * p.wg_tap_cols : n_blk * BLOCK_N) + c * 32;
                 if (EPI == EPI_BF16 || EPI == EPI_BF16_STATS) {
                     if (p.tma_store) {
                         // bf16 rows -> 64B-swizzled staging tile (conflict-free 16 B stores) -> one bulk tensor store of the
@@ -409,10 +415,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 } else {  // EPI_RED_F32: accumulate the split-K partial tile into fp32 memory
                     float* orow_p = reinterpret_cast<float*>(p.out) + orow * p.ldo + gcol;
-                    if (row_ok) {
+                    if (row_ok && (p.wg_taps == 0 || c * 32 < p.wg_tap_cols)) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
-                            if (gcol + g * 4 + 4 <= p.N) {
+                            if (gcol + g * 4 + 4 <= p.N && (p.wg_taps == 0 || c * 32 + g * 4 + 4 <= p.wg_tap_cols)) {
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow_p + g * 4),
                                              "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
                                              "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
@@ -716,6 +722,31 @@ extern "C" int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* 
     }
     if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, fit_stages<64, 64, EPI_BF16_STATS, false>(), 64>(tmA, tmB, p, st);
     return launch_gemm<64, EPI_BF16, false, fit_stages<64, 64, EPI_BF16, false>(), 64>(tmA, tmB, p, st);
+}
+
+// Weight gradient of the dense 3x3 stem convolution (Xception.py:122, conv2) in ONE launch:
+//   gk[Cout][tap*Cin + i] += sum_r dy_grid[r][o] * x[r + kh*Wg + kw][i]     (tap = kh*3 + kw, r over the F*Hg*Wg input grid)
+// dy_grid is zero outside the valid output window, so the shifted pairing is exact (wrap-around terms multiply zeros).
+extern "C" int xcp_conv3x3_wgrad(const void* dy_grid, const void* x, float* gk, int F, int Hg, int Wg, int Cin, int Cout, int device,
+                                 void* stream) {
+    XCP_REQUIRE(Cin % 8 == 0 && Cin <= 64 && Cout % 8 == 0 && Cout <= 128, "xcp_conv3x3_wgrad: Cin <= 64, Cout <= 128, multiples of 8");
+    XCP_CUDA(cudaSetDevice(device));
+    const long long R = (long long)F * Hg * Wg;
+    XCP_REQUIRE(R < (1LL << 31) - 65536, "xcp_conv3x3_wgrad: grid too large for 32-bit TMA coordinates");
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_2d(&tmA, dy_grid, (uint64_t)Cout, (uint64_t)R, (uint64_t)Cout * 2, 64, 64, 128)) return e;
+    if (int e = make_tmap_2d(&tmB, x, (uint64_t)Cin, (uint64_t)R, (uint64_t)Cin * 2, 64, 64, 128)) return e;
+    GemmParams p{};
+    p.M = Cout; p.N = 9 * Cin; p.K = (int)R; p.out = gk; p.ldo = 9 * Cin;
+    p.num_m_tiles = 1;
+    p.num_n_tiles = 9;
+    p.num_k_blocks = (int)((R + 63) / 64);
+    p.k_blocks_per_split = 64;                     // 4096 grid rows per unit: short units keep the 9 tap CTAs of a split in step
+    p.splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+    p.wg_taps = 9; p.wg_tap_cols = Cin;
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) p.a_row_shift[kh * 3 + kw] = kh * Wg + kw;
+    return launch_gemm<64, EPI_RED_F32, true, fit_stages<64, 64, EPI_RED_F32, false>(), 64>(tmA, tmB, p, (cudaStream_t)stream);
 }
 
 // Debug cross-check (SIMT).  mn_major=0: out = A[M,K] B[N,K]^T ; 1: out = A[K,M]^T B[K,N].

@@ -149,19 +149,13 @@ def conv3x3_gemm_dgrad(dy_grid: torch.Tensor, wk_t: torch.Tensor):
 
 
 def conv3x3_wgrad(dy_grid: torch.Tensor, x: torch.Tensor, gk: torch.Tensor):
-    """gk[Cout, 9*Cin] (fp32) += per-tap dy_grid^T @ shifted(x): nine MN-major tcgen05 GEMMs on shifted views."""
+    """gk[Cout, 9*Cin] (fp32) += per-tap dy_grid^T @ shifted(x): one MN-major tcgen05 launch, the 9 taps are N tiles that
+    stream the same rows of both operands together."""
+    _chk(dy_grid, BF16, "conv3x3_wgrad.dy"); _chk(x, BF16, "conv3x3_wgrad.x")
     F_, Hg, Wg, Cout = dy_grid.shape
     Cin = x.shape[3]
-    R = F_ * Hg * Wg
-    dy2 = dy_grid.view(R, Cout)
-    x2 = x.view(R, Cin)
-    for kh in range(3):
-        for kw in range(3):
-            sh = kh * Wg + kw
-            tap = kh * 3 + kw
-            xv = x2[sh:]
-            _lib.call("xcp_gemm_wgrad", _p(dy2), Cout, _p(xv), Cin, ctypes.c_void_p(gk.data_ptr() + tap * Cin * 4), 9 * Cin,
-                      R - sh, Cout, Cin, x.device.index, _s())
+    assert gk.dtype == F32 and gk.shape == (Cout, 9 * Cin)
+    _lib.call("xcp_conv3x3_wgrad", _p(dy_grid), _p(x), _p(gk), F_, Hg, Wg, Cin, Cout, x.device.index, _s())
 
 
 # ------------------------------------------------------------------------------------------------ stem / dw

@@ -101,3 +101,24 @@ if not which or "ew" in which:
         _, idx = ops.pool_add_fwd(y, sc, sh, ys, sc, sh, want_idx=True)
         report(f"bn_bwd pool 2pass   {H}x{H}x{C}", timeit(lambda: ops.bn_bwd(ops.SRC_POOL, y, st, gamma, dg, db, G=Gp, idx=idx)), gb * 2.5)
         del y, skip, ys, G, Gp, idx
+
+if "stem" in which:
+    F_ = Fr
+    x1 = rnd(F_, 149, 149, 32); dy2 = rnd(F_, 149, 149, 64)
+    gk = torch.zeros(64, 9 * 32, device=dev)
+    gb = (x1.numel() + dy2.numel()) * 2 / 1e9
+    report("conv2 wgrad fused (9 taps as N tiles)", timeit(lambda: ops.conv3x3_wgrad(dy2, x1, gk)), gb)
+    R = F_ * 149 * 149
+    def nine():
+        for t in range(9):
+            sh = (t // 3) * 149 + (t % 3)
+            ops._lib.call("xcp_gemm_wgrad", ops._p(dy2), 64, ops._p(x1.view(R, 32)[sh:]), 32,
+                          __import__("ctypes").c_void_p(gk.data_ptr() + t * 32 * 4), 9 * 32, R - sh, 64, 32, 0, ops._s())
+    report("conv2 wgrad as 9 GEMM launches", timeit(nine), gb)
+    xin = torch.rand(F_, 3, 299, 299, device=dev); w1 = torch.randn(32, 3, 3, 3, device=dev)
+    report("stem conv1 fwd", timeit(lambda: ops.stem_conv1_fwd(xin, w1)), (xin.numel() * 4 + F_ * 149 * 149 * 32 * 2) / 1e9)
+    dy1 = rnd(F_, 149, 149, 32); dw1 = torch.zeros(32, 3, 3, 3, device=dev)
+    report("stem conv1 wgrad", timeit(lambda: ops.stem_conv1_wgrad(xin, dy1, dw1)), (xin.numel() * 4 + dy1.numel() * 2) / 1e9)
+    wk, wkt = ops.pack_conv3x3(torch.randn(64, 32, 3, 3, device=dev), True)
+    report("conv2 fwd implicit GEMM + stats", timeit(lambda: ops.conv3x3_gemm_fwd(x1, wk, True)), (x1.numel() + F_ * 147 * 147 * 64) * 2 / 1e9)
+    report("conv2 dgrad implicit GEMM", timeit(lambda: ops.conv3x3_gemm_dgrad(dy2, wkt)), (x1.numel() + dy2.numel()) * 2 / 1e9)
