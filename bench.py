@@ -310,9 +310,17 @@ def run_ours(args):
         key = max(gemm_stats, key=lambda k: gemm_stats[k]["flops"])
         st = gemm_stats[key]
         ach = st["flops"] / (st["ms"] * 1e-3) / 1e12
+        traffic = None                  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))
+            if tj.get("shape") == key:
+                traffic = tj["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "gemm_kernel<256,EPI_BF16_STATS> (pointwise 1x1, %s)" % key, "achieved": ach,
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
-                "traffic": None, "peak_source": peaks["_src"] + " (sustained: kernel timed inside a long step)",
+                "traffic": traffic, "algorithmic_bytes": st["flops"] / st["n"] / (2.0 * 768) * 2 * 2 if "K=768 N=768" in key else None,
+                "peak_source": peaks["_src"] + " (sustained: kernel timed inside a long step)",
                 "launches_timed": st["n"], "avg_launch_us": st["ms"] * 1e3 / st["n"]}
     # ---- CPU baseline (bounded sample) on rank 0
     cpu = None
