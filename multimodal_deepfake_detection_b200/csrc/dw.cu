@@ -591,6 +591,8 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
     // resident CTAs per SM: 2 (<= 128 registers per thread, spill-free, deep ring) measured 10-20 % faster than 3 (80
     // registers, spills) on every Xception shape (gpurun r1m)
     const int minb = 2;
+    // halo budget 400 pixels (51 KB per stage): a sweep over 100..400 (gpurun r2c) showed larger tiles always win and that the
+    // ring depth (2 vs 3) does not matter -- the kernel is not prefetch-distance bound
     DwGeom g = make_geom(F, H, W, C, minb == 3 ? 272 : 400, 7);
     const int stage_bytes = (g.TW + 2) * (g.TH + 2) * 128;
     g.stages = ((minb == 3 ? 73 : 110) * 1024) / stage_bytes;

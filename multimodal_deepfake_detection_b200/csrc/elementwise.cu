@@ -217,21 +217,30 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
         load_affine8(scale, shift, cg * 8, sc, sh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+        // all 9 taps are loaded up front from clamped (always valid) addresses and masked afterwards: nine independent
+        // 16-byte loads in flight per thread instead of a chain of bounds-checked ones
+        uint4 raw[9];
+        bool ok[9];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
             const int h = 2 * ho - 1 + kh;
-            if (h < 0 || h >= H) continue;
+            const int hc = min(max(h, 0), H - 1);
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const int w = 2 * wo - 1 + kw;
-                if (w < 0 || w >= W) continue;
-                float v[8];
-                unpack8(__ldg(y + (((long long)f * H + h) * W + w) * ncg + cg), v);
+                const int wc = min(max(w, 0), W - 1);
+                ok[kh * 3 + kw] = (h == hc) && (w == wc);
+                raw[kh * 3 + kw] = __ldg(y + (((long long)f * H + hc) * W + wc) * ncg + cg);
+            }
+        }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float z = fmaf(v[j], sc[j], sh[j]);
-                    if (z > best[j]) { best[j] = z; bi[j] = kh * 3 + kw; }
-                }
+        for (int k = 0; k < 9; ++k) {
+            float v[8];
+            unpack8(raw[k], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float z = ok[k] ? fmaf(v[j], sc[j], sh[j]) : -INFINITY;
+                if (z > best[j]) { best[j] = z; bi[j] = k; }
             }
         }
         float s[8];
