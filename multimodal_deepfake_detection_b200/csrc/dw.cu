@@ -46,31 +46,33 @@ static DwGeom make_geom(int F, int H, int W, int C, int max_halo_pixels, int max
     double best_cost = 1e30;
     for (int ns = 1; ns <= max_warps; ++ns) {
         if (ns > 1 && SW * (ns - 1) >= W) break;          // already wider than the image
-        DwGeom g{};
-        g.F = F; g.H = H; g.W = W; g.C = C;
-        g.strips = ns;
-        g.TW = SW * ns;
-        g.n_w = (W + g.TW - 1) / g.TW;
-        const int th_max = max_halo_pixels / (g.TW + 2) - 2;
-        if (th_max < 1) continue;
-        g.n_h = (H + th_max - 1) / th_max;
-        g.TH = (H + g.n_h - 1) / g.n_h;
-        g.RS = max_warps / ns;
-        if (g.RS < 1) g.RS = 1;
-        if (g.RS > g.TH) g.RS = g.TH;
-        g.rows_per_slice = (g.TH + g.RS - 1) / g.RS;
-        g.RS = (g.TH + g.rows_per_slice - 1) / g.rows_per_slice;
-        g.c_tiles = (C + 63) / 64;
-        g.sp_tiles = F * g.n_h * g.n_w;
-        const double rps = g.rows_per_slice;
-        const double col_waste = (double)g.n_w * g.TW / W;
-        const double row_waste = (double)g.n_h * g.RS * rps / H;
-        const double instr = 3.0 * ((double)LW / SW) * (rps + 2.0) / rps + 6.5;
-        const double halo = (double)(g.TW + 2) * (g.TH + 2) / ((double)g.TW * g.TH);
-        const int warps = ns * g.RS;
-        const double cost = instr * col_waste * row_waste * (1.0 + 0.25 * (halo - 1.0)) *
-                            (1.0 + 0.3 * (double)(max_warps - warps) / max_warps);
-        if (cost < best_cost) { best_cost = cost; best = g; }
+        for (int rs_try = 1; rs_try * ns <= max_warps; ++rs_try) {
+            DwGeom g{};
+            g.F = F; g.H = H; g.W = W; g.C = C;
+            g.strips = ns;
+            g.TW = SW * ns;
+            g.n_w = (W + g.TW - 1) / g.TW;
+            const int th_max = max_halo_pixels / (g.TW + 2) - 2;
+            if (th_max < 1) continue;
+            g.n_h = (H + th_max - 1) / th_max;
+            g.TH = (H + g.n_h - 1) / g.n_h;
+            g.RS = rs_try;
+            if (g.RS > g.TH) break;
+            g.rows_per_slice = (g.TH + g.RS - 1) / g.RS;
+            if ((g.TH + g.rows_per_slice - 1) / g.rows_per_slice != g.RS) continue;     // this slice count leaves a slice empty
+            g.c_tiles = (C + 63) / 64;
+            g.sp_tiles = F * g.n_h * g.n_w;
+            const double rps = g.rows_per_slice;
+            const double col_waste = (double)g.n_w * g.TW / W;
+            const double row_waste = (double)g.n_h * g.RS * rps / H;
+            const double instr = 3.0 * ((double)LW / SW) * (rps + 2.0) / rps + 6.5;
+            const double halo = (double)(g.TW + 2) * (g.TH + 2) / ((double)g.TW * g.TH);
+            const int warps = ns * g.RS;
+            // few warps per SM cannot hide the LDS -> FMA -> STG latency chain: strong penalty below ~3/4 of the budget
+            const double cost = instr * col_waste * row_waste * (1.0 + 0.25 * (halo - 1.0)) *
+                                (1.0 + 0.6 * (double)(max_warps - warps) / max_warps);
+            if (cost < best_cost) { best_cost = cost; best = g; }
+        }
     }
     return best;
 }
@@ -97,7 +99,7 @@ struct DwFwdParams {
 constexpr int DW_MAX_STAGES = 4;
 
 template <bool AFFINE, bool RELU, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB)
 dw3x3_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const DwFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -368,8 +370,8 @@ struct DwBwdParams {
     int c_real;                   // logical channel count (<= C, the physical pitch): dw has c_real rows
 };
 
-template <bool AFFINE, bool RELU, int ADDM>
-__global__ void __launch_bounds__(256, 2)
+template <bool AFFINE, bool RELU, int ADDM, int MINB>
+__global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB)
 dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmF, const DwBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -588,14 +590,17 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
     XCP_REQUIRE((scale == nullptr) == (shift == nullptr), "xcp_dw3x3_fwd: scale/shift must both be given or both null");
     XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_fwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
-    // resident CTAs per SM: 2 (<= 128 registers per thread, spill-free, deep ring) measured 10-20 % faster than 3 (80
-    // registers, spills) on every Xception shape (gpurun r1m)
-    const int minb = 2;
-    // halo budget 400 pixels (51 KB per stage): a sweep over 100..400 (gpurun r2c) showed larger tiles always win and that the
-    // ring depth (2 vs 3) does not matter -- the kernel is not prefetch-distance bound
-    DwGeom g = make_geom(F, H, W, C, minb == 3 ? 272 : 400, 7);
+    // resident CTAs per SM: ONE 512-thread CTA (15 compute warps, tiles up to 800 staged pixels) or two 256-thread CTAs
+    // (7 compute warps each, tiles up to 400 pixels); both run spill-free at <= 128 registers (three 80-register CTAs spilled
+    // and were 10-20 % slower, gpurun r1m).  The single large CTA has less halo and tile-rounding waste and wins on the big
+    // entry-flow images (276 vs 369 us at 147x147x128, 128 frames) and at 19x19; the pair wins at 37x37 and 10x10 (gpurun r2e).
+    static int dbg_minb = -1;
+    if (dbg_minb < 0) { const char* e = getenv("XCP_DW_MINB"); dbg_minb = e ? atoi(e) : 0; }
+    const int hw = H > W ? H : W;
+    const int minb = dbg_minb > 0 ? dbg_minb : ((hw >= 64 || (hw > 12 && hw <= 24)) ? 1 : 2);
+    DwGeom g = make_geom(F, H, W, C, minb == 1 ? 800 : 400, minb == 1 ? 15 : 7);
     const int stage_bytes = (g.TW + 2) * (g.TH + 2) * 128;
-    g.stages = ((minb == 3 ? 73 : 110) * 1024) / stage_bytes;
+    g.stages = ((minb == 1 ? 220 : 110) * 1024) / stage_bytes;
     if (g.stages > DW_MAX_STAGES) g.stages = DW_MAX_STAGES;
     if (g.stages < 2) g.stages = 2;
     CUtensorMap tm;
@@ -607,9 +612,9 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FWD(A, R)                                                                                                 \
     {                                                                                                                    \
-        if (minb == 3) {                                                                                                 \
-            XCP_CUDA(cudaFuncSetAttribute(dw3x3_fwd_kernel<A, R, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-            dw3x3_fwd_kernel<A, R, 3><<<grid, threads, smem, st>>>(tm, p);                                               \
+        if (minb == 1) {                                                                                                 \
+            XCP_CUDA(cudaFuncSetAttribute(dw3x3_fwd_kernel<A, R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            dw3x3_fwd_kernel<A, R, 1><<<grid, threads, smem, st>>>(tm, p);                                               \
         } else {                                                                                                         \
             XCP_CUDA(cudaFuncSetAttribute(dw3x3_fwd_kernel<A, R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             dw3x3_fwd_kernel<A, R, 2><<<grid, threads, smem, st>>>(tm, p);                                               \
@@ -632,9 +637,15 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     XCP_REQUIRE(dw != nullptr && (scale == nullptr || bnsum != nullptr), "xcp_dw3x3_bwd: dw / bnsum missing");
     XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_bwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
-    DwGeom g = make_geom(F, H, W, C, add_full != nullptr ? 170 : 200, 7);
-    const int stage_bytes = ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH * (add_full != nullptr ? 2 : 1)) * 128;
-    g.stages = (108 * 1024) / stage_bytes;                       // two resident CTAs per SM
+    // one 512-thread CTA per SM (15 compute warps) measured faster than two 256-thread CTAs on every shape (477 vs 623 us at
+    // 147x147x128, 213 vs 309 us at 37x37x728, 65 vs 76 us at 19x19x728; gpurun r2e) except with the staged identity-skip tile
+    static int dbg_minb = -1;
+    if (dbg_minb < 0) { const char* e = getenv("XCP_DW_MINB"); dbg_minb = e ? atoi(e) : 0; }
+    const int minb = dbg_minb > 0 ? dbg_minb : (add_full != nullptr ? 2 : 1);
+    const int n_centre = add_full != nullptr ? 2 : 1;
+    DwGeom g = make_geom(F, H, W, C, minb == 1 ? (add_full != nullptr ? 330 : 470) : (add_full != nullptr ? 170 : 200), minb == 1 ? 15 : 7);
+    const int stage_bytes = ((g.TW + 2) * (g.TH + 2) + g.TW * g.TH * n_centre) * 128;
+    g.stages = ((minb == 1 ? 216 : 108) * 1024) / stage_bytes;
     if (g.stages > DW_MAX_STAGES) g.stages = DW_MAX_STAGES;
     if (g.stages < 2) g.stages = 2;
     CUtensorMap tmG, tmX, tmF;
@@ -645,14 +656,19 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
                   (const __nv_bfloat16*)add_half, dw, bnsum, c_real};
     const int smem = g.stages * stage_bytes + 256;
     const int threads = 32 * (g.strips * g.RS + 1);
-    const int grid = dw_grid(g, 2);
+    const int grid = dw_grid(g, minb);
     const int addm = (add_full != nullptr ? 1 : 0) | (add_half != nullptr ? 2 : 0);
     const int variant = ((scale != nullptr) ? 8 : 0) | (relu ? 4 : 0) | addm;
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_BWD(A, R, M)                                                                                          \
-    case ((A ? 8 : 0) | (R ? 4 : 0) | M): {                                                                          \
-        XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<A, R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        dw3x3_bwd_kernel<A, R, M><<<grid, threads, smem, st>>>(tmG, tmX, tmF, p);                                         \
+#define LAUNCH_BWD(A, R, M)                                                                                                 \
+    case ((A ? 8 : 0) | (R ? 4 : 0) | M): {                                                                                 \
+        if (minb == 1) {                                                                                                    \
+            XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<A, R, M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            dw3x3_bwd_kernel<A, R, M, 1><<<grid, threads, smem, st>>>(tmG, tmX, tmF, p);                                    \
+        } else {                                                                                                            \
+            XCP_CUDA(cudaFuncSetAttribute(dw3x3_bwd_kernel<A, R, M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            dw3x3_bwd_kernel<A, R, M, 2><<<grid, threads, smem, st>>>(tmG, tmX, tmF, p);                                    \
+        }                                                                                                                   \
     } break;
     switch (variant) {
         LAUNCH_BWD(false, false, 0) LAUNCH_BWD(false, false, 1) LAUNCH_BWD(false, false, 2) LAUNCH_BWD(false, false, 3)
