@@ -41,8 +41,8 @@ struct GemmParams {
     int conv_taps;        // 0 = plain GEMM
     int a_row_shift[9];
     // weight gradient of the dense 3x3 conv (MN-major): N tile n_blk = filter tap; its B operand is the same activation
-    // matrix read n-tile-independently at column 0 but shifted by a_row_shift[n_blk] rows, its output lands at column
-    // n_blk * wg_tap_cols.  Taps are the fastest-varying unit index, so the 9 CTAs of a K split stream the same rows of
+    // matrix read at column 0 but shifted by a_row_shift[tap] rows (an N tile holds BLOCK_N/64 taps, one 64-column box each),
+    // its output lands at column tap * wg_tap_cols.  Taps are the fastest-varying unit index, so the 9 CTAs of a K split stream the same rows of
     // both operands through L2 together and DRAM sees them once (9 separate GEMMs re-read dY nine times).
     int wg_taps, wg_tap_cols;
     int conv_grid_w, conv_grid_h, conv_out_w, conv_out_h;  // epilogue compaction of the "input grid" rows
@@ -170,7 +170,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int a = 0; a < B_ROWS / 64; ++a) {
                         if (CTA2) tma_load_2d_cg2(sB + s * B_BYTES + a * (64 * 128), &tmB, (full0_leader + 8u * (uint32_t)s), n0 + a * 64, kb * 64);
-                        else if (p.wg_taps > 0) tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], a * 64, kb * 64 + p.a_row_shift[n_blk]);
+                        else if (p.wg_taps > 0) {
+                            // N tile = B_ROWS/64 filter taps; 64-column box `a` is tap n_blk*(B_ROWS/64)+a: the activation rows shifted
+                            // by that tap's offset (taps past the last one: a box entirely past the last row -> zero fill)
+                            const int tap = n_blk * (B_ROWS / 64) + a;
+                            const int row = tap < p.wg_taps ? kb * 64 + p.a_row_shift[tap] : p.K + 64;
+                            tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], 0, row);
+                        }
                         else tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], n0 + a * 64, kb * 64);
                     }
                 }
@@ -285,7 +291,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tmem_ld_16x256b_x4(tcol + ((uint32_t)(q * 32 + 16) << 16), fb);
                 }
                 tmem_ld_wait();
-                const int gcol = (p.wg_taps > 0 ? n_blk * p.wg_tap_cols : n_blk * BLOCK_N) + c * 32;
+                // conv weight gradient: tile column c*32 belongs to tap n_blk*(BLOCK_N/64) + c/2, channel offset (c & 1)*32
+                const int wg_tap = n_blk * (BLOCK_N / 64) + (c >> 1);
+                const int gcol = p.wg_taps > 0 ? wg_tap * p.wg_tap_cols + (c & 1) * 32 : n_blk * BLOCK_N + c * 32;
                 if (EPI == EPI_BF16 || EPI == EPI_BF16_STATS) {
                     if (p.tma_store) {
                         // bf16 rows -> 64B-swizzled staging tile (conflict-free 16 B stores) -> one bulk tensor store of the
@@ -415,10 +423,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 } else {  // EPI_RED_F32: accumulate the split-K partial tile into fp32 memory
                     float* orow_p = reinterpret_cast<float*>(p.out) + orow * p.ldo + gcol;
-                    if (row_ok && (p.wg_taps == 0 || c * 32 < p.wg_tap_cols)) {
+                    if (row_ok && (p.wg_taps == 0 || (wg_tap < p.wg_taps && (c & 1) * 32 < p.wg_tap_cols))) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
-                            if (gcol + g * 4 + 4 <= p.N && (p.wg_taps == 0 || c * 32 + g * 4 + 4 <= p.wg_tap_cols)) {
+                            if (gcol + g * 4 + 4 <= p.N && (p.wg_taps == 0 || (c & 1) * 32 + g * 4 + 4 <= p.wg_tap_cols)) {
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow_p + g * 4),
                                              "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
                                              "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
@@ -739,14 +747,14 @@ extern "C" int xcp_conv3x3_wgrad(const void* dy_grid, const void* x, float* gk, 
     GemmParams p{};
     p.M = Cout; p.N = 9 * Cin; p.K = (int)R; p.out = gk; p.ldo = 9 * Cin;
     p.num_m_tiles = 1;
-    p.num_n_tiles = 9;
+    p.num_n_tiles = 3;                             // 4 taps (4 x 64 staged columns) per N tile: dY is staged once per 4 taps
     p.num_k_blocks = (int)((R + 63) / 64);
-    p.k_blocks_per_split = 64;                     // 4096 grid rows per unit: short units keep the 9 tap CTAs of a split in step
+    p.k_blocks_per_split = 64;                     // 4096 grid rows per unit: short units keep the tap CTAs of a split in step
     p.splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
     p.wg_taps = 9; p.wg_tap_cols = Cin;
     for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) p.a_row_shift[kh * 3 + kw] = kh * Wg + kw;
-    return launch_gemm<64, EPI_RED_F32, true, fit_stages<64, 64, EPI_RED_F32, false>(), 64>(tmA, tmB, p, (cudaStream_t)stream);
+    return launch_gemm<256, EPI_RED_F32, true, fit_stages<256, 64, EPI_RED_F32, false>(), 64>(tmA, tmB, p, (cudaStream_t)stream);
 }
 
 // Debug cross-check (SIMT).  mn_major=0: out = A[M,K] B[N,K]^T ; 1: out = A[K,M]^T B[K,N].
