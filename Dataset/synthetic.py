@@ -5,8 +5,9 @@ from torch.utils.data import DataLoader, Dataset
 
 
 class SyntheticClips(Dataset):
-    def __init__(self, n=64, frames=16, size=299, seed=0, variable_length=False):
+    def __init__(self, n=64, frames=16, size=299, seed=0, variable_length=False, raw_uint8=False):
         self.n, self.frames, self.size, self.seed, self.var = n, frames, size, seed, variable_length
+        self.raw_uint8 = raw_uint8            # uint8 (T,H,W,3) frames as stored on disk instead of float (T,3,H,W)/255
         g = torch.Generator().manual_seed(seed)
         self.labels = torch.randint(0, 2, (n,), generator=g).tolist()
         self.samples = [("synthetic_%d" % i, self.labels[i], None) for i in range(n)]   # label at index 1 (train_visual.py:525)
@@ -18,6 +19,9 @@ class SyntheticClips(Dataset):
     def __getitem__(self, i):
         g = torch.Generator().manual_seed(self.seed * 100003 + i)
         t = self.frames if not self.var else max(2, self.frames - (i % 3))
+        if self.raw_uint8:
+            return (torch.randint(0, 256, (t, self.size, self.size, 3), generator=g, dtype=torch.uint8),
+                    torch.tensor(self.labels[i], dtype=torch.float32))
         return torch.rand(t, 3, self.size, self.size, generator=g), torch.tensor(self.labels[i], dtype=torch.float32)
 
 
@@ -25,7 +29,7 @@ def collate_clips(batch):
     """video_dataloader.py:53-68: zero-pad to the longest clip -> (B,Tmax,3,H,W), labels (B,)."""
     vids, labs = zip(*batch)
     tmax = max(v.shape[0] for v in vids)
-    out = torch.zeros(len(vids), tmax, *vids[0].shape[1:])
+    out = torch.zeros(len(vids), tmax, *vids[0].shape[1:], dtype=vids[0].dtype)     # float (T,3,H,W) or raw uint8 (T,H,W,3) clips
     for i, v in enumerate(vids):
         out[i, :v.shape[0]] = v
     return out, torch.stack(labs)

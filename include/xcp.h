@@ -50,12 +50,15 @@ int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* stats, int 
 int xcp_conv3x3_wgrad(const void* dy_grid, const void* x, float* gk, int F, int Hg, int Wg, int Cin, int Cout, int device,
                       void* stream);
 
-/* ---- stem conv1 3->32 k3 s2 p0 (Xception.py:118,168): fp32 NCHW in, bf16 NHWC out + BN partials [xcp_stem_conv1_parts()][2][32] */
+/* ---- stem conv1 3->32 k3 s2 p0 (Xception.py:118,168): bf16 NHWC out + BN partials [xcp_stem_conv1_parts()][2][32].
+ * Input x: x_u8_nhwc = 0 -> fp32 NCHW [F,3,H,W] in [0,1] (the tensor video_dataloader.py:35 builds); 1 -> uint8 NHWC [F,H,W,3]
+ * (the on-disk frame format, video_dataloader.py:27-35), scaled by 1/255 inside the kernel. */
 int xcp_stem_conv1_parts(int F, int H, int W, int device);
-int xcp_stem_conv1_fwd(const float* x, const float* w, void* y, float* partials, int F, int H, int W, int device, void* stream);
+int xcp_stem_conv1_fwd(const void* x, int x_u8_nhwc, const float* w, void* y, float* partials, int F, int H, int W, int device,
+                       void* stream);
 /* weight gradient: im2col (bf16 [M,32]) + MN-major tcgen05 split-K GEMM; `workspace` = xcp_stem_conv1_wgrad_ws_bytes() bytes */
 long long xcp_stem_conv1_wgrad_ws_bytes(int F, int H, int W);
-int xcp_stem_conv1_wgrad(const float* x, const void* dy, float* dW, void* workspace, int F, int H, int W, int device,
+int xcp_stem_conv1_wgrad(const void* x, int x_u8_nhwc, const void* dy, float* dW, void* workspace, int F, int H, int W, int device,
                          void* stream);
 
 /* ---- depthwise 3x3 s1 p1 (SeparableConv2d.conv1, Xception.py:41,45) fused with the preceding ReLU

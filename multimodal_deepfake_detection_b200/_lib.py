@@ -26,9 +26,9 @@ SIGNATURES = {
     "xcp_conv3x3_gemm": "ppppiiiiiiiiip",
     "xcp_conv3x3_wgrad": "pppiiiiiip",
     "xcp_stem_conv1_parts": "iiii",
-    "xcp_stem_conv1_fwd": "ppppiiiip",
+    "xcp_stem_conv1_fwd": "pipppiiiip",
     "xcp_stem_conv1_wgrad_ws_bytes": "iii",
-    "xcp_stem_conv1_wgrad": "ppppiiiip",
+    "xcp_stem_conv1_wgrad": "pipppiiiip",
     "xcp_dw3x3_fwd": "ppppipiiiiip",
     "xcp_dw3x3_bwd": "pppppipppppiiiiiip",
     "xcp_bn_finalize": "piiidppppffppppip",

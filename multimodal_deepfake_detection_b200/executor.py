@@ -298,7 +298,8 @@ def _bump_nbt(nbt: list):
 
 
 def xception_forward(net, x: torch.Tensor, save: bool = True):
-    """net: Models.Xception.Xception (ours).  x: fp32 NCHW [F,3,H,W] on a B200.  Returns (feat fp32 [F,2048], tape)."""
+    """net: Models.Xception.Xception (ours).  x: fp32 NCHW [F,3,H,W] in [0,1] or raw uint8 NHWC frames [F,H,W,3] on a B200.
+    Returns (feat fp32 [F,2048], tape)."""
     cache: PackCache = net._pack_cache
     nbt: list = []
     tp = XceptionTape()

@@ -214,7 +214,7 @@ class _XceptionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, *params):
         save = any(ctx.needs_input_grad[2:])
-        feat, tape = ex.xception_forward(net, x.float(), save=save)
+        feat, tape = ex.xception_forward(net, x if x.dtype == torch.uint8 else x.float(), save=save)
         ctx.net, ctx.tape = net, tape
         return feat
 
@@ -292,7 +292,10 @@ class Xception(nn.Module):
     def features(self, x):
         """conv1 ... bn4/relu/GAP of Xception.forward (Xception.py:168-198): [F,3,H,W] -> [F,2048]."""
         _require_cuda(x, "Xception")
-        if x.dim() != 4 or x.shape[1] != 3:
+        if x.dtype == torch.uint8:                     # raw frames, NHWC [F,H,W,3]: scaled by 1/255 inside the stem kernel
+            if x.dim() != 4 or x.shape[3] != 3:
+                raise XcpError("Xception: uint8 frames must be NHWC [F,H,W,3], got %s" % (tuple(x.shape),))
+        elif x.dim() != 4 or x.shape[1] != 3:
             raise XcpError("Xception: expected an input of shape [F,3,H,W], got %s" % (tuple(x.shape),))
         return _XceptionFn.apply(self, x, *self._backbone_params())
 
@@ -458,8 +461,12 @@ class XceptionLSTMV(_XceptionLSTMBase):
         if device is not None and not torch.is_tensor(device):
             self.feature_extractor.to(device)
             video_batch = video_batch.to(device)
-        b, t, c, h, w = video_batch.shape
-        frames = video_batch.reshape(b * t, c, h, w)
+        if video_batch.dtype == torch.uint8:          # raw clips (B,T,H,W,3) as stored on disk (video_dataloader.py:27-35)
+            b, t, h, w, c = video_batch.shape
+            frames = video_batch.reshape(b * t, h, w, c)
+        else:
+            b, t, c, h, w = video_batch.shape
+            frames = video_batch.reshape(b * t, c, h, w)
         feats = self.feature_extractor(frames)
         return feats.view(b, t, -1)
 

@@ -159,20 +159,34 @@ def conv3x3_wgrad(dy_grid: torch.Tensor, x: torch.Tensor, gk: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------------ stem / dw
+def _stem_input(x: torch.Tensor, who: str):
+    """-> (is_u8, F, H, W).  fp32 NCHW [F,3,H,W] (the reference's tensor) or uint8 NHWC [F,H,W,3] (raw frames, scaled by
+    1/255 inside the kernels)."""
+    if not x.is_cuda or not x.is_contiguous():
+        raise _lib.XcpError(f"{who}: expected a contiguous CUDA tensor (this package has no CPU path)")
+    if x.dtype == torch.uint8:
+        if x.dim() != 4 or x.shape[3] != 3:
+            raise _lib.XcpError(f"{who}: uint8 frames must be NHWC [F,H,W,3], got {tuple(x.shape)}")
+        return True, x.shape[0], x.shape[1], x.shape[2]
+    if x.dtype != F32 or x.dim() != 4 or x.shape[1] != 3:
+        raise _lib.XcpError(f"{who}: expected fp32 NCHW [F,3,H,W] or uint8 NHWC [F,H,W,3], got {x.dtype} {tuple(x.shape)}")
+    return False, x.shape[0], x.shape[2], x.shape[3]
+
+
 def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor):
-    _chk(x, F32, "stem_conv1.x"); _chk(w, F32, "stem_conv1.w")
-    F_, _, H, W = x.shape
+    _chk(w, F32, "stem_conv1.w")
+    u8, F_, H, W = _stem_input(x, "stem_conv1.x")
     H1, W1 = (H - 3) // 2 + 1, (W - 3) // 2 + 1
     y = torch.empty((F_, H1, W1, 32), device=x.device, dtype=BF16)
     parts = torch.empty((_lib.call("xcp_stem_conv1_parts", F_, H, W, x.device.index), 2, 32), device=x.device, dtype=F32)
-    _lib.call("xcp_stem_conv1_fwd", _p(x), _p(w), _p(y), _p(parts), F_, H, W, x.device.index, _s())
+    _lib.call("xcp_stem_conv1_fwd", _p(x), int(u8), _p(w), _p(y), _p(parts), F_, H, W, x.device.index, _s())
     return y, parts
 
 
 def stem_conv1_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
-    F_, _, H, W = x.shape
+    u8, F_, H, W = _stem_input(x, "stem_conv1_wgrad.x")
     ws = torch.empty((_lib.call("xcp_stem_conv1_wgrad_ws_bytes", F_, H, W),), device=x.device, dtype=torch.uint8)
-    _lib.call("xcp_stem_conv1_wgrad", _p(x), _p(dy), _p(dw), _p(ws), F_, H, W, x.device.index, _s())
+    _lib.call("xcp_stem_conv1_wgrad", _p(x), int(u8), _p(dy), _p(dw), _p(ws), F_, H, W, x.device.index, _s())
 
 
 def dw3x3_fwd(x: torch.Tensor, w9: torch.Tensor, scale=None, shift=None, relu: bool = False, out=None):

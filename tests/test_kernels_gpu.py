@@ -425,3 +425,41 @@ def test_adam_and_clip():
         ops.grad_sumsq(g, ss)
         ops.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-4, False, step, sumsq=ss, max_norm=1.0)
         assert rel_err(p, pt.detach()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ uint8 ingest
+def test_stem_conv1_uint8_nhwc_ingest_matches_float_path():
+    """Raw uint8 NHWC frames (video_dataloader.py:27-35 on-disk layout) through the stem == the reference's
+    float(T,3,H,W)/255 tensor through the stem (the in-kernel u8/255 and torch's scalar division differ by <= 1 ulp of the
+    fp32 input, i.e. at most a bf16 rounding flip in the output; 4x fewer input bytes)."""
+    g = torch.Generator().manual_seed(31)
+    u8 = torch.randint(0, 256, (3, 75, 61, 3), generator=g, dtype=torch.uint8).to(DEV)
+    xf = (u8.permute(0, 3, 1, 2).float() / 255.0).contiguous()
+    w = rnd(32, 3, 3, 3, seed=32, scale=0.3)
+    y_f, p_f = ops.stem_conv1_fwd(xf, w)
+    y_u, p_u = ops.stem_conv1_fwd(u8, w)
+    assert rel_err(y_u, y_f) < 1e-3 and rel_err(p_u.sum(0), p_f.sum(0)) < 1e-5
+    ref = F.conv2d(xf, w, stride=2)
+    assert rel_err(y_u.float().permute(0, 3, 1, 2), ref) < 4e-3
+    assert rel_err(p_u[:, 0].sum(0), ref.sum((0, 2, 3))) < 1e-4          # BN partial sums come from the fp32 accumulators
+    assert rel_err(p_u[:, 1].sum(0), (ref * ref).sum((0, 2, 3))) < 1e-4
+    dy = rnd(*y_f.shape, seed=33, dtype=torch.bfloat16)
+    dw_f = torch.zeros_like(w); dw_u = torch.zeros_like(w)
+    ops.stem_conv1_wgrad(xf, dy, dw_f)
+    ops.stem_conv1_wgrad(u8, dy, dw_u)
+    assert rel_err(dw_u, dw_f) < 1e-5                                   # same patches; split-K RED order differs
+
+
+def test_model_accepts_uint8_clips():
+    from multimodal_deepfake_detection_b200 import XceptionLSTMV
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = XceptionLSTMV(32).to(DEV).eval()
+    g = torch.Generator().manual_seed(34)
+    u8 = torch.randint(0, 256, (2, 3, 75, 75, 3), generator=g, dtype=torch.uint8).to(DEV)            # (B,T,H,W,3)
+    xf = (u8.permute(0, 1, 4, 2, 3).float() / 255.0).contiguous()                                     # (B,T,3,H,W)
+    with torch.no_grad():
+        a = m.extract_features(u8)
+        b = m.extract_features(xf)
+    assert a.shape == (2, 3, 2048) and rel_err(a, b) < 5e-3

@@ -117,6 +117,8 @@ if "stem" in which:
     report("conv2 wgrad as 9 GEMM launches", timeit(nine), gb)
     xin = torch.rand(F_, 3, 299, 299, device=dev); w1 = torch.randn(32, 3, 3, 3, device=dev)
     report("stem conv1 fwd", timeit(lambda: ops.stem_conv1_fwd(xin, w1)), (xin.numel() * 4 + F_ * 149 * 149 * 32 * 2) / 1e9)
+    xu8 = torch.randint(0, 256, (F_, 299, 299, 3), device=dev, dtype=torch.uint8)
+    report("stem conv1 fwd (uint8 NHWC frames)", timeit(lambda: ops.stem_conv1_fwd(xu8, w1)), (xu8.numel() + F_ * 149 * 149 * 32 * 2) / 1e9)
     dy1 = rnd(F_, 149, 149, 32); dw1 = torch.zeros(32, 3, 3, 3, device=dev)
     report("stem conv1 wgrad", timeit(lambda: ops.stem_conv1_wgrad(xin, dy1, dw1)), (xin.numel() * 4 + dy1.numel() * 2) / 1e9)
     wk, wkt = ops.pack_conv3x3(torch.randn(64, 32, 3, 3, device=dev), True)
