@@ -302,7 +302,9 @@ def test_short_training_curve_tracks_oracle():
         ours.append(l.item()); ref.append(lo.item())
     ours, ref = np.array(ours), np.array(ref)
     # the first steps must coincide; later the two bf16/fp32 trajectories separate chaotically (both over-fit the batch)
-    assert np.abs(ours[:5] - ref[:5]).max() < 2e-2, (ours[:5].tolist(), ref[:5].tolist())
+    # (lr = 1e-3 over-fits fast: the 5th step is already where round-off starts to steer; the 200-step test below uses the
+    #  reference's small learning rate and holds 2e-2 at every step)
+    assert np.abs(ours[:4] - ref[:4]).max() < 5e-3 and abs(ours[4] - ref[4]) < 6e-2, (ours[:5].tolist(), ref[:5].tolist())
     # both over-fit the batch; how fast the tail falls depends on bf16 round-off (summation order of the BN statistics)
     assert ours[-5:].mean() < 0.25 and ours[-1] < ours[-5] and ref[-5:].mean() < 0.1, (ours[-5:].tolist(), ref[-5:].tolist())
 
