@@ -44,6 +44,20 @@ struct DwGeom {
 static DwGeom make_geom(int F, int H, int W, int C, int max_halo_pixels, int max_warps) {
     DwGeom best{};
     double best_cost = 1e30;
+    {   // tuning hook: XCP_DW_GEOM="strips,slices,tile_rows" forces a geometry (tools/dw_tune.py); unset in production
+        const char* e = getenv("XCP_DW_GEOM");
+        int ns = 0, rs = 0, th = 0;
+        if (e != nullptr && sscanf(e, "%d,%d,%d", &ns, &rs, &th) == 3 && ns > 0 && rs > 0 && th > 0) {
+            DwGeom g{};
+            g.F = F; g.H = H; g.W = W; g.C = C;
+            g.strips = ns; g.TW = SW * ns; g.n_w = (W + g.TW - 1) / g.TW;
+            g.n_h = (H + th - 1) / th; g.TH = (H + g.n_h - 1) / g.n_h;
+            g.rows_per_slice = (g.TH + rs - 1) / rs;
+            g.RS = (g.TH + g.rows_per_slice - 1) / g.rows_per_slice;
+            g.c_tiles = (C + 63) / 64; g.sp_tiles = F * g.n_h * g.n_w;
+            return g;
+        }
+    }
     for (int ns = 1; ns <= max_warps; ++ns) {
         if (ns > 1 && SW * (ns - 1) >= W) break;          // already wider than the image
         for (int rs_try = 1; rs_try * ns <= max_warps; ++rs_try) {
@@ -594,8 +608,8 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
     // (7 compute warps each, tiles up to 400 pixels); both run spill-free at <= 128 registers (three 80-register CTAs spilled
     // and were 10-20 % slower, gpurun r1m).  The single large CTA has less halo and tile-rounding waste and wins on the big
     // entry-flow images (276 vs 369 us at 147x147x128, 128 frames) and at 19x19; the pair wins at 37x37 and 10x10 (gpurun r2e).
-    static int dbg_minb = -1;
-    if (dbg_minb < 0) { const char* e = getenv("XCP_DW_MINB"); dbg_minb = e ? atoi(e) : 0; }
+    int dbg_minb = 0;
+    { const char* e = getenv("XCP_DW_MINB"); dbg_minb = e ? atoi(e) : 0; }          // tuning hook (tools/dw_tune.py)
     const int hw = H > W ? H : W;
     const int minb = dbg_minb > 0 ? dbg_minb : ((hw >= 64 || (hw > 12 && hw <= 24)) ? 1 : 2);
     DwGeom g = make_geom(F, H, W, C, minb == 1 ? 800 : 400, minb == 1 ? 15 : 7);
@@ -639,8 +653,8 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     XCP_CUDA(cudaSetDevice(device));
     // one 512-thread CTA per SM (15 compute warps) measured faster than two 256-thread CTAs on every shape (477 vs 623 us at
     // 147x147x128, 213 vs 309 us at 37x37x728, 65 vs 76 us at 19x19x728; gpurun r2e) except with the staged identity-skip tile
-    static int dbg_minb = -1;
-    if (dbg_minb < 0) { const char* e = getenv("XCP_DW_MINB"); dbg_minb = e ? atoi(e) : 0; }
+    int dbg_minb = 0;
+    { const char* e = getenv("XCP_DW_MINB"); dbg_minb = e ? atoi(e) : 0; }          // tuning hook (tools/dw_tune.py)
     const int minb = dbg_minb > 0 ? dbg_minb : (add_full != nullptr ? 2 : 1);
     const int n_centre = add_full != nullptr ? 2 : 1;
     DwGeom g = make_geom(F, H, W, C, minb == 1 ? (add_full != nullptr ? 330 : 470) : (add_full != nullptr ? 170 : 200), minb == 1 ? 15 : 7);
