@@ -21,6 +21,7 @@
 // the first ncu pass showed the 1-CTA 128x256 tiles were limited by exactly that operand traffic (tensor pipe
 // 34-39 % active, DRAM traffic = algorithmic bytes), and the smaller stage also buys a 6-deep ring.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace xcp {
 
@@ -45,6 +46,12 @@ struct GemmParams {
     // its output lands at column tap * wg_tap_cols.  Taps are the fastest-varying unit index, so the 9 CTAs of a K split stream the same rows of
     // both operands through L2 together and DRAM sees them once (9 separate GEMMs re-read dY nine times).
     int wg_taps, wg_tap_cols;
+    // halo mode of the implicit GEMM (conv_halo = 1): the 128 output rows of a tile need input rows [m0 + halo_row0,
+    // m0 + halo_row0 + halo_rows): they are staged ONCE (2-deep ring of halo tiles) and the 9 taps are shifted views into that
+    // buffer (descriptor start + (a_row_shift[tap] - halo_row0) rows; the 128B/64B swizzle is a function of the absolute
+    // shared-memory address, so a view that starts mid-atom stays consistent with what TMA wrote).  The 9 weight tiles are
+    // resident.  Without it every tap re-reads its A tile through L2: 9 x the activation bytes per tile.
+    int conv_halo, halo_row0, halo_rows, halo_box_rows, halo_bytes;
     int conv_grid_w, conv_grid_h, conv_out_w, conv_out_h;  // epilogue compaction of the "input grid" rows
 };
 
@@ -97,7 +104,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * A_BYTES;
-    uint8_t* after = sB + STAGES * B_BYTES;
+    uint8_t* after = (!MN_MAJOR && !CTA2 && p.conv_halo) ? smem + 2 * p.halo_bytes + 9 * B_BYTES : sB + STAGES * B_BYTES;
     float* s_tr = reinterpret_cast<float*>(after);                       // [8][32][36]  (144-byte rows: conflict-free v4 stores); BLOCK_N == 64 only
     float* s_part = s_tr + ((STATS && BLOCK_N == 64) ? 8 * 32 * 36 : 0);                    // [4][2][BLOCK_N]
     uint8_t* s_store = reinterpret_cast<uint8_t*>(s_part + (STATS ? 4 * 2 * BLOCK_N : 0));      // [8 warps][2][32 rows x 64 B], 64B-swizzled
@@ -133,7 +140,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int num_units = tiles_mn * p.splits;
     const int m_row0_mul = CTA2 ? 2 * BLOCK_M : BLOCK_M;
 
-    if (warp == 0 && lane == 0) {
+    if (!MN_MAJOR && !CTA2 && p.conv_halo && warp < 2) {
+        // ================================================ implicit GEMM, halo mode (see GemmParams): producer + MMA issuer
+        uint8_t* sH = smem;                               // [2][halo_bytes]
+        uint8_t* sW = smem + 2 * p.halo_bytes;            // [9][B_BYTES] resident weights (barrier full[2])
+        if (warp == 0 && lane == 0) {
+            mbar_arrive_expect_tx(&full[2], 9 * B_BYTES);
+            for (int t = 0; t < 9; ++t) tma_load_2d(sW + t * B_BYTES, &tmB, &full[2], t * BLOCK_K, 0);
+            int s = 0; uint32_t ph = 0;
+            for (int u = worker; u < num_units; u += num_workers) {
+                const int row0 = u * BLOCK_M + p.halo_row0;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full[s], (uint32_t)p.halo_bytes);
+                for (int r = 0; r < p.halo_rows; r += p.halo_box_rows)
+                    tma_load_2d(sH + s * p.halo_bytes + r * (BLOCK_K * 2), &tmA, &full[s], 0, row0 + r);
+                if (++s == 2) { s = 0; ph ^= 1; }
+            }
+        } else if (warp == 1 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+            const uint32_t h_base = smem_u32(sH), w_base = smem_u32(sW);
+            mbar_wait(&full[2], 0);
+            int s = 0; uint32_t ph = 0; uint32_t iter = 0;
+            for (int u = worker; u < num_units; u += num_workers, ++iter) {
+                const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aph ^ 1);
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+#pragma unroll 1
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t a_tap = h_base + s * p.halo_bytes + (uint32_t)(p.a_row_shift[t] - p.halo_row0) * (BLOCK_K * 2);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t adesc = make_smem_desc(a_tap + k * (UMMA_K * 2), 0, SBO, LAYOUT);
+                        const uint64_t bdesc = make_smem_desc(w_base + t * B_BYTES + k * (UMMA_K * 2), 0, SBO, LAYOUT);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, (t > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&tmem_full[as]);
+                if (++s == 2) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 0 && lane == 0) {
         // ------------------------------------------------ TMA producer (one per CTA; in pair mode both signal the leader)
         int s = 0; uint32_t ph = 0;
         const uint32_t full0_leader = CTA2 ? mapa_cluster(smem_u32(&full[0]), 0) : 0u;   // leader's full[0] (barriers are 8 B apart)
@@ -266,13 +315,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // (h, w) fall inside the valid output window and compact them.
             bool row_ok = grow < p.M;
             long long orow = grow;
-            if (p.conv_taps > 0) {
-                const int gw = p.conv_grid_w, gh = p.conv_grid_h;
-                const long long f = grow / ((long long)gw * gh);
-                const int rem = (int)(grow - f * gw * gh);
-                const int h = rem / gw, w = rem - h * gw;
-                row_ok = row_ok && (h < p.conv_out_h) && (w < p.conv_out_w);
-                orow = (f * p.conv_out_h + h) * p.conv_out_w + w;
+            if (p.conv_taps > 0) {          // (the host guarantees M < 2^31: 32-bit divisions)
+                const uint32_t gw = (uint32_t)p.conv_grid_w, gh = (uint32_t)p.conv_grid_h, g32 = (uint32_t)grow;
+                const uint32_t f = g32 / (gw * gh);
+                const uint32_t rem = g32 - f * gw * gh;
+                const uint32_t h = rem / gw, w = rem - h * gw;
+                row_ok = row_ok && ((int)h < p.conv_out_h) && ((int)w < p.conv_out_w);
+                orow = ((long long)f * p.conv_out_h + h) * p.conv_out_w + w;
             }
 #pragma unroll
             for (int ci = 0; ci < NCW; ++ci) {
@@ -723,6 +772,30 @@ extern "C" int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* 
         for (int kw = 0; kw < 3; ++kw) p.a_row_shift[kh * 3 + kw] = sign * (kh * Wg + kw);
     p.conv_grid_w = Wg; p.conv_grid_h = Hg; p.conv_out_w = Wo; p.conv_out_h = Ho;
     p.stats_per_cta = 1;
+    // halo mode: stage the rows a tile needs once instead of once per tap, if two halo tiles + the 9 weight tiles fit
+    {
+        const int span = 2 * Wg + 2;                                   // largest |row shift|
+        const int need = BLOCK_M + span;
+        const int nbox = (need + 255) / 256;
+        const int box_rows = (((need + nbox - 1) / nbox) + 7) / 8 * 8;
+        const int rows = nbox * box_rows;
+        const int row_bytes = Cin * 2;
+        const int halo_bytes = ((rows * row_bytes) + 1023) / 1024 * 1024;
+        const int w_bytes = 9 * 64 * Cin * 2;
+        // shared memory the instantiation below is launched with (same formulas as gemm_smem_bytes / fit_stages)
+        const int fixed = stats != nullptr ? gemm_fixed_smem<64, 64, EPI_BF16_STATS, false>() : gemm_fixed_smem<64, 64, EPI_BF16, false>();
+        const int stage = BLOCK_M * Cin * 2 + 64 * Cin * 2;
+        int stages = (232448 - fixed) / stage;
+        if (stages > 8) stages = 8;
+        const int launched = fixed + stages * stage;
+        static const char* off = getenv("XCP_CONV_NO_HALO");        // A/B switch for tools/kernel_bench.py
+        if (off == nullptr && box_rows <= 256 && 2 * halo_bytes + w_bytes + fixed <= launched) {
+            p.conv_halo = 1;
+            p.halo_row0 = sign > 0 ? 0 : -span;
+            p.halo_rows = rows; p.halo_box_rows = box_rows; p.halo_bytes = halo_bytes;
+            if (int e = make_tmap_2d(&tmA, a, (uint64_t)Cin, (uint64_t)Mg, (uint64_t)Cin * 2, Cin, box_rows, Cin * 2)) return e;
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 32) {
         if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, fit_stages<64, 32, EPI_BF16_STATS, false>(), 32>(tmA, tmB, p, st);
