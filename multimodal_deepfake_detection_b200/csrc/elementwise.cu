@@ -235,11 +235,19 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
         const int wo = (int)(t % Wo); t /= Wo;
         const int ho = (int)(t % Ho);
         const int f = (int)(t / Ho);
-        float sc[8], sh[8], best[8];
-        int bi[8];
+        float sc[8], sh[8];
         load_affine8(scale, shift, cg * 8, sc, sh);
+        // z = sc*y + sh is monotonic in y, so the window maximum is taken on the RAW bf16 values, two channels per
+        // instruction (HMNMX2 + a packed compare mask for the arg-max), and the affine is applied once to the winner.
+        // Channels with a negative scale have their sign flipped on load so that "max" is right for them too.
+        // (The scalar version spent 45 instructions per output element, 5 per tap and channel, and ran at 40 % of HBM.)
+        uint32_t sgn[4], best[4], bi[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+        for (int pp = 0; pp < 4; ++pp) {
+            sgn[pp] = (sc[2 * pp] < 0.f ? 0x8000u : 0u) | (sc[2 * pp + 1] < 0.f ? 0x80000000u : 0u);
+            best[pp] = 0xff80ff80u;                       // (-inf, -inf)
+            bi[pp] = 0u;
+        }
         // all 9 taps are loaded up front from clamped (always valid) addresses and masked afterwards: nine independent
         // 16-byte loads in flight per thread instead of a chain of bounds-checked ones
         uint4 raw[9];
@@ -258,24 +266,40 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
         }
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            float v[8];
-            unpack8(raw[k], v);
+            const uint32_t wv[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+            const uint32_t kk = (uint32_t)k * 0x00010001u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float z = ok[k] ? fmaf(v[j], sc[j], sh[j]) : -INFINITY;
-                if (z > best[j]) { best[j] = z; bi[j] = k; }
+            for (int pp = 0; pp < 4; ++pp) {
+                const uint32_t v = ok[k] ? (wv[pp] ^ sgn[pp]) : 0xff80ff80u;
+                __nv_bfloat162 vb, bb;
+                *reinterpret_cast<uint32_t*>(&vb) = v;
+                *reinterpret_cast<uint32_t*>(&bb) = best[pp];
+                const uint32_t m = __hgt2_mask(vb, bb);                    // 0xffff per half where v > best (first maximum wins ties)
+                const __nv_bfloat162 mx = __hmax2(vb, bb);
+                best[pp] = *reinterpret_cast<const uint32_t*>(&mx);
+                bi[pp] = (bi[pp] & ~m) | (kk & m);
             }
+        }
+        float bestf[8];
+        int bidx[8];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            const uint32_t yv = best[pp] ^ sgn[pp];
+            bestf[2 * pp] = fmaf(bf16_lo(yv), sc[2 * pp], sh[2 * pp]);
+            bestf[2 * pp + 1] = fmaf(bf16_hi(yv), sc[2 * pp + 1], sh[2 * pp + 1]);
+            bidx[2 * pp] = (int)(bi[pp] & 0xffffu);
+            bidx[2 * pp + 1] = (int)(bi[pp] >> 16);
         }
         float s[8];
         unpack8(ldg_nc_v4(ys + i), s);
         load_affine8(scale_s, shift_s, cg * 8, sc, sh);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) best[j] += fmaf(s[j], sc[j], sh[j]);
-        out[i] = pack8(best);
+        for (int j = 0; j < 8; ++j) bestf[j] += fmaf(s[j], sc[j], sh[j]);
+        out[i] = pack8(bestf);
         if (idx != nullptr) {
             uint2 o;
-            o.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-            o.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+            o.x = (uint32_t)bidx[0] | ((uint32_t)bidx[1] << 8) | ((uint32_t)bidx[2] << 16) | ((uint32_t)bidx[3] << 24);
+            o.y = (uint32_t)bidx[4] | ((uint32_t)bidx[5] << 8) | ((uint32_t)bidx[6] << 16) | ((uint32_t)bidx[7] << 24);
             idx[i] = o;
         }
     }
