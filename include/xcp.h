@@ -154,6 +154,27 @@ int xcp_adam_multi(const void* table, int n_tensors, const void* chunks, int n_c
                    float eps, float weight_decay, int decoupled, float* sumsq_ws, float max_norm, float grad_scale, int device,
                    void* stream);
 
+/* ---- fp32 validation path (forward only; north_star parity tolerance "fp32 logits within 1e-4 relative").  Plain fp32 FMA
+ * kernels on NHWC fp32 activations that read the fp32 master parameters in torch's layouts; correctness instruments for the
+ * plan's layout / indexing / BatchNorm bookkeeping, not the production path (host side: fp32_plan.py).
+ * Xception.py:44-47 (separable conv), :89-99 (block), :167-199 (network). */
+int xcp_f32_conv3x3(const float* x, int x_nchw, const float* w, float* out, int F, int H, int W, int Ci, int Co, int stride,
+                    int device, void* stream);                        /* padding 0; w [Co][Ci][3][3]; out NHWC */
+int xcp_f32_dw3x3(const float* x, const float* w, float* out, int F, int H, int W, int C, int device, void* stream);
+int xcp_f32_gemm(const float* a, const float* w, const float* bias, float* out, long long M, int N, int K, int device,
+                 void* stream);                                       /* out[M,N] = a[M,K] . w[N,K]^T (+ bias) */
+int xcp_f32_bn_stats_parts(long long M);                              /* rows of the partials buffer for M pixels */
+int xcp_f32_bn_stats(const float* y, float* partials, long long M, int C, int device, void* stream); /* -> xcp_bn_finalize */
+int xcp_f32_affine(const float* y, const float* scale, const float* shift, int relu, float* out, long long n, int C,
+                   int device, void* stream);                         /* scale == NULL: (optional) ReLU only */
+int xcp_f32_pool_add(const float* y, const float* skip, float* out, int F, int H, int W, int C, int device, void* stream);
+int xcp_f32_add(const float* a, const float* b, float* out, long long n, int device, void* stream);
+int xcp_f32_gather(const float* x, float* out, int F, int H, int W, int C, int stride, int device, void* stream);
+int xcp_f32_gap(const float* x, float* out, int F, int HW, int C, int device, void* stream);
+/* nn.LSTM(I,H,1,batch_first) recurrence, zero initial state; xproj = x . W_ih^T [B*T,4H] (xcp_f32_gemm), w_hh fp32 [4H,H] */
+int xcp_f32_lstm_fwd(const float* xproj, const float* b_ih, const float* b_hh, const float* w_hh, float* h_out, float* hn,
+                     float* cn, int B, int T, int H, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,14 +62,25 @@ SIGNATURES = {
     "xcp_grad_sumsq": "plpiip",
     "xcp_adam_step": "pppplfffffiipffip",
     "xcp_adam_multi": "pipifffffipffip",
+    "xcp_f32_conv3x3": "pippiiiiiiip",
+    "xcp_f32_dw3x3": "pppiiiiip",
+    "xcp_f32_gemm": "ppppliiip",
+    "xcp_f32_bn_stats_parts": "l",
+    "xcp_f32_bn_stats": "ppliip",
+    "xcp_f32_affine": "pppipliip",
+    "xcp_f32_pool_add": "pppiiiiip",
+    "xcp_f32_add": "ppplip",
+    "xcp_f32_gather": "ppiiiiiip",
+    "xcp_f32_gap": "ppiiiip",
+    "xcp_f32_lstm_fwd": "pppppppiiiip",
 }
 _RET_LONGLONG = {"xcp_stem_conv1_wgrad_ws_bytes"}
 _NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp_stem_conv1_parts",
-              "xcp_stem_conv1_wgrad_ws_bytes"}
+              "xcp_stem_conv1_wgrad_ws_bytes", "xcp_f32_bn_stats_parts"}
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; 0 = host-only query)
 _LAUNCHES = {"xcp_version": 0, "xcp_check_device": 0, "xcp_bnbwd_num_parts": 0, "xcp_gemm_stats_parts": 0,
-             "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
+             "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_f32_bn_stats_parts": 0, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
              "xcp_arcface_loss": 2, "xcp_adam_multi": 2}
 _count = 0
 

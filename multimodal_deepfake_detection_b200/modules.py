@@ -16,6 +16,7 @@ There is no CPU or eager fallback: a CPU tensor or an unsupported configuration 
 from __future__ import annotations
 
 import math
+import os
 import warnings
 from typing import List, Optional
 
@@ -289,9 +290,26 @@ class Xception(nn.Module):
         fc_ids = {id(p) for p in self.fc.parameters()} if isinstance(self.fc, nn.Module) else set()
         return [p for p in self.parameters() if id(p) not in fc_ids]
 
+    # ---- arithmetic: "bf16" = the tcgen05 production plan; "fp32" = the forward-only validation plan (fp32_plan.py)
+    def set_precision(self, precision: str):
+        if precision not in ("bf16", "fp32"):
+            raise XcpError("Xception.set_precision: 'bf16' or 'fp32', got %r" % (precision,))
+        self.__dict__["_precision"] = precision
+        return self
+
+    @property
+    def precision(self) -> str:
+        return self.__dict__.get("_precision") or os.environ.get("XCP_PRECISION", "bf16")
+
     def features(self, x):
         """conv1 ... bn4/relu/GAP of Xception.forward (Xception.py:168-198): [F,3,H,W] -> [F,2048]."""
         _require_cuda(x, "Xception")
+        if self.precision == "fp32":
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self._backbone_params()):
+                raise XcpError("Xception: the fp32 validation plan is forward-only -- call it under torch.no_grad() "
+                               "(training runs on the bf16 plan: set_precision('bf16'))")
+            from . import fp32_plan
+            return fp32_plan.xception_features(self, x)
         if x.dtype == torch.uint8:                     # raw frames, NHWC [F,H,W,3]: scaled by 1/255 inside the stem kernel
             if x.dim() != 4 or x.shape[3] != 3:
                 raise XcpError("Xception: uint8 frames must be NHWC [F,H,W,3], got %s" % (tuple(x.shape),))
@@ -364,6 +382,16 @@ class FusedLSTM(nn.LSTM):
     """nn.LSTM(input, hidden, 1, batch_first=True) with identical parameters / state_dict keys
     (XceptionLSTMV.py:18-23); forward = one tcgen05 input-projection GEMM + one persistent recurrent kernel."""
 
+    def set_precision(self, precision: str):
+        if precision not in ("bf16", "fp32"):
+            raise XcpError("FusedLSTM.set_precision: 'bf16' or 'fp32', got %r" % (precision,))
+        self.__dict__["_precision"] = precision
+        return self
+
+    @property
+    def precision(self) -> str:
+        return self.__dict__.get("_precision") or os.environ.get("XCP_PRECISION", "bf16")
+
     def forward(self, input, hx=None):
         _require_cuda(input, "FusedLSTM")
         if hx is not None or self.num_layers != 1 or self.bidirectional or not self.batch_first or self.proj_size != 0:
@@ -371,6 +399,12 @@ class FusedLSTM(nn.LSTM):
                            "(1 layer, unidirectional, batch_first, zero initial state)")
         if input.dim() != 3:
             raise XcpError("FusedLSTM: expected [B,T,%d]" % self.input_size)
+        if self.precision == "fp32":                 # forward-only validation arithmetic (fp32_plan.py)
+            if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+                raise XcpError("FusedLSTM: the fp32 validation plan is forward-only -- call it under torch.no_grad()")
+            from . import fp32_plan
+            out, hn, cn = fp32_plan.lstm(self, input)
+            return out, (hn.unsqueeze(0), cn.unsqueeze(0))
         out, hn, cn = _LSTMFn.apply(self, input, self.weight_ih_l0, self.weight_hh_l0, self.bias_ih_l0, self.bias_hh_l0)
         return out, (hn.unsqueeze(0), cn.unsqueeze(0))
 
@@ -429,6 +463,13 @@ class _XceptionLSTMBase(nn.Module):
         )
         self.fc_out = nn.Linear(1024, 1)
         self.sigmoid = nn.Sigmoid()
+
+    def set_precision(self, precision: str):
+        """"bf16": tensor-core production plan; "fp32": forward-only validation arithmetic for the backbone and the LSTM
+        (the MLP head is fp32 in both)."""
+        self.feature_extractor.set_precision(precision)
+        self.lstm.set_precision(precision)
+        return self
 
     def _head_params(self):
         ps = []
