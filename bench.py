@@ -298,6 +298,28 @@ def run_ours(args):
         infer(i)
     ms_inf = timed(infer, args.steps)
     infer_fps = world * B * T_FRAMES * args.steps / (ms_inf * 1e-3)
+    # latency of ONE clip (the per-video loop of test_visual.py:609-624): eager launches vs one CUDA-graph replay (row f-3)
+    one_clip = None
+    if rank == 0:
+        from multimodal_deepfake_detection_b200.graph import GraphedInference
+        clip1 = dev_clips[:1].contiguous()
+        fwd1 = lambda c: model(model.extract_features(c, dev))  # noqa: E731
+
+        def lat(fn, n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(n):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        with torch.no_grad():
+            for _ in range(3):
+                fwd1(clip1)
+            ms_eager1 = lat(lambda: fwd1(clip1), 10)
+        g1 = GraphedInference(fwd1, (clip1,), modules=[model])
+        g1(clip1)
+        one_clip = {"frames": T_FRAMES, "eager_ms": ms_eager1, "graph_ms": lat(lambda: g1(clip1), 20)}
+        del g1
     model.train()
 
     if rank != 0:
@@ -341,7 +363,8 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / max(args.steps, 1)},
         "gpu_launches": launches,
         "infer": {"value": infer_fps, "unit": "frames/s", "ms_per_pass": ms_inf / max(args.steps, 1),
-                  "what": "XceptionLSTMV eval-mode forward (BN folded, no_grad), %d clips x %d frames per GPU per pass" % (B, T_FRAMES)},
+                  "what": "XceptionLSTMV eval-mode forward (BN folded, no_grad), %d clips x %d frames per GPU per pass" % (B, T_FRAMES),
+                  "one_clip_latency": one_clip},
         "roofline": roof,
         "cpu_baseline": cpu,
         "loss": last.get("loss"),

@@ -85,6 +85,50 @@ class GraphedTrainStep:
         return self.replay()
 
 
+class GraphedInference:
+    """Capture an eval-mode forward (`fn(*inputs) -> tensor or tuple of tensors`) into a CUDA graph (SURVEY.md §8 row f-3;
+    the per-clip loop of test_visual.py:609-624).  With BatchNorm folded from the running statistics nothing in the
+    forward depends on the batch, so a single clip is ~190 launches of a few microseconds each: eager Python cannot
+    issue them as fast as the GPU retires them, one cudaGraphLaunch can.
+
+    >>> infer = GraphedInference(lambda clips: model(model.extract_features(clips)), (clips,), modules=[model])
+    >>> probs = infer(next_clips)                  # static output buffer: clone it to keep it across calls
+
+    The modules must be in eval() mode (train-mode BatchNorm would update running statistics at every replay) and their
+    parameters must not change between capture and replay (the graph reads the bf16 weight packs made at capture)."""
+
+    def __init__(self, fn: Callable[..., object], example_inputs: Sequence[torch.Tensor], modules: Sequence[torch.nn.Module] = (),
+                 warmup: int = 2):
+        if not example_inputs or not all(t.is_cuda for t in example_inputs):
+            raise XcpError("GraphedInference: example inputs must be CUDA tensors (no CPU path)")
+        for root in modules:
+            if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.training for m in root.modules()):
+                raise XcpError("GraphedInference: put the model in eval() mode first (train-mode BatchNorm updates its running "
+                               "statistics on every replay)")
+        self.static_inputs = [t.clone() for t in example_inputs]
+        self._fn = fn
+        dev = self.static_inputs[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):                  # weight packs, tensor maps and workspaces are built here
+                fn(*self.static_inputs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_outputs = fn(*self.static_inputs)
+        self.replays = 0
+
+    def __call__(self, *inputs: torch.Tensor):
+        for dst, src in zip(self.static_inputs, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self.static_outputs
+
+
 class HostPrefetcher:
     """Double-buffered pinned-host -> device staging on a copy stream (what DataLoader(pin_memory=True) +
     .to(device, non_blocking=True) gives the reference's loops, video_dataloader.py:40-51, train_visual.py:564):

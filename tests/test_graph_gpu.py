@@ -87,3 +87,32 @@ def test_host_prefetcher_delivers_batches_in_order():
         if i + 1 < 5:
             k = pre.submit(host[i + 1])
         assert float(got.mean()) == float(i)
+
+
+def test_graphed_inference_matches_eager_eval():
+    """one clip's eval-mode forward replayed from a CUDA graph returns what eager launches return."""
+    from multimodal_deepfake_detection_b200.graph import GraphedInference
+    from multimodal_deepfake_detection_b200._lib import XcpError
+    torch.manual_seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = XceptionLSTMV(32).to(DEV)
+    g = torch.Generator().manual_seed(9)
+    clips = [torch.rand(1, 4, 3, 96, 96, generator=g).to(DEV) for _ in range(3)]
+    fn = lambda c: m(m.extract_features(c, torch.device(DEV)))  # noqa: E731
+    with pytest.raises(XcpError):
+        GraphedInference(fn, (clips[0],), modules=[m])          # still in train mode
+    m.eval()
+    with torch.no_grad():
+        eager = [fn(c).clone() for c in clips]
+    infer = GraphedInference(fn, (clips[0],), modules=[m])
+    for c, e in zip(clips, eager):
+        out = infer(c)
+        assert torch.equal(out, e)
+    assert infer.replays == 3
+    # raw uint8 frames (row f-2) through the same capture path
+    u8 = torch.randint(0, 256, (1, 4, 96, 96, 3), generator=g, dtype=torch.uint8).to(DEV)
+    with torch.no_grad():
+        e8 = fn(u8).clone()
+    infer8 = GraphedInference(fn, (u8,), modules=[m])
+    assert torch.equal(infer8(u8), e8)
