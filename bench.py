@@ -187,11 +187,14 @@ def run_ours(args):
     dev_clips = host_clips[0].to(dev)
     dev_y = host_y[0].to(dev)
 
+    from multimodal_deepfake_detection_b200 import BCELoss
+    criterion = BCELoss()
+
     def step(clips, y):
         opt.zero_grad(set_to_none=True)
         feats = model.extract_features(clips, dev)
         prob = model(feats)
-        loss = F.binary_cross_entropy(prob, y)          # train_audio.py:20,39 criterion on the sigmoid output
+        loss = criterion(prob, y)                       # train_audio.py:20,39 criterion on the sigmoid output (one kernel)
         loss.backward()
         if bucketer is not None:
             bucketer.finish()

@@ -133,6 +133,8 @@ int xcp_sigmoid_fwd(const float* z, float* p, int n, int device, void* stream);
 int xcp_sigmoid_bwd(const float* p, const float* dp, float* dz, int n, int device, void* stream);
 int xcp_bce_fwd_bwd(const float* z, const float* y, float smoothing, float* probs, float* loss, float* dz, int B, int device,
                     void* stream);
+/* nn.BCELoss() (mean) on probabilities + its gradient wrt p in one launch (train_audio.py:20,39); dp may be NULL */
+int xcp_bce_prob_fwd_bwd(const float* p, const float* y, float* loss, float* dp, int n, int device, void* stream);
 int xcp_arcface_loss(const float* x, const float* w, const long long* labels, float s, float m, int loss_mode,
                      const float* class_w, float gamma, const float* dlogits_in, float* logits, float* loss, float* loss_rows,
                      float* dx, float* dw, int B, int D, float gscale, int device, void* stream);

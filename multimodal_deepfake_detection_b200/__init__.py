@@ -3,7 +3,7 @@ Tonmoy1321/Multimodal-DeepFake-Detection.  See DESIGN.md and include/xcp.h.
 
 Importing this package does not touch CUDA and does not load the shared library (DataLoader workers import it);
 the first kernel call dlopen()s libxcp_sm100.so and fails loudly if it is missing."""
-from .modules import (ArcFaceHead, AUFaceCrossDetector, Block, CBFocalLoss, FusedLinear, FusedLSTM, FusionHead,  # noqa: F401
+from .modules import (ArcFaceHead, AUFaceCrossDetector, BCELoss, Block, CBFocalLoss, FusedLinear, FusedLSTM, FusionHead,  # noqa: F401
                       LabelSmoothingBCEWithLogitsLoss,
                       SeparableConv2d, Xception, XceptionLSTMA, XceptionLSTMV, model_urls, xception)
 from ._lib import XcpError, LIB_PATH  # noqa: F401

@@ -56,6 +56,7 @@ SIGNATURES = {
     "xcp_sigmoid_fwd": "ppiip",
     "xcp_sigmoid_bwd": "pppiip",
     "xcp_bce_fwd_bwd": "ppfpppiip",
+    "xcp_bce_prob_fwd_bwd": "ppppiip",
     "xcp_arcface_loss": "pppffipfppppppiifip",
     "xcp_fusion_pool_reg": "ppppppiiifffip",
     "xcp_fusion_pool_bwd": "pppiiiip",

@@ -296,6 +296,27 @@ __global__ void bce_fwd_bwd_kernel(const float* __restrict__ z, const float* __r
     }
 }
 
+// nn.BCELoss(reduction="mean") on probabilities (train_audio.py:20,39): loss = -mean(y*max(log p,-100) + (1-y)*max(log(1-p),-100))
+// and dp = dL/dp = (p - y) / max(p(1-p), 1e-12) / n  (torch's binary_cross_entropy_backward), in one launch.
+__global__ void bce_prob_fwd_bwd_kernel(const float* __restrict__ p, const float* __restrict__ y, float* __restrict__ loss,
+                                        float* __restrict__ dp, int n) {
+    __shared__ float s[32];
+    float l = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float pp = p[i], t = y[i];
+        l -= t * fmaxf(logf(pp), -100.f) + (1.f - t) * fmaxf(logf(1.f - pp), -100.f);
+        if (dp) dp[i] = (pp - t) / fmaxf((1.f - pp) * pp, 1e-12f) / (float)n;
+    }
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int i = 0; i < (blockDim.x + 31) / 32; ++i) tot += s[i];
+        *loss = tot / (float)n;
+    }
+}
+
 // ============================================================================================ ArcFace (+CE / CB-focal)
 // One warp per sample.  logits[b][c] = s * (c == y ? cos(theta + m) : cos), cos = <x/|x|, w_c/|w_c|> clamped.
 // loss_mode 0: CrossEntropy mean ; 1: class-balanced focal (gamma, class weights).  labels < 0 => inference logits only.
@@ -540,6 +561,13 @@ extern "C" int xcp_bce_fwd_bwd(const float* z, const float* y, float smoothing, 
     XCP_CUDA(cudaSetDevice(device));
     bce_fwd_bwd_kernel<<<1, 256, 0, ST>>>(z, y, smoothing, probs, loss, dz, B);
     return check_cuda(cudaGetLastError(), "bce launch");
+}
+
+extern "C" int xcp_bce_prob_fwd_bwd(const float* p, const float* y, float* loss, float* dp, int n, int device, void* stream) {
+    XCP_REQUIRE(n > 0, "xcp_bce_prob_fwd_bwd: empty batch");
+    XCP_CUDA(cudaSetDevice(device));
+    bce_prob_fwd_bwd_kernel<<<1, 256, 0, ST>>>(p, y, loss, dp, n);
+    return check_cuda(cudaGetLastError(), "bce_prob launch");
 }
 
 // ArcFace logits (+ CE or CB-focal loss and gradients when labels != null).  loss (scalar) is overwritten,

@@ -164,7 +164,8 @@ def visual_epoch(model, arcface, loader, device, optimizer=None):
 # ------------------------------------------------------------------------------------------------ audio (BCE on sigmoid)
 def audio_epoch(model, loader, device, optimizer=None):
     """train_audio.py:33-46 / 55-67: BCELoss on the sigmoid output; returns (mean loss, accuracy)."""
-    import torch.nn.functional as F
+    from .modules import BCELoss
+    criterion = BCELoss()
     train = optimizer is not None
     total = torch.zeros((), device=device)
     hits = torch.zeros((), device=device)
@@ -175,7 +176,7 @@ def audio_epoch(model, loader, device, optimizer=None):
             audio, labels = audio.to(device, non_blocking=True), labels.to(device, non_blocking=True)
             feats = model.extract_features(audio, device)
             out = model(feats)
-            loss = F.binary_cross_entropy(out, labels)
+            loss = criterion(out, labels)
             if train:
                 optimizer.zero_grad(set_to_none=True)
                 loss.backward()

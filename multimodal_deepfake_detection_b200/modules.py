@@ -622,6 +622,31 @@ class _BCEFn(torch.autograd.Function):
         return (dz.view(ctx.shape) * dloss), None, None
 
 
+class _BCEProbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, probs, targets):
+        p = probs.float().contiguous()
+        y = targets.float().contiguous()
+        if p.numel() != y.numel():
+            raise XcpError("BCELoss: input %s and target %s differ in size" % (tuple(probs.shape), tuple(targets.shape)))
+        loss, dp = ops.bce_prob_fwd_bwd(p, y, want_grad=ctx.needs_input_grad[0])
+        ctx.dp, ctx.shape = dp, probs.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        return (ctx.dp.view(ctx.shape) * dloss), None
+
+
+class BCELoss(nn.Module):
+    """nn.BCELoss() (mean reduction, log clamped at -100) as the reference applies it to the sigmoid output
+    (train_audio.py:20,39): loss and dL/dp in one kernel."""
+
+    def forward(self, input, target):
+        _require_cuda(input, "BCELoss")
+        return _BCEProbFn.apply(input, target)
+
+
 class LabelSmoothingBCEWithLogitsLoss(nn.Module):
     """train_au_patch.py:203-211 -- BCE-with-logits on targets*(1-s)+0.5*s, loss and gradient in one kernel."""
 

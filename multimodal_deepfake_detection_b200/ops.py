@@ -292,7 +292,11 @@ def bn_bwd(mode: int, y, st: BNState, gamma, dgamma, dbeta, G=None, idx=None, df
     if want_dy:
         if grid_hw is not None:
             gh, gw = grid_hw
-            dy = torch.zeros((F_, gh, gw, C), device=dev, dtype=BF16)
+            dy = torch.empty((F_, gh, gw, C), device=dev, dtype=BF16)     # the kernel fills [0:H, 0:W]; only the border
+            if gh > H:                                                     # strips need the zeros (memset plumbing)
+                dy[:, H:].zero_()
+            if gw > W:
+                dy[:, :H, W:].zero_()
         else:
             dy = torch.empty_like(y)
     _lib.add_launches(-(1 if presums is not None else 0) - (0 if want_dy else 1))
@@ -434,6 +438,16 @@ def bce_fwd_bwd(z, y, smoothing: float = 0.0, want_grad: bool = True):
     dz = torch.empty((B, 1), device=z.device, dtype=F32) if want_grad else None
     _lib.call("xcp_bce_fwd_bwd", _p(z), _p(y), smoothing, _p(probs), _p(loss), _p(dz), B, z.device.index, _s())
     return probs, loss, dz
+
+
+def bce_prob_fwd_bwd(p, y, want_grad: bool = True):
+    """nn.BCELoss() on probabilities: -> (loss scalar, dL/dp)."""
+    _chk(p, F32, "bce_prob.p"); _chk(y, F32, "bce_prob.y")
+    n = p.numel()
+    loss = torch.empty((), device=p.device, dtype=F32)
+    dp = torch.empty_like(p) if want_grad else None
+    _lib.call("xcp_bce_prob_fwd_bwd", _p(p), _p(y), _p(loss), _p(dp), n, p.device.index, _s())
+    return loss, dp
 
 
 def arcface_loss(x, w, labels, s, m, loss_mode=0, class_w=None, gamma=2.0, dw=None, want_dx=True, gscale=1.0):

@@ -110,3 +110,37 @@ def test_full_size_clip_step_smoke():
     missing = [k for k, p in m.named_parameters() if p.requires_grad and p.grad is None]
     assert not missing, missing[:5]
     assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+def test_800_frames_cross_the_32_bit_element_boundary(net):
+    """Maximum sizes: 800 frames of 3x299x299 (50 clips per GPU) make the 147x147x128 activations 2.2e9 elements / 4.4 GB each,
+    past 2^31 in elements and bytes.  Every frame is the same image, so (eval-mode BN) every feature row must equal the row
+    computed from a 3-frame batch bit for bit, and with a per-frame-identical upstream gradient every parameter gradient
+    must be (800 / 16) x the 16-frame gradient up to the order of the fp32 RED accumulations."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 150e9:
+        pytest.skip("needs ~110 GB of free HBM")
+    net.eval()
+    g = torch.Generator().manual_seed(21)
+    frame = torch.rand(1, 3, 299, 299, generator=g).to(DEV)
+    grow = (torch.randn(1, 2048, generator=g) * 1e-2).to(DEV)
+    with torch.no_grad():
+        small = net.features(frame.expand(3, -1, -1, -1).contiguous())
+        big = net.features(frame.expand(800, -1, -1, -1).contiguous())
+    assert big.shape == (800, 2048)
+    assert torch.equal(big, small[:1].expand(800, -1))
+
+    def grads(n):
+        net.zero_grad(set_to_none=True)
+        f = net.features(frame.expand(n, -1, -1, -1).contiguous())
+        f.backward(grow.expand(n, -1).contiguous())
+        out = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        net.zero_grad(set_to_none=True)
+        return out
+    g16 = grads(16)
+    torch.cuda.empty_cache()
+    g800 = grads(800)
+    torch.cuda.empty_cache()
+    errs = {k: rel(g800[k], 50.0 * g16[k]) for k in g16}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 5e-3, (worst, errs[worst])

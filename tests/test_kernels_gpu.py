@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from multimodal_deepfake_detection_b200 import ops  # noqa: E402
+from multimodal_deepfake_detection_b200 import _lib, ops  # noqa: E402
 
 DEV = "cuda"
 
@@ -375,6 +375,29 @@ def test_head_linear_bce():
     l2.backward()
     _, loss_s, dz_s = ops.bce_fwd_bwd(z2.detach(), y, smoothing=0.1)
     assert abs(loss_s.item() - l2.item()) < 1e-5 and rel_err(dz_s, z2.grad) < 1e-4
+
+
+def test_bce_loss_module_matches_nn_bceloss():
+    """BCELoss (train_audio.py:20,39) vs torch.nn.BCELoss incl. saturated probabilities (log clamp at -100, gradient
+    denominator clamp at 1e-12), a non-unit upstream gradient and a (B,1) / (B,) mix of shapes."""
+    from multimodal_deepfake_detection_b200 import BCELoss
+    g = torch.Generator().manual_seed(60)
+    for n in (1, 4, 32, 300):
+        p = torch.rand(n, 1, generator=g).to(DEV)
+        if n >= 4:
+            p[0], p[1], p[2] = 0.0, 1.0, 1e-30
+        y = torch.randint(0, 2, (n, 1), generator=g).float().to(DEV)
+        pr = p.clone().requires_grad_(True)
+        po = p.clone().requires_grad_(True)
+        lr = torch.nn.BCELoss()(pr, y)
+        lo = BCELoss()(po, y)
+        (lr * 3.0).backward(); (lo * 3.0).backward()
+        assert abs(lr.item() - lo.item()) <= 1e-5 * max(1.0, abs(lr.item()))
+        assert rel_err(po.grad, pr.grad) < 1e-5
+    with torch.no_grad():
+        assert BCELoss()(p, y).requires_grad is False
+    with pytest.raises(_lib.XcpError):
+        BCELoss()(p, y[:-1])
 
 
 def test_arcface_and_fusion_against_golden(golden):
