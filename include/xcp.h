@@ -110,6 +110,11 @@ int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int Cp, int HW, in
 int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int Rp, int Cp, int device, void* stream);
 int xcp_pack_dw(const float* w, float* w9, int C, int Cp, int device, void* stream);                      /* w9 = [9][Cp] */
 int xcp_unpack_dw_grad(const float* g9, float* gw, int C, int accumulate, int device, void* stream);
+/* multi-tensor xcp_pack_weight / xcp_pack_dw: `table` = n_tensors x {const float* src; void* out; void* out_t; int R, Cc, Rp,
+ * Cp; int kind; int tile0} (48 bytes, device memory).  kind 0: [R,Cc] fp32 -> bf16 [Rp,Cp] (+ transpose [Cp,Rp] unless
+ * out_t is NULL), ceil(Rp/32)*ceil(Cp/32) tiles; kind 1: depthwise [R=C,1,3,3] -> fp32 [9][Cp], ceil(9*Cp/1024) tiles;
+ * tile0 = running sum of the tile counts, n_tiles = their total. */
+int xcp_pack_multi(const void* table, int n_tensors, int n_tiles, int device, void* stream);
 int xcp_pack_conv3x3(const float* w, void* wk, void* wk_t, int O, int I, int device, void* stream);
 int xcp_unpack_conv3x3_grad(const float* gk, float* gw, int O, int I, int device, void* stream);
 /* F.interpolate(size=(S,S), mode="bilinear", align_corners=False) of [planes, n, 1] (XceptionLSTMA.py:45-46) */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "xcp_nhwc_to_nchw": "ppiiiiip",
     "xcp_pack_weight": "pppiiiiip",
     "xcp_pack_dw": "ppiiip",
+    "xcp_pack_multi": "piiip",
     "xcp_unpack_dw_grad": "ppiiip",
     "xcp_pack_conv3x3": "pppiiip",
     "xcp_unpack_conv3x3_grad": "ppiiip",

@@ -764,6 +764,58 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
+// Multi-tensor form of pack_weight / pack_dw: one launch re-packs every pointwise and depthwise weight the optimizer just
+// changed (~165 tensors per step, each a 3-4 us launch on its own).  Blocks find their tensor by binary search over the
+// table's running tile offsets; kind 0 = 32x32 transpose tiles of a [R,Cc] -> bf16 [Rp,Cp] (+ [Cp,Rp]) matrix,
+// kind 1 = 1024-element tiles of a depthwise [C,1,3,3] -> fp32 [9][Cp].
+struct PackTensor {
+    const float* src;
+    void* out;
+    void* out_t;
+    int R, Cc, Rp, Cp;
+    int kind, tile0;
+};
+static_assert(sizeof(PackTensor) == 48, "PackTensor layout is mirrored on the host (executor.PackCache.prefetch)");
+
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackTensor* __restrict__ tab, int n) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.x;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tab[mid].tile0 <= b) lo = mid; else hi = mid - 1;
+    }
+    const PackTensor T = tab[lo];
+    const int tile = b - T.tile0;
+    if (T.kind == 1) {
+        const int C = T.R, Cp = T.Cp, end = min((tile + 1) * 1024, 9 * Cp);
+        float* w9 = (float*)T.out;
+        for (int i = tile * 1024 + threadIdx.x; i < end; i += 256) {
+            const int c = i / 9, k = i % 9;
+            w9[(long long)k * Cp + c] = c < C ? T.src[i] : 0.f;
+        }
+        return;
+    }
+    const int tiles_x = (T.Cp + 31) >> 5;
+    const int r0 = (tile / tiles_x) * 32, c0 = (tile % tiles_x) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __nv_bfloat16* out = (__nv_bfloat16*)T.out;
+    __nv_bfloat16* out_t = (__nv_bfloat16*)T.out_t;
+    for (int r = ty; r < 32; r += 8) {
+        const int rr = r0 + r, cc = c0 + tx;
+        const float v = (rr < T.R && cc < T.Cc) ? T.src[(long long)rr * T.Cc + cc] : 0.f;
+        t[r][tx] = v;
+        if (rr < T.Rp && cc < T.Cp && out != nullptr) out[(long long)rr * T.Cp + cc] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    if (out_t != nullptr) {
+        for (int r = ty; r < 32; r += 8) {
+            const int cc = c0 + r, rr = r0 + tx;
+            if (rr < T.Rp && cc < T.Cp) out_t[(long long)cc * T.Rp + rr] = __float2bfloat16(t[tx][r]);
+        }
+    }
+}
+
 // depthwise weights [C,1,3,3] fp32 -> tap-major [9][C] fp32 ; and the reverse accumulation for gradients
 __global__ void pack_dw_kernel(const float* __restrict__ w, float* __restrict__ w9, int C, int Cp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1012,6 +1064,13 @@ extern "C" int xcp_pack_weight(const float* w, void* out, void* out_t, int R, in
     dim3 grid((Cp + 31) / 32, (Rp + 31) / 32), block(32, 8);
     pack_weight_kernel<<<grid, block, 0, ST>>>(w, (__nv_bfloat16*)out, (__nv_bfloat16*)out_t, R, Cc, Rp, Cp);
     return check_cuda(cudaGetLastError(), "pack_weight launch");
+}
+
+extern "C" int xcp_pack_multi(const void* table, int n_tensors, int n_tiles, int device, void* stream) {
+    XCP_REQUIRE(table != nullptr && n_tensors > 0 && n_tiles > 0, "xcp_pack_multi: empty table");
+    XCP_CUDA(cudaSetDevice(device));
+    pack_multi_kernel<<<n_tiles, 256, 0, ST>>>((const PackTensor*)table, n_tensors);
+    return check_cuda(cudaGetLastError(), "pack_multi launch");
 }
 
 extern "C" int xcp_pack_dw(const float* w, float* w9, int C, int Cp, int device, void* stream) {

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
 from . import ops
@@ -66,6 +67,66 @@ class PackCache:
         val = fn(p.detach())
         self._c[key] = (tag, val)
         return val
+
+    def prefetch(self, items):
+        """Re-pack every stale pointwise ("pw") / depthwise ("dw") weight of `items` = [(param, kind)] with ONE
+        xcp_pack_multi launch (after an optimizer step all ~165 of them are stale).  Existing pack buffers are
+        overwritten in place, so in steady state the device-side table never changes and nothing is uploaded."""
+        stale = []
+        for p, kind in items:
+            key = (id(p), kind)
+            tag = (p.data_ptr(), p._version, self.generation, PARAM_EPOCH[0], p.device)
+            hit = self._c.get(key)
+            if hit is None or hit[0] != tag:
+                stale.append((p, kind, key, tag, hit))
+        if len(stale) < 4:
+            return                                        # the lazy per-tensor path handles a few
+        dev = stale[0][0].device
+        rows = np.zeros((len(stale), 6), dtype=np.uint64)
+        ints = rows.view(np.int32).reshape(len(stale), 12)
+        tile0 = 0
+        vals = []
+        for i, (p, kind, key, tag, hit) in enumerate(stale):
+            t = p.detach()
+            if t.device != dev or t.dtype != ops.F32 or not t.is_contiguous():
+                return
+            old = hit[1] if hit is not None else None
+            if kind == "pw":
+                R, Cc = t.shape[0], t.shape[1]
+                Rp, Cp = ops.phys(R), ops.phys(Cc)
+                if old is not None and old[0].shape == (Rp, Cp) and old[0].device == dev and old[1] is not None:
+                    out, out_t = old
+                else:
+                    out = torch.empty((Rp, Cp), device=dev, dtype=ops.BF16)
+                    out_t = torch.empty((Cp, Rp), device=dev, dtype=ops.BF16)
+                rows[i, 0:3] = (t.data_ptr(), out.data_ptr(), out_t.data_ptr())
+                ints[i, 6:12] = (R, Cc, Rp, Cp, 0, tile0)
+                tile0 += ((Rp + 31) // 32) * ((Cp + 31) // 32)
+                vals.append((out, out_t))
+            else:
+                C = t.shape[0]
+                Cp = ops.phys(C)
+                if old is not None and torch.is_tensor(old) and old.shape == (9, Cp) and old.device == dev:
+                    out = old
+                else:
+                    out = torch.empty((9, Cp), device=dev, dtype=ops.F32)
+                rows[i, 0:3] = (t.data_ptr(), out.data_ptr(), 0)
+                ints[i, 6:12] = (C, 9, 0, Cp, 1, tile0)
+                tile0 += (9 * Cp + 1023) // 1024
+                vals.append(out)
+        raw = rows.tobytes()
+        ent = self.__dict__.get("_table")
+        if ent is None or ent[0] != raw:
+            host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+            buf = torch.empty((len(raw),), device=dev, dtype=torch.uint8)
+            buf.copy_(host, non_blocking=True)
+            keep = self.__dict__.setdefault("_table_keep", [])
+            if torch.cuda.is_current_stream_capturing():
+                keep.append((host, buf))                  # a captured memcpy node re-reads the pinned buffer at every replay
+            ent = self._table = (raw, buf, host)
+        ops.pack_multi(ent[1], len(stale), tile0)
+        for (p, kind, key, tag, hit), val in zip(stale, vals):
+            self._c[key] = (tag, val)
 
     def pw(self, w: torch.Tensor):
         """[N,K,1,1] fp32 -> (bf16 [Np,Kp], bf16 [Kp,Np]), zero-padded to the physical channel pitches (ops.phys)"""
@@ -301,6 +362,15 @@ def xception_forward(net, x: torch.Tensor, save: bool = True):
     """net: Models.Xception.Xception (ours).  x: fp32 NCHW [F,3,H,W] in [0,1] or raw uint8 NHWC frames [F,H,W,3] on a B200.
     Returns (feat fp32 [F,2048], tape)."""
     cache: PackCache = net._pack_cache
+    items = []
+    for spec in net._block_specs:
+        for u in spec.units:
+            items += [(u.sep.conv1.weight, "dw"), (u.sep.pointwise.weight, "pw")]
+        if spec.skip is not None:
+            items.append((spec.skip.weight, "pw"))
+    for u in net._exit_specs:
+        items += [(u.sep.conv1.weight, "dw"), (u.sep.pointwise.weight, "pw")]
+    cache.prefetch(items)                                                     # one launch for every stale weight pack
     nbt: list = []
     tp = XceptionTape()
     F_ = x.shape[0]

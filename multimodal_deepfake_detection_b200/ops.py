@@ -346,6 +346,11 @@ def pack_dw(w: torch.Tensor, pad: bool = False):
     return w9
 
 
+def pack_multi(table: torch.Tensor, n_tensors: int, n_tiles: int):
+    """One launch over a device-side table of pointwise / depthwise weights (executor.PackCache.prefetch builds it)."""
+    _lib.call("xcp_pack_multi", _p(table), n_tensors, n_tiles, table.device.index, _s())
+
+
 def unpack_dw_grad(g9: torch.Tensor, gw: torch.Tensor, accumulate: bool):
     _lib.call("xcp_unpack_dw_grad", _p(g9), _p(gw), g9.shape[1], int(accumulate), g9.device.index, _s())
 

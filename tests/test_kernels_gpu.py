@@ -377,6 +377,38 @@ def test_head_linear_bce():
     assert abs(loss_s.item() - l2.item()) < 1e-5 and rel_err(dz_s, z2.grad) < 1e-4
 
 
+def test_pack_multi_matches_per_tensor_packs():
+    """executor.PackCache.prefetch (one xcp_pack_multi launch) == the per-tensor pack kernels, incl. 728 -> 768 zero padding,
+    in-place refresh after a parameter update and a table that changes."""
+    from multimodal_deepfake_detection_b200 import executor as ex
+    g = torch.Generator().manual_seed(70)
+    pws = [torch.randn(n, k, 1, 1, generator=g).to(DEV) for n, k in ((128, 64), (728, 256), (728, 728), (1024, 728), (2048, 1536), (40, 24))]
+    dws = [torch.randn(c, 1, 3, 3, generator=g).to(DEV) for c in (64, 728, 1536, 24)]
+    items = [(w, "pw") for w in pws] + [(w, "dw") for w in dws]
+    cache = ex.PackCache()
+    cache.prefetch(items)
+
+    def check():
+        for w in pws:
+            a, at = cache.pw(w)
+            b, bt = ops.pack_weight(w.view(w.shape[0], w.shape[1]), True, pad=True)
+            assert torch.equal(a, b) and torch.equal(at, bt)
+        for w in dws:
+            assert torch.equal(cache.dw(w), ops.pack_dw(w, pad=True))
+    n0 = _lib.launch_count()
+    check()
+    ptrs = [cache.pw(w)[0].data_ptr() for w in pws]
+    for w in pws + dws:
+        w.mul_(1.5)                                   # bumps Tensor._version: every pack is stale again
+    cache.prefetch(items)
+    check()
+    assert ptrs == [cache.pw(w)[0].data_ptr() for w in pws]          # refreshed in place
+    ex.bump_param_epoch()                             # raw-pointer update (FusedAdam): stale through the epoch
+    pws[2].data.add_(1.0)
+    cache.prefetch(items[:5] + items[6:])             # a different table
+    check()
+
+
 def test_bce_loss_module_matches_nn_bceloss():
     """BCELoss (train_audio.py:20,39) vs torch.nn.BCELoss incl. saturated probabilities (log clamp at -100, gradient
     denominator clamp at 1e-12), a non-unit upstream gradient and a (B,1) / (B,) mix of shapes."""
