@@ -22,6 +22,11 @@ class AudioDataset(Dataset):
         return mf.unsqueeze(1).repeat(1, 3, 1), torch.tensor([label])
 
 
-def get_audio_dataloader(folder_path, batch_size=8, shuffle=True):
+def get_audio_dataloader(folder_path, batch_size=8, shuffle=True, waveforms=False):
+    """waveforms=True (no reference counterpart): yield raw 16 kHz waveforms (B, samples) for the GPU
+    MFCC front-end (multimodal_deepfake_detection_b200.audio_frontend.MFCC) instead of pre-computed MFCC files."""
+    if waveforms:
+        from .synthetic import SyntheticWaveforms, collate_waveforms
+        return DataLoader(SyntheticWaveforms(), batch_size=batch_size, shuffle=shuffle, collate_fn=collate_waveforms)
     ds = AudioDataset(folder_path) if folder_path and os.path.isdir(folder_path) else SyntheticAudio()
     return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, collate_fn=collate_fn)

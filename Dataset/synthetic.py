@@ -58,6 +58,31 @@ class SyntheticAudio(Dataset):
         return mf.repeat(1, 3, 1), torch.tensor([float(self.labels[i])])   # (T,3,13) by channel repeat, audio_dataloader.py:25-26
 
 
+class SyntheticWaveforms(Dataset):
+    """16 kHz mono waveforms (what `ffmpeg -ar 16000 -ac 1` hands librosa, wavfake_audio_dataset.py:30-41) for the GPU
+    front-end route: (samples,) fp32 + label; `frames` MFCC frames need (frames - 1) * 160 samples."""
+
+    def __init__(self, n=64, frames=120, sr=16000, seed=0):
+        self.n, self.samples, self.sr, self.seed = n, (frames - 1) * int(0.010 * sr) + int(0.010 * sr) // 2, sr, seed
+        g = torch.Generator().manual_seed(seed)
+        self.labels = torch.randint(0, 2, (n,), generator=g).tolist()
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed * 104729 + i)
+        t = torch.arange(self.samples) / self.sr
+        f0 = 110.0 + 200.0 * torch.rand((), generator=g)
+        wav = 0.3 * torch.sin(2 * torch.pi * f0 * t) + 0.1 * torch.sin(2 * torch.pi * 3.1 * f0 * t) + 0.02 * torch.randn(self.samples, generator=g)
+        return wav.float(), torch.tensor([float(self.labels[i])])
+
+
+def collate_waveforms(batch):
+    wavs, labs = zip(*batch)
+    return torch.stack(wavs), torch.stack(labs)
+
+
 def collate_audio(batch):
     feats, labs = zip(*batch)
     tmax = max(f.shape[0] for f in feats)

@@ -182,6 +182,15 @@ int xcp_f32_gap(const float* x, float* out, int F, int HW, int C, int device, vo
 int xcp_f32_lstm_fwd(const float* xproj, const float* b_ih, const float* b_hh, const float* w_hh, float* h_out, float* hn,
                      float* cn, int B, int T, int H, int device, void* stream);
 
+/* ---- audio front-end: waveform -> MFCC on the device, replacing the offline
+ * librosa.feature.mfcc(y, sr, n_mfcc=13, n_fft=int(0.025 sr), hop_length=int(0.010 sr)).T of wavfake_audio_dataset.py:17-19,40-44
+ * (centre-padded periodic-Hann STFT power, Slaney mel filters, power_to_db(top_db), orthonormal DCT-II).
+ * wav [B][L] fp32; melfb_t [n_fft/2+1][n_mels] fp32 (host-built constant); logmel_ws [B][T][n_mels] fp32 and gmax_ws [B] int
+ * are scratch; out [B][T][n_mfcc] fp32 with T = xcp_mfcc_frames(L, hop) = 1 + L/hop.  pad_reflect: librosa < 0.10 padding. */
+int xcp_mfcc_frames(int L, int hop);
+int xcp_mfcc(const float* wav, int B, int L, const float* melfb_t, int n_fft, int hop, int n_mels, int n_mfcc, int pad_reflect,
+             float amin, float top_db, float* logmel_ws, int* gmax_ws, float* out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,14 +75,16 @@ SIGNATURES = {
     "xcp_f32_gather": "ppiiiiiip",
     "xcp_f32_gap": "ppiiiip",
     "xcp_f32_lstm_fwd": "pppppppiiiip",
+    "xcp_mfcc_frames": "ii",
+    "xcp_mfcc": "piipiiiiiffpppip",
 }
 _RET_LONGLONG = {"xcp_stem_conv1_wgrad_ws_bytes"}
 _NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp_stem_conv1_parts",
-              "xcp_stem_conv1_wgrad_ws_bytes", "xcp_f32_bn_stats_parts"}
+              "xcp_stem_conv1_wgrad_ws_bytes", "xcp_f32_bn_stats_parts", "xcp_mfcc_frames"}
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; 0 = host-only query)
 _LAUNCHES = {"xcp_version": 0, "xcp_check_device": 0, "xcp_bnbwd_num_parts": 0, "xcp_gemm_stats_parts": 0,
-             "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_f32_bn_stats_parts": 0, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
+             "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_f32_bn_stats_parts": 0, "xcp_mfcc_frames": 0, "xcp_mfcc": 2, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
              "xcp_arcface_loss": 2, "xcp_adam_multi": 2}
 _count = 0
 

@@ -162,8 +162,10 @@ def visual_epoch(model, arcface, loader, device, optimizer=None):
 
 
 # ------------------------------------------------------------------------------------------------ audio (BCE on sigmoid)
-def audio_epoch(model, loader, device, optimizer=None):
-    """train_audio.py:33-46 / 55-67: BCELoss on the sigmoid output; returns (mean loss, accuracy)."""
+def audio_epoch(model, loader, device, optimizer=None, frontend=None, frames: int = 120):
+    """train_audio.py:33-46 / 55-67: BCELoss on the sigmoid output; returns (mean loss, accuracy).
+    With `frontend` (audio_frontend.MFCC) a 2-D batch is taken as raw waveforms (B, samples) and turned into the
+    (B, frames, 3, 13) MFCC tensor on the device (row f-4) instead of coming from the offline librosa files."""
     from .modules import BCELoss
     criterion = BCELoss()
     train = optimizer is not None
@@ -174,6 +176,10 @@ def audio_epoch(model, loader, device, optimizer=None):
     with torch.set_grad_enabled(train):
         for audio, labels in loader:
             audio, labels = audio.to(device, non_blocking=True), labels.to(device, non_blocking=True)
+            if audio.dim() == 2:
+                if frontend is None:
+                    raise XcpError("audio_epoch: got raw waveforms %s but no MFCC front-end" % (tuple(audio.shape),))
+                audio = frontend.clips(audio, frames=frames)
             feats = model.extract_features(audio, device)
             out = model(feats)
             loss = criterion(out, labels)

@@ -47,6 +47,15 @@ def test_train_audio(small_run):
     assert best == best and best < 50.0
 
 
+def test_train_audio_from_waveforms(small_run, monkeypatch):
+    """the same script fed with raw 16 kHz waveforms, MFCCs computed on the GPU every step."""
+    monkeypatch.setenv("XCP_AUDIO_FROM_WAV", "1")
+    monkeypatch.setenv("XCP_EPOCHS", "1")
+    best = _fresh("train_audio").main()
+    assert (small_run / "ck" / "best_model_audio.pth").exists()
+    assert best == best and best < 50.0
+
+
 def test_train_then_test_au_face(small_run):
     auc = _fresh("train_au_face").main()
     ck = torch.load(small_run / "ck" / "auface_cross_best_auc_arcface_cb.pth")
