@@ -9,7 +9,7 @@ can be fed to the reference modules, to this oracle and to the sm_100a path.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may import this file.  The product
-package never does (``tests/test_no_oracle_in_product.py`` enforces that).
+package never does (``tests/test_cabi_and_host_cpu.py::test_product_never_imports_the_oracle`` enforces that).
 
 Parity pinning: the reference ships NO golden vectors or tests,
 so this oracle is pinned against the reference *itself*: ``oracle/gen_golden.py``
