@@ -493,10 +493,23 @@ extern "C" int xcp_cast_f32_bf16(const float* x, void* out, long long n, int dev
     return check_cuda(cudaGetLastError(), "cast launch");
 }
 
+namespace xcp {
+// lstm_cluster.cu: cluster kernels for H = 256 / 512; -1000 = not applicable here (fall back to the single-CTA kernels)
+int lstm_fwd_cluster(const float* xproj, const float* b_ih, const float* b_hh, const void* w_hh_t, float* h_out, float* gates,
+                     float* cstate, float* hn, float* cn, int B, int T, int H, cudaStream_t st);
+int lstm_bwd_cluster(const float* dout, const float* dhn, const float* dcn, const float* gates, const float* cstate,
+                     const float* hstate, const void* w_hh, void* dgates, void* hprev, float* dbias_ih, float* dbias_hh, int B,
+                     int T, int H, cudaStream_t st);
+}  // namespace xcp
+
 extern "C" int xcp_lstm_fwd(const float* xproj, const float* b_ih, const float* b_hh, const void* w_hh_t, float* h_out,
                             float* gates, float* cstate, float* hn, float* cn, int B, int T, int H, int device, void* stream) {
     XCP_REQUIRE(B > 0 && T > 0 && H > 0 && H % 8 == 0 && H <= 4096, "xcp_lstm_fwd: bad shape B=%d T=%d H=%d", B, T, H);
     XCP_CUDA(cudaSetDevice(device));
+    {
+        const int rc = xcp::lstm_fwd_cluster(xproj, b_ih, b_hh, w_hh_t, h_out, gates, cstate, hn, cn, B, T, H, ST);
+        if (rc != -1000) return rc;
+    }
     const int nt = 4 * H < 1024 ? 4 * H : 1024;
     XCP_REQUIRE(H <= 4 * nt, "xcp_lstm_fwd: H too large for the register-resident cell state");
     size_t smem = (size_t)5 * H * sizeof(float);
@@ -514,6 +527,10 @@ extern "C" int xcp_lstm_bwd(const float* dout, const float* dhn, const float* dc
                             int B, int T, int H, int device, void* stream) {
     XCP_REQUIRE(B > 0 && T > 0 && H > 0 && H % 8 == 0, "xcp_lstm_bwd: bad shape");
     XCP_CUDA(cudaSetDevice(device));
+    {
+        const int rc = xcp::lstm_bwd_cluster(dout, dhn, dcn, gates, cstate, hstate, w_hh, dgates, hprev, dbias_ih, dbias_hh, B, T, H, ST);
+        if (rc != -1000) return rc;
+    }
     const int nt = 4 * H < 1024 ? 4 * H : 1024;
     const size_t smem = (size_t)9 * H * sizeof(float);
     XCP_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

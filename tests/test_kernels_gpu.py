@@ -320,7 +320,8 @@ def test_layout_and_packing():
 
 
 # ------------------------------------------------------------------------------------------------ LSTM / head
-@pytest.mark.parametrize("B,T,H", [(4, 16, 128), (2, 5, 32), (3, 7, 512)])
+@pytest.mark.parametrize("B,T,H", [(4, 16, 128), (2, 5, 32), (3, 7, 512), (8, 120, 512), (11, 9, 512), (1, 1, 512), (5, 6, 256),
+                                   (16, 33, 256)])
 def test_lstm_fwd_bwd(B, T, H):
     lstm = torch.nn.LSTM(2048, H, 1, batch_first=True).to(DEV)
     with torch.no_grad():   # the recurrent weights are held in bf16 by the kernel
@@ -347,6 +348,41 @@ def test_lstm_fwd_bwd(B, T, H):
     _, w_ih_t = ops.pack_weight(lstm.weight_ih_l0.detach())
     dx, _ = ops.gemm_tn(dgates, w_ih_t, ops.EPI_F32)
     assert rel_err(dx.view(B, T, 2048), x.grad) < 1e-2
+
+
+def test_lstm_cluster_kernels_match_single_cta_kernels(monkeypatch):
+    """H = 512: the cluster kernels (W_hh in registers, DSMEM h exchange) against the single-CTA kernels on the same inputs,
+    incl. the initial dh_n / dc_n gradients, and their speed at the audio model's T = 120."""
+    import time
+    B, T, H = 8, 120, 512
+    g = torch.Generator().manual_seed(80)
+    w = (torch.randn(4 * H, H, generator=g) * 0.04).to(DEV)
+    w_b, w_t = ops.pack_weight(w)
+    xproj = (torch.randn(B * T, 4 * H, generator=g) * 0.5).to(DEV)
+    bi, bh = (torch.randn(4 * H, generator=g) * 0.1).to(DEV), (torch.randn(4 * H, generator=g) * 0.1).to(DEV)
+    dout = torch.randn(B, T, H, generator=g).to(DEV)
+    dhn, dcn = torch.randn(B, H, generator=g).to(DEV), torch.randn(B, H, generator=g).to(DEV)
+
+    def run():
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        h, gates, cst, hn, cn = ops.lstm_fwd(xproj, bi, bh, w_t, B, T, H)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        dbi = torch.zeros(4 * H, device=DEV); dbh = torch.zeros(4 * H, device=DEV)
+        dgates, hprev = ops.lstm_bwd(dout, dhn, dcn, gates, cst, h, w_b, dbi, dbh, B, T, H)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        return (h, gates, cst, hn, cn, dgates.float(), hprev.float(), dbi, dbh), (t1 - t0) * 1e3, (t2 - t1) * 1e3
+    run()
+    new, f_new, b_new = run()
+    monkeypatch.setenv("XCP_LSTM_NO_CLUSTER", "1")
+    run()
+    old, f_old, b_old = run()
+    monkeypatch.delenv("XCP_LSTM_NO_CLUSTER")
+    print("lstm H=512 T=120 B=8: fwd %.2f -> %.2f ms, bwd %.2f -> %.2f ms" % (f_old, f_new, b_old, b_new))
+    names = ("h", "gates", "c", "hn", "cn", "dgates", "hprev", "dbi", "dbh")
+    for n, a, b in zip(names, new, old):
+        tol = 2e-2 if n in ("dgates", "dbi", "dbh") else 2e-3
+        assert rel_err(a, b) < tol, (n, rel_err(a, b))
+    assert f_new < f_old and b_new < b_old
 
 
 def test_head_linear_bce():
