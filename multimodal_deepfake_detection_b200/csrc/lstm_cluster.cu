@@ -245,11 +245,14 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict_
     cluster_sync_all();                                    // nobody leaves while a peer may still be writing into its smem
 }
 
+// One-time per (kernel, device): opt in to the shared-memory size / non-portable cluster size and ask the driver whether a
+// cluster of `cs` CTAs can be co-scheduled.  Cached, because none of this may run while a stream is being captured into a
+// CUDA graph (the first call always happens in an eager warm-up step).
 template <typename K>
-int launch_cluster(K kern, int cs, int B, size_t smem, cudaStream_t st, void** args, const char* what) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess && cs > 8) e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) { cudaGetLastError(); return LSTM_CLUSTER_NA; }
+int launch_cluster(K kern, int* state /* [64], per device: 0 unknown, 1 usable, -1 not usable */, int cs, int B, size_t smem,
+                   cudaStream_t st, void** args, const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return LSTM_CLUSTER_NA;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(cs * ((B + LC_NB - 1) / LC_NB)));
     cfg.blockDim = dim3(LC_THREADS);
@@ -259,9 +262,17 @@ int launch_cluster(K kern, int cs, int B, size_t smem, cudaStream_t st, void** a
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    int nclusters = 0;
-    e = cudaOccupancyMaxActiveClusters(&nclusters, (const void*)kern, &cfg);
-    if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); return LSTM_CLUSTER_NA; }       // cannot co-schedule the cluster
+    if (state[dev] == 0) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return LSTM_CLUSTER_NA; }
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess && cs > 8) e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        int nclusters = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nclusters, (const void*)kern, &cfg);
+        if (e != cudaSuccess) cudaGetLastError();
+        state[dev] = (e == cudaSuccess && nclusters >= 1) ? 1 : -1;
+    }
+    if (state[dev] < 0) return LSTM_CLUSTER_NA;
     return check_cuda(cudaLaunchKernelExC(&cfg, (const void*)kern, args), what);
 }
 
@@ -277,8 +288,9 @@ int lstm_fwd_cluster(const float* xproj, const float* b_ih, const float* b_hh, c
     if (cluster_disabled() || (H != 256 && H != 512)) return LSTM_CLUSTER_NA;
     void* args[] = {&xproj, &b_ih, &b_hh, &w_hh_t, &h_out, &gates, &cstate, &hn, &cn, &B, &T};
     const size_t smem = (size_t)2 * 2 * LC_NB * (H + 8) * 2 + (size_t)LC_NB * 132 * 4 + 2 * LC_NB * 32 * 2;
-    if (H == 512) return launch_cluster(lstm_fwd_cluster_kernel<512>, 16, B, smem, st, args, "lstm_fwd_cluster launch");
-    return launch_cluster(lstm_fwd_cluster_kernel<256>, 8, B, smem, st, args, "lstm_fwd_cluster launch");
+    static int st512[64] = {0}, st256[64] = {0};
+    if (H == 512) return launch_cluster(lstm_fwd_cluster_kernel<512>, st512, 16, B, smem, st, args, "lstm_fwd_cluster launch");
+    return launch_cluster(lstm_fwd_cluster_kernel<256>, st256, 8, B, smem, st, args, "lstm_fwd_cluster launch");
 }
 
 int lstm_bwd_cluster(const float* dout, const float* dhn, const float* dcn, const float* gates, const float* cstate,
@@ -287,7 +299,8 @@ int lstm_bwd_cluster(const float* dout, const float* dhn, const float* dcn, cons
     if (cluster_disabled() || (H != 256 && H != 512)) return LSTM_CLUSTER_NA;
     void* args[] = {&dout, &dhn, &dcn, &gates, &cstate, &hstate, &w_hh, &dgates, &hprev, &dbias_ih, &dbias_hh, &B, &T};
     const size_t smem = (size_t)2 * 2 * LC_NB * (4 * H + 8) * 2 + (size_t)2 * LC_NB * 128 * 2 + (size_t)4 * 32 * (LC_NB + 1) * 4;
-    if (H == 512) return launch_cluster(lstm_bwd_cluster_kernel<512>, 16, B, smem, st, args, "lstm_bwd_cluster launch");
-    return launch_cluster(lstm_bwd_cluster_kernel<256>, 8, B, smem, st, args, "lstm_bwd_cluster launch");
+    static int st512[64] = {0}, st256[64] = {0};
+    if (H == 512) return launch_cluster(lstm_bwd_cluster_kernel<512>, st512, 16, B, smem, st, args, "lstm_bwd_cluster launch");
+    return launch_cluster(lstm_bwd_cluster_kernel<256>, st256, 8, B, smem, st, args, "lstm_bwd_cluster launch");
 }
 }  // namespace xcp

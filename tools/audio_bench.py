@@ -60,7 +60,7 @@ def main():
     step(x, y)
     launches = _lib.launch_count()
     ms_eager = timed(lambda: step(x, y), a.steps)
-    ms_graph, last = ms_eager, step(x, y)
+    ms_graph, last = ms_eager, step(x, y).detach()      # (a live loss would pin the eager autograd graph across the capture)
     if not a.no_graph:
         graphed = GraphedTrainStep(step, (x, y), modules=[m], warmup=1)
         last = graphed.replay()
