@@ -598,12 +598,96 @@ static int dw_grid(const DwGeom& g, int ctas_per_sm) {
 using namespace xcp;
 
 // out[F,H,W,C] = depthwise3x3( act(x) ),  act(x) = relu?( scale*x + shift ) with scale/shift optional.
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiny images (S x S, S <= 8: the 8x8 / 4x4 / 2x2 maps of the audio model's 64x64 patches, XceptionLSTMA.py:46).  A TMA halo
+// tile per image would move (S+2)^2 / S^2 = 2.25x the bytes at S = 4 in 6x6-pixel boxes; instead one thread owns a whole
+// image of one channel pair in registers: S^2 coalesced 4-byte loads (a warp reads 128 contiguous bytes per pixel), the
+// BN-affine / ReLU prologue once per pixel, all S^2 outputs from registers with compile-time border handling.  Every
+// input byte is read once and every output byte written once.
+template <int S, bool AFFINE, bool RELU>
+__global__ void __launch_bounds__(128)
+dw3x3_small_fwd_kernel(const __nv_bfloat162* __restrict__ x, const float* __restrict__ w9, const float* __restrict__ scale,
+                       const float* __restrict__ shift, __nv_bfloat162* __restrict__ out, long long n_items, int C) {
+    const int C2 = C >> 1;
+    const long long idx = blockIdx.x * 128LL + threadIdx.x;
+    if (idx >= n_items) return;
+    const int c2 = (int)(idx % C2);
+    const long long f = idx / C2;
+    float2 wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[k] = *reinterpret_cast<const float2*>(w9 + (long long)k * C + 2 * c2);
+    float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+    if (AFFINE) { sc = *reinterpret_cast<const float2*>(scale + 2 * c2); sh = *reinterpret_cast<const float2*>(shift + 2 * c2); }
+    const __nv_bfloat162* xp = x + f * (S * S) * C2 + c2;
+    float2 a[S][S];
+#pragma unroll
+    for (int y = 0; y < S; ++y)
+#pragma unroll
+        for (int xx = 0; xx < S; ++xx) {
+            float2 v = __bfloat1622float2(xp[(long long)(y * S + xx) * C2]);
+            if (AFFINE) { v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); }
+            if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+            a[y][xx] = v;
+        }
+    __nv_bfloat162* op = out + f * (S * S) * C2 + c2;
+#pragma unroll
+    for (int y = 0; y < S; ++y)
+#pragma unroll
+        for (int xx = 0; xx < S; ++xx) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int yy = y + ky - 1, xq = xx + kx - 1;
+                    if (yy >= 0 && yy < S && xq >= 0 && xq < S) {
+                        acc.x = fmaf(a[yy][xq].x, wk[ky * 3 + kx].x, acc.x);
+                        acc.y = fmaf(a[yy][xq].y, wk[ky * 3 + kx].y, acc.y);
+                    }
+                }
+            op[(long long)(y * S + xx) * C2] = __floats2bfloat162_rn(acc.x, acc.y);
+        }
+}
+
+template <int S>
+static int launch_dw_small(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int C,
+                           cudaStream_t st) {
+    const long long n_items = (long long)F * (C / 2);
+    const unsigned grid = (unsigned)((n_items + 127) / 128);
+    const __nv_bfloat162* xi = (const __nv_bfloat162*)x;
+    __nv_bfloat162* o = (__nv_bfloat162*)out;
+    if (scale != nullptr) {
+        if (relu) dw3x3_small_fwd_kernel<S, true, true><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C);
+        else dw3x3_small_fwd_kernel<S, true, false><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C);
+    } else {
+        if (relu) dw3x3_small_fwd_kernel<S, false, true><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C);
+        else dw3x3_small_fwd_kernel<S, false, false><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C);
+    }
+    return check_cuda(cudaGetLastError(), "dw3x3_small_fwd launch");
+}
+
 extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out,
                              int F, int H, int W, int C, int device, void* stream) {
     XCP_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "xcp_dw3x3_fwd: bad shape F=%d H=%d W=%d C=%d", F, H, W, C);
     XCP_REQUIRE((scale == nullptr) == (shift == nullptr), "xcp_dw3x3_fwd: scale/shift must both be given or both null");
     XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_fwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
+    if (H == W && H <= 8) {
+        const char* e = getenv("XCP_DW_NO_SMALL");                                    // A/B hook
+        if (!(e && e[0] == '1')) {
+            cudaStream_t st = (cudaStream_t)stream;
+            switch (H) {
+                case 1: return launch_dw_small<1>(x, w9, scale, shift, relu, out, F, C, st);
+                case 2: return launch_dw_small<2>(x, w9, scale, shift, relu, out, F, C, st);
+                case 3: return launch_dw_small<3>(x, w9, scale, shift, relu, out, F, C, st);
+                case 4: return launch_dw_small<4>(x, w9, scale, shift, relu, out, F, C, st);
+                case 5: return launch_dw_small<5>(x, w9, scale, shift, relu, out, F, C, st);
+                case 6: return launch_dw_small<6>(x, w9, scale, shift, relu, out, F, C, st);
+                case 7: return launch_dw_small<7>(x, w9, scale, shift, relu, out, F, C, st);
+                default: return launch_dw_small<8>(x, w9, scale, shift, relu, out, F, C, st);
+            }
+        }
+    }
     // resident CTAs per SM: ONE 512-thread CTA (15 compute warps, tiles up to 800 staged pixels) or two 256-thread CTAs
     // (7 compute warps each, tiles up to 400 pixels); both run spill-free at <= 128 registers (three 80-register CTAs spilled
     // and were 10-20 % slower, gpurun r1m).  The single large CTA has less halo and tile-rounding waste and wins on the big

@@ -127,7 +127,10 @@ def test_stem_conv1(F_, H):
 
 # ------------------------------------------------------------------------------------------------ depthwise
 DW_SHAPES = [(2, 147, 147, 64), (2, 74, 74, 128), (3, 37, 37, 256), (2, 19, 19, 728), (3, 10, 10, 1024), (1, 5, 7, 16), (9, 37, 37, 728),
-             (2, 2, 2, 728), (1, 33, 31, 8)]
+             (2, 2, 2, 728), (1, 33, 31, 8),
+             # tiny square maps of the audio model (register-resident forward kernel), incl. the 768-pitch width
+             (7, 4, 4, 768), (5, 8, 8, 256), (3, 2, 2, 1536), (4, 3, 3, 64), (2, 1, 1, 64), (130, 4, 4, 768), (3, 5, 5, 1024), (2, 7, 7, 8),
+             (2, 6, 6, 128), (2, 8, 4, 64)]
 
 
 @pytest.mark.parametrize("shape", DW_SHAPES)

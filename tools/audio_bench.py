@@ -70,10 +70,16 @@ def main():
         for _ in range(2):
             m(m.extract_features(x, dev))
         ms_inf = timed(lambda: m(m.extract_features(x, dev)), a.steps)
+    ms_inf_graph = None
+    if not a.no_graph:
+        from multimodal_deepfake_detection_b200.graph import GraphedInference
+        gi = GraphedInference(lambda xx: m(m.extract_features(xx, dev)), (x,), modules=[m])
+        gi(x)
+        ms_inf_graph = timed(lambda: gi(x), a.steps)
     print(json.dumps({"workload": "XceptionLSTMA(512) train step, %s backbone" % ("unfrozen" if a.unfrozen else "frozen"),
                       "clips": a.batch, "frames_per_clip": a.frames, "launches_per_step": launches, "eager_ms": ms_eager,
                       "graph_ms": ms_graph, "clips_per_s_graph": a.batch / (ms_graph * 1e-3),
-                      "patches_per_s_graph": a.batch * a.frames / (ms_graph * 1e-3), "infer_eager_ms": ms_inf,
+                      "patches_per_s_graph": a.batch * a.frames / (ms_graph * 1e-3), "infer_eager_ms": ms_inf, "infer_graph_ms": ms_inf_graph,
                       "infer_patches_per_s": a.batch * a.frames / (ms_inf * 1e-3), "loss": float(last.detach())}))
 
 
