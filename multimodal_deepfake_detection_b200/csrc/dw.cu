@@ -599,7 +599,8 @@ using namespace xcp;
 
 // out[F,H,W,C] = depthwise3x3( act(x) ),  act(x) = relu?( scale*x + shift ) with scale/shift optional.
 // ---------------------------------------------------------------------------------------------------------------------
-// Tiny images (S x S, S <= 8: the 8x8 / 4x4 / 2x2 maps of the audio model's 64x64 patches, XceptionLSTMA.py:46).  A TMA halo
+// Tiny images (S x S, S <= 8: the 8x8 / 4x4 / 2x2 maps of the audio model's 64x64 patches, XceptionLSTMA.py:46; measured at
+// 960 patches, tools/dw_rows_ab.py: 8x8x768 76.8 -> 47.1 us, 4x4x768 66.6 -> 17.4 us, 2x2x1536 101.4 -> 13.3 us).  A TMA halo
 // tile per image would move (S+2)^2 / S^2 = 2.25x the bytes at S = 4 in 6x6-pixel boxes; instead one thread owns a whole
 // image of one channel pair in registers: S^2 coalesced 4-byte loads (a warp reads 128 contiguous bytes per pixel), the
 // BN-affine / ReLU prologue once per pixel, all S^2 outputs from registers with compile-time border handling.  Every
@@ -649,6 +650,94 @@ dw3x3_small_fwd_kernel(const __nv_bfloat162* __restrict__ x, const float* __rest
         }
 }
 
+// Narrow images (W = 10 / 15: the exit flow at 299x299, block 2 of the audio model).  One thread owns a channel
+// pair of one image and walks down its rows with a three-row fp32 window in registers (rows y-1, y, y+1, already through the
+// BN-affine / ReLU prologue) while the raw loads of row y+2 are in flight: every input element is loaded exactly once with
+// warp-coalesced 128-byte accesses, no halo is re-read, nothing is staged in shared memory, and there is no tile geometry
+// (the TMA halo-tile kernel above moves 6-wide boxes for 4 output columns and is latency bound on such small images).
+template <int W, bool AFFINE, bool RELU>
+__global__ void __launch_bounds__(128, 3)
+dw3x3_rows_fwd_kernel(const __nv_bfloat162* __restrict__ x, const float* __restrict__ w9, const float* __restrict__ scale,
+                      const float* __restrict__ shift, __nv_bfloat162* __restrict__ out, long long n_items, int C, int H) {
+    const int C2 = C >> 1;
+    const long long idx = blockIdx.x * 128LL + threadIdx.x;
+    if (idx >= n_items) return;
+    const int c2 = (int)(idx % C2);
+    const long long f = idx / C2;
+    float2 wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[k] = *reinterpret_cast<const float2*>(w9 + (long long)k * C + 2 * c2);
+    float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+    if (AFFINE) { sc = *reinterpret_cast<const float2*>(scale + 2 * c2); sh = *reinterpret_cast<const float2*>(shift + 2 * c2); }
+    const __nv_bfloat162* xp = x + f * H * W * C2 + c2;
+    __nv_bfloat162* op = out + f * H * W * C2 + c2;
+    const long long rs = (long long)W * C2;                 // row stride in channel pairs
+
+    float2 r0[W], r1[W], r2[W];
+    __nv_bfloat162 raw[W];
+    auto fetch = [&](int y) {                                // issue the loads of row y (zeros outside the image)
+#pragma unroll
+        for (int i = 0; i < W; ++i) raw[i] = (y < H) ? xp[y * rs + (long long)i * C2] : __floats2bfloat162_rn(0.f, 0.f);
+    };
+    auto convert = [&](float2 (&dst)[W], int y) {            // prologue of row y into the window (zero row outside the image)
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            float2 v = __bfloat1622float2(raw[i]);
+            if (AFFINE) { v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); }
+            if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+            if (y >= H) v = make_float2(0.f, 0.f);
+            dst[i] = v;
+        }
+    };
+    auto emit = [&](const float2 (&a)[W], const float2 (&b)[W], const float2 (&c)[W], int y) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int j = i + kx - 1;
+                if (j >= 0 && j < W) {
+                    acc.x = fmaf(a[j].x, wk[kx].x, acc.x); acc.y = fmaf(a[j].y, wk[kx].y, acc.y);
+                    acc.x = fmaf(b[j].x, wk[3 + kx].x, acc.x); acc.y = fmaf(b[j].y, wk[3 + kx].y, acc.y);
+                    acc.x = fmaf(c[j].x, wk[6 + kx].x, acc.x); acc.y = fmaf(c[j].y, wk[6 + kx].y, acc.y);
+                }
+            }
+            op[y * rs + (long long)i * C2] = __floats2bfloat162_rn(acc.x, acc.y);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < W; ++i) r0[i] = make_float2(0.f, 0.f);          // row -1
+    fetch(0); convert(r1, 0);
+    fetch(1); convert(r2, 1);
+    fetch(2);
+    // three steps per trip so the window rotates by renaming, not by copying
+    for (int y = 0; y < H; y += 3) {
+        emit(r0, r1, r2, y);
+        convert(r0, y + 2); fetch(y + 3);
+        if (y + 1 < H) emit(r1, r2, r0, y + 1);
+        convert(r1, y + 3); fetch(y + 4);
+        if (y + 2 < H) emit(r2, r0, r1, y + 2);
+        convert(r2, y + 4); fetch(y + 5);
+    }
+}
+
+template <int W>
+static int launch_dw_rows(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int H,
+                          int C, cudaStream_t st) {
+    const long long n_items = (long long)F * (C / 2);
+    const unsigned grid = (unsigned)((n_items + 127) / 128);
+    const __nv_bfloat162* xi = (const __nv_bfloat162*)x;
+    __nv_bfloat162* o = (__nv_bfloat162*)out;
+    if (scale != nullptr) {
+        if (relu) dw3x3_rows_fwd_kernel<W, true, true><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C, H);
+        else dw3x3_rows_fwd_kernel<W, true, false><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C, H);
+    } else {
+        if (relu) dw3x3_rows_fwd_kernel<W, false, true><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C, H);
+        else dw3x3_rows_fwd_kernel<W, false, false><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, C, H);
+    }
+    return check_cuda(cudaGetLastError(), "dw3x3_rows_fwd launch");
+}
+
 template <int S>
 static int launch_dw_small(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int C,
                            cudaStream_t st) {
@@ -686,6 +775,17 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
                 case 7: return launch_dw_small<7>(x, w9, scale, shift, relu, out, F, C, st);
                 default: return launch_dw_small<8>(x, w9, scale, shift, relu, out, F, C, st);
             }
+        }
+    }
+    // measured (tools/dw_rows_ab.py, gpurun r2q, 256 / 960 frames): 10x10x1024 50.3 -> 43.9 us, 10x10x1536 70.6 -> 58.3 us,
+    // 15x15x256 74.8 -> 65.5 us; at W = 19 the 114-register window leaves 12 warps per SM and it only ties the TMA kernel
+    // (94 vs 91 us), so 19x19 stays on the tile kernel.
+    if ((W == 10 || W == 15) && H <= 64) {
+        const char* e = getenv("XCP_DW_NO_ROWS");                                     // A/B hook
+        if (!(e && e[0] == '1')) {
+            cudaStream_t st = (cudaStream_t)stream;
+            if (W == 10) return launch_dw_rows<10>(x, w9, scale, shift, relu, out, F, H, C, st);
+            return launch_dw_rows<15>(x, w9, scale, shift, relu, out, F, H, C, st);
         }
     }
     // resident CTAs per SM: ONE 512-thread CTA (15 compute warps, tiles up to 800 staged pixels) or two 256-thread CTAs
