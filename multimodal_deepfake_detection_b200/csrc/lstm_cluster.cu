@@ -77,13 +77,21 @@ lstm_fwd_cluster_kernel(const float* __restrict__ xproj, const float* __restrict
     float c_reg = 0.f;
     cluster_sync_all();                                   // every CTA's h buffers are zeroed before anybody writes into them
 
+    float xn[4] = {0.f, 0.f, 0.f, 0.f};                  // input projection of the NEXT step (loads stay in flight over a step)
+    if (valid) {
+        const float* xr = xproj + ((long long)bg * T) * G + u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xn[g] = xr[g * H];
+    }
     for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
-        float xp[4] = {0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-            const float* xr = xproj + ((long long)bg * T + t) * G + u;
+        float xp[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) xp[g] = xr[g * H];
+        for (int g = 0; g < 4; ++g) xp[g] = xn[g];
+        if (valid && t + 1 < T) {
+            const float* xr = xproj + ((long long)bg * T + t + 1) * G + u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) xn[g] = xr[g * H];
         }
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         {
@@ -174,17 +182,29 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict_
     float db[4] = {0.f, 0.f, 0.f, 0.f};
     cluster_sync_all();
 
+    // saved state of the step being processed; the loads for step t-1 are issued while step t's exchange + MMAs run
+    float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, c = 0.f, cprev = 0.f, hp = 0.f, dov = 0.f;
+    if (valid) {
+        const long long o = (long long)bg * T + T - 1;
+        ig = gates[o * G + u]; fg = gates[o * G + H + u]; gg = gates[o * G + 2 * H + u]; og = gates[o * G + 3 * H + u];
+        c = cst[o * H + u];
+        if (T > 1) { cprev = cst[(o - 1) * H + u]; hp = hst[(o - 1) * H + u]; }
+        if (dout) dov = dout[o * H + u];
+    }
     for (int t = T - 1; t >= 0; --t) {
         const int buf = t & 1;
         float d[4] = {0.f, 0.f, 0.f, 0.f};
+        float n_ig = 0.f, n_fg = 0.f, n_gg = 0.f, n_og = 0.f, n_cprev = 0.f, n_hp = 0.f, n_dov = 0.f;
         if (valid) {
             const long long o = (long long)bg * T + t;
-            const float ig = gates[o * G + u], fg = gates[o * G + H + u], gg = gates[o * G + 2 * H + u], og = gates[o * G + 3 * H + u];
-            const float c = cst[o * H + u];
-            const float cprev = t > 0 ? cst[(o - 1) * H + u] : 0.f;
-            const float hp = t > 0 ? hst[(o - 1) * H + u] : 0.f;
+            if (t > 0) {
+                n_ig = gates[(o - 1) * G + u]; n_fg = gates[(o - 1) * G + H + u];
+                n_gg = gates[(o - 1) * G + 2 * H + u]; n_og = gates[(o - 1) * G + 3 * H + u];
+                if (t > 1) { n_cprev = cst[(o - 2) * H + u]; n_hp = hst[(o - 2) * H + u]; }
+                if (dout) n_dov = dout[(o - 1) * H + u];
+            }
             const float tc = tanhf(c);
-            const float dh = dh_rec + (dout ? dout[o * H + u] : 0.f);
+            const float dh = dh_rec + dov;
             const float dc = dc_reg + dh * og * (1.f - tc * tc);
             d[0] = dc * gg * ig * (1.f - ig);
             d[1] = dc * cprev * fg * (1.f - fg);
@@ -234,6 +254,7 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict_
         }
         __syncthreads();
         dh_rec = s_part[ul * PP + b] + s_part[(32 + ul) * PP + b] + s_part[(64 + ul) * PP + b] + s_part[(96 + ul) * PP + b];
+        ig = n_ig; fg = n_fg; gg = n_gg; og = n_og; c = cprev; cprev = n_cprev; hp = n_hp; dov = n_dov;
     }
     if (valid) {
 #pragma unroll
