@@ -69,7 +69,7 @@ def cpu_oracle_clips_per_s(steps: int, warmup: int, threads: int):
         opt.step()
         for k, v in ns.items():
             leaves[k] = v
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
@@ -325,6 +325,33 @@ def run_ours(args):
         del g1
     model.train()
 
+    # ---- the reference's FIRST training phase (train_visual.py:551-556, epochs < freeze_epochs): backbone frozen, BatchNorm
+    # still in train mode (:558), only the LSTM + head get gradients.  Reported beside the headline (SURVEY.md §8d asks for both
+    # modes); rank 0 only, eager launches, never allowed to disturb the line above.
+    frozen = None
+    if rank == 0:
+        try:
+            for p in model.feature_extractor.parameters():
+                p.requires_grad = False
+            head_params = [p for p in model.parameters() if p.requires_grad]
+            opt_f = FusedAdam(head_params, lr=1e-5, weight_decay=1e-4)
+
+            def frozen_step():
+                opt_f.zero_grad(set_to_none=True)
+                loss = criterion(model(model.extract_features(dev_clips, dev)), dev_y)
+                loss.backward()
+                opt_f.step()
+            for _ in range(3):
+                frozen_step()
+            ms_frozen = lat(frozen_step, max(args.steps, 3))
+            frozen = {"value": B / (ms_frozen * 1e-3), "unit": "clips/s", "ms_per_step": ms_frozen, "n_gpus": 1,
+                      "what": "same step with the backbone frozen (train-mode BN forward, LSTM + head trained), one GPU, eager"}
+        except Exception as e:       # noqa: BLE001 - an auxiliary number must not take the bench line down
+            frozen = {"error": "%s: %s" % (type(e).__name__, e)}
+        finally:
+            for p in model.feature_extractor.parameters():
+                p.requires_grad = True
+
     if rank != 0:
         finish()
         return
@@ -368,6 +395,7 @@ def run_ours(args):
         "infer": {"value": infer_fps, "unit": "frames/s", "ms_per_pass": ms_inf / max(args.steps, 1),
                   "what": "XceptionLSTMV eval-mode forward (BN folded, no_grad), %d clips x %d frames per GPU per pass" % (B, T_FRAMES),
                   "one_clip_latency": one_clip},
+        "frozen_backbone": frozen,
         "roofline": roof,
         "cpu_baseline": cpu,
         "loss": last.get("loss"),
