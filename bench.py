@@ -100,6 +100,85 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# optional third arm (SURVEY.md §8d "the honest competitor"): the SAME module tree and weights driven through stock PyTorch
+# (cuDNN / cuBLAS kernels, bf16 autocast, channels_last, fused torch Adam) on the same B200.  None of this package's kernels
+# run here: the nn.Conv2d / nn.BatchNorm2d / nn.MaxPool2d / nn.LSTM / nn.Linear submodules execute their own torch forward.
+def run_torch_stock(args):
+    import warnings
+
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    from multimodal_deepfake_detection_b200 import SeparableConv2d, XceptionLSTMV
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1234)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = XceptionLSTMV(HIDDEN).to(dev).train()
+    for p in model.parameters():
+        p.requires_grad = True
+    model = model.to(memory_format=torch.channels_last)
+    net = model.feature_extractor
+
+    def sep(m, x):
+        return m.pointwise(m.conv1(x))
+
+    def block(b, inp):
+        x = inp
+        for m in b.rep:
+            x = sep(m, x) if isinstance(m, SeparableConv2d) else m(x)
+        return x + (b.skipbn(b.skip(inp)) if b.skip is not None else inp)
+
+    def features(frames):
+        x = F.relu(net.bn1(net.conv1(frames)))
+        x = F.relu(net.bn2(net.conv2(x)))
+        for i in range(1, 13):
+            x = block(getattr(net, "block%d" % i), x)
+        x = F.relu(net.bn3(sep(net.conv3, x)))
+        x = F.relu(net.bn4(sep(net.conv4, x)))
+        return F.adaptive_avg_pool2d(x, (1, 1)).flatten(1)
+
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True)
+    B = args.clips
+    g = torch.Generator().manual_seed(0)
+    clips = torch.rand(B, T_FRAMES, 3, HW, HW, generator=g).to(dev)
+    y = torch.randint(0, 2, (B, 1), generator=g).float().to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            frames = clips.view(B * T_FRAMES, 3, HW, HW).contiguous(memory_format=torch.channels_last)
+            feats = features(frames).view(B, T_FRAMES, -1)
+            out, _ = nn.LSTM.forward(model.lstm, feats)
+        with torch.autocast("cuda", enabled=False):
+            prob = model.sigmoid(model.fc_out(model.fc_layers(out[:, -1, :].float())))
+            loss = F.binary_cross_entropy(prob, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"impl": "torch-stock", "metric": METRIC, "value": B / (ms * 1e-3), "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16 autocast",
+                      "data": "synthetic", "loss": float(loss.detach()),
+                      "config": {"workload": "XceptionLSTMV(128) train step, backbone unfrozen, train-mode BN, BCE, torch.optim.Adam(fused)",
+                                 "clips_per_gpu": B, "frames_per_clip": T_FRAMES, "frame": "3x299x299",
+                                 "launch": "eager stock PyTorch %s, cuDNN %s, channels_last" % (torch.__version__, torch.backends.cudnn.version())}}),
+          flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -410,10 +489,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clips", type=int, default=16, help="clips per GPU per step")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-stock"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager per-kernel launches instead of CUDA-graph replays")
     args = ap.parse_args()
+    if args.impl == "torch-stock":
+        run_torch_stock(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
