@@ -248,6 +248,45 @@ def test_xception_lstmv_train_step_grads_vs_oracle():
     assert statistics.median(ours) < 1.5 * statistics.median(theirs) + 2e-2, (statistics.median(ours), statistics.median(theirs))
 
 
+@pytest.mark.parametrize("hidden,B,T", [(512, 5, 24), (256, 11, 9)])
+def test_wide_lstm_and_head_train_step_vs_oracle(hidden, B, T):
+    """XceptionLSTMA(hidden_dim=512) (train_audio.py:15) / the 256-wide fusion streams: LSTM (thread-block-cluster kernels) +
+    head + BCELoss on fixed per-frame features against the oracle -- loss, probabilities and every LSTM / head gradient.
+    The kernels hold W_ih, W_hh and the features in bf16, so the oracle is fed the same bf16-rounded values (its arithmetic
+    stays fp32): with seeded random weights the ReLU masks of the four head layers make the *gradient* discontinuous, and
+    rounding the weights alone moves the fp32 oracle's own gradients by 5-9 % (tools/lstm_grad_probe.py) while the
+    probabilities move by 3e-6."""
+    from multimodal_deepfake_detection_b200 import BCELoss
+    m, full = _lstm_models(hidden, XceptionLSTMA)
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.eval()
+    g = torch.Generator().manual_seed(31)
+    feats = (torch.rand(B, T, 2048, generator=g) * 0.6).to(DEV)
+    y = torch.randint(0, 2, (B, 1), generator=g).float().to(DEV)
+    fo = _leaf(full)
+    with torch.no_grad():
+        for k in ("lstm.weight_ih_l0", "lstm.weight_hh_l0"):
+            fo[k].copy_(fo[k].to(torch.bfloat16).float())
+    feats = feats.to(torch.bfloat16).float()
+    out_o, _, _ = O.lstm_forward(fo, feats)
+    prob_o = O.head_forward(fo, out_o[:, -1])
+    loss_o = F.binary_cross_entropy(prob_o, y)
+    loss_o.backward()
+    fin = feats.clone().requires_grad_(True)
+    prob = m(fin)
+    loss = BCELoss()(prob, y)
+    loss.backward()
+    assert (prob - prob_o).abs().max().item() < 2e-3 and abs(loss.item() - loss_o.item()) < 2e-3
+    assert rel(m.lstm(feats)[0], out_o) < 5e-3
+    params = dict(m.named_parameters())
+    errs = {k: rel(params[k].grad, fo[k].grad) for k in params if not k.startswith("feature_extractor")}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 1e-2, (worst, errs[worst])
+    assert fin.grad is not None and torch.isfinite(fin.grad).all()
+
+
 def test_dropout_head_statistics():
     m, _ = _lstm_models(32, XceptionLSTMV)
     m.train()
