@@ -420,6 +420,10 @@ def run_ours(args):
                 loss = criterion(model(model.extract_features(dev_clips, dev)), dev_y)
                 loss.backward()
                 opt_f.step()
+            try:      # the graph capture above created AccumulateGrad nodes on its side stream; eager steps here only warn about it
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except AttributeError:
+                pass
             for _ in range(3):
                 frozen_step()
             ms_frozen = lat(frozen_step, max(args.steps, 3))

@@ -721,6 +721,101 @@ dw3x3_rows_fwd_kernel(const __nv_bfloat162* __restrict__ x, const float* __restr
     }
 }
 
+// Same walk with the channel pitch C as a compile-time constant and packed f32x2 arithmetic: every load / store of a row is
+// one base register + an immediate offset (no per-access 64-bit address arithmetic), the prologue is one FFMA2 + two FMNMX
+// and each tap one FFMA2 per channel pair: 17 instructions per pixel pair instead of 39 (ncu r2w: the generic kernel above
+// was issue-limited at 48 % issue-active with 10 warps per SM).
+template <int W, int C, bool AFFINE, bool RELU, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+dw3x3_rowsc_fwd_kernel(const uint32_t* __restrict__ x, const float* __restrict__ w9, const float* __restrict__ scale,
+                       const float* __restrict__ shift, uint32_t* __restrict__ out, long long n_items, int H) {
+    constexpr int C2 = C / 2;
+    const long long idx = blockIdx.x * 128LL + threadIdx.x;
+    if (idx >= n_items) return;
+    const int c2 = (int)(idx % C2);
+    const long long f = idx / C2;
+    u64 wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const float2 t = *reinterpret_cast<const float2*>(w9 + k * C + 2 * c2); wk[k] = pk2(t.x, t.y); }
+    u64 sc = pk2(1.f, 1.f), sh = pk2(0.f, 0.f);
+    if (AFFINE) {
+        const float2 a = *reinterpret_cast<const float2*>(scale + 2 * c2), b = *reinterpret_cast<const float2*>(shift + 2 * c2);
+        sc = pk2(a.x, a.y); sh = pk2(b.x, b.y);
+    }
+    const uint32_t* xrow = x + f * H * (W * C2) + c2;       // row being FETCHED
+    uint32_t* orow = out + f * H * (W * C2) + c2;           // row being EMITTED
+
+    u64 r0[W], r1[W], r2[W];
+    uint32_t raw[W];
+    int yf = 0;                                              // next row to fetch
+    auto fetch = [&]() {
+        if (yf < H) {
+#pragma unroll
+            for (int i = 0; i < W; ++i) raw[i] = xrow[i * C2];
+        }
+        xrow += W * C2; ++yf;
+    };
+    auto convert = [&](u64 (&dst)[W], bool inside) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            u64 v = pk2(__uint_as_float(raw[i] << 16), __uint_as_float(raw[i] & 0xffff0000u));
+            if (AFFINE) v = fma2(v, sc, sh);
+            if (RELU) { float lo, hi; upk2(v, lo, hi); v = pk2(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
+            dst[i] = inside ? v : 0ull;
+        }
+    };
+    auto emit = [&](const u64 (&a)[W], const u64 (&b)[W], const u64 (&c)[W]) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            u64 acc = 0ull;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int j = i + kx - 1;
+                if (j >= 0 && j < W) {
+                    acc = fma2(a[j], wk[kx], acc);
+                    acc = fma2(b[j], wk[3 + kx], acc);
+                    acc = fma2(c[j], wk[6 + kx], acc);
+                }
+            }
+            float lo, hi;
+            upk2(acc, lo, hi);
+            const __nv_bfloat162 o = __floats2bfloat162_rn(lo, hi);
+            orow[i * C2] = *reinterpret_cast<const uint32_t*>(&o);
+        }
+        orow += W * C2;
+    };
+#pragma unroll
+    for (int i = 0; i < W; ++i) r0[i] = 0ull;               // row -1
+    fetch(); convert(r1, true);                             // row 0
+    fetch(); convert(r2, 1 < H);                            // row 1
+    fetch();                                                // row 2 in flight
+    for (int y = 0; y < H; y += 3) {
+        emit(r0, r1, r2);
+        convert(r0, y + 2 < H); fetch();
+        if (y + 1 < H) emit(r1, r2, r0);
+        convert(r1, y + 3 < H); fetch();
+        if (y + 2 < H) emit(r2, r0, r1);
+        convert(r2, y + 4 < H); fetch();
+    }
+}
+
+template <int W, int C, int MINB>
+static int launch_dw_rowsc(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int H,
+                           cudaStream_t st) {
+    const long long n_items = (long long)F * (C / 2);
+    const unsigned grid = (unsigned)((n_items + 127) / 128);
+    const uint32_t* xi = (const uint32_t*)x;
+    uint32_t* o = (uint32_t*)out;
+    if (scale != nullptr) {
+        if (relu) dw3x3_rowsc_fwd_kernel<W, C, true, true, MINB><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, H);
+        else dw3x3_rowsc_fwd_kernel<W, C, true, false, MINB><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, H);
+    } else {
+        if (relu) dw3x3_rowsc_fwd_kernel<W, C, false, true, MINB><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, H);
+        else dw3x3_rowsc_fwd_kernel<W, C, false, false, MINB><<<grid, 128, 0, st>>>(xi, w9, scale, shift, o, n_items, H);
+    }
+    return check_cuda(cudaGetLastError(), "dw3x3_rowsc_fwd launch");
+}
+
 template <int W>
 static int launch_dw_rows(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int H,
                           int C, cudaStream_t st) {
@@ -777,9 +872,21 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
             }
         }
     }
-    // measured (tools/dw_rows_ab.py, gpurun r2q, 256 / 960 frames): 10x10x1024 50.3 -> 43.9 us, 10x10x1536 70.6 -> 58.3 us,
-    // 15x15x256 74.8 -> 65.5 us; at W = 19 the 114-register window leaves 12 warps per SM and it only ties the TMA kernel
-    // (94 vs 91 us), so 19x19 stays on the tile kernel.
+    // generic-pitch variant (tools/dw_rows_ab.py, gpurun r2q, 256 / 960 frames): 10x10x1024 50.3 -> 43.9 us, 15x15x256
+    // 74.8 -> 65.5 us; at W = 19 it only ties the TMA kernel (94 vs 91 us: spills at 168 registers), so other 19-wide pitches
+    // stay on the tile kernel.
+    // compile-time-pitch FFMA2 variant for the three shapes of the 299x299 plan (tools/dw_rows_ab.py, gpurun r2x, 256 frames):
+    // 19x19x768 89.1 -> 78.8 us (3.6 TB/s; 252 registers, 8 warps/SM), 10x10x1024 50.1 -> 32.8 us, 10x10x1536 70.8 -> 45.2 us
+    if ((W == 10 || W == 19) && H <= 64) {
+        const char* e = getenv("XCP_DW_NO_ROWS");                                     // A/B hook
+        const char* e2 = getenv("XCP_DW_NO_ROWSC");
+        if (!(e && e[0] == '1') && !(e2 && e2[0] == '1')) {
+            cudaStream_t st = (cudaStream_t)stream;
+            if (W == 19 && C == 768) return launch_dw_rowsc<19, 768, 2>(x, w9, scale, shift, relu, out, F, H, st);
+            if (W == 10 && C == 1024) return launch_dw_rowsc<10, 1024, 4>(x, w9, scale, shift, relu, out, F, H, st);
+            if (W == 10 && C == 1536) return launch_dw_rowsc<10, 1536, 4>(x, w9, scale, shift, relu, out, F, H, st);
+        }
+    }
     if ((W == 10 || W == 15) && H <= 64) {
         const char* e = getenv("XCP_DW_NO_ROWS");                                     // A/B hook
         if (!(e && e[0] == '1')) {

@@ -32,10 +32,11 @@ for H, C, frames in ((19, 768, F), (10, 1024, F), (10, 1536, F), (15, 256, 960),
     out = torch.empty_like(x)
     gb = 2 * x.numel() * 2 / 1e9
     res = {}
-    for tag, env in (("tma", "1"), ("regs", "0")):
+    for tag, env, envc in (("tma", "1", "1"), ("rows", "0", "1"), ("regs", "0", "0")):      # regs = best register-window kernel
         os.environ["XCP_DW_NO_ROWS"] = env
         os.environ["XCP_DW_NO_SMALL"] = env
+        os.environ["XCP_DW_NO_ROWSC"] = envc
         res[tag] = (timeit(lambda: ops.dw3x3_fwd(x, w9, sc, sh, True, out=out)), out.clone())
     d = (res["tma"][1].float() - res["regs"][1].float()).norm() / res["tma"][1].float().norm()
-    print("dw_fwd affine+relu %3dx%-3dx%-4d F=%-4d  tma %7.1f us %6.0f GB/s | regs %7.1f us %6.0f GB/s | rel diff %.1e" % (
-        H, H, C, frames, res["tma"][0] * 1e3, gb / res["tma"][0] * 1e3, res["regs"][0] * 1e3, gb / res["regs"][0] * 1e3, d))
+    print("dw_fwd affine+relu %3dx%-3dx%-4d F=%-4d  tma %7.1f us %6.0f GB/s | generic rows %7.1f us | regs %7.1f us %6.0f GB/s | rel diff %.1e" % (
+        H, H, C, frames, res["tma"][0] * 1e3, gb / res["tma"][0] * 1e3, res["rows"][0] * 1e3, res["regs"][0] * 1e3, gb / res["regs"][0] * 1e3, d))
