@@ -11,8 +11,8 @@
 //     as a bf16 hi + lo pair, which keeps the recurrent input at ~fp32 accuracy (the weights are bf16, as before);
 //   * the cell update runs on (unit, clip) threads with c in registers, and the new h slice is pushed into every peer's
 //     shared memory with 16-byte DSMEM stores, followed by one cluster barrier per step (double-buffered h, no second barrier).
-// The backward mirrors it: CTA r owns dh[:, 32 r : 32 r + 32]; the 4H gate gradients of a step are broadcast the same way,
-// and dh_{t-1} = W_hh^T dg is one MMA pass whose K = 4H is split over the four warp pairs (smem reduction).
+// The backward mirrors it: CTA r owns dh[:, 32 r : 32 r + 32] and the gate gradients of those units; dh_{t-1} = W_hh^T dg is
+// computed as per-CTA partials over all H units (K = the CTA's own 128 gate rows) that are reduce-scattered over DSMEM.
 // Reference: nn.LSTM(2048, H, 1, batch_first=True), XceptionLSTMV.py:18-23,67-68; XceptionLSTMA.py:14-19,56-57.
 #include <cstdlib>
 #include "common.cuh"
@@ -145,33 +145,41 @@ lstm_fwd_cluster_kernel(const float* __restrict__ xproj, const float* __restrict
 
 // ---------------------------------------------------------------------------------------------------------- backward
 // wb = W_hh bf16 [4H][H] (the pack xcp_lstm_bwd already receives).  Outputs as lstm_bwd_kernel.
+// dh_{t-1}[k] = sum_j W_hh[j][k] dg_t[j].  CTA r owns the gate gradients of its own 32 units (128 rows j), so it multiplies
+// them -- straight from its own shared memory -- with its [H x 128] slice of W_hh^T (registers) into a PARTIAL dh over all H
+// units, and the partials are reduce-scattered: the 32-unit segment that CTA p owns goes into p's receive buffer (fp32,
+// 1 KB per sender), and after the cluster barrier every CTA adds its CS incoming partials.  Per step a CTA pushes CS x 1 KB
+// over DSMEM -- the same volume as the forward's h exchange, and a quarter of broadcasting the 4H gate gradients.
 template <int H>
 __global__ void __launch_bounds__(LC_THREADS, 1)
 lstm_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict__ dhn, const float* __restrict__ dcn,
                         const float* __restrict__ gates, const float* __restrict__ cst, const float* __restrict__ hst,
                         const __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ dgates, __nv_bfloat16* __restrict__ hprev,
                         float* __restrict__ dbias_ih, float* __restrict__ dbias_hh, int B, int T) {
-    constexpr int G = 4 * H, CS = H / LC_U, KS = H / 16, GPAD = G + 8, PP = LC_NB + 1;
+    constexpr int G = 4 * H, CS = H / LC_U, MTW = H / 16 / 8, JP = 128 + 8, HP = H + 4;
     extern __shared__ __align__(16) uint8_t lc_smem[];
-    __nv_bfloat16* s_dg = reinterpret_cast<__nv_bfloat16*>(lc_smem);                        // [2 buf][hi, lo][NB][GPAD]
-    __nv_bfloat16* s_stage = s_dg + (size_t)2 * 2 * LC_NB * GPAD;                           // [hi, lo][NB][4 x 32]
-    float* s_part = reinterpret_cast<float*>(s_stage + 2 * LC_NB * 128);                    // [4 K-quarters][32 units][PP]
+    float* s_recv = reinterpret_cast<float*>(lc_smem);                                      // [2 buf][CS senders][NB][32]
+    float* s_out = s_recv + 2 * CS * LC_NB * 32;                                            // [NB][HP] partial dh over all units
+    __nv_bfloat16* s_dg = reinterpret_cast<__nv_bfloat16*>(s_out + LC_NB * HP);            // [hi, lo][NB][JP] own gate gradients
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t r = cluster_ctarank();
     const int cl = blockIdx.x / CS;
-    const int mt = w & 1, kq = w >> 1;
 
-    // A[k][j] = W_hh[j][k]: rows = own hidden units (2 m16 tiles), K = the warp's quarter of the 4H gate rows
-    uint32_t wf[KS][4];
-    {
-        const int k0 = (int)r * LC_U + mt * 16 + (lane >> 2);
+    // A[k][jl] = W_hh[j(jl)][k]: rows = ALL hidden units (warp w: m16 tiles w*MTW ..), K = the CTA's 128 gate rows
+    // (local gate row jl = g*32 + ul  <->  j = g*H + 32 r + ul)
+    uint32_t wf[MTW][8][4];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int j0 = kq * H + ks * 16 + (lane & 3) * 2;
-            wf[ks][0] = pack_bf16(wb[(long long)j0 * H + k0], wb[(long long)(j0 + 1) * H + k0]);
-            wf[ks][1] = pack_bf16(wb[(long long)j0 * H + k0 + 8], wb[(long long)(j0 + 1) * H + k0 + 8]);
-            wf[ks][2] = pack_bf16(wb[(long long)(j0 + 8) * H + k0], wb[(long long)(j0 + 9) * H + k0]);
-            wf[ks][3] = pack_bf16(wb[(long long)(j0 + 8) * H + k0 + 8], wb[(long long)(j0 + 9) * H + k0 + 8]);
+    for (int mt = 0; mt < MTW; ++mt) {
+        const int k0 = (w * MTW + mt) * 16 + (lane >> 2);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const int jl = ks * 16 + (lane & 3) * 2;                                       // jl, jl+1 stay inside one gate (even)
+            const long long j0 = (long long)((jl >> 5) * H + (int)r * LC_U + (jl & 31));
+            const long long j8 = (long long)(((jl + 8) >> 5) * H + (int)r * LC_U + ((jl + 8) & 31));
+            wf[mt][ks][0] = pack_bf16(wb[j0 * H + k0], wb[(j0 + 1) * H + k0]);
+            wf[mt][ks][1] = pack_bf16(wb[j0 * H + k0 + 8], wb[(j0 + 1) * H + k0 + 8]);
+            wf[mt][ks][2] = pack_bf16(wb[j8 * H + k0], wb[(j8 + 1) * H + k0]);
+            wf[mt][ks][3] = pack_bf16(wb[j8 * H + k0 + 8], wb[(j8 + 1) * H + k0 + 8]);
         }
     }
     const int ul = tid & 31, b = tid >> 5, u = (int)r * LC_U + ul;
@@ -180,9 +188,7 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict_
     float dh_rec = (valid && dhn) ? dhn[(long long)bg * H + u] : 0.f;
     float dc_reg = (valid && dcn) ? dcn[(long long)bg * H + u] : 0.f;
     float db[4] = {0.f, 0.f, 0.f, 0.f};
-    cluster_sync_all();
-
-    // saved state of the step being processed; the loads for step t-1 are issued while step t's exchange + MMAs run
+    // saved state of the step being processed; the loads for step t-1 are issued while step t's MMAs + exchange run
     float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, c = 0.f, cprev = 0.f, hp = 0.f, dov = 0.f;
     if (valid) {
         const long long o = (long long)bg * T + T - 1;
@@ -191,6 +197,8 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict_
         if (T > 1) { cprev = cst[(o - 1) * H + u]; hp = hst[(o - 1) * H + u]; }
         if (dout) dov = dout[o * H + u];
     }
+    cluster_sync_all();
+
     for (int t = T - 1; t >= 0; --t) {
         const int buf = t & 1;
         float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -222,38 +230,50 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dout, const float* __restrict_
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const __nv_bfloat16 hi = __float2bfloat16(d[g]);
-            s_stage[b * 128 + g * 32 + ul] = hi;
-            s_stage[(LC_NB + b) * 128 + g * 32 + ul] = __float2bfloat16(d[g] - __bfloat162float(hi));
+            s_dg[b * JP + g * 32 + ul] = hi;
+            s_dg[(LC_NB + b) * JP + g * 32 + ul] = __float2bfloat16(d[g] - __bfloat162float(hi));
         }
         __syncthreads();
-        // 2 x 8 x 4 x 32 bf16 = 256 chunks of 16 bytes to every CTA: dg[clip][g H + 32 r + ...]
-        for (int i = tid; i < 256 * CS; i += LC_THREADS) {
-            const int peer = i >> 8, q = i & 255, a = q >> 7, nb = (q & 127) >> 4, g = (q & 15) >> 2, part = q & 3;
-            const uint4 v = *reinterpret_cast<const uint4*>(s_stage + (a * LC_NB + nb) * 128 + g * 32 + part * 8);
-            const uint32_t dst = smem_u32(s_dg + ((size_t)(buf * 2 + a) * LC_NB + nb) * GPAD + g * H + (int)r * LC_U + part * 8);
+        {
+            float acc[MTW][4];
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) { acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f; }
+            const __nv_bfloat16* gh = s_dg + (lane >> 2) * JP + (lane & 3) * 2;
+            const __nv_bfloat16* gl = gh + LC_NB * JP;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t h0 = *reinterpret_cast<const uint32_t*>(gh + ks * 16), h1 = *reinterpret_cast<const uint32_t*>(gh + ks * 16 + 8);
+                const uint32_t l0 = *reinterpret_cast<const uint32_t*>(gl + ks * 16), l1 = *reinterpret_cast<const uint32_t*>(gl + ks * 16 + 8);
+#pragma unroll
+                for (int mt = 0; mt < MTW; ++mt) {
+                    mma_16816(acc[mt], wf[mt][ks], h0, h1);
+                    mma_16816(acc[mt], wf[mt][ks], l0, l1);
+                }
+            }
+            const int n = (lane & 3) * 2;
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                const int k = (w * MTW + mt) * 16 + (lane >> 2);
+                s_out[n * HP + k] = acc[mt][0]; s_out[(n + 1) * HP + k] = acc[mt][1];
+                s_out[n * HP + k + 8] = acc[mt][2]; s_out[(n + 1) * HP + k + 8] = acc[mt][3];
+            }
+        }
+        __syncthreads();
+        // reduce-scatter: the segment of units owned by CTA p (8 clips x 32 floats = 64 chunks of 16 bytes) -> p's slot r
+        for (int i = tid; i < 64 * CS; i += LC_THREADS) {
+            const int peer = i >> 6, q = i & 63, nb = q >> 3, part = q & 7;
+            const uint4 v = *reinterpret_cast<const uint4*>(s_out + nb * HP + peer * LC_U + part * 4);
+            const uint32_t dst = smem_u32(s_recv + (((size_t)buf * CS + r) * LC_NB + nb) * 32 + part * 4);
             st_cluster_v4(mapa_cluster(dst, (uint32_t)peer), v);
         }
         cluster_sync_all();
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
         {
-            const __nv_bfloat16* gh = s_dg + ((size_t)(buf * 2 + 0) * LC_NB + (lane >> 2)) * GPAD + kq * H + (lane & 3) * 2;
-            const __nv_bfloat16* gl = s_dg + ((size_t)(buf * 2 + 1) * LC_NB + (lane >> 2)) * GPAD + kq * H + (lane & 3) * 2;
+            const float* rp = s_recv + (size_t)buf * CS * LC_NB * 32 + b * 32 + ul;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const uint32_t h0 = *reinterpret_cast<const uint32_t*>(gh + ks * 16), h1 = *reinterpret_cast<const uint32_t*>(gh + ks * 16 + 8);
-                const uint32_t l0 = *reinterpret_cast<const uint32_t*>(gl + ks * 16), l1 = *reinterpret_cast<const uint32_t*>(gl + ks * 16 + 8);
-                mma_16816(acc, wf[ks], h0, h1);
-                mma_16816(acc, wf[ks], l0, l1);
-            }
+            for (int sdx = 0; sdx < CS; sdx += 2) { a0 += rp[sdx * LC_NB * 32]; a1 += rp[(sdx + 1) * LC_NB * 32]; }
+            dh_rec = a0 + a1;
         }
-        {
-            const int kl = mt * 16 + (lane >> 2), n = (lane & 3) * 2;
-            float* p = s_part + (size_t)kq * 32 * PP;
-            p[kl * PP + n] = acc[0]; p[kl * PP + n + 1] = acc[1];
-            p[(kl + 8) * PP + n] = acc[2]; p[(kl + 8) * PP + n + 1] = acc[3];
-        }
-        __syncthreads();
-        dh_rec = s_part[ul * PP + b] + s_part[(32 + ul) * PP + b] + s_part[(64 + ul) * PP + b] + s_part[(96 + ul) * PP + b];
         ig = n_ig; fg = n_fg; gg = n_gg; og = n_og; c = cprev; cprev = n_cprev; hp = n_hp; dov = n_dov;
     }
     if (valid) {
@@ -319,7 +339,7 @@ int lstm_bwd_cluster(const float* dout, const float* dhn, const float* dcn, cons
                      int T, int H, cudaStream_t st) {
     if (cluster_disabled() || (H != 256 && H != 512)) return LSTM_CLUSTER_NA;
     void* args[] = {&dout, &dhn, &dcn, &gates, &cstate, &hstate, &w_hh, &dgates, &hprev, &dbias_ih, &dbias_hh, &B, &T};
-    const size_t smem = (size_t)2 * 2 * LC_NB * (4 * H + 8) * 2 + (size_t)2 * LC_NB * 128 * 2 + (size_t)4 * 32 * (LC_NB + 1) * 4;
+    const size_t smem = (size_t)2 * (H / LC_U) * LC_NB * 32 * 4 + (size_t)LC_NB * (H + 4) * 4 + (size_t)2 * LC_NB * (128 + 8) * 2;
     static int st512[64] = {0}, st256[64] = {0};
     if (H == 512) return launch_cluster(lstm_bwd_cluster_kernel<512>, st512, 16, B, smem, st, args, "lstm_bwd_cluster launch");
     return launch_cluster(lstm_bwd_cluster_kernel<256>, st256, 8, B, smem, st, args, "lstm_bwd_cluster launch");
