@@ -882,6 +882,8 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
         const char* e2 = getenv("XCP_DW_NO_ROWSC");
         if (!(e && e[0] == '1') && !(e2 && e2[0] == '1')) {
             cudaStream_t st = (cudaStream_t)stream;
+            // (a column-split form -- two threads per row, 12-column windows, 166 registers, 12 warps per SM instead of 8 --
+            //  was slower: 84.1 us vs 79.9 us, gpurun r3a; the extra halo loads and instructions outweigh the occupancy)
             if (W == 19 && C == 768) return launch_dw_rowsc<19, 768, 2>(x, w9, scale, shift, relu, out, F, H, st);
             if (W == 10 && C == 1024) return launch_dw_rowsc<10, 1024, 4>(x, w9, scale, shift, relu, out, F, H, st);
             if (W == 10 && C == 1536) return launch_dw_rowsc<10, 1536, 4>(x, w9, scale, shift, relu, out, F, H, st);
