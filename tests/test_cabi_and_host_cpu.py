@@ -75,6 +75,9 @@ def test_sass_is_blackwell_native():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "FFMA2"):     # tcgen05.mma, TMA load, tcgen05.ld, packed fp32 FMA
         assert mnemonic in out, mnemonic
     assert "HGMMA" not in out
+    # the cluster LSTM kernels: cluster-wide barriers around the DSMEM h / dh exchange, W_hh fragments fed to HMMA from registers
+    for mnemonic in ("UCGABAR_ARV", "UCGABAR_WAIT", "HMMA.16816"):
+        assert mnemonic in out, mnemonic
 
 
 def test_product_never_imports_the_oracle():
