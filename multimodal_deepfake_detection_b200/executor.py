@@ -120,10 +120,13 @@ class PackCache:
             host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
             buf = torch.empty((len(raw),), device=dev, dtype=torch.uint8)
             buf.copy_(host, non_blocking=True)
-            keep = self.__dict__.setdefault("_table_keep", [])
-            if torch.cuda.is_current_stream_capturing():
-                keep.append((host, buf))                  # a captured memcpy node re-reads the pinned buffer at every replay
             ent = self._table = (raw, buf, host)
+        if torch.cuda.is_current_stream_capturing():
+            # the graph being captured keeps this table's raw device pointer (and possibly a memcpy node that re-reads the
+            # pinned source at every replay): it must outlive the graph even if a later eager call builds another table
+            keep = self.__dict__.setdefault("_table_keep", [])
+            if not any(k[1] is ent[1] for k in keep):
+                keep.append((ent[2], ent[1]))
         ops.pack_multi(ent[1], len(stale), tile0)
         for (p, kind, key, tag, hit), val in zip(stale, vals):
             self._c[key] = (tag, val)

@@ -34,7 +34,7 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._tables = {}        # group index -> dict(key, table, chunks, n_chunks, keep)
         self._chunk_cache = {}
-        self._keep = []          # pinned staging buffers referenced by captured memcpy nodes
+        self._keep = []          # tables a CUDA-graph capture has seen: referenced by raw pointer from the graph, never freed
 
     # ---- state -----------------------------------------------------------------------------------------------
     def _init_group_state(self, gi: int, group):
@@ -88,6 +88,7 @@ class FusedAdam(torch.optim.Optimizer):
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr()) for p in live)
         ent = self._tables.get(gi)
         if ent is not None and ent["key"] == key:
+            self._pin_if_capturing(ent)
             return ent
         rows = np.empty((len(live), 6), dtype=np.uint64)
         for ti, p in enumerate(live):
@@ -109,11 +110,18 @@ class FusedAdam(torch.optim.Optimizer):
         host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
         buf = torch.empty((len(raw),), device=dev, dtype=torch.uint8)
         buf.copy_(host, non_blocking=True)
-        if torch.cuda.is_current_stream_capturing():
-            self._keep.append(host)         # the captured memcpy node re-reads this buffer at every replay
         ent = {"key": key, "buf": buf, "host": host, "n_tensors": len(live), "n_chunks": len(chunks), "chunk_off": 48 * len(live)}
         self._tables[gi] = ent
+        self._pin_if_capturing(ent)
         return ent
+
+    def _pin_if_capturing(self, ent):
+        """A graph captured while this table is current keeps its raw device pointer (and, if the upload itself was captured,
+        a memcpy node that re-reads the pinned source at every replay): such a table must outlive the graph, so it is never
+        freed.  Tables only ever used by eager steps are dropped when the gradient pointers change."""
+        if not ent.get("pinned") and torch.cuda.is_current_stream_capturing():
+            ent["pinned"] = True
+            self._keep.append((ent["host"], ent["buf"]))
 
     @torch.no_grad()
     def step(self, closure=None):
