@@ -179,3 +179,22 @@ def test_loop_metrics_match_sklearn():
         t, f_, t_ = youden_threshold(y, p)
         assert abs((t_ - f_) - np.max(tpr - fpr)) < 1e-12
     assert binary_metrics([1, 1, 1], [0.2, 0.3, 0.9])["EER"] == 1.0      # single-class sentinel of the reference
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the metric / unit of the product arm, the
+    `cpu_baseline` description of the run and a zero-copy `e2e`; it must work without a GPU."""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("train clips/sec XceptionLSTMV") and d["unit"] == "clips/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] and d["vs_baseline"] is None
