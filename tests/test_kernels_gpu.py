@@ -130,7 +130,9 @@ DW_SHAPES = [(2, 147, 147, 64), (2, 74, 74, 128), (3, 37, 37, 256), (2, 19, 19, 
              (2, 2, 2, 728), (1, 33, 31, 8),
              # tiny square maps of the audio model (register-resident forward kernel), incl. the 768-pitch width
              (7, 4, 4, 768), (5, 8, 8, 256), (3, 2, 2, 1536), (4, 3, 3, 64), (2, 1, 1, 64), (130, 4, 4, 768), (3, 5, 5, 1024), (2, 7, 7, 8),
-             (2, 6, 6, 128), (2, 8, 4, 64)]
+             (2, 6, 6, 128), (2, 8, 4, 64),
+             # row-walking kernels (W = 10 / 15 / 19) on non-square maps: every H mod 3, H < 3, generic and compile-time pitch
+             (2, 11, 10, 1024), (1, 5, 19, 768), (2, 2, 15, 64), (1, 1, 10, 64), (2, 12, 10, 1536), (1, 20, 15, 256), (2, 3, 19, 768)]
 
 
 @pytest.mark.parametrize("shape", DW_SHAPES)
