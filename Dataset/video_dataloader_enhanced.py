@@ -1,6 +1,7 @@
 """`Dataset.video_dataloader_enhanced` as imported by train_visual.py:451 / test_visual.py:466 (absent from the reference;
 signature from the call sites).  Without the LAV-DF / FakeAVCeleb trees it serves synthetic clips."""
 import os
+import zlib
 
 from torch.utils.data import DataLoader
 
@@ -15,5 +16,5 @@ def get_face_dataloader(folder_path=None, mode="lavdf_raw", subset="train", lavd
         ds = FaceDataset(folder_path)
         ds.samples = [(f, 0 if os.path.basename(f).lower().startswith("real") else 1, None) for f in ds.files]
     else:
-        ds = SyntheticClips(n=synthetic_clips, frames=min(max_frames, 16), size=frame_size[0], seed=hash(subset) % 1000)
+        ds = SyntheticClips(n=synthetic_clips, frames=min(max_frames, 16), size=frame_size[0], seed=zlib.crc32(subset.encode()) % 1000)   # (str hash() is salted per process)
     return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, collate_fn=collate_fn)
