@@ -101,6 +101,31 @@ def require_b200() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def init_data_parallel():
+    """One process per GPU under torchrun (WORLD_SIZE / RANK / LOCAL_RANK): select the GPU, join the NCCL group.
+    Returns (world, rank).  A plain `python train_visual.py` run is world 1 and touches nothing."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 1, 0
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, int(os.environ.get("RANK", "0"))
+
+
+def broadcast_module_state(modules, src: int = 0, buffers_only: bool = False):
+    """Replica synchronisation: parameters + buffers at start-up, BatchNorm running statistics (which stay per-rank during
+    training, like the reference's plain BatchNorm2d under DDP) before every evaluation so all ranks take the same
+    scheduler / early-stopping decisions."""
+    import torch.distributed as dist
+    for m in modules:
+        tensors = list(m.buffers()) if buffers_only else list(m.parameters()) + list(m.buffers())
+        for t in tensors:
+            dist.broadcast(t.data, src)
+
+
 def env_int(name: str, default: int) -> int:
     """Bounded-run knobs for smoke tests on synthetic data (XCP_EPOCHS, XCP_SYNTH_CLIPS, XCP_FRAME_SIZE, ...)."""
     try:
@@ -133,8 +158,9 @@ def visual_batch(model, arcface, video, labels, seq_lengths, train: bool):
     return loss, torch.softmax(logits.detach(), dim=1)[:, 1]
 
 
-def visual_epoch(model, arcface, loader, device, optimizer=None):
-    """A full pass; optimizer=None evaluates.  Returns (mean loss, metrics dict, ClassCounter result)."""
+def visual_epoch(model, arcface, loader, device, optimizer=None, after_backward=None):
+    """A full pass; optimizer=None evaluates.  Returns (mean loss, metrics dict, ClassCounter result).
+    `after_backward` (data parallel: ddp.GradBucketer.finish) runs between loss.backward() and optimizer.step()."""
     train = optimizer is not None
     total = torch.zeros((), device=device)
     counter = ClassCounter(device)
@@ -150,6 +176,8 @@ def visual_epoch(model, arcface, loader, device, optimizer=None):
             loss, probs = visual_batch(model, arcface, video, labels, seq_lengths, train)
             if train:
                 loss.backward()
+                if after_backward is not None:
+                    after_backward()
                 optimizer.step()                         # FusedAdam(max_norm=1.0): clip_grad_norm_ + Adam in one launch
             total += loss.detach()
             counter.update(probs, labels)

@@ -90,3 +90,22 @@ def test_two_rank_nccl_gradient_average():
         p.join(300)
         assert p.exitcode == 0
     assert ret.get(timeout=5) < 2e-2
+
+
+def test_train_visual_under_torchrun_on_two_gpus(tmp_path):
+    """`torchrun --nproc-per-node 2 train_visual.py`: sharded clips, bucketed gradient all-reduce in both training phases
+    (frozen backbone, then unfrozen), rank 0 alone prints and writes the reference's checkpoint format."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, XCP_EPOCHS="2", XCP_FREEZE_EPOCHS="1", XCP_SYNTH_CLIPS="8", XCP_FRAME_SIZE="75", XCP_WORKERS="0",
+               XCP_CKPT_DIR=str(tmp_path / "ck"), XCP_MAX_FRAMES="4")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29900 + os.getpid() % 90), "train_visual.py"], cwd=root, env=env, timeout=280,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    assert r.stdout.count("Training finished.") == 1 and r.stdout.count("Epoch 2/2") == 1          # rank 0 is the only speaker
+    ck = torch.load(tmp_path / "ck" / "XceptionLSTMV_ArcFace_Best.pth")
+    assert set(ck) == {"model", "arcface"} and len(ck["model"]) == 288
