@@ -190,7 +190,7 @@ def visual_epoch(model, arcface, loader, device, optimizer=None, after_backward=
 
 
 # ------------------------------------------------------------------------------------------------ audio (BCE on sigmoid)
-def audio_epoch(model, loader, device, optimizer=None, frontend=None, frames: int = 120):
+def audio_epoch(model, loader, device, optimizer=None, frontend=None, frames: int = 120, after_backward=None):
     """train_audio.py:33-46 / 55-67: BCELoss on the sigmoid output; returns (mean loss, accuracy).
     With `frontend` (audio_frontend.MFCC) a 2-D batch is taken as raw waveforms (B, samples) and turned into the
     (B, frames, 3, 13) MFCC tensor on the device (row f-4) instead of coming from the offline librosa files."""
@@ -214,6 +214,8 @@ def audio_epoch(model, loader, device, optimizer=None, frontend=None, frames: in
             if train:
                 optimizer.zero_grad(set_to_none=True)
                 loss.backward()
+                if after_backward is not None:           # data parallel: ddp.GradBucketer.finish
+                    after_backward()
                 optimizer.step()
             total += loss.detach()
             hits += ((out.detach() > 0.5).float() == labels).sum()

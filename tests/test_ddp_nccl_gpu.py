@@ -109,3 +109,20 @@ def test_train_visual_under_torchrun_on_two_gpus(tmp_path):
     assert r.stdout.count("Training finished.") == 1 and r.stdout.count("Epoch 2/2") == 1          # rank 0 is the only speaker
     ck = torch.load(tmp_path / "ck" / "XceptionLSTMV_ArcFace_Best.pth")
     assert set(ck) == {"model", "arcface"} and len(ck["model"]) == 288
+
+
+def test_train_audio_under_torchrun_on_two_gpus(tmp_path):
+    """`torchrun --nproc-per-node 2 train_audio.py` (the reference used nn.DataParallel here, train_audio.py:16-18)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, XCP_EPOCHS="2", XCP_EVAL_EVERY="1", XCP_AUDIO_HIDDEN="64", XCP_WORKERS="0", XCP_CKPT_DIR=str(tmp_path / "ck"))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29800 + os.getpid() % 90), "train_audio.py"], cwd=root, env=env, timeout=280,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    assert r.stdout.count("Epoch [2/2]") == 1 and r.stdout.count("Evaluation Loss") == 2            # rank 0 is the only speaker
+    sd = torch.load(tmp_path / "ck" / "best_model_audio.pth")
+    assert len(sd) == 288 and sd["lstm.weight_ih_l0"].shape == (256, 2048)
