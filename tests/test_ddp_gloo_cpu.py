@@ -53,6 +53,27 @@ def _worker(rank, world, port, ret):
     assert len(bk._buckets) >= 3
     assert covered[0][0] == 0 and covered[-1][1] >= sum(p.numel() for p in params)
     assert list(shard_clips(8, rank, world)) == list(range(rank, 8, 2))
+    # what the torchrun routes of train_visual.py / train_audio.py rely on: an explicit extra-parameter list (LSTM + head +
+    # a separate ArcFace module, some of them frozen = no gradient) and the replica synchronisation helper
+    from multimodal_deepfake_detection_b200.loops import broadcast_module_state, init_data_parallel
+    arc = torch.nn.Linear(10, 2)
+    frozen = torch.nn.Linear(3, 3)
+    extra = list(head.parameters()) + list(arc.parameters()) + list(frozen.parameters())
+    for p in list(head.parameters()) + list(arc.parameters()):
+        p.grad = torch.full_like(p, float(10 * (rank + 1)))
+    bk.finish(extra)
+    for p in list(head.parameters()) + list(arc.parameters()):
+        assert torch.allclose(p.grad, torch.full_like(p, 15.0))
+    assert all(p.grad is None for p in frozen.parameters())
+    bn = torch.nn.BatchNorm1d(4)
+    with torch.no_grad():
+        bn.running_mean.fill_(float(rank + 1)); bn.weight.fill_(float(rank + 5))
+    broadcast_module_state([bn], buffers_only=True)
+    assert torch.all(bn.running_mean == 1.0) and torch.all(bn.weight == float(rank + 5))       # buffers only
+    broadcast_module_state([bn])
+    assert torch.all(bn.weight == 5.0)
+    os.environ.pop("WORLD_SIZE", None)
+    assert init_data_parallel() == (1, 0)                           # plain `python script.py`: nothing is touched
     if rank == 0:
         ret.put(len(bk._buckets))
     dist.destroy_process_group()
