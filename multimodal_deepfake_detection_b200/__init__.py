@@ -8,5 +8,7 @@ from .modules import (ArcFaceHead, AUFaceCrossDetector, BCELoss, Block, CBFocalL
                       SeparableConv2d, Xception, XceptionLSTMA, XceptionLSTMV, model_urls, xception)
 from ._lib import XcpError, LIB_PATH  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .audio_frontend import MFCC  # noqa: F401
+from .graph import GraphedInference, GraphedTrainStep, HostPrefetcher  # noqa: F401
 
 __version__ = "0.1.0"
