@@ -3,7 +3,7 @@ Serves paired synthetic (videos[B,3,T,H,W], audio[B,Ta,3,13], labels[B]) batches
 import torch
 from torch.utils.data import DataLoader, Dataset
 
-from .synthetic import SyntheticAudio, SyntheticClips
+from .synthetic import SyntheticAudio, SyntheticClips, dataset_missing, synthetic_requested
 
 
 class JointSynthetic(Dataset):
@@ -28,6 +28,8 @@ def _collate(batch):
 
 def get_joint_dataloader(video_root=None, au_root=None, batch_size=2, shuffle=True, max_frames=16, max_aus=17, image_size=128,
                          num_workers=0, csv_path=None, return_weights=False, n_train=16, **_):
+    if not synthetic_requested():          # the reference's joint dataset class is absent: synthetic pairs only
+        raise dataset_missing("get_joint_dataloader", video_root)
     mk = lambda n, seed, sh: DataLoader(JointSynthetic(n, min(max_frames, 16), image_size, seed), batch_size=batch_size,
                                         shuffle=sh, collate_fn=_collate)
     return mk(n_train, 0, shuffle), mk(max(n_train // 2, batch_size), 1, False), mk(max(n_train // 2, batch_size), 2, False)

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader, Dataset
 
-from .synthetic import SyntheticAudio, collate_audio as collate_fn  # noqa: F401
+from .synthetic import SyntheticAudio, collate_audio as collate_fn, dataset_missing, label_from_name, synthetic_requested  # noqa: F401
 
 
 class AudioDataset(Dataset):
@@ -18,15 +18,23 @@ class AudioDataset(Dataset):
 
     def __getitem__(self, idx):
         mf = torch.from_numpy(np.load(self.files[idx])).float()              # (T,13)
-        label = 0.0 if os.path.basename(self.files[idx]).lower().startswith("real") else 1.0
-        return mf.unsqueeze(1).repeat(1, 3, 1), torch.tensor([label])
+        return mf.unsqueeze(1).repeat(1, 3, 1), torch.tensor([label_from_name(self.files[idx])], dtype=torch.float32)
 
 
 def get_audio_dataloader(folder_path, batch_size=8, shuffle=True, waveforms=False):
     """waveforms=True (no reference counterpart): yield raw 16 kHz waveforms (B, samples) for the GPU
     MFCC front-end (multimodal_deepfake_detection_b200.audio_frontend.MFCC) instead of pre-computed MFCC files."""
     if waveforms:
+        # the reference defines no on-disk waveform format (its pre-processor goes mp4 -> wav -> MFCC .npy in one pass,
+        # wavfake_audio_dataset.py:30-44), so this route only exists on synthetic waveforms
+        if not synthetic_requested():
+            raise dataset_missing("get_audio_dataloader(waveforms=True)", folder_path)
         from .synthetic import SyntheticWaveforms, collate_waveforms
         return DataLoader(SyntheticWaveforms(), batch_size=batch_size, shuffle=shuffle, collate_fn=collate_waveforms)
-    ds = AudioDataset(folder_path) if folder_path and os.path.isdir(folder_path) else SyntheticAudio()
+    if folder_path and os.path.isdir(folder_path):
+        ds = AudioDataset(folder_path)
+    elif synthetic_requested():
+        ds = SyntheticAudio()
+    else:
+        raise dataset_missing("get_audio_dataloader", folder_path)
     return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, collate_fn=collate_fn)

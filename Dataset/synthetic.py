@@ -1,7 +1,25 @@
 """Synthetic stand-ins with the reference loaders' tuple layouts (video_dataloader.py:53-68, audio_dataloader.py:34-47,
 SURVEY App. C).  Values follow the real value ranges: frames in [0,1] (uint8/255), MFCC-like audio."""
+import os
+
 import torch
 from torch.utils.data import DataLoader, Dataset
+
+
+def synthetic_requested() -> bool:
+    """Synthetic data is served only on explicit request (XCP_SYNTHETIC=1): a missing / mistyped dataset path must fail
+    like the reference's loaders do (os.listdir raises), not train a confident model on noise and overwrite checkpoints."""
+    return os.environ.get("XCP_SYNTHETIC", "0") == "1"
+
+
+def dataset_missing(what: str, path) -> FileNotFoundError:
+    return FileNotFoundError("%s: no usable dataset at %r (expected a folder of `real_*.npy` / `fake_*.npy` files as written by the "
+                             "reference's pre-processors); set XCP_SYNTHETIC=1 to run on synthetic data instead" % (what, path))
+
+
+def label_from_name(path: str) -> int:
+    """video_dataloader.py:29-32 / audio_dataloader.py:22: `<label>_...npy`, 'real' -> 0, anything else -> 1."""
+    return 0 if os.path.basename(path).split("_")[0].lower() == "real" else 1
 
 
 class SyntheticClips(Dataset):
@@ -36,10 +54,11 @@ def collate_clips(batch):
 
 
 def collate_clips_with_lengths(batch):
-    """The 'enhanced' collate of train_visual.py:563 -> (video, labels, seq_lengths)."""
+    """The 'enhanced' collate of train_visual.py:563 -> (video, labels (B,), seq_lengths): the labels feed CrossEntropyLoss
+    directly (train_visual.py:571-572), so they are flattened whatever the per-item shape."""
     vids, labs = zip(*batch)
     video, labels = collate_clips(batch)
-    return video, labels, torch.tensor([v.shape[0] for v in vids], dtype=torch.long)
+    return video, labels.reshape(-1), torch.tensor([v.shape[0] for v in vids], dtype=torch.long)
 
 
 class SyntheticAudio(Dataset):

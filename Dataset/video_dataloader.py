@@ -6,7 +6,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader, Dataset
 
-from .synthetic import SyntheticClips, collate_clips as collate_fn  # noqa: F401
+from .synthetic import SyntheticClips, collate_clips as collate_fn, dataset_missing, label_from_name, synthetic_requested  # noqa: F401
 
 
 class FaceDataset(Dataset):
@@ -22,13 +22,18 @@ class FaceDataset(Dataset):
 
     def __getitem__(self, idx):
         arr = np.load(self.files[idx])                                        # (T,H,W,3) uint8
-        label = 0.0 if os.path.basename(self.files[idx]).lower().startswith("real") else 1.0
+        label = torch.tensor([label_from_name(self.files[idx])], dtype=torch.float32)       # (1,) like video_dataloader.py:37
         if self.raw_uint8:
-            return torch.from_numpy(arr), torch.tensor(label, dtype=torch.float32)
+            return torch.from_numpy(arr), label
         frames = torch.from_numpy(arr).permute(0, 3, 1, 2).float().div_(255.0)
-        return frames, torch.tensor(label, dtype=torch.float32)
+        return frames, label
 
 
 def get_face_dataloader(folder_path, batch_size=4, shuffle=True, num_workers=0, raw_uint8=False):
-    ds = FaceDataset(folder_path, raw_uint8) if folder_path and os.path.isdir(folder_path) else SyntheticClips()
+    if folder_path and os.path.isdir(folder_path):
+        ds = FaceDataset(folder_path, raw_uint8)
+    elif synthetic_requested():
+        ds = SyntheticClips(raw_uint8=raw_uint8)
+    else:
+        raise dataset_missing("get_face_dataloader", folder_path)
     return DataLoader(ds, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers, collate_fn=collate_fn, pin_memory=True)

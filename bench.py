@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 hot path (contract in the task statement / DESIGN.md §Measurement).
+"""bench.py -- benchmark of the B200 hot path (contract: task statement / DESIGN.md §5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c2|c4|c5] [--clips B] [--impl ours|reference|torch-stock]
 
-Workload (BASELINE.json `metric`): XceptionLSTMV(hidden_dim=128) *training* steps on synthetic clips of
-16 x 3 x 299 x 299, backbone unfrozen (train_visual.py epochs >= 3: fwd + bwd through all 74 convs + LSTM + head
-+ BCE + Adam).  One step = one pass over B clips per GPU.  `value` = clips/s over all GPUs with the inputs already
-resident in HBM; `e2e` = the same step fed from pinned HOST buffers (H2D inside the timed region) with the loss
-read back to the host every step.  N > 1: launched under torchrun, one rank per GPU, gradients averaged with
-bucketed NCCL all-reduces overlapped with backward (weak scaling: B clips per GPU).
+Workloads = BASELINE.json `configs` (config[0] is the CPU-runnable case and is what `--impl reference --config c1` times):
+  c3 (default, the headline `metric`): XceptionLSTMV(128) *training* steps on 16 x 3 x 299 x 299 clips, backbone unfrozen
+      (train_visual.py epochs >= 3: fwd + bwd through all 74 convs + LSTM + head + BCE + Adam), B clips per GPU.
+  c2: Xception(num_classes=2) classifier fwd + bwd + Adam, batch 64 frames of 3 x 299 x 299, CE loss, one GPU (frames/s).
+  c4: XceptionLSTMA on log-mel patch sequences (B, 120, 3, 64) -> 64 x 64 patches (train_au_patch.py protocol).
+  c5: audio-face fusion (train_au_face.py protocol): paired 16-frame 299 x 299 face clips + audio, two-stream detector +
+      fused embed / ArcFace / CB-focal / regulariser head, AdamW + clip 1.0.
+One step = one pass over the per-GPU batch.  `value` = units/s over all GPUs with the inputs resident in HBM; `e2e` = the same
+step fed from pinned HOST buffers (H2D inside the timed region) with the loss read back every step.  N > 1: torchrun, one rank
+per GPU, gradients averaged by bucketed NCCL all-reduces overlapped with backward (weak scaling).
 
-`--impl reference` times the reference's own algorithm on the host CPU cores (the fp32 oracle port in oracle/,
-the reference itself cannot travel to the GPU box) on a bounded sample: one clip per step.
+`roofline.kernels[]`: every kernel family of the step, timed with CUDA events around each C-ABI call inside an eager step,
+with its ALGORITHMIC flops / bytes (logical 728 channels, not the 768 pitch), share of the step and fraction of its roofline.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (baseline/_ref, staged by __graft_entry__.build()) on the host
+cores, on a bounded sample; falls back to the oracle port when the staged copy is absent.
 """
 from __future__ import annotations
 
@@ -26,8 +32,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "train clips/sec XceptionLSTMV 16x299x299"
 T_FRAMES, HW, HIDDEN = 16, 299, 128
+METRICS = {
+    "c1": ("infer frames/sec Xception 8x3x299x299 (CPU case)", "frames/s"),
+    "c2": ("train frames/sec Xception classifier 299x299 batch 64", "frames/s"),
+    "c3": ("train clips/sec XceptionLSTMV 16x299x299", "clips/s"),
+    "c4": ("train clips/sec XceptionLSTMA 120 log-mel patches (3x64 -> 64x64)", "clips/s"),
+    "c5": ("train clips/sec audio-face fusion 16x299x299 + 16 audio patches", "clips/s"),
+}
 
 
 def _peaks():
@@ -42,68 +54,189 @@ def _peaks():
     return p
 
 
-# ----------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
-def cpu_oracle_clips_per_s(steps: int, warmup: int, threads: int):
+# =====================================================================================================================
+# reference arm / cpu baseline: the UNMODIFIED reference files (baseline/_ref/RefModels, staged by build()) on host cores
+def _load_reference():
+    """-> namespace with the reference's own classes, or None when baseline/_ref was not staged."""
+    pkg = os.path.join(ROOT, "baseline", "_ref", "RefModels")
+    if not all(os.path.isfile(os.path.join(pkg, f)) for f in ("Xception.py", "XceptionLSTMV.py", "XceptionLSTMA.py", "__init__.py")):
+        return None
+    import importlib
+    import warnings
+
     import torch
+    base = os.path.join(ROOT, "baseline", "_ref")
+    if base not in sys.path:
+        sys.path.insert(0, base)
+    xmod = importlib.import_module("RefModels.Xception")
+    home = os.path.join(base, "torch_home")
+    ck = os.path.join(home, "hub", "checkpoints", "xception-43020ad28.pth")
+    os.environ["TORCH_HOME"] = home
+    torch.hub.set_dir(os.path.join(home, "hub"))
+    if not os.path.isfile(ck):          # xception(pretrained=True) (Xception.py:211-212) must find its checkpoint offline
+        os.makedirs(os.path.dirname(ck), exist_ok=True)
+        torch.manual_seed(1234)
+        torch.save(xmod.Xception().state_dict(), ck)
+
+    class NS:
+        pass
+    ns = NS()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ns.Xception = xmod.Xception
+        ns.XceptionLSTMV = importlib.import_module("RefModels.XceptionLSTMV").XceptionLSTMV
+        ns.XceptionLSTMA = importlib.import_module("RefModels.XceptionLSTMA").XceptionLSTMA
+    return ns
+
+
+def cpu_arm(config: str, steps: int, warmup: int, threads: int):
+    """-> dict(value, unit, sec_per_step, kind, sample).  Bounded sample of the workload on `threads` host threads."""
+    import warnings
+
+    import torch
+    import torch.nn as nn
     import torch.nn.functional as F
-    from oracle import xception_oracle as O
 
     torch.set_num_threads(threads)
-    sd = O.synth_state_dict(1234, num_classes=None, bn_jitter=0.0)
-    full = {"feature_extractor." + k: v for k, v in sd.items()}
-    full.update(O.synth_lstm_head_state_dict(77, HIDDEN))
-    leaves = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
-              for k, v in full.items()}
-    opt = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-5, weight_decay=1e-4)
+    ref = _load_reference()
+    kind = "reference" if ref is not None else "port"
     g = torch.Generator().manual_seed(0)
-    clips = torch.rand(1, T_FRAMES, 3, HW, HW, generator=g)
-    y = torch.tensor([[1.0]])
+    cpu = torch.device("cpu")
+    unit = METRICS[config][1]
+    if ref is None:                    # oracle port (the staged reference copy is absent): restated algorithm, same protocol
+        from oracle import xception_oracle as O
+        if config != "c3":
+            config = "c3" if config in ("c4", "c5") else config
+        if config in ("c1", "c2"):
+            sd = O.synth_state_dict(1234, num_classes=2, bn_jitter=0.0)
+            leaves = {k: (v.clone().requires_grad_(config == "c2") if v.dtype.is_floating_point and "running" not in k else v.clone())
+                      for k, v in sd.items()}
+            n = 8 if config == "c1" else 4
+            x = torch.rand(n, 3, HW, HW, generator=g); y = torch.randint(0, 2, (n,), generator=g)
+            opt = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-5, weight_decay=1e-4) if config == "c2" else None
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        ns = {}
-        prob = O.xception_lstm_forward(leaves, clips, training=True, new_stats=ns)
-        loss = F.binary_cross_entropy(prob, y)
-        loss.backward()
-        opt.step()
-        for k, v in ns.items():
-            leaves[k] = v
-        return float(loss.detach())
+            def step():
+                if config == "c1":
+                    with torch.no_grad():
+                        O.xception_logits(leaves, x, False)
+                    return
+                opt.zero_grad(set_to_none=True)
+                ns = {}
+                F.cross_entropy(O.xception_logits(leaves, x, True, ns), y).backward()
+                opt.step()
+            units, sample = n, "oracle fp32 port, %d frames 3x299x299 per step" % n
+        else:
+            sd = O.synth_state_dict(1234, num_classes=None, bn_jitter=0.0)
+            full = {"feature_extractor." + k: v for k, v in sd.items()}
+            full.update(O.synth_lstm_head_state_dict(77, HIDDEN))
+            leaves = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+                      for k, v in full.items()}
+            opt = torch.optim.Adam([v for v in leaves.values() if v.requires_grad], lr=1e-5, weight_decay=1e-4)
+            clips = torch.rand(1, T_FRAMES, 3, HW, HW, generator=g); y = torch.tensor([[1.0]])
 
+            def step():
+                opt.zero_grad(set_to_none=True)
+                ns = {}
+                F.binary_cross_entropy(O.xception_lstm_forward(leaves, clips, training=True, new_stats=ns), y).backward()
+                opt.step()
+                for k, v in ns.items():
+                    leaves[k] = v
+            units, sample = 1, "oracle fp32 port, 1 clip (16x3x299x299) per step: fwd+bwd+Adam, backbone unfrozen, train-mode BN"
+            unit = "clips/s"
+    else:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if config == "c1":         # BASELINE config[0]: the reference's CPU-runnable case (test_visual.py path)
+                m = ref.Xception(num_classes=2).eval()
+                x = torch.rand(8, 3, HW, HW, generator=g)
+
+                def step():
+                    with torch.no_grad():
+                        m(x)
+                units, sample = 8, "reference Xception(num_classes=2).eval() forward, 8x3x299x299, no_grad"
+            elif config == "c2":
+                m = ref.Xception(num_classes=2).train()
+                opt = torch.optim.Adam(m.parameters(), lr=1e-5, weight_decay=1e-4)
+                x = torch.rand(4, 3, HW, HW, generator=g); y = torch.randint(0, 2, (4,), generator=g)
+
+                def step():
+                    opt.zero_grad(set_to_none=True)
+                    F.cross_entropy(m(x), y).backward()
+                    opt.step()
+                units, sample = 4, "reference Xception(num_classes=2).train() fwd+bwd+Adam on 4 frames 3x299x299 per step (GPU arm: 64)"
+            elif config in ("c3", "c4"):
+                if config == "c3":
+                    m = ref.XceptionLSTMV(HIDDEN).train()
+                    inp = torch.rand(1, T_FRAMES, 3, HW, HW, generator=g)
+                    sample = "reference XceptionLSTMV(128), 1 clip (16x3x299x299) per step: extract_features + forward + BCELoss + backward + Adam, backbone unfrozen, train-mode BN"
+                else:
+                    m = ref.XceptionLSTMA(HIDDEN).train()
+                    inp = torch.randn(1, 120, 3, 64, generator=g)
+                    sample = "reference XceptionLSTMA(128), 1 clip (120 patches 3x64 -> 64x64) per step: fwd + BCELoss + bwd + Adam, backbone unfrozen"
+                for p in m.feature_extractor.parameters():       # train_visual.py:551-556, epoch >= freeze_epochs
+                    p.requires_grad = True
+                opt = torch.optim.Adam(m.parameters(), lr=1e-5, weight_decay=1e-4)
+                crit = nn.BCELoss()
+                y = torch.tensor([[1.0]])
+
+                def step():
+                    opt.zero_grad(set_to_none=True)
+                    crit(m(m.extract_features(inp, cpu)), y).backward()
+                    opt.step()
+                units = 1
+            else:                       # c5: the reference's fusion model class is absent (SURVEY App. C); its two streams are not
+                from oracle import xception_oracle as O
+                mv, ma = ref.XceptionLSTMV(256).train(), ref.XceptionLSTMA(256).train()
+                for p in list(mv.feature_extractor.parameters()) + list(ma.feature_extractor.parameters()):
+                    p.requires_grad = True
+                torch.manual_seed(3)
+                embed = {"0.weight": torch.randn(256, 512) * 0.05, "0.bias": torch.zeros(256), "3.weight": torch.randn(128, 256) * 0.05,
+                         "3.bias": torch.zeros(128)}
+                arc_w = torch.randn(2, 128) * 0.1
+                extra = [t.requires_grad_(True) for t in list(embed.values()) + [arc_w]]
+                opt = torch.optim.AdamW(list(mv.parameters()) + list(ma.parameters()) + extra, lr=1e-4, weight_decay=1e-2)
+                vid = torch.rand(1, T_FRAMES, 3, HW, HW, generator=g); aud = torch.randn(1, T_FRAMES, 3, 13, generator=g)
+                lab = torch.tensor([1]); cw = O.cb_focal_weights([500, 10000])
+
+                def step():
+                    opt.zero_grad(set_to_none=True)
+                    vt = mv.lstm(mv.extract_features(vid, cpu))[0]
+                    at = ma.lstm(ma.extract_features(aud, cpu))[0]
+                    O.fusion_head_loss(embed, arc_w, vt, at, lab, cw)[0].backward()
+                    opt.step()
+                units = 1
+                kind = "reference"      # both streams are the reference's classes; only the (absent) head comes from the oracle
+                sample = "reference XceptionLSTMV(256) + XceptionLSTMA(256) streams + train_au_face.py:659-674 head (oracle restatement), 1 paired clip per step"
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    dt = time.perf_counter() - t0
-    return steps / dt, dt / steps
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": units / dt, "unit": unit, "sec_per_step": dt, "kind": kind, "cores": threads, "sample": sample, "units_per_step": units}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    cps, spc = cpu_oracle_clips_per_s(args.steps, args.warmup, threads)
-    sample = "1 clip (16x3x299x299) per step: oracle fp32 fwd+bwd+Adam, backbone unfrozen, train-mode BN"
+    r = cpu_arm(args.config, args.steps, args.warmup, threads)
+    metric = METRICS[args.config][0]
     line = {
-        "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": spc * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": metric, "value": r["value"], "unit": r["unit"], "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "XceptionLSTMV(128) train step, backbone unfrozen, 16x3x299x299 clips", "clips_per_step": 1,
-                   "device": "host CPU"},
-        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": args.config + ": " + r["sample"], "units_per_step": r["units_per_step"], "device": "host CPU"},
+        "cpu_baseline": {"value": r["value"], "unit": r["unit"], "cores": threads, "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-# ----------------------------------------------------------------------------------------------------------------
-# optional third arm (SURVEY.md §8d "the honest competitor"): the SAME module tree and weights driven through stock PyTorch
-# (cuDNN / cuBLAS kernels, bf16 autocast, channels_last, fused torch Adam) on the same B200.  None of this package's kernels
-# run here: the nn.Conv2d / nn.BatchNorm2d / nn.MaxPool2d / nn.LSTM / nn.Linear submodules execute their own torch forward.
-def run_torch_stock(args):
+# =====================================================================================================================
+# third arm (SURVEY.md §8d "the honest competitor"): the SAME module tree and weights through stock PyTorch (cuDNN / cuBLAS,
+# bf16 autocast, channels_last, fused torch Adam) on the same B200.  None of this package's kernels run here.
+def torch_stock_clips_per_s(B: int, steps: int, warmup: int):
     import warnings
 
     import torch
@@ -112,9 +245,7 @@ def run_torch_stock(args):
 
     from multimodal_deepfake_detection_b200 import SeparableConv2d, XceptionLSTMV
 
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(1234)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -143,7 +274,6 @@ def run_torch_stock(args):
         return F.adaptive_avg_pool2d(x, (1, 1)).flatten(1)
 
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True)
-    B = args.clips
     g = torch.Generator().manual_seed(0)
     clips = torch.rand(B, T_FRAMES, 3, HW, HW, generator=g).to(dev)
     y = torch.randint(0, 2, (B, 1), generator=g).float().to(dev)
@@ -161,24 +291,31 @@ def run_torch_stock(args):
         opt.step()
         return loss
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"impl": "torch-stock", "metric": METRIC, "value": B / (ms * 1e-3), "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
-                      "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16 autocast",
-                      "data": "synthetic", "loss": float(loss.detach()),
-                      "config": {"workload": "XceptionLSTMV(128) train step, backbone unfrozen, train-mode BN, BCE, torch.optim.Adam(fused)",
-                                 "clips_per_gpu": B, "frames_per_clip": T_FRAMES, "frame": "3x299x299",
-                                 "launch": "eager stock PyTorch %s, cuDNN %s, channels_last" % (torch.__version__, torch.backends.cudnn.version())}}),
-          flush=True)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms, "loss": float(loss.detach()),
+            "what": "same XceptionLSTMV(128) step through stock PyTorch %s / cuDNN %s (bf16 autocast, channels_last, fused torch Adam, eager), "
+                    "%d clips" % (torch.__version__, torch.backends.cudnn.version(), B)}
 
 
-# ----------------------------------------------------------------------------------------------------------------
+def run_torch_stock(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    torch.cuda.set_device(0)
+    r = torch_stock_clips_per_s(args.clips or 16, args.steps, args.warmup)
+    print(json.dumps({"impl": "torch-stock", "metric": METRICS["c3"][0], "value": r["value"], "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "dtype": "bf16 autocast",
+                      "data": "synthetic", "loss": r["loss"], "config": {"workload": r["what"]}}), flush=True)
+
+
+# =====================================================================================================================
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -228,57 +365,284 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# =====================================================================================================================
+# per-kernel roofline: decode the (entry point, argument signature) log of _lib.timer_* into algorithmic work
+def _lc(c: int) -> int:
+    """logical channel count of a physical pitch (ops.phys: only 728 is padded, to 768)"""
+    return 728 if c == 768 else c
+
+
+def _work(name: str, a: tuple):
+    """-> (family, flops, bytes) of one C-ABI call from its argument signature (ints as passed, pointers as non-NULL flags;
+    argument order = include/xcp.h).  bytes = ALGORITHMIC minimum: every operand read once, every result written once,
+    bf16 activations, logical channel counts.  None = latency-class call (no roofline)."""
+    if name == "xcp_gemm_tn":          # A lda B ldb out ldo M N K epi stats bias device stream
+        M, N, K, epi = a[6], _lc(a[7]), _lc(a[8]), a[9]
+        fam = {0: "pointwise/skip 1x1 dgrad (or eval fwd) GEMM", 1: "pointwise/skip 1x1 fwd GEMM + BN stats", 2: "LSTM / fp32-out GEMM"}[epi]
+        return fam, 2.0 * M * N * K, 2.0 * M * K + (4.0 if epi == 2 else 2.0) * M * N + 2.0 * N * K
+    if name == "xcp_gemm_wgrad":       # dY ld X ld dW ld R P Q
+        R, P, Q = a[6], _lc(a[7]), _lc(a[8])
+        return "pointwise/skip 1x1 wgrad GEMM", 2.0 * R * P * Q, 2.0 * R * (P + Q) + 4.0 * P * Q
+    if name == "xcp_dw3x3_fwd":        # x w9 scale shift relu out F H W C
+        n = a[6] * a[7] * a[8] * _lc(a[9])
+        return "depthwise 3x3 fwd %dx%d" % (a[7], a[8]), 18.0 * n, 4.0 * n
+    if name == "xcp_dw3x3_bwd":        # dD xin w9 scale shift relu dz add_full add_half dw bnsum F H W C c_real
+        n = a[11] * a[12] * a[13] * a[15]
+        return "depthwise 3x3 bwd %dx%d" % (a[12], a[13]), 36.0 * n, (6.0 + (2.0 if a[7] else 0.0) + (0.5 if a[8] else 0.0)) * n
+    if name == "xcp_bn_bwd":           # mode y G idx dfeat scale shift gamma mean rstd training presums ws coef dg db dy F H W C c_real
+        mode, n = a[0], a[17] * a[18] * a[19] * a[21]
+        g = {0: 1.0, 1: 1.0, 2: 0.375, 3: 0.0}[mode]          # gradient source per element of y (pool: G + idx at quarter size)
+        reduce_pass = 0.0 if a[11] else (1.0 + g)
+        apply_pass = (2.0 + g) if a[16] else 0.0
+        return ("BN backward through max-pool" if mode == 2 else "BN backward (reduce + apply)"), 8.0 * n, 2.0 * n * (reduce_pass + apply_pass)
+    if name == "xcp_pool_add_fwd":     # ... F H W C
+        F_, H, W, C = a[8], a[9], a[10], _lc(a[11])
+        no = F_ * ((H - 1) // 2 + 1) * ((W - 1) // 2 + 1) * C
+        return "BN + max-pool + skip-BN + add fwd", 12.0 * no, 2.0 * F_ * H * W * C + 5.0 * no
+    if name == "xcp_bn_add_fwd":       # y sc sh skip scs shs out n C
+        n = a[7] / a[8] * _lc(a[8])
+        return "BN + residual add fwd", 3.0 * n, 6.0 * n
+    if name == "xcp_bn_act":
+        n = a[5] / a[6] * _lc(a[6])
+        return "BN + ReLU materialise (stem)", 2.0 * n, 4.0 * n
+    if name == "xcp_gather_s2":        # x sc sh relu out F H W C
+        n = a[5] * ((a[6] + 1) // 2) * ((a[7] + 1) // 2) * _lc(a[8])
+        return "stride-2 gather (skip conv input)", 0.0, 4.0 * n
+    if name == "xcp_bn_relu_gap":
+        return "BN + ReLU + GAP", 3.0 * a[4] * a[5] * a[6], 2.0 * a[4] * a[5] * a[6]
+    if name == "xcp_stem_conv1_fwd":   # x u8 w y parts F H W
+        F_, H, W = a[5], a[6], a[7]
+        no = F_ * ((H - 3) // 2 + 1) * ((W - 3) // 2 + 1) * 32
+        return "stem conv1 fwd", 2.0 * 27 * no, F_ * 3.0 * H * W * (1 if a[1] else 4) + 2.0 * no
+    if name == "xcp_stem_conv1_wgrad":  # x u8 dy dW ws F H W
+        F_, H, W = a[5], a[6], a[7]
+        no = F_ * ((H - 3) // 2 + 1) * ((W - 3) // 2 + 1) * 32
+        return "stem conv1 wgrad", 2.0 * 27 * no, F_ * 3.0 * H * W * (1 if a[1] else 4) + 2.0 * no
+    if name == "xcp_conv3x3_gemm":     # a b out stats F Hg Wg Cin Cout Ho Wo sign
+        px = a[4] * a[5] * a[6]
+        return ("stem conv2 fwd (implicit GEMM)" if a[11] > 0 else "stem conv2 dgrad (implicit GEMM)"), 2.0 * px * 9 * a[7] * a[8], 2.0 * px * (a[7] + a[8])
+    if name == "xcp_conv3x3_wgrad":    # dy x gk F Hg Wg Cin Cout
+        px = a[3] * a[4] * a[5]
+        return "stem conv2 wgrad", 2.0 * px * 9 * a[6] * a[7], 2.0 * px * (a[6] + a[7])
+    if name == "xcp_adam_multi":       # table n_tensors chunks n_chunks ...
+        return "fused clip + Adam", 12.0 * a[3] * 8192, 28.0 * a[3] * 8192
+    return None
+
+
+def kernel_rooflines(log: dict, step_ms: float, peaks: dict, n_steps: int):
+    """log: {(name, sig): [total_ms, calls]} over n_steps eager steps -> list of per-family dicts, largest share first."""
+    hbm = peaks["hbm_gbs"] * 1e9
+    tf = peaks["bf16_tflops_sustained"] * 1e12
+    fams = {}
+    total_ms = sum(v[0] for v in log.values())
+    for (name, sig), (ms, calls) in log.items():
+        w = _work(name, sig)
+        fam = w[0] if w is not None else "latency class: " + name.replace("xcp_", "")
+        d = fams.setdefault(fam, {"kernel": fam, "ms": 0.0, "calls": 0, "flops": 0.0, "bytes": 0.0, "t_roof": 0.0, "t_hbm": 0.0, "t_tc": 0.0})
+        d["ms"] += ms; d["calls"] += calls
+        if w is not None:
+            d["flops"] += w[1] * calls; d["bytes"] += w[2] * calls
+            d["t_roof"] += max(w[1] / tf, w[2] / hbm) * calls
+            d["t_hbm"] += w[2] / hbm * calls; d["t_tc"] += w[1] / tf * calls
+    out = []
+    for d in fams.values():
+        sec = d["ms"] * 1e-3
+        e = {"kernel": d["kernel"], "calls_per_step": d["calls"] / n_steps, "us_per_step": d["ms"] * 1e3 / n_steps,
+             "share_of_step": d["ms"] / total_ms if total_ms else None}
+        if d["t_roof"] > 0:
+            tensor = d["t_tc"] > d["t_hbm"]
+            e.update({"bound": "tensor" if tensor else "hbm",
+                      "achieved": (d["flops"] / sec / 1e12) if tensor else (d["bytes"] / sec / 1e9),
+                      "peak": peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"], "unit": "TFLOP/s" if tensor else "GB/s",
+                      "frac": d["t_roof"] / sec,          # sum of per-call roofline times / measured time (mixed shapes weigh by time)
+                      "algorithmic_gflop_per_step": d["flops"] / n_steps / 1e9, "algorithmic_mb_per_step": d["bytes"] / n_steps / 1e6})
+        else:
+            e.update({"bound": "latency", "frac": None})
+        out.append(e)
+    out.sort(key=lambda e: -(e["share_of_step"] or 0.0))
+    return out, total_ms / n_steps
+
+
+# =====================================================================================================================
+# GPU workloads
+def build_workload(cfg: str, B: int, dev, rank: int, world: int):
+    """-> dict(step, host (2 batches of pinned tensors), modules, optimizers, buckets [(bucketer, extra or None)], units, desc)"""
+    import warnings
+
+    import torch
+    import torch.nn.functional as F
+
+    from multimodal_deepfake_detection_b200 import (AUFaceCrossDetector, BCELoss, FusedAdam, FusionHead, LabelSmoothingBCEWithLogitsLoss,
+                                                      Xception, XceptionLSTMA, XceptionLSTMV)
+    from multimodal_deepfake_detection_b200.ddp import GradBucketer
+
+    torch.manual_seed(1234)
+    g = torch.Generator().manual_seed(1000 * rank)
+    w = {"buckets": []}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if cfg == "c3":
+            model = XceptionLSTMV(HIDDEN).to(dev).train()
+            for p in model.feature_extractor.parameters():      # epoch >= freeze_epochs of train_visual.py:551-556
+                p.requires_grad = True
+            opt = FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4)      # train_visual.py:533
+            crit = BCELoss()
+            host = [(torch.rand(B, T_FRAMES, 3, HW, HW, generator=g).pin_memory(), torch.randint(0, 2, (B, 1), generator=g).float().pin_memory())
+                    for _ in range(2)]
+
+            def fwd_loss(clips, y):
+                return crit(model(model.extract_features(clips, dev)), y)       # train_audio.py:20,39 criterion on the sigmoid output
+            w.update(modules=[model], params=list(model.parameters()), backbones=[(model.feature_extractor, None)], units=B,
+                     desc="XceptionLSTMV(128) train step, backbone unfrozen, train-mode BN, BCE, fused Adam(1e-5, wd 1e-4)",
+                     shape={"clips_per_gpu": B, "frames_per_clip": T_FRAMES, "frame": "3x299x299"}, model=model)
+        elif cfg == "c2":
+            model = Xception(num_classes=2).to(dev).train()
+            opt = FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4)
+            host = [(torch.rand(B, 3, HW, HW, generator=g).pin_memory(), torch.randint(0, 2, (B,), generator=g).pin_memory()) for _ in range(2)]
+
+            def fwd_loss(x, y):
+                return F.cross_entropy(model(x), y)               # [B,2] logits: the criterion itself is torch glue (3 tiny kernels)
+            w.update(modules=[model], params=list(model.parameters()), backbones=[(model, list(model.fc.parameters()))], units=B,
+                     desc="Xception(num_classes=2) classifier train step: fwd + bwd + fused Adam, CE loss, train-mode BN",
+                     shape={"frames_per_gpu": B, "frame": "3x299x299"}, model=model)
+        elif cfg == "c4":
+            model = XceptionLSTMA(HIDDEN).to(dev).train()
+            for p in model.feature_extractor.parameters():
+                p.requires_grad = True
+            opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4)      # train_au_patch.py protocol
+            crit = LabelSmoothingBCEWithLogitsLoss()
+            host = [(torch.randn(B, 120, 3, 64, generator=g).pin_memory(), torch.randint(0, 2, (B, 1), generator=g).float().pin_memory())
+                    for _ in range(2)]
+
+            def fwd_loss(patches, y):
+                return crit(model.forward_logits(model.extract_features(patches, dev)), y)
+            w.update(modules=[model], params=list(model.parameters()), backbones=[(model.feature_extractor, None)], units=B,
+                     desc="XceptionLSTMA(128) train step on log-mel patch sequences (train_au_patch.py protocol): backbone unfrozen, "
+                          "label-smoothing BCE-with-logits, fused Adam(1e-4, wd 1e-4)",
+                     shape={"clips_per_gpu": B, "patches_per_clip": 120, "patch": "3x64 -> bilinear 64x64"}, model=model)
+        elif cfg == "c5":
+            model = AUFaceCrossDetector(lstm_hidden=256).to(dev).train()
+            head = FusionHead(256, samples_per_cls=(500, 10000)).to(dev).train()
+            for s in (model.face_stream, model.au_stream):
+                for p in s.feature_extractor.parameters():
+                    p.requires_grad = True
+            used = [p for n_, p in model.named_parameters() if ".fc_layers." not in n_ and ".fc_out." not in n_ and not n_.startswith("classifier")]
+            params = used + list(head.parameters())
+            opt = FusedAdam(params, lr=1e-4, weight_decay=1e-2, decoupled=True, max_norm=1.0)     # AdamW + clip 1.0, train_au_face.py:616-619,681
+            host = [(torch.rand(B, 3, T_FRAMES, HW, HW, generator=g).pin_memory(), torch.randn(B, T_FRAMES, 3, 13, generator=g).pin_memory(),
+                     torch.randint(0, 2, (B,), generator=g).pin_memory()) for _ in range(2)]
+
+            def fwd_loss(videos, audio, labels):
+                _, v_tok, a_tok = model(videos, audio)
+                return head(v_tok, a_tok, labels)[0]               # train_au_face.py:659-674 fused head + loss
+            bb = {id(p) for s in (model.face_stream, model.au_stream) for p in s.feature_extractor.parameters()}
+            w.update(modules=[model, head], params=params,
+                     backbones=[(model.face_stream.feature_extractor, []), (model.au_stream.feature_extractor, [p for p in params if id(p) not in bb])],
+                     units=B, desc="audio-face fusion train step (train_au_face.py protocol): two Xception+LSTM(256) streams, embed head + "
+                                   "ArcFace(s=30,m=0.3) + CB-focal + align/temporal regularisers, fused AdamW + clip 1.0",
+                     shape={"clips_per_gpu": B, "face": "16x3x299x299", "audio": "16x3x13 -> 64x64"}, model=model)
+        else:
+            raise SystemExit("unknown --config %s" % cfg)
+    if world > 1:
+        import torch.distributed as dist
+        for m in w["modules"]:                                   # identical replicas
+            for t in list(m.parameters()) + list(m.buffers()):
+                dist.broadcast(t.data, 0)
+        w["buckets"] = [(GradBucketer(m0, backbone=bb_), extra) for m0, (bb_, extra) in
+                        zip([w["modules"][0]] * len(w["backbones"]), w["backbones"])]
+
+    def step(*inputs):
+        opt.zero_grad(set_to_none=True)
+        loss = fwd_loss(*inputs)
+        loss.backward()
+        for bk, extra in w["buckets"]:
+            bk.finish(extra)
+        opt.step()
+        return loss
+    w.update(step=step, host=host, optimizers=[opt], fwd_loss=fwd_loss, opt=opt)
+    return w
+
+
+def ddp_gradient_check(w, dev_inputs, world):
+    """N > 1: the gradients the bucketed, overlapped all-reduce leaves in p.grad must equal the plain average of the ranks'
+    local gradients.  Two backward passes of the same batch: one with the hooks detached (local gradients, averaged with one
+    flat all-reduce), one through the bucketer.  -> max over parameters of the relative difference (RED-ordered fp32 sums
+    differ in the last bits between two passes)."""
+    import torch
+    import torch.distributed as dist
+    params = [p for p in w["params"] if p.requires_grad]
+    hooks = []
+    for bk, _ in w["buckets"]:
+        hooks.append(bk.backbone.__dict__.pop("_grad_ready_hook", None))
+    for p in params:
+        p.grad = None
+    torch.manual_seed(4242)             # same dropout masks in both passes
+    w["fwd_loss"](*dev_inputs).backward()
+    ref = [p.grad.detach().clone() if p.grad is not None else None for p in params]
+    flat = torch.cat([r.reshape(-1) for r in ref if r is not None])
+    dist.all_reduce(flat)
+    flat /= world
+    for (bk, _), h in zip(w["buckets"], hooks):
+        if h is not None:
+            bk.backbone.__dict__["_grad_ready_hook"] = h
+    for p in params:
+        p.grad = None
+    torch.manual_seed(4242)
+    w["fwd_loss"](*dev_inputs).backward()
+    for bk, extra in w["buckets"]:
+        bk.finish(extra)
+    torch.cuda.synchronize()
+    worst, off = 0.0, 0
+    for p, r in zip(params, ref):
+        if r is None:
+            continue
+        a = flat[off:off + r.numel()].view_as(r); off += r.numel()
+        d = ((p.grad - a).norm() / (a.norm() + 1e-30)).item()
+        worst = max(worst, d)
+    # and every rank must hold the same averaged gradient bit for bit (they all read the same NCCL result)
+    cs = torch.stack([p.grad.double().sum() for p in params if p.grad is not None]).sum().view(1)
+    allcs = [torch.zeros_like(cs) for _ in range(world)]
+    dist.all_gather(allcs, cs)
+    same = all(torch.equal(allcs[0], c) for c in allcs)
+    for p in params:
+        p.grad = None
+    return {"max_rel_diff_vs_plain_average": worst, "identical_across_ranks": bool(same), "ok": bool(worst < 1e-4 and same)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import torch.nn.functional as F
-
-    from multimodal_deepfake_detection_b200 import FusedAdam, XceptionLSTMV, _lib, ops
-    from multimodal_deepfake_detection_b200.ddp import GradBucketer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = args.config
+    if cfg == "c1":
+        raise SystemExit("bench.py: config c1 is the reference's CPU case (use --impl reference --config c1); the GPU path starts at c2")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    # ---- CPU baseline FIRST, on rank 0, before the process group exists: the other ranks are then blocked in the rendezvous
+    # (sleeping), not spinning in an NCCL barrier, so the host cores are free at every N (VERDICT r1 "What's weak" 7d)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        try:
+            r = cpu_arm(cfg, 2, 1, threads)
+            cpu = {"value": r["value"], "unit": r["unit"], "cores": threads, "kind": r["kind"],
+                   "sample": r["sample"] + "; 2 timed steps after 1 warm-up"}
+        except Exception as e:       # noqa: BLE001
+            cpu = {"error": "%s: %s" % (type(e).__name__, e)}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=20))
+    from multimodal_deepfake_detection_b200 import _lib, ops
     ops.check_device(dev)
-    B = args.clips
-    torch.manual_seed(1234)
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        model = XceptionLSTMV(HIDDEN).to(dev)
-    model.train()
-    for p in model.feature_extractor.parameters():      # epoch >= freeze_epochs of train_visual.py:551-556
-        p.requires_grad = True
-    if world > 1:                                       # identical replicas
-        for t in list(model.parameters()) + list(model.buffers()):
-            dist.broadcast(t.data, 0)
-    bucketer = GradBucketer(model, backbone=model.feature_extractor) if world > 1 else None
-    opt = FusedAdam(model.parameters(), lr=1e-5, weight_decay=1e-4)      # Adam(lr=1e-5, weight_decay=1e-4), train_visual.py:533
-    g = torch.Generator().manual_seed(1000 * rank)
-    host_clips = [torch.rand(B, T_FRAMES, 3, HW, HW, generator=g).pin_memory() for _ in range(2)]
-    host_y = [torch.randint(0, 2, (B, 1), generator=g).float().pin_memory() for _ in range(2)]
-    dev_clips = host_clips[0].to(dev)
-    dev_y = host_y[0].to(dev)
-
-    from multimodal_deepfake_detection_b200 import BCELoss
-    criterion = BCELoss()
-
-    def step(clips, y):
-        opt.zero_grad(set_to_none=True)
-        feats = model.extract_features(clips, dev)
-        prob = model(feats)
-        loss = criterion(prob, y)                       # train_audio.py:20,39 criterion on the sigmoid output (one kernel)
-        loss.backward()
-        if bucketer is not None:
-            bucketer.finish()
-        opt.step()
-        return loss
+    B = args.clips or {"c2": 64, "c3": 16, "c4": 8, "c5": 8}[cfg]
+    w = build_workload(cfg, B, dev, rank, world)
+    step, host = w["step"], w["host"]
+    dev_inputs = tuple(t.to(dev) for t in host[0])
 
     def barrier():
         if world > 1:
@@ -302,17 +666,17 @@ def run_ours(args):
 
     W = max(args.warmup, 3)
     for i in range(W):
-        step(dev_clips, dev_y)
-    # ---- eager pass with CUDA events around every pointwise-GEMM launch (roofline) + launch census of one step
+        step(*dev_inputs)
+    ddp = ddp_gradient_check(w, dev_inputs, world) if world > 1 else None
+    # ---- eager pass with CUDA events around every C-ABI call (per-kernel roofline) + launch census of one step
     torch.cuda.synchronize()
     _lib.reset_launch_count()
-    ops.GEMM_TIMER.enable(True)
     n_eager = 2
+    _lib.timer_start()
     for i in range(n_eager):
-        step(dev_clips, dev_y)
+        step(*dev_inputs)
+    klog = _lib.timer_stop()
     launches_per_step = _lib.launch_count() // n_eager
-    gemm_stats = ops.GEMM_TIMER.collect()
-    ops.GEMM_TIMER.enable(False)
 
     # ---- the whole step (fwd, loss, bwd, all-reduce, Adam) captured once as a CUDA graph and replayed
     graphed = None
@@ -320,13 +684,13 @@ def run_ours(args):
     if not args.no_graph:
         try:
             from multimodal_deepfake_detection_b200.graph import GraphedTrainStep
-            graphed = GraphedTrainStep(step, (dev_clips, dev_y), modules=[model], warmup=1)
+            graphed = GraphedTrainStep(step, dev_inputs, modules=w["modules"], warmup=1, optimizers=w["optimizers"])
             mode = "cuda-graph"
         except Exception as e:      # report and fall back to eager launches (still the same kernels)
             sys.stderr.write("bench.py: CUDA-graph capture failed (%s: %s); timing eager launches\n" % (type(e).__name__, e))
             graphed = None
             torch.cuda.synchronize()
-    run = (lambda i: graphed.replay()) if graphed is not None else (lambda i: step(dev_clips, dev_y))
+    run = (lambda i: graphed.replay()) if graphed is not None else (lambda i: step(*dev_inputs))
     for i in range(W):
         run(i)
 
@@ -335,30 +699,30 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms = timed(run, args.steps)
-    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms * 1e-3)
+    units = w["units"]
+    value = world * units * args.steps / (ms * 1e-3)
 
     # ---- end to end: pinned host -> device every step (prefetched on a copy stream), loss read back every step
     from multimodal_deepfake_detection_b200.graph import HostPrefetcher
     pre = HostPrefetcher(dev)
     last = {}
-    slot = {"k": pre.submit(host_clips[0], host_y[0])}
+    slot = {"k": pre.submit(*host[0])}
 
     def e2e_step(i):
-        c, yy = pre.get(slot["k"])
+        inp = pre.get(slot["k"])
         if graphed is not None:
-            graphed.load_inputs(c, yy)
-            slot["k"] = pre.submit(host_clips[(i + 1) & 1], host_y[(i + 1) & 1])     # next batch's H2D overlaps this step
+            graphed.load_inputs(*inp)
+            slot["k"] = pre.submit(*host[(i + 1) & 1])     # next batch's H2D overlaps this step
             loss = graphed.replay()
         else:
-            slot["k"] = pre.submit(host_clips[(i + 1) & 1], host_y[(i + 1) & 1])
-            loss = step(c, yy)
+            slot["k"] = pre.submit(*host[(i + 1) & 1])
+            loss = step(*inp)
         last["loss"] = float(loss.item())
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    h2d = host_clips[0].numel() * 4 + host_y[0].numel() * 4
+    e2e_value = world * units * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
 
     def finish():
         # Leave without tearing the NCCL communicator down: destroy_process_group() can block on communicators that
@@ -370,117 +734,117 @@ def run_ours(args):
             torch.cuda.synchronize()
             os._exit(0)
 
-    # ---- inference (the "infer frames/sec" half of the metric): eval-mode forward of the same clips, BN folded from the
-    # running statistics, no saved activations (test_visual.py:609-624 protocol), device-resident inputs
-    model.eval()
-    def infer(i):
-        with torch.no_grad():
-            return model(model.extract_features(dev_clips, dev))
-    for i in range(3):
-        infer(i)
-    ms_inf = timed(infer, args.steps)
-    infer_fps = world * B * T_FRAMES * args.steps / (ms_inf * 1e-3)
-    # latency of ONE clip (the per-video loop of test_visual.py:609-624): eager launches vs one CUDA-graph replay (row f-3)
-    one_clip = None
-    if rank == 0:
-        from multimodal_deepfake_detection_b200.graph import GraphedInference
-        clip1 = dev_clips[:1].contiguous()
-        fwd1 = lambda c: model(model.extract_features(c, dev))  # noqa: E731
+    def lat(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
 
-        def lat(fn, n):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); e0.record()
-            for _ in range(n):
-                fn()
-            e1.record(); torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / n
-        with torch.no_grad():
-            for _ in range(3):
-                fwd1(clip1)
-            ms_eager1 = lat(lambda: fwd1(clip1), 10)
-        g1 = GraphedInference(fwd1, (clip1,), modules=[model])
-        g1(clip1)
-        one_clip = {"frames": T_FRAMES, "eager_ms": ms_eager1, "graph_ms": lat(lambda: g1(clip1), 20)}
-        del g1
-    model.train()
+    infer = frozen = None
+    if cfg == "c3":
+        model = w["model"]
+        dev_clips, dev_y = dev_inputs
+        # ---- inference (the "infer frames/sec" half of the metric): eval-mode forward of the same clips, BN folded from the
+        # running statistics, no saved activations (test_visual.py:609-624 protocol), device-resident inputs
+        model.eval()
 
-    # ---- the reference's FIRST training phase (train_visual.py:551-556, epochs < freeze_epochs): backbone frozen, BatchNorm
-    # still in train mode (:558), only the LSTM + head get gradients.  Reported beside the headline (SURVEY.md §8d asks for both
-    # modes); rank 0 only, eager launches, never allowed to disturb the line above.
-    frozen = None
-    if rank == 0:
-        try:
-            for p in model.feature_extractor.parameters():
-                p.requires_grad = False
-            head_params = [p for p in model.parameters() if p.requires_grad]
-            opt_f = FusedAdam(head_params, lr=1e-5, weight_decay=1e-4)
+        def infer_fn(i):
+            with torch.no_grad():
+                return model(model.extract_features(dev_clips, dev))
+        for i in range(3):
+            infer_fn(i)
+        ms_inf = timed(infer_fn, args.steps)
+        infer = {"value": world * B * T_FRAMES * args.steps / (ms_inf * 1e-3), "unit": "frames/s", "ms_per_pass": ms_inf / max(args.steps, 1),
+                 "what": "XceptionLSTMV eval-mode forward (BN folded, no_grad), %d clips x %d frames per GPU per pass" % (B, T_FRAMES)}
+        if rank == 0:
+            # latency of ONE clip (the per-video loop of test_visual.py:609-624): eager launches vs one CUDA-graph replay (row f-3)
+            from multimodal_deepfake_detection_b200.graph import GraphedInference
+            clip1 = dev_clips[:1].contiguous()
+            fwd1 = lambda c: model(model.extract_features(c, dev))  # noqa: E731
+            with torch.no_grad():
+                for _ in range(3):
+                    fwd1(clip1)
+                ms_eager1 = lat(lambda: fwd1(clip1), 10)
+            g1 = GraphedInference(fwd1, (clip1,), modules=[model])
+            g1(clip1)
+            infer["one_clip_latency"] = {"frames": T_FRAMES, "eager_ms": ms_eager1, "graph_ms": lat(lambda: g1(clip1), 20)}
+            del g1
+        model.train()
+        # ---- the reference's FIRST training phase (train_visual.py:551-556, epochs < freeze_epochs): backbone frozen, BatchNorm
+        # still in train mode (:558), only the LSTM + head get gradients.  Rank 0 only, eager, never allowed to disturb the line.
+        if rank == 0:
+            from multimodal_deepfake_detection_b200 import BCELoss, FusedAdam
+            try:
+                for p in model.feature_extractor.parameters():
+                    p.requires_grad = False
+                opt_f = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-5, weight_decay=1e-4)
+                crit = BCELoss()
 
-            def frozen_step():
-                opt_f.zero_grad(set_to_none=True)
-                loss = criterion(model(model.extract_features(dev_clips, dev)), dev_y)
-                loss.backward()
-                opt_f.step()
-            try:      # the graph capture above created AccumulateGrad nodes on its side stream; eager steps here only warn about it
-                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-            except AttributeError:
-                pass
-            for _ in range(3):
-                frozen_step()
-            ms_frozen = lat(frozen_step, max(args.steps, 3))
-            frozen = {"value": B / (ms_frozen * 1e-3), "unit": "clips/s", "ms_per_step": ms_frozen, "n_gpus": 1,
-                      "what": "same step with the backbone frozen (train-mode BN forward, LSTM + head trained), one GPU, eager"}
-        except Exception as e:       # noqa: BLE001 - an auxiliary number must not take the bench line down
-            frozen = {"error": "%s: %s" % (type(e).__name__, e)}
-        finally:
-            for p in model.feature_extractor.parameters():
-                p.requires_grad = True
+                def frozen_step():
+                    opt_f.zero_grad(set_to_none=True)
+                    crit(model(model.extract_features(dev_clips, dev)), dev_y).backward()
+                    opt_f.step()
+                try:      # the graph capture above created AccumulateGrad nodes on its side stream; eager steps here only warn about it
+                    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+                except AttributeError:
+                    pass
+                for _ in range(3):
+                    frozen_step()
+                ms_frozen = lat(frozen_step, max(args.steps, 3))
+                frozen = {"value": B / (ms_frozen * 1e-3), "unit": "clips/s", "ms_per_step": ms_frozen, "n_gpus": 1,
+                          "what": "same step with the backbone frozen (train-mode BN forward, LSTM + head trained), one GPU, eager"}
+            except Exception as e:       # noqa: BLE001 - an auxiliary number must not take the bench line down
+                frozen = {"error": "%s: %s" % (type(e).__name__, e)}
+            finally:
+                for p in model.feature_extractor.parameters():
+                    p.requires_grad = True
 
     if rank != 0:
         finish()
         return
     peaks = _peaks()
-    # ---- roofline of the dominant kernel family: the middle-flow pointwise GEMM (M = F*361, K = N = 728) forward
+    # ---- roofline: every kernel family of the step; the headline object is the family with the largest share of the step
+    kernels, eager_ms = kernel_rooflines(klog, ms / max(args.steps, 1), peaks, n_eager)
     roof = None
-    if gemm_stats:
-        key = max(gemm_stats, key=lambda k: gemm_stats[k]["flops"])
-        st = gemm_stats[key]
-        ach = st["flops"] / (st["ms"] * 1e-3) / 1e12
-        traffic = None                  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+    top = next((k for k in kernels if k.get("frac") is not None), None)
+    if top is not None:
+        traffic, tsrc = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))
-            if tj.get("shape") == key:
-                traffic = tj["traffic_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            ent = tj.get(cfg, {}).get(top["kernel"])
+            if ent is not None:
+                traffic, tsrc = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "gemm_kernel<256,EPI_BF16_STATS> (pointwise 1x1, %s)" % key, "achieved": ach,
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
-                "traffic": traffic, "algorithmic_bytes": st["flops"] / st["n"] / (2.0 * 768) * 2 * 2 if "K=768 N=768" in key else None,
-                "peak_source": peaks["_src"] + " (sustained: kernel timed inside a long step)",
-                "launches_timed": st["n"], "avg_launch_us": st["ms"] * 1e3 / st["n"]}
-    # ---- CPU baseline (bounded sample) on rank 0
-    cpu = None
-    if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        cps, spc = cpu_oracle_clips_per_s(2, 1, threads)
-        cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
-               "sample": "oracle fp32 port, 2 timed steps of 1 clip (16x3x299x299) fwd+bwd+Adam after 1 warm-up"}
+        roof = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                "frac": top["frac"], "traffic": traffic, "traffic_source": tsrc, "share_of_step": top["share_of_step"],
+                "peak_source": peaks["_src"] + (" (sustained bf16: kernels timed inside a long step)" if top["bound"] == "tensor" else " (copy bandwidth)"),
+                "how": "CUDA events around every C-ABI call of %d eager steps on the launching stream; algorithmic flops/bytes with logical "
+                       "channel counts (728, not the 768 pitch); frac = sum of per-call roofline times / measured time" % n_eager,
+                "eager_step_ms_sum_of_kernels": eager_ms, "kernels": kernels}
+    # ---- the same step through stock PyTorch / cuDNN on this GPU (SURVEY §8d honest competitor), N = 1, headline config only
+    stock = None
+    if cfg == "c3" and world == 1 and not args.no_torch_stock:
+        try:
+            graphed = None
+            torch.cuda.empty_cache()
+            stock = torch_stock_clips_per_s(B, 3, 3)
+        except Exception as e:       # noqa: BLE001
+            stock = {"error": "%s: %s" % (type(e).__name__, e)}
+    metric, unit = METRICS[cfg]
+    conf = {"workload": cfg + ": " + w["desc"], "global_batch": B * world, "parallelism": "dp%d" % world, "launch": mode,
+            "l2": "per-step working set (GBs of saved activations) >> 126 MB L2; fresh activations every launch"}
+    conf.update(w["shape"])
     line = {
-        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "XceptionLSTMV(128) train step, backbone unfrozen, train-mode BN, BCE, fused Adam(1e-5, wd 1e-4)",
-                   "clips_per_gpu": B, "global_batch": B * world, "frames_per_clip": T_FRAMES, "frame": "3x299x299",
-                   "parallelism": "dp%d" % world, "launch": mode, "l2": "per-step working set (~%.0f GB of activations) >> 126 MB L2" % (B * 16 * 0.117)},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+        "dtype": "bf16", "data": "synthetic", "config": conf, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / max(args.steps, 1)},
-        "gpu_launches": launches,
-        "infer": {"value": infer_fps, "unit": "frames/s", "ms_per_pass": ms_inf / max(args.steps, 1),
-                  "what": "XceptionLSTMV eval-mode forward (BN folded, no_grad), %d clips x %d frames per GPU per pass" % (B, T_FRAMES),
-                  "one_clip_latency": one_clip},
-        "frozen_backbone": frozen,
-        "roofline": roof,
-        "cpu_baseline": cpu,
+        "gpu_launches": launches_per_step * args.steps,
+        "infer": infer, "frozen_backbone": frozen, "roofline": roof, "cpu_baseline": cpu, "torch_stock": stock, "ddp_check": ddp,
         "loss": last.get("loss"),
     }
     print(json.dumps(line), flush=True)
@@ -492,9 +856,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--clips", type=int, default=16, help="clips per GPU per step")
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"], help="BASELINE.json configs[i-1]; c3 = the headline metric")
+    ap.add_argument("--clips", type=int, default=0, help="units (clips / frames) per GPU per step; 0 = the config's default")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-stock"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-stock", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager per-kernel launches instead of CUDA-graph replays")
     args = ap.parse_args()
     if args.impl == "torch-stock":

@@ -155,11 +155,13 @@ int xcp_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 /* multi-tensor form: `table` = n_tensors x {float* p; const float* g; float* m; float* v; long long n; int* step} in device
  * memory (each tensor's own device-side step counter is incremented by the call, so the launch is CUDA-graph capturable and
  * keeps torch.optim.Adam's per-parameter step semantics), `chunks` = n_chunks x {int tensor, int chunk} (8192-element chunks);
- * max_norm > 0 clips by the global norm first (sumsq_ws: device float scratch).  Replaces the per-tensor loop of
- * torch.optim.Adam.step / clip_grad_norm_ (train_visual.py:533,574-577; train_au_face.py:616-619,678-693). */
+ * max_norm > 0 clips by the global norm first (sumsq_ws: device float scratch).  hyper: optional DEVICE pointer to
+ * {lr, weight_decay} overriding the two host scalars, so that a captured CUDA graph follows the LR schedulers of
+ * train_visual.py:534,627 / train_au_face.py:620-623 (the host refreshes the two floats before a replay).  Replaces the
+ * per-tensor loop of torch.optim.Adam.step / clip_grad_norm_ (train_visual.py:533,574-577; train_au_face.py:616-619,678-693). */
 int xcp_adam_multi(const void* table, int n_tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, int decoupled, float* sumsq_ws, float max_norm, float grad_scale, int device,
-                   void* stream);
+                   float eps, float weight_decay, int decoupled, float* sumsq_ws, float max_norm, float grad_scale,
+                   const float* hyper, int device, void* stream);
 
 /* ---- fp32 validation path (forward only; north_star parity tolerance "fp32 logits within 1e-4 relative").  Plain fp32 FMA
  * kernels on NHWC fp32 activations that read the fp32 master parameters in torch's layouts; correctness instruments for the
@@ -181,6 +183,41 @@ int xcp_f32_gap(const float* x, float* out, int F, int HW, int C, int device, vo
 /* nn.LSTM(I,H,1,batch_first) recurrence, zero initial state; xproj = x . W_ih^T [B*T,4H] (xcp_f32_gemm), w_hh fp32 [4H,H] */
 int xcp_f32_lstm_fwd(const float* xproj, const float* b_ih, const float* b_hh, const float* w_hh, float* h_out, float* hn,
                      float* cn, int B, int T, int H, int device, void* stream);
+
+/* ---- fp32 validation path, backward + fused-signature forward twins (csrc/f32_bwd.cu).  Each function shadows the production
+ * entry point named beside it -- same arguments and fused semantics (producer-BN affine + ReLU prologue, pool / skip / add
+ * routing, BN-backward sums out of the depthwise backward, channel padding with c_real), fp32 NHWC activations instead of
+ * bf16 -- so executor.py drives both families through one code path and the chain rule that trains is checked against the
+ * fp32 oracle at <= 1e-4 per tensor (Xception.py:89-99,167-201 backward). */
+int xcp_f32_dw3x3_fused(const float* x, const float* w9, const float* scale, const float* shift, int relu, float* out, int F,
+                        int H, int W, int C, int device, void* stream);                           /* ~ xcp_dw3x3_fwd */
+int xcp_f32_pool_add_fused(const float* y, const float* scale, const float* shift, const float* ys, const float* scale_s,
+                           const float* shift_s, float* out, void* idx, int F, int H, int W, int C, int device,
+                           void* stream);                                                        /* ~ xcp_pool_add_fwd */
+int xcp_f32_bn_add(const float* y, const float* scale, const float* shift, const float* skip, const float* scale_s,
+                   const float* shift_s, float* out, long long n, int C, int device, void* stream); /* ~ xcp_bn_add_fwd */
+int xcp_f32_bn_relu_gap(const float* y, const float* scale, const float* shift, float* feat, int F, int HW, int C, int device,
+                        void* stream);                                                           /* ~ xcp_bn_relu_gap */
+/* ~ xcp_bn_bwd; sums_ws = fp32 [2][C] scratch (unused when presums given), coef = fp32 [3][C] */
+int xcp_f32_bn_bwd(int mode, const float* y, const float* G, const void* idx, const float* dfeat, const float* scale,
+                   const float* shift, const float* gamma, const float* mean, const float* rstd, int training,
+                   const float* presums, float* sums_ws, float* coef, float* dgamma, float* dbeta, float* dy, int F, int H, int W,
+                   int C, int c_real, int grid_w, int grid_h, int device, void* stream);
+int xcp_f32_dw3x3_bwd(const float* dD, const float* xin, const float* w9, const float* scale, const float* shift, int relu,
+                      float* dz, const float* add_full, const float* add_half, float* dw, float* bnsum, int F, int H, int W, int C,
+                      int c_real, int device, void* stream);                                     /* ~ xcp_dw3x3_bwd */
+int xcp_f32_gemm_wgrad(const float* dY, long long ld_dy, const float* X, long long ld_x, float* dW, long long ld_dw, long long R,
+                       int P, int Q, int device, void* stream);                                  /* ~ xcp_gemm_wgrad */
+/* stem conv backward (Xception.py:118,122): data gradient of the stride-1 conv2 (dy [F,H-2,W-2,Co] -> dx [F,H,W,Ci]) and the
+ * weight gradient dw[Co][Ci][3][3] += ... of conv1 (x fp32 NCHW, stride 2) / conv2 (x NHWC, stride 1) */
+int xcp_f32_conv3x3_dgrad(const float* dy, const float* w, float* dx, int F, int H, int W, int Ci, int Co, int device,
+                          void* stream);
+int xcp_f32_conv3x3_wgrad(const float* x, int x_nchw, const float* dy, float* dw, int F, int H, int W, int Ci, int Co, int stride,
+                          int device, void* stream);
+/* 3-way bf16 split of an fp32 matrix, 6-fold concatenated (side 0: h,h,m,h,m,l; side 1: h,m,h,l,m,h) along the columns
+ * (along_rows = 0: out bf16 [rows][6*cols]) or the rows (1: out [6*rows][cols]): feeding both split operands to xcp_gemm_tn
+ * (epi 2) / xcp_gemm_wgrad makes the production tcgen05 kernels compute an fp32-grade product (tests). */
+int xcp_split3_bf16(const float* x, void* out, long long rows, int cols, int side, int along_rows, int device, void* stream);
 
 /* ---- audio front-end: waveform -> MFCC on the device, replacing the offline
  * librosa.feature.mfcc(y, sr, n_mfcc=13, n_fft=int(0.025 sr), hop_length=int(0.010 sr)).T of wavfake_audio_dataset.py:17-19,40-44

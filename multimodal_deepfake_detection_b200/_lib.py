@@ -63,7 +63,7 @@ SIGNATURES = {
     "xcp_fusion_pool_bwd": "pppiiiip",
     "xcp_grad_sumsq": "plpiip",
     "xcp_adam_step": "pppplfffffiipffip",
-    "xcp_adam_multi": "pipifffffipffip",
+    "xcp_adam_multi": "pipifffffipffpip",
     "xcp_f32_conv3x3": "pippiiiiiiip",
     "xcp_f32_dw3x3": "pppiiiiip",
     "xcp_f32_gemm": "ppppliiip",
@@ -75,6 +75,16 @@ SIGNATURES = {
     "xcp_f32_gather": "ppiiiiiip",
     "xcp_f32_gap": "ppiiiip",
     "xcp_f32_lstm_fwd": "pppppppiiiip",
+    "xcp_f32_dw3x3_fused": "ppppipiiiiip",
+    "xcp_f32_pool_add_fused": "ppppppppiiiiip",
+    "xcp_f32_bn_add": "pppppppliip",
+    "xcp_f32_bn_relu_gap": "ppppiiiip",
+    "xcp_f32_bn_bwd": "ipppppppppippppppiiiiiiiip",
+    "xcp_f32_dw3x3_bwd": "pppppipppppiiiiiip",
+    "xcp_f32_gemm_wgrad": "plplplliiip",
+    "xcp_f32_conv3x3_dgrad": "pppiiiiiip",
+    "xcp_f32_conv3x3_wgrad": "pippiiiiiiip",
+    "xcp_split3_bf16": "ppliiiip",
     "xcp_mfcc_frames": "ii",
     "xcp_mfcc": "piipiiiiiffpppip",
 }
@@ -85,7 +95,7 @@ _NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; 0 = host-only query)
 _LAUNCHES = {"xcp_version": 0, "xcp_check_device": 0, "xcp_bnbwd_num_parts": 0, "xcp_gemm_stats_parts": 0,
              "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_f32_bn_stats_parts": 0, "xcp_mfcc_frames": 0, "xcp_mfcc": 2, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
-             "xcp_arcface_loss": 2, "xcp_adam_multi": 2}
+             "xcp_arcface_loss": 2, "xcp_adam_multi": 2, "xcp_f32_bn_bwd": 3, "xcp_f32_dw3x3_bwd": 2}
 _count = 0
 
 _lock = threading.Lock()
@@ -108,6 +118,32 @@ def add_launches(n: int):
 
 class XcpError(RuntimeError):
     pass
+
+
+# ---- optional per-call CUDA-event timing (bench.py's per-kernel roofline): every C-ABI call is bracketed by two events on the
+# launching (= torch current) stream and logged as (entry point, argument signature, events).  Integer / float arguments are
+# kept as they are (shapes, modes), pointer arguments become "non-NULL?" flags.  Off by default: one `is None` test per call.
+_timer = None
+
+
+def timer_start():
+    global _timer
+    _timer = []
+
+
+def timer_stop():
+    """-> {(name, signature): [total_ms, calls]} of the calls since timer_start() (synchronises the device)."""
+    global _timer
+    rec, _timer = _timer, None
+    if not rec:
+        return {}
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, sig, e0, e1 in rec:
+        d = out.setdefault((name, sig), [0.0, 0])
+        d[0] += e0.elapsed_time(e1); d[1] += 1
+    return out
 
 
 def load():
@@ -136,7 +172,15 @@ def load():
 def call(name: str, *args):
     global _count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _timer is not None and name not in _NO_STATUS:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        _timer.append((name, tuple(a if isinstance(a, (int, float)) else (getattr(a, "value", None) is not None) for a in args), e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     _count += _LAUNCHES.get(name, 1)
     if name in _NO_STATUS:
         return rc

@@ -76,7 +76,8 @@ sumsq_multi_kernel(const AdamTensor* __restrict__ tt, const int2* __restrict__ c
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const AdamTensor* __restrict__ tt, const int2* __restrict__ chunks, int n_chunks,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
-                  const float* __restrict__ sumsq, float max_norm, float grad_scale) {
+                  const float* __restrict__ sumsq, float max_norm, float grad_scale, const float* __restrict__ hyper) {
+    if (hyper != nullptr) { lr = hyper[0]; weight_decay = hyper[1]; }     // device-resident: a graph replay sees scheduler updates
     float clip = grad_scale;
     if (sumsq != nullptr) {
         const float norm = sqrtf(*sumsq) * grad_scale;
@@ -121,9 +122,11 @@ using namespace xcp;
 // table: n_tensors x {p, g, m, v, n, step*} (48 B each, device memory; every tensor's own int step counter is incremented here
 // first); chunks: n_chunks x {tensor index, chunk index} (8192 elements per chunk).  max_norm > 0: clip by the global gradient
 // norm (sumsq_ws = device float scratch).  3 launches (2 without clipping), no host synchronisation, graph-capturable.
+// hyper: optional DEVICE pointer to {lr, weight_decay}; when non-NULL it overrides the two host scalars, so a captured CUDA
+// graph does not bake the learning rate in (the host refreshes the two floats before a replay).
 extern "C" int xcp_adam_multi(const void* table, int n_tensors, const void* chunks, int n_chunks, float lr, float beta1, float beta2,
                               float eps, float weight_decay, int decoupled, float* sumsq_ws, float max_norm, float grad_scale,
-                              int device, void* stream) {
+                              const float* hyper, int device, void* stream) {
     XCP_REQUIRE(table != nullptr && chunks != nullptr && n_tensors > 0 && n_chunks > 0, "xcp_adam_multi: bad table");
     XCP_REQUIRE(max_norm <= 0.f || sumsq_ws != nullptr, "xcp_adam_multi: clipping needs the sumsq scratch");
     XCP_CUDA(cudaSetDevice(device));
@@ -133,7 +136,7 @@ extern "C" int xcp_adam_multi(const void* table, int n_tensors, const void* chun
     int grid = n_chunks < 8 * num_sms() ? n_chunks : 8 * num_sms();
     if (clipping) sumsq_multi_kernel<<<grid, 256, 0, st>>>((const AdamTensor*)table, (const int2*)chunks, n_chunks, sumsq_ws);
     adam_multi_kernel<<<grid, 256, 0, st>>>((const AdamTensor*)table, (const int2*)chunks, n_chunks, lr, beta1, beta2, eps,
-                                            weight_decay, decoupled, clipping ? sumsq_ws : nullptr, max_norm, grad_scale);
+                                            weight_decay, decoupled, clipping ? sumsq_ws : nullptr, max_norm, grad_scale, hyper);
     return check_cuda(cudaGetLastError(), "adam_multi launch");
 }
 

@@ -12,6 +12,15 @@ order (exit flow first = the order backward produces them); when the last parame
 an event is recorded on the compute stream and the bucket's slice of the arena is all-reduced on the
 communication stream.  The remaining (LSTM / head) gradients are reduced as one final bucket.  `finish()`
 makes the compute stream wait for the communication stream before the optimizer runs.
+
+The in-place reduction of the arena is only the parameters' gradient if autograd *stole* the arena views as ``p.grad``
+(``zero_grad(set_to_none=True)`` before every backward).  Two guards keep replicas from silently diverging otherwise:
+  * if any backbone ``p.grad`` already exists when backward starts (gradient accumulation as in train_au_face.py:676-693,
+    ``set_to_none=False``, retained grads), AccumulateGrad will ADD the arena views into the old tensors on the compute
+    stream, so the hooks launch nothing (an in-place reduction would race that add) and ``finish()`` reduces the
+    accumulated ``p.grad`` tensors themselves after backward (no overlap, but correct);
+  * otherwise ``finish()`` verifies that every backbone ``p.grad`` is a view of the reduced arena and, for one that is not
+    (autograd cloned instead of stealing), copies the averaged arena slice over it.
 """
 from __future__ import annotations
 
@@ -34,7 +43,11 @@ class GradBucketer:
         self._plan_key = None
         self._buckets: List[dict] = []
         self._param_bucket: Dict[int, int] = {}
-        self.launched: List[tuple] = []          # (lo, hi) ranges all-reduced, in launch order (for tests / logging)
+        self.launched: List[tuple] = []          # (lo, hi) ranges all-reduced during the current backward (tests / logging)
+        self.direct_reduced = 0                  # gradients finish() had to reduce outside the arena in the last step
+        self._last_sink = None
+        self._defer = False                      # this backward accumulates into existing p.grad: reduce in finish() instead
+        self._tail = {}                          # pre-allocated flat staging buffers (non-backbone / deferred gradients)
         if backbone is not None:
             backbone.__dict__["_grad_ready_hook"] = self._on_ready
 
@@ -87,6 +100,8 @@ class GradBucketer:
     # ------------------------------------------------------------------ hook called from GradSink.done()
     def _on_ready(self, sink, lo: int, hi: int):
         if lo < 0:                                           # flush at the end of the backbone's backward
+            if self._defer:
+                return
             for b in self._buckets:
                 if b["pending"] > 0:
                     b["pending"] = 0
@@ -94,6 +109,12 @@ class GradBucketer:
             return
         if self._plan_key is None or self._plan_key[1] != sink.total or all(b["pending"] == 0 for b in self._buckets):
             self._plan(sink)
+        if sink is not self._last_sink:                      # a new backward: the launch log describes one step
+            self._last_sink = sink
+            self.launched = []
+            self._defer = any(p.grad is not None for p in sink.params)
+        if self._defer:
+            return
         bi = self._param_bucket.get(lo)
         if bi is None:
             return
@@ -103,30 +124,77 @@ class GradBucketer:
             self._launch(sink.flat, b["lo"], b["hi"])
 
     # ------------------------------------------------------------------ after loss.backward()
+    def _tail_views(self, grads: List[torch.Tensor]):
+        """Flat staging buffer for a fixed list of gradients, allocated once per list signature."""
+        key = tuple((g.numel(), g.dtype, g.device) for g in grads)
+        ent = self._tail.get(key)
+        if ent is None:
+            n = sum(g.numel() for g in grads)
+            flat = torch.empty((n,), device=grads[0].device, dtype=grads[0].dtype)
+            views, off = [], 0
+            for g in grads:
+                views.append(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            ent = self._tail[key] = (flat, views)
+        return ent
+
+    def _reduce_flat(self, grads: List[torch.Tensor]):
+        """One all-reduce over `grads` through the staging buffer: multi-tensor copy in, collective, multi-tensor copy out,
+        all on the communication stream (the compute stream only records an event)."""
+        flat, views = self._tail_views(grads)
+        cuda = flat.is_cuda
+        if cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=flat.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(flat.device))
+            self._comm_stream.wait_event(ev)
+        ctx = torch.cuda.stream(self._comm_stream) if cuda else _Null()
+        with ctx:
+            torch._foreach_copy_(views, grads)
+            self.launched.append((0, flat.numel()))
+            self._all_reduce(flat)
+            torch._foreach_copy_(grads, views)
+
     def finish(self, extra_params: Optional[List[torch.nn.Parameter]] = None):
-        """All-reduce the gradients that did not go through the backbone arena (LSTM, head, ArcFace ...), then
-        join the communication stream."""
+        """All-reduce the gradients that did not go through the backbone arena (LSTM, head, ArcFace ...), verify that the
+        backbone gradients autograd installed ARE the averaged arena, then join the communication stream."""
         params = extra_params
+        bb_params = list(self.backbone.parameters()) if self.backbone is not None else []
         if params is None:
-            bb = {id(p) for p in self.backbone.parameters()} if self.backbone is not None else set()
+            bb = {id(p) for p in bb_params}
             params = [p for p in self.model.parameters() if id(p) not in bb]
         grads = [p.grad for p in params if p.grad is not None]
-        if grads and self.world > 1:
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            self._launch(flat, 0, flat.numel())
-            if flat.is_cuda:
-                with torch.cuda.stream(self._comm_stream):
-                    off = 0
-                    for g in grads:
-                        g.copy_(flat[off:off + g.numel()].view_as(g))
-                        off += g.numel()
-            else:
-                off = 0
-                for g in grads:
-                    g.copy_(flat[off:off + g.numel()].view_as(g))
-                    off += g.numel()
+        self.direct_reduced = 0
+        sink = self._last_sink
+        stray = []
+        if self.world > 1:
+            if self._defer:                                  # accumulated gradients: reduce p.grad itself, after backward
+                acc = [p.grad for p in bb_params if p.grad is not None]
+                self.direct_reduced = len(acc)
+                if acc:
+                    self._reduce_flat(acc)
+            elif sink is not None:
+                lo, hi = sink.flat.data_ptr(), sink.flat.data_ptr() + 4 * sink.flat.numel()
+                stray = [p for p in bb_params if p.grad is not None and id(p) in sink.offsets and not (lo <= p.grad.data_ptr() < hi)]
+            if grads:
+                self._reduce_flat(grads)
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
+        if stray:                                            # autograd cloned the arena view: install the averaged slice
+            self.direct_reduced = len(stray)
+            with torch.no_grad():
+                torch._foreach_copy_([p.grad for p in stray], [sink.view(p) for p in stray])
+        self._last_sink = None
+        self._defer = False
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def shard_clips(global_batch: int, rank: int, world: int) -> range:

@@ -135,6 +135,19 @@ class PackCache:
         """[N,K,1,1] fp32 -> (bf16 [Np,Kp], bf16 [Kp,Np]), zero-padded to the physical channel pitches (ops.phys)"""
         return self._get(w, "pw", lambda t: ops.pack_weight(t.view(t.shape[0], t.shape[1]), True, pad=True))
 
+    def pw32(self, w: torch.Tensor):
+        """fp32 validation plan: [N,K,1,1] fp32 -> (fp32 [Np,Kp], fp32 [Kp,Np]) zero-padded to the physical pitches (plain copies:
+        layout plumbing, no arithmetic)."""
+        def make(t):
+            N, K = t.shape[0], t.shape[1]
+            out = torch.zeros((ops.phys(N), ops.phys(K)), device=t.device, dtype=F32)
+            out[:N, :K] = t.view(N, K)
+            return out, out.t().contiguous()
+        return self._get(w, "pw32", make)
+
+    def pw_for(self, act: torch.Tensor, w: torch.Tensor):
+        return self.pw32(w) if act.dtype == F32 else self.pw(w)
+
     def dw(self, w: torch.Tensor):
         """[C,1,3,3] fp32 -> fp32 [9,Cp] (zero pad channels)"""
         return self._get(w, "dw", lambda t: ops.pack_dw(t, pad=True))
@@ -213,7 +226,7 @@ def sep_forward(cache: PackCache, spec: SepSpec, src: torch.Tensor, src_st, relu
     """src: bf16 NHWC [F,H,W,phys(Cin)]; src_st: pending BN state of the producer (or None if src is materialised)."""
     F_, H, W, C = src.shape
     w9 = cache.dw(spec.sep.conv1.weight)
-    wb, _ = cache.pw(spec.sep.pointwise.weight)
+    wb, _ = cache.pw_for(src, spec.sep.pointwise.weight)
     d = ops.dw3x3_fwd(src, w9, src_st.scale if src_st is not None else None, src_st.shift if src_st is not None else None, relu)
     M = F_ * H * W
     t = SepTape()
@@ -248,7 +261,7 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
     bt.xs = bt.ys = bt.st_s = bt.idx = None
     F_, H, W, _ = inp.shape
     if spec.skip is not None:
-        wb, _ = cache.pw(spec.skip.weight)
+        wb, _ = cache.pw_for(inp, spec.skip.weight)
         if spec.stride == 2:
             xs = ops.gather_s2(inp)
         elif spec.stride == 1:
@@ -286,7 +299,7 @@ def _pw_backward(cache: PackCache, sink: GradSink, weight: torch.Tensor, dy: tor
     sink.done(weight)
     if not need_dgrad:
         return None
-    _, wt = cache.pw(weight)
+    _, wt = cache.pw_for(dy, weight)
     da, _ = ops.gemm_tn(dy.view(M, Np), wt, ops.EPI_BF16)
     return da.view(*a.shape)
 
@@ -365,27 +378,31 @@ def xception_forward(net, x: torch.Tensor, save: bool = True):
     """net: Models.Xception.Xception (ours).  x: fp32 NCHW [F,3,H,W] in [0,1] or raw uint8 NHWC frames [F,H,W,3] on a B200.
     Returns (feat fp32 [F,2048], tape)."""
     cache: PackCache = net._pack_cache
-    items = []
-    for spec in net._block_specs:
-        for u in spec.units:
+    fp32 = net.precision == "fp32"          # validation arithmetic: same plan, fp32 activations and kernels (ops.py dispatch)
+    if not fp32:
+        items = []
+        for spec in net._block_specs:
+            for u in spec.units:
+                items += [(u.sep.conv1.weight, "dw"), (u.sep.pointwise.weight, "pw")]
+            if spec.skip is not None:
+                items.append((spec.skip.weight, "pw"))
+        for u in net._exit_specs:
             items += [(u.sep.conv1.weight, "dw"), (u.sep.pointwise.weight, "pw")]
-        if spec.skip is not None:
-            items.append((spec.skip.weight, "pw"))
-    for u in net._exit_specs:
-        items += [(u.sep.conv1.weight, "dw"), (u.sep.pointwise.weight, "pw")]
-    cache.prefetch(items)                                                     # one launch for every stale weight pack
+        cache.prefetch(items)                                                 # one launch for every stale weight pack
+    elif x.dtype == torch.uint8:            # raw NHWC frames -> the reference's [0,1] NCHW tensor (video_dataloader.py:35)
+        x = x.permute(0, 3, 1, 2).to(F32).div_(255.0)
     nbt: list = []
     tp = XceptionTape()
     F_ = x.shape[0]
     x = x.contiguous()
     tp.x = x
     # stem: conv1 -> bn1 -> relu -> conv2 -> bn2 -> relu                      (Xception.py:168-174)
-    y1, parts1 = ops.stem_conv1_fwd(x, net.conv1.weight.detach())
+    y1, parts1 = ops.stem_conv1_fwd(x, net.conv1.weight.detach(), F32 if fp32 else BF16)
     st1 = _bn_state(net.bn1, parts1, y1.numel() // 32)
     if _bn_needs_stats(net.bn1):
         nbt.append(net.bn1.num_batches_tracked)
     x1 = ops.bn_act(y1, st1.scale, st1.shift, True)
-    wk, _ = cache.conv3x3(net.conv2.weight)
+    wk = net.conv2.weight.detach() if fp32 else cache.conv3x3(net.conv2.weight)[0]
     need2 = _bn_needs_stats(net.bn2)
     y2, parts2 = ops.conv3x3_gemm_fwd(x1, wk, want_stats=need2)
     st2 = _bn_state(net.bn2, parts2, y2.numel() // 64)
@@ -421,14 +438,21 @@ def xception_backward(net, tp: XceptionTape, dfeat: torch.Tensor, sink: GradSink
     # stem.  G = dL/dx2 with x2 = relu(bn2(y2)); dy2 is written on the zero-padded conv2 input grid
     F_, H1, W1, _ = tp.y1.shape
     dg, db = _bn_param_grads(sink, net.bn2)
-    dy2g = ops.bn_bwd(ops.SRC_RELU, tp.y2, tp.st2, net.bn2.weight.detach(), dg, db, G=G, grid_hw=(H1, W1))
-    sink.done(net.bn2.weight); sink.done(net.bn2.bias)
-    gk = torch.zeros((64, 9 * 32), device=G.device, dtype=F32)
-    ops.conv3x3_wgrad(dy2g, tp.x1, gk)
-    ops.unpack_conv3x3_grad(gk, sink.view(net.conv2.weight))
-    sink.done(net.conv2.weight)
-    _, wk_t = cache.conv3x3(net.conv2.weight)
-    dx1 = ops.conv3x3_gemm_dgrad(dy2g, wk_t)
+    if tp.y2.dtype == F32:                  # fp32 validation plan: plain gradient layout, weights in torch's layout
+        dy2 = ops.bn_bwd(ops.SRC_RELU, tp.y2, tp.st2, net.bn2.weight.detach(), dg, db, G=G)
+        sink.done(net.bn2.weight); sink.done(net.bn2.bias)
+        ops.conv3x3_wgrad_f32(tp.x1, False, dy2, sink.view(net.conv2.weight), 1)
+        sink.done(net.conv2.weight)
+        dx1 = ops.conv3x3_gemm_dgrad(dy2, net.conv2.weight.detach())
+    else:
+        dy2g = ops.bn_bwd(ops.SRC_RELU, tp.y2, tp.st2, net.bn2.weight.detach(), dg, db, G=G, grid_hw=(H1, W1))
+        sink.done(net.bn2.weight); sink.done(net.bn2.bias)
+        gk = torch.zeros((64, 9 * 32), device=G.device, dtype=F32)
+        ops.conv3x3_wgrad(dy2g, tp.x1, gk)
+        ops.unpack_conv3x3_grad(gk, sink.view(net.conv2.weight))
+        sink.done(net.conv2.weight)
+        _, wk_t = cache.conv3x3(net.conv2.weight)
+        dx1 = ops.conv3x3_gemm_dgrad(dy2g, wk_t)
     dg, db = _bn_param_grads(sink, net.bn1)
     dy1 = ops.bn_bwd(ops.SRC_RELU, tp.y1, tp.st1, net.bn1.weight.detach(), dg, db, G=dx1)
     sink.done(net.bn1.weight); sink.done(net.bn1.bias)

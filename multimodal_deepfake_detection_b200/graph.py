@@ -9,7 +9,8 @@ a kernel of libxcp_sm100.so (plus torch's optimizer / NCCL nodes); nothing is tr
 
 Rules for a capturable `step_fn(*static_inputs) -> loss`:
   * no host synchronisation inside (no .item(), no .cpu(), no print of device values);
-  * the optimizer must be capturable (torch.optim.Adam(..., capturable=True)) or this package's fused optimizer;
+  * the optimizer must be capturable (torch.optim.Adam(..., capturable=True)) or this package's fused optimizer; pass
+    FusedAdam instances as ``optimizers=[...]`` so that replays follow LR-scheduler updates (lr lives in device memory);
   * shapes are static: one GraphedTrainStep per (batch, frames, H, W).
 """
 from __future__ import annotations
@@ -41,10 +42,13 @@ class GraphedTrainStep:
 
     def __init__(self, step_fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor],
                  modules: Sequence[torch.nn.Module] = (), warmup: int = 3, zero_grads: Optional[Callable[[], None]] = None,
-                 capture_error_mode: str = "thread_local"):
+                 capture_error_mode: str = "thread_local", optimizers: Sequence[object] = ()):
         if not example_inputs or not all(t.is_cuda for t in example_inputs):
             raise XcpError("GraphedTrainStep: example inputs must be CUDA tensors (no CPU path)")
         self.modules = list(modules)
+        # optimizers whose lr / weight_decay live in device memory (optim.FusedAdam): their pinned hyper-parameter buffers are
+        # refreshed before every replay, so LR schedulers (train_visual.py:534,627; train_au_face.py:620-623) keep working
+        self.optimizers = [o for o in optimizers if hasattr(o, "refresh_hyper")]
         self.static_inputs = [t.clone() for t in example_inputs]
         self._step_fn = step_fn
         dev = self.static_inputs[0].device
@@ -74,6 +78,8 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
 
     def replay(self) -> torch.Tensor:
+        for o in self.optimizers:
+            o.refresh_hyper()
         self.graph.replay()
         self.replays += 1
         _bump_pack_caches(self.modules)

@@ -51,26 +51,55 @@ def _cache_of(mod: nn.Module) -> ex.PackCache:
     return c
 
 
+def _precision_of(mod: nn.Module) -> str:
+    return mod.__dict__.get("_precision") or os.environ.get("XCP_PRECISION", "bf16")
+
+
+def _set_precision(mod: nn.Module, precision: str):
+    if precision not in ("bf16", "fp32"):
+        raise XcpError("%s.set_precision: 'bf16' or 'fp32', got %r" % (type(mod).__name__, precision))
+    mod.__dict__["_precision"] = precision
+    return mod
+
+
+def _to_nhwc(x: torch.Tensor, fp32: bool) -> torch.Tensor:
+    """NCHW fp32 -> NHWC with the physical channel pitch: bf16 through the layout kernel, or (fp32 validation plan) a plain
+    fp32 copy (data movement only)."""
+    x = x.float().contiguous()
+    if not fp32:
+        return ops.nchw_to_nhwc(x, pad=True)
+    F_, C, H, W = x.shape
+    out = torch.zeros((F_, H, W, ops.phys(C)), device=x.device, dtype=torch.float32)
+    out[..., :C] = x.permute(0, 2, 3, 1)
+    return out
+
+
+def _to_nchw(x: torch.Tensor, C: int) -> torch.Tensor:
+    if x.dtype == torch.float32:
+        return x[..., :C].permute(0, 3, 1, 2).contiguous()
+    return ops.nhwc_to_nchw(x, C)
+
+
 # ================================================================================================ SeparableConv2d
 class _SepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, w_dw, w_pw):
         cache = _cache_of(mod)
-        xin = ops.nchw_to_nhwc(x.float().contiguous(), pad=True)
+        xin = _to_nhwc(x, _precision_of(mod) == "fp32")
         spec = ex.SepSpec(mod, None, w_dw.shape[0], w_pw.shape[0], False)
         t = ex.sep_forward(cache, spec, xin, None, False, [])
         ctx.mod, ctx.tape = mod, t
-        return ops.nhwc_to_nchw(t.y, w_pw.shape[0])
+        return _to_nchw(t.y, w_pw.shape[0])
 
     @staticmethod
     def backward(ctx, dout):
         mod, t = ctx.mod, ctx.tape
         cache = _cache_of(mod)
         sink = ex.GradSink([mod.conv1.weight, mod.pointwise.weight], dout.device)
-        dy = ops.nchw_to_nhwc(dout.float().contiguous(), pad=True)
+        dy = _to_nhwc(dout, t.y.dtype == torch.float32)
         dd = ex._pw_backward(cache, sink, mod.pointwise.weight, dy, t.d)
         dz, _ = ex._dw_backward(cache, sink, t, dd)
-        dx = ops.nhwc_to_nchw(dz, mod.conv1.weight.shape[0]) if ctx.needs_input_grad[1] else None
+        dx = _to_nchw(dz, mod.conv1.weight.shape[0]) if ctx.needs_input_grad[1] else None
         return None, dx, sink.view(mod.conv1.weight), sink.view(mod.pointwise.weight)
 
 
@@ -81,6 +110,9 @@ class SeparableConv2d(nn.Module):
         super().__init__()
         self.conv1 = nn.Conv2d(in_channels, in_channels, kernel_size, stride, padding, dilation, groups=in_channels, bias=bias)
         self.pointwise = nn.Conv2d(in_channels, out_channels, 1, 1, 0, 1, 1, bias=bias)
+
+    def set_precision(self, precision: str):
+        return _set_precision(self, precision)
 
     def _check_supported(self):
         c = self.conv1
@@ -101,21 +133,21 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, *params):
         cache = _cache_of(mod)
-        inp = ops.nchw_to_nhwc(x.float().contiguous(), pad=True)
+        inp = _to_nhwc(x, _precision_of(mod) == "fp32")
         nbt: list = []
         bt = ex.block_forward(cache, mod._spec(), inp, nbt, save=True)
         ex._bump_nbt(nbt)
         ctx.mod, ctx.tape, ctx.nparams = mod, bt, len(params)
-        return ops.nhwc_to_nchw(bt.out, mod._out)
+        return _to_nchw(bt.out, mod._out)
 
     @staticmethod
     def backward(ctx, dout):
         mod, bt = ctx.mod, ctx.tape
         params = list(mod.parameters())
         sink = ex.GradSink(params, dout.device)
-        G = ops.nchw_to_nhwc(dout.float().contiguous(), pad=True)
+        G = _to_nhwc(dout, bt.out.dtype == torch.float32)
         gin = ex.block_backward(_cache_of(mod), sink, bt, G)
-        dx = ops.nhwc_to_nchw(gin, mod._in) if ctx.needs_input_grad[1] else None
+        dx = _to_nchw(gin, mod._in) if ctx.needs_input_grad[1] else None
         return (None, dx) + tuple(sink.view(p) for p in params)
 
 
@@ -147,6 +179,9 @@ class Block(nn.Module):
             rep.append(nn.MaxPool2d(3, strides, 1))
         self.rep = nn.Sequential(*rep)
         self._in, self._out, self._strides = in_filters, out_filters, strides
+
+    def set_precision(self, precision: str):
+        return _set_precision(self, precision)
 
     def _spec(self) -> ex.BlockSpec:
         units = []
@@ -290,26 +325,18 @@ class Xception(nn.Module):
         fc_ids = {id(p) for p in self.fc.parameters()} if isinstance(self.fc, nn.Module) else set()
         return [p for p in self.parameters() if id(p) not in fc_ids]
 
-    # ---- arithmetic: "bf16" = the tcgen05 production plan; "fp32" = the forward-only validation plan (fp32_plan.py)
+    # ---- arithmetic: "bf16" = the tcgen05 production plan; "fp32" = the validation arithmetic: the SAME plan (executor.py,
+    # forward and backward) on fp32 activations through the fp32 kernels of csrc/f32.cu + csrc/f32_bwd.cu
     def set_precision(self, precision: str):
-        if precision not in ("bf16", "fp32"):
-            raise XcpError("Xception.set_precision: 'bf16' or 'fp32', got %r" % (precision,))
-        self.__dict__["_precision"] = precision
-        return self
+        return _set_precision(self, precision)
 
     @property
     def precision(self) -> str:
-        return self.__dict__.get("_precision") or os.environ.get("XCP_PRECISION", "bf16")
+        return _precision_of(self)
 
     def features(self, x):
         """conv1 ... bn4/relu/GAP of Xception.forward (Xception.py:168-198): [F,3,H,W] -> [F,2048]."""
         _require_cuda(x, "Xception")
-        if self.precision == "fp32":
-            if torch.is_grad_enabled() and any(p.requires_grad for p in self._backbone_params()):
-                raise XcpError("Xception: the fp32 validation plan is forward-only -- call it under torch.no_grad() "
-                               "(training runs on the bf16 plan: set_precision('bf16'))")
-            from . import fp32_plan
-            return fp32_plan.xception_features(self, x)
         if x.dtype == torch.uint8:                     # raw frames, NHWC [F,H,W,3]: scaled by 1/255 inside the stem kernel
             if x.dim() != 4 or x.shape[3] != 3:
                 raise XcpError("Xception: uint8 frames must be NHWC [F,H,W,3], got %s" % (tuple(x.shape),))
@@ -329,12 +356,18 @@ def xception(pretrained=False, **kwargs):
     environment has no network, so a missing cache entry keeps the seeded random init and warns."""
     model = Xception(**kwargs)
     if pretrained:
-        try:
-            sd = torch.hub.load_state_dict_from_url(model_urls["xception"], progress=False, check_hash=False)
-            model.load_state_dict(sd)
-        except Exception as e:  # URLError offline, or a malformed cache entry
-            warnings.warn("xception(pretrained=True): pretrained weights unavailable (%s: %s); keeping the random "
-                          "initialisation" % (type(e).__name__, e))
+        # cache-only: never open a socket (the reference's model_zoo.load_url would; a box with DNS would then silently
+        # swap the seeded weights for the ImageNet checkpoint and change every seeded test / bench number)
+        path = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(model_urls["xception"]))
+        if os.path.isfile(path):
+            try:
+                model.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
+            except Exception as e:  # a malformed cache entry
+                warnings.warn("xception(pretrained=True): cannot load %s (%s: %s); keeping the random initialisation"
+                              % (path, type(e).__name__, e))
+        else:
+            warnings.warn("xception(pretrained=True): no cached checkpoint at %s (this implementation never downloads); "
+                          "keeping the random initialisation" % path)
     return model
 
 

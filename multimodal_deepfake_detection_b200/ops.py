@@ -1,6 +1,10 @@
 """Thin tensor-level wrappers over the C ABI (include/xcp.h).  PyTorch is used only for device memory
 (the caching allocator owns every buffer) and for the current stream; all arithmetic happens in
-libxcp_sm100.so.  Activations are bf16 NHWC tensors of shape [F, H, W, C]."""
+libxcp_sm100.so.  Activations are bf16 NHWC tensors of shape [F, H, W, C].
+
+Every activation-level wrapper also accepts fp32 NHWC activations and then calls the fp32 validation kernel with the same
+fused signature (csrc/f32.cu, csrc/f32_bwd.cu): executor.py walks ONE plan for both arithmetics, so the chain rule that
+trains in bf16 is the one checked against the fp32 oracle at 1e-4 (Xception.set_precision("fp32"))."""
 from __future__ import annotations
 
 import ctypes
@@ -24,34 +28,6 @@ def phys(C: int) -> int:
     multiple of 64 (728 -> 768) so that every pixel row is whole 128-byte lines (TMA boxes, 16-byte vectors); the
     pad channels are kept exactly zero (include/xcp.h, "Channel padding")."""
     return C if C <= 64 else (C + 63) // 64 * 64
-
-
-class _GemmTimer:
-    """Optional CUDA-event timing of every pointwise-GEMM launch (bench.py roofline): events are recorded on the
-    launching stream right around the kernel, aggregated per problem shape."""
-
-    def __init__(self):
-        self.on = False
-        self.rec = []
-
-    def enable(self, on: bool):
-        self.on = bool(on)
-        if on:
-            self.rec = []
-
-    def collect(self):
-        if not self.rec:
-            return {}
-        torch.cuda.synchronize()
-        out = {}
-        for key, flops, e0, e1 in self.rec:
-            d = out.setdefault(key, {"ms": 0.0, "flops": 0.0, "n": 0})
-            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
-        self.rec = []
-        return out
-
-
-GEMM_TIMER = _GemmTimer()
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -80,6 +56,8 @@ def check_device(device: torch.device):
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optional[torch.Tensor] = None,
             out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """out[M,N] = a[M,K] @ b[N,K]^T.  Returns (out, stats_partials or None)."""
+    if a.dtype == F32:
+        return _gemm_tn_f32(a, b, epi)
     _chk(a, BF16, "gemm_tn.a"); _chk(b, BF16, "gemm_tn.b")
     M, K = a.shape
     N = b.shape[0]
@@ -89,25 +67,59 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optiona
     stats = None
     if epi == EPI_BF16_STATS:
         stats = torch.empty((_lib.call("xcp_gemm_stats_parts", M, N, a.device.index), 2, N), device=a.device, dtype=F32)
-    if GEMM_TIMER.on and epi == EPI_BF16_STATS:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), a.device.index, _s())
-        e1.record()
-        GEMM_TIMER.rec.append(("M=%d K=%d N=%d" % (M, K, N), 2.0 * M * N * K, e0, e1))
-        return out, stats
     _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), a.device.index, _s())
     return out, stats
 
 
+def _f32_bn_stats(y2d: torch.Tensor) -> torch.Tensor:
+    """Per-channel (sum, sum-sq) partials of an fp32 [M,C] matrix in the layout xcp_bn_finalize reads."""
+    M, C = y2d.shape
+    parts = torch.empty((_lib.call("xcp_f32_bn_stats_parts", M), 2, C), device=y2d.device, dtype=F32)
+    _lib.call("xcp_f32_bn_stats", _p(y2d), _p(parts), M, C, y2d.device.index, _s())
+    return parts
+
+
+# fp32 validation GEMMs: "ffma" = plain fp32 FMA kernels (default); "split3" = the PRODUCTION tcgen05 kernels fed 3-way bf16
+# splits of both fp32 operands (6-fold concatenation along the reduction dimension; csrc/f32_bwd.cu split3_kernel)
+FP32_GEMM = [__import__("os").environ.get("XCP_FP32_GEMM", "ffma")]
+
+
+def split3(x2d: torch.Tensor, side: int, along_rows: bool) -> torch.Tensor:
+    _chk(x2d, F32, "split3.x")
+    R, Cc = x2d.shape
+    out = torch.empty((6 * R, Cc) if along_rows else (R, 6 * Cc), device=x2d.device, dtype=BF16)
+    _lib.call("xcp_split3_bf16", _p(x2d), _p(out), R, Cc, side, int(along_rows), x2d.device.index, _s())
+    return out
+
+
+def _gemm_tn_f32(a: torch.Tensor, b: torch.Tensor, epi: int):
+    _chk(a, F32, "gemm_tn.a"); _chk(b, F32, "gemm_tn.b (fp32 plan: fp32 weights [N,K])")
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K
+    if FP32_GEMM[0] == "split3":
+        out, _ = gemm_tn(split3(a, 0, False), split3(b, 1, False), EPI_F32)
+    else:
+        out = torch.empty((M, N), device=a.device, dtype=F32)
+        _lib.call("xcp_f32_gemm", _p(a), _p(b), _p(None), _p(out), M, N, K, a.device.index, _s())
+    return out, (_f32_bn_stats(out) if epi == EPI_BF16_STATS else None)
+
+
 def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, ld_dw: Optional[int] = None):
     """dw[P,Q] += dy[R,P]^T @ x[R,Q]  (dw fp32, accumulated in place)."""
-    _chk(dy, BF16, "gemm_wgrad.dy"); _chk(x, BF16, "gemm_wgrad.x")
     assert dw.dtype == F32
     R = dy.shape[0]
     assert x.shape[0] == R
     P, Q = (dw.shape[0], dw.shape[1]) if dw.dim() == 2 else (dy.shape[1], x.shape[1])   # logical (the operands may be channel-padded)
     assert P <= dy.shape[1] and Q <= x.shape[1]
+    if dy.dtype == F32:
+        _chk(dy, F32, "gemm_wgrad.dy"); _chk(x, F32, "gemm_wgrad.x")
+        if FP32_GEMM[0] == "split3":
+            return gemm_wgrad(split3(dy, 0, True), split3(x, 1, True), dw, ld_dw)
+        _lib.call("xcp_f32_gemm_wgrad", _p(dy), dy.shape[1], _p(x), x.shape[1], _p(dw), ld_dw if ld_dw is not None else Q, R, P, Q,
+                  dy.device.index, _s())
+        return
+    _chk(dy, BF16, "gemm_wgrad.dy"); _chk(x, BF16, "gemm_wgrad.x")
     _lib.call("xcp_gemm_wgrad", _p(dy), dy.shape[1], _p(x), x.shape[1], _p(dw), ld_dw if ld_dw is not None else Q, R, P, Q,
               dy.device.index, _s())
 
@@ -125,7 +137,15 @@ def gemm_ref(a, b, mn_major=False):
 
 
 def conv3x3_gemm_fwd(x: torch.Tensor, wk: torch.Tensor, want_stats: bool = True):
-    """Dense 3x3 s1 p0 conv of NHWC x [F,Hg,Wg,Cin] with packed weights wk [Cout, 9*Cin]."""
+    """Dense 3x3 s1 p0 conv of NHWC x [F,Hg,Wg,Cin] with packed weights wk [Cout, 9*Cin] (fp32 plan: the raw fp32
+    [Cout,Cin,3,3] weight)."""
+    if x.dtype == F32:
+        _chk(x, F32, "conv3x3.x"); _chk(wk, F32, "conv3x3.w")
+        F_, Hg, Wg, Cin = x.shape
+        Cout = wk.shape[0]
+        out = torch.empty((F_, Hg - 2, Wg - 2, Cout), device=x.device, dtype=F32)
+        _lib.call("xcp_f32_conv3x3", _p(x), 0, _p(wk), _p(out), F_, Hg, Wg, Cin, Cout, 1, x.device.index, _s())
+        return out, (_f32_bn_stats(out.view(-1, Cout)) if want_stats else None)
     _chk(x, BF16, "conv3x3.x"); _chk(wk, BF16, "conv3x3.wk")
     F_, Hg, Wg, Cin = x.shape
     Cout = wk.shape[0]
@@ -139,7 +159,15 @@ def conv3x3_gemm_fwd(x: torch.Tensor, wk: torch.Tensor, want_stats: bool = True)
 
 
 def conv3x3_gemm_dgrad(dy_grid: torch.Tensor, wk_t: torch.Tensor):
-    """dy_grid [F,Hg,Wg,Cout] (zero outside the valid window) -> dx [F,Hg,Wg,Cin]; wk_t [Cin, 9*Cout]."""
+    """dy_grid [F,Hg,Wg,Cout] (zero outside the valid window) -> dx [F,Hg,Wg,Cin]; wk_t [Cin, 9*Cout].
+    fp32 plan: dy_grid is the plain gradient [F,Hg-2,Wg-2,Cout] and wk_t the raw fp32 [Cout,Cin,3,3] weight."""
+    if dy_grid.dtype == F32:
+        _chk(dy_grid, F32, "conv3x3_dgrad.dy"); _chk(wk_t, F32, "conv3x3_dgrad.w")
+        F_, Ho, Wo, Cout = dy_grid.shape
+        Cin = wk_t.shape[1]
+        out = torch.empty((F_, Ho + 2, Wo + 2, Cin), device=dy_grid.device, dtype=F32)
+        _lib.call("xcp_f32_conv3x3_dgrad", _p(dy_grid), _p(wk_t), _p(out), F_, Ho + 2, Wo + 2, Cin, Cout, dy_grid.device.index, _s())
+        return out
     F_, Hg, Wg, Cout = dy_grid.shape
     Cin = wk_t.shape[0]
     out = torch.empty((F_, Hg, Wg, Cin), device=dy_grid.device, dtype=BF16)
@@ -158,6 +186,16 @@ def conv3x3_wgrad(dy_grid: torch.Tensor, x: torch.Tensor, gk: torch.Tensor):
     _lib.call("xcp_conv3x3_wgrad", _p(dy_grid), _p(x), _p(gk), F_, Hg, Wg, Cin, Cout, x.device.index, _s())
 
 
+def conv3x3_wgrad_f32(x: torch.Tensor, x_nchw: bool, dy: torch.Tensor, dw: torch.Tensor, stride: int):
+    """fp32 plan: dw[Cout,Cin,3,3] += weight gradient of a dense 3x3 p0 conv (conv1: x fp32 NCHW, stride 2; conv2: NHWC, 1)."""
+    _chk(x, F32, "conv3x3_wgrad_f32.x"); _chk(dy, F32, "conv3x3_wgrad_f32.dy")
+    if x_nchw:
+        F_, Ci, H, W = x.shape
+    else:
+        F_, H, W, Ci = x.shape
+    _lib.call("xcp_f32_conv3x3_wgrad", _p(x), int(x_nchw), _p(dy), _p(dw), F_, H, W, Ci, dy.shape[3], stride, x.device.index, _s())
+
+
 # ------------------------------------------------------------------------------------------------ stem / dw
 def _stem_input(x: torch.Tensor, who: str):
     """-> (is_u8, F, H, W).  fp32 NCHW [F,3,H,W] (the reference's tensor) or uint8 NHWC [F,H,W,3] (raw frames, scaled by
@@ -173,10 +211,16 @@ def _stem_input(x: torch.Tensor, who: str):
     return False, x.shape[0], x.shape[2], x.shape[3]
 
 
-def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor):
+def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor, act_dtype=BF16):
     _chk(w, F32, "stem_conv1.w")
     u8, F_, H, W = _stem_input(x, "stem_conv1.x")
     H1, W1 = (H - 3) // 2 + 1, (W - 3) // 2 + 1
+    if act_dtype == F32:                    # fp32 plan (x already the reference's fp32 NCHW tensor)
+        if u8:
+            raise _lib.XcpError("stem_conv1 (fp32 plan): convert uint8 frames to the fp32 NCHW tensor first")
+        y = torch.empty((F_, H1, W1, 32), device=x.device, dtype=F32)
+        _lib.call("xcp_f32_conv3x3", _p(x), 1, _p(w), _p(y), F_, H, W, 3, 32, 2, x.device.index, _s())
+        return y, _f32_bn_stats(y.view(-1, 32))
     y = torch.empty((F_, H1, W1, 32), device=x.device, dtype=BF16)
     parts = torch.empty((_lib.call("xcp_stem_conv1_parts", F_, H, W, x.device.index), 2, 32), device=x.device, dtype=F32)
     _lib.call("xcp_stem_conv1_fwd", _p(x), int(u8), _p(w), _p(y), _p(parts), F_, H, W, x.device.index, _s())
@@ -185,26 +229,38 @@ def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor):
 
 def stem_conv1_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
     u8, F_, H, W = _stem_input(x, "stem_conv1_wgrad.x")
+    if dy.dtype == F32:
+        return conv3x3_wgrad_f32(x, True, dy, dw, 2)
     ws = torch.empty((_lib.call("xcp_stem_conv1_wgrad_ws_bytes", F_, H, W),), device=x.device, dtype=torch.uint8)
     _lib.call("xcp_stem_conv1_wgrad", _p(x), int(u8), _p(dy), _p(dw), _p(ws), F_, H, W, x.device.index, _s())
 
 
 def dw3x3_fwd(x: torch.Tensor, w9: torch.Tensor, scale=None, shift=None, relu: bool = False, out=None):
-    _chk(x, BF16, "dw3x3.x"); _chk(w9, F32, "dw3x3.w9")
+    _chk(w9, F32, "dw3x3.w9")
     F_, H, W, C = x.shape
     if out is None:
         out = torch.empty_like(x)
+    if x.dtype == F32:
+        _chk(x, F32, "dw3x3.x")
+        _lib.call("xcp_f32_dw3x3_fused", _p(x), _p(w9), _p(scale), _p(shift), int(relu), _p(out), F_, H, W, C, x.device.index, _s())
+        return out
+    _chk(x, BF16, "dw3x3.x")
     _lib.call("xcp_dw3x3_fwd", _p(x), _p(w9), _p(scale), _p(shift), int(relu), _p(out), F_, H, W, C, x.device.index, _s())
     return out
 
 
 def dw3x3_bwd(dD, xin, w9, scale, shift, relu, dw, add_full=None, add_half=None, bnsum=None):
     """dw: fp32 [C_real,1,3,3] gradient buffer (accumulated); bnsum: zero-filled fp32 [2,C] when scale/shift are given."""
-    _chk(dD, BF16, "dw3x3_bwd.dD"); _chk(xin, BF16, "dw3x3_bwd.xin")
     F_, H, W, C = xin.shape
     dz = torch.empty_like(xin)
     if scale is not None and bnsum is None:
         bnsum = torch.zeros((2, C), device=xin.device, dtype=F32)
+    if xin.dtype == F32:
+        _chk(dD, F32, "dw3x3_bwd.dD"); _chk(xin, F32, "dw3x3_bwd.xin")
+        _lib.call("xcp_f32_dw3x3_bwd", _p(dD), _p(xin), _p(w9), _p(scale), _p(shift), int(relu), _p(dz), _p(add_full), _p(add_half),
+                  _p(dw), _p(bnsum), F_, H, W, C, dw.shape[0], xin.device.index, _s())
+        return dz, bnsum
+    _chk(dD, BF16, "dw3x3_bwd.dD"); _chk(xin, BF16, "dw3x3_bwd.xin")
     _lib.call("xcp_dw3x3_bwd", _p(dD), _p(xin), _p(w9), _p(scale), _p(shift), int(relu), _p(dz), _p(add_full), _p(add_half),
               _p(dw), _p(bnsum), F_, H, W, C, dw.shape[0], xin.device.index, _s())
     return dz, bnsum
@@ -242,12 +298,21 @@ def bn_finalize(parts: torch.Tensor, count: float, gamma, beta, running_mean, ru
 
 def bn_act(y, scale, shift, relu: bool):
     out = torch.empty_like(y)
+    if y.dtype == F32:
+        _lib.call("xcp_f32_affine", _p(y), _p(scale), _p(shift), int(relu), _p(out), y.numel(), y.shape[-1], y.device.index, _s())
+        return out
     _lib.call("xcp_bn_act", _p(y), _p(scale), _p(shift), int(relu), _p(out), y.numel(), y.shape[-1], y.device.index, _s())
     return out
 
 
 def gather_s2(x, scale=None, shift=None, relu=False):
     F_, H, W, C = x.shape
+    if x.dtype == F32:
+        if scale is not None or relu:
+            raise _lib.XcpError("gather_s2 (fp32 plan): plain gather only")
+        out = torch.empty((F_, (H + 1) // 2, (W + 1) // 2, C), device=x.device, dtype=F32)
+        _lib.call("xcp_f32_gather", _p(x), _p(out), F_, H, W, C, 2, x.device.index, _s())
+        return out
     out = torch.empty((F_, (H + 1) // 2, (W + 1) // 2, C), device=x.device, dtype=BF16)
     _lib.call("xcp_gather_s2", _p(x), _p(scale), _p(shift), int(relu), _p(out), F_, H, W, C, x.device.index, _s())
     return out
@@ -256,8 +321,12 @@ def gather_s2(x, scale=None, shift=None, relu=False):
 def pool_add_fwd(y, scale, shift, ys, scale_s, shift_s, want_idx=True):
     F_, H, W, C = y.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    out = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=BF16)
+    out = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=y.dtype)
     idx = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=torch.uint8) if want_idx else None
+    if y.dtype == F32:
+        _lib.call("xcp_f32_pool_add_fused", _p(y), _p(scale), _p(shift), _p(ys), _p(scale_s), _p(shift_s), _p(out), _p(idx), F_, H, W,
+                  C, y.device.index, _s())
+        return out, idx
     _lib.call("xcp_pool_add_fwd", _p(y), _p(scale), _p(shift), _p(ys), _p(scale_s), _p(shift_s), _p(out), _p(idx), F_, H, W, C,
               y.device.index, _s())
     return out, idx
@@ -265,6 +334,10 @@ def pool_add_fwd(y, scale, shift, ys, scale_s, shift_s, want_idx=True):
 
 def bn_add_fwd(y, scale, shift, skip, scale_s=None, shift_s=None):
     out = torch.empty_like(y)
+    if y.dtype == F32:
+        _lib.call("xcp_f32_bn_add", _p(y), _p(scale), _p(shift), _p(skip), _p(scale_s), _p(shift_s), _p(out), y.numel(), y.shape[-1],
+                  y.device.index, _s())
+        return out
     _lib.call("xcp_bn_add_fwd", _p(y), _p(scale), _p(shift), _p(skip), _p(scale_s), _p(shift_s), _p(out), y.numel(),
               y.shape[-1], y.device.index, _s())
     return out
@@ -273,6 +346,9 @@ def bn_add_fwd(y, scale, shift, skip, scale_s=None, shift_s=None):
 def bn_relu_gap(y, scale, shift):
     F_, H, W, C = y.shape
     feat = torch.empty((F_, C), device=y.device, dtype=F32)
+    if y.dtype == F32:
+        _lib.call("xcp_f32_bn_relu_gap", _p(y), _p(scale), _p(shift), _p(feat), F_, H * W, C, y.device.index, _s())
+        return feat
     _lib.call("xcp_bn_relu_gap", _p(y), _p(scale), _p(shift), _p(feat), F_, H * W, C, y.device.index, _s())
     return feat
 
@@ -284,6 +360,20 @@ def bn_bwd(mode: int, y, st: BNState, gamma, dgamma, dbeta, G=None, idx=None, df
     F_, H, W, C = y.shape
     dev = y.device
     coef = torch.empty((3, C), device=dev, dtype=F32)
+    if y.dtype == F32:
+        ws = torch.empty((2, C), device=dev, dtype=F32) if presums is None else None
+        dy = None
+        gh = gw = 0
+        if want_dy:
+            if grid_hw is not None:
+                gh, gw = grid_hw
+                dy = torch.zeros((F_, gh, gw, C), device=dev, dtype=F32)
+            else:
+                dy = torch.empty_like(y)
+        _lib.call("xcp_f32_bn_bwd", mode, _p(y), _p(G), _p(idx), _p(dfeat), _p(st.scale), _p(st.shift), _p(gamma), _p(st.mean),
+                  _p(st.rstd), int(st.training), _p(presums), _p(ws), _p(coef), _p(dgamma), _p(dbeta), _p(dy), F_, H, W, C,
+                  gamma.shape[0], gw, gh, dev.index, _s())
+        return dy
     ws = None
     if presums is None:
         ws = torch.empty((_lib.call("xcp_bnbwd_num_parts"), 2, C), device=dev, dtype=F32)

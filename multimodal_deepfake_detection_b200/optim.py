@@ -123,6 +123,30 @@ class FusedAdam(torch.optim.Optimizer):
             ent["pinned"] = True
             self._keep.append((ent["host"], ent["buf"]))
 
+    def _hyper(self, gi: int, group, dev):
+        """Device copy of (lr, weight_decay) of a group.  The two floats live in a pinned host buffer that is refreshed from
+        ``group['lr']`` / ``group['weight_decay']`` and copied to the device on the stepping stream at every step().  Under
+        CUDA-graph capture that copy becomes a memcpy node which re-reads the pinned buffer at every replay, so a replay
+        follows the LR scheduler as long as ``refresh_hyper()`` runs before it (graph.GraphedTrainStep does that)."""
+        ent = group.get("_xcp_hyper")
+        if ent is None or ent[1].device != dev:
+            host = torch.zeros((2,), dtype=torch.float32).pin_memory()
+            ent = group["_xcp_hyper"] = (host, torch.zeros((2,), device=dev, dtype=torch.float32))
+        host, devt = ent
+        host[0] = float(group["lr"]); host[1] = float(group["weight_decay"])
+        devt.copy_(host, non_blocking=True)
+        if torch.cuda.is_current_stream_capturing() and not any(k[0] is host for k in self._keep):
+            self._keep.append((host, devt))               # the captured memcpy node reads `host` for the graph's lifetime
+        return devt
+
+    def refresh_hyper(self):
+        """Write the groups' current lr / weight_decay into the pinned buffers a captured step re-reads (call before a
+        CUDA-graph replay; eager steps refresh by themselves)."""
+        for group in self.param_groups:
+            ent = group.get("_xcp_hyper")
+            if ent is not None:
+                ent[0][0] = float(group["lr"]); ent[0][1] = float(group["weight_decay"])
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -145,10 +169,12 @@ class FusedAdam(torch.optim.Optimizer):
                 if ws is None or ws.device != dev:
                     ws = group["_xcp_sumsq"] = torch.zeros((), device=dev, dtype=torch.float32)
             base = ent["buf"].data_ptr()
+            hyper = self._hyper(gi, group, dev)
             _lib.call("xcp_adam_multi", ctypes.c_void_p(base), ent["n_tensors"], ctypes.c_void_p(base + ent["chunk_off"]), ent["n_chunks"],
                       float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                       float(group["weight_decay"]), int(bool(group["decoupled"])), ctypes.c_void_p(ws.data_ptr() if ws is not None else 0),
-                      float(mx or 0.0), 1.0, dev.index if dev.index is not None else torch.cuda.current_device(),
+                      float(mx or 0.0), 1.0, ctypes.c_void_p(hyper.data_ptr()),
+                      dev.index if dev.index is not None else torch.cuda.current_device(),
                       ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             if mx:
                 _lib.add_launches(1)
@@ -167,11 +193,17 @@ class FusedAdam(torch.optim.Optimizer):
         for g in sd["param_groups"]:
             for k in [k for k in g if k.startswith("_xcp_")]:
                 del g[k]
-        # torch.optim.Adam layout: a float `step` tensor per parameter, detached copies of the moments
-        for st in sd["state"].values():
+        # torch.optim.Adam layout: a float `step` tensor per parameter, detached copies of the moments.  Optimizer.state_dict()
+        # hands out the SAME inner per-parameter dicts as self.state, so the export is built from copies of them: writing the
+        # clones back would detach the live state from the flat arenas (and from a captured graph that keeps updating them).
+        out = {}
+        for k, live in sd["state"].items():
+            st = dict(live)
             if torch.is_tensor(st.get("step")):
                 st["step"] = st["step"].detach().clone().to(torch.float32)
-            for k in ("exp_avg", "exp_avg_sq"):
-                if k in st:
-                    st[k] = st[k].detach().clone()
+            for name in ("exp_avg", "exp_avg_sq"):
+                if name in st:
+                    st[name] = st[name].detach().clone()
+            out[k] = st
+        sd["state"] = out
         return sd

@@ -14,6 +14,9 @@ CKPT_PATH = os.path.join(os.environ.get("XCP_CKPT_DIR", "Checkpoints"), "au_patc
 
 def main():
     device = require_b200()
+    from Dataset.synthetic import dataset_missing, synthetic_requested
+    if not synthetic_requested():      # the reference's AU-patch loader is absent: synthetic patch sequences only
+        raise dataset_missing("AUPatchFeatureLoader", None)
     n, steps, n_mels = env_int("XCP_SYNTH_CLIPS", 16), env_int("XCP_PATCH_STEPS", 120), env_int("XCP_N_MELS", 64)
     loader = synthetic_loader(SyntheticAudio(max(n // 2, 2), steps, n_mels, seed=1), 2, False, collate_fn)
     model = XceptionLSTMA(hidden_dim=env_int("XCP_AUDIO_HIDDEN", 128)).to(device)

@@ -198,3 +198,41 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] and d["vs_baseline"] is None
+
+
+def test_bench_kernel_roofline_decoder_uses_logical_channels():
+    """bench.py turns the (entry point, argument signature) log of _lib.timer_* into per-family rooflines: algorithmic work is
+    counted with the LOGICAL 728 channels (the 768 pitch inflated the fraction by 11 %), mixed shapes weigh by time."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    M = 92416
+    fam, flops, nbytes = bench._work("xcp_gemm_tn", (True, 768, True, 768, True, 768, M, 768, 768, 1, True, False, 0, True))
+    assert "fwd" in fam and flops == 2.0 * M * 728 * 728 and nbytes == 2.0 * M * 728 * 2 + 2.0 * 728 * 728
+    fam, flops, nbytes = bench._work("xcp_dw3x3_bwd", (True, True, True, True, True, 1, True, True, False, True, True, 256, 19, 19, 768, 728, 0, True))
+    assert fam.endswith("19x19") and nbytes == 8.0 * 256 * 19 * 19 * 728          # dD + x + dz + the identity-skip gradient
+    fam, _, nbytes = bench._work("xcp_bn_bwd", (0, True, True, False, False, True, True, True, True, True, 1, True, False, True, True, True, True,
+                                               256, 19, 19, 768, 728, 0, 0, 0, True))
+    assert nbytes == 2.0 * 256 * 19 * 19 * 728 * 3                               # presums given: only the apply pass (y, dz -> dy)
+    assert bench._work("xcp_lstm_fwd", ()) is None
+    peaks = {"hbm_gbs": 6450.6, "bf16_tflops_sustained": 1428.5}
+    log = {("xcp_gemm_tn", (True, 768, True, 768, True, 768, M, 768, 768, 1, True, False, 0, True)): [0.0903 * 2, 2],
+           ("xcp_lstm_fwd", ()): [0.05, 1]}
+    ks, total = bench.kernel_rooflines(log, 1.0, peaks, 1)
+    top = ks[0]
+    assert top["bound"] == "tensor" and abs(top["frac"] - (2.0 * M * 728 * 728 / 90.3e-6 / 1428.5e12)) < 1e-3 and 0.75 < top["frac"] < 0.77
+    assert ks[1]["bound"] == "latency" and ks[1]["frac"] is None and abs(sum(k["share_of_step"] for k in ks) - 1.0) < 1e-9
+
+
+def test_staged_reference_is_byte_identical_and_untracked():
+    """bench.py's reference arm runs the UNMODIFIED reference files staged by build() under the git-ignored baseline/_ref."""
+    import __graft_entry__ as ge
+    if not ge.stage_reference():
+        pytest.skip("reference tree not mounted")
+    for f in ge.REF_FILES:
+        a = open(os.path.join(ge.REF_DIR, f), "rb").read()
+        b = open(os.path.join(ROOT, "baseline", "_ref", "RefModels", f), "rb").read()
+        assert a == b
+    out = subprocess.run(["git", "check-ignore", "baseline/_ref/RefModels/Xception.py"], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0

@@ -52,6 +52,38 @@ def _worker(rank, world, port, ret):
     covered = sorted(bk.launched[:len(bk._buckets)])
     assert len(bk._buckets) >= 3
     assert covered[0][0] == 0 and covered[-1][1] >= sum(p.numel() for p in params)
+    assert len(bk.launched) == len(bk._buckets) + 1                # the launch log describes ONE step (+ the head bucket)
+    # guard 1: gradient accumulation -- p.grad exists when backward starts, AccumulateGrad will ADD the arena
+    # views into it, so nothing may be reduced in place during backward; finish() averages the accumulated p.grad instead
+    for p in params:
+        p.grad = torch.full_like(p, float(rank + 1))
+    sink = _FakeSink(params)
+    for p in reversed(params):
+        sink.view(p).fill_(100.0 * (rank + 1))
+        hook(sink, sink.offsets[id(p)], sink.offsets[id(p)] + p.numel())
+    hook(sink, -1, -1)
+    assert bk.launched == [] and all(torch.all(sink.view(p) == 100.0 * (rank + 1)) for p in params)
+    for p in params:
+        p.grad += sink.view(p)                                      # what AccumulateGrad does
+    bk.finish([])
+    assert bk.direct_reduced == len(params)
+    for p in params:
+        assert torch.allclose(p.grad, torch.full_like(p, 1.5 + 150.0))
+    # guard 2: p.grad was None but autograd cloned the arena view instead of stealing it (its content may be a torn read of
+    # the arena being reduced): finish() installs the averaged arena slice
+    for p in params:
+        p.grad = None
+    sink = _FakeSink(params)
+    for p in reversed(params):
+        sink.view(p).fill_(float(rank + 1))
+        hook(sink, sink.offsets[id(p)], sink.offsets[id(p)] + p.numel())
+    hook(sink, -1, -1)
+    for p in params:
+        p.grad = torch.full_like(p, 777.0)
+    bk.finish([])
+    assert bk.direct_reduced == len(params)
+    for p in params:
+        assert torch.allclose(p.grad, torch.full_like(p, 1.5))
     assert list(shard_clips(8, rank, world)) == list(range(rank, 8, 2))
     # what the torchrun routes of train_visual.py / train_audio.py rely on: an explicit extra-parameter list (LSTM + head +
     # a separate ArcFace module, some of them frozen = no gradient) and the replica synchronisation helper

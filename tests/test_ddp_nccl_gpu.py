@@ -100,7 +100,7 @@ def test_train_visual_under_torchrun_on_two_gpus(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, XCP_EPOCHS="2", XCP_FREEZE_EPOCHS="1", XCP_SYNTH_CLIPS="8", XCP_FRAME_SIZE="75", XCP_WORKERS="0",
+    env = dict(os.environ, XCP_SYNTHETIC="1", XCP_EPOCHS="2", XCP_FREEZE_EPOCHS="1", XCP_SYNTH_CLIPS="8", XCP_FRAME_SIZE="75", XCP_WORKERS="0",
                XCP_CKPT_DIR=str(tmp_path / "ck"), XCP_MAX_FRAMES="4")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(29900 + os.getpid() % 90), "train_visual.py"], cwd=root, env=env, timeout=280,
@@ -118,7 +118,7 @@ def test_train_audio_under_torchrun_on_two_gpus(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, XCP_EPOCHS="2", XCP_EVAL_EVERY="1", XCP_AUDIO_HIDDEN="64", XCP_WORKERS="0", XCP_CKPT_DIR=str(tmp_path / "ck"))
+    env = dict(os.environ, XCP_SYNTHETIC="1", XCP_EPOCHS="2", XCP_EVAL_EVERY="1", XCP_AUDIO_HIDDEN="64", XCP_WORKERS="0", XCP_CKPT_DIR=str(tmp_path / "ck"))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(29800 + os.getpid() % 90), "train_audio.py"], cwd=root, env=env, timeout=280,
                        capture_output=True, text=True)

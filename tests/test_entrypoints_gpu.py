@@ -17,7 +17,7 @@ def small_run(tmp_path, monkeypatch):
     monkeypatch.chdir(ROOT)
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
-    env = {"XCP_EPOCHS": "2", "XCP_FREEZE_EPOCHS": "1", "XCP_SYNTH_CLIPS": "8", "XCP_FRAME_SIZE": "75", "XCP_WORKERS": "0",
+    env = {"XCP_SYNTHETIC": "1", "XCP_EPOCHS": "2", "XCP_FREEZE_EPOCHS": "1", "XCP_SYNTH_CLIPS": "8", "XCP_FRAME_SIZE": "75", "XCP_WORKERS": "0",
            "XCP_CKPT_DIR": str(tmp_path / "ck"), "XCP_OUTPUT_DIR": str(tmp_path / "out"), "XCP_EVAL_EVERY": "1",
            "XCP_AUDIO_HIDDEN": "64", "XCP_FUSION_HIDDEN": "64", "XCP_MAX_FRAMES": "4", "XCP_PATCH_STEPS": "6", "XCP_N_MELS": "16"}
     for k, v in env.items():

@@ -1,4 +1,5 @@
-"""fp32 validation plan (csrc/f32.cu + fp32_plan.py) against the UNMODIFIED reference's golden vectors and the fp32 oracle.
+"""fp32 validation plan (csrc/f32.cu + csrc/f32_bwd.cu behind the SAME executor as the bf16 plan) against the UNMODIFIED
+reference's golden vectors and the fp32 oracle, forward AND backward.
 
 north_star tolerance: fp32 logits within 1e-4 relative.  `rel` is the relative L2 error; `relmax` the max-abs error over the
 largest reference magnitude (stricter for single outliers)."""
@@ -148,7 +149,7 @@ def test_fp32_train_mode_batch_statistics(golden, sd2):
         assert rel(cur[k + ".running_var"], ns[k + ".running_var"]) < TOL, k
 
 
-def test_fp32_uint8_frames_and_forward_only_guard(sd2):
+def test_fp32_uint8_frames_and_precision_switch(sd2):
     g = torch.Generator().manual_seed(13)
     u8 = torch.randint(0, 256, (2, 96, 96, 3), generator=g, dtype=torch.uint8).to(DEV)
     net = _net(sd2)
@@ -156,8 +157,6 @@ def test_fp32_uint8_frames_and_forward_only_guard(sd2):
         a = net.features(u8)
         b = O.xception_features(sd2, u8.permute(0, 3, 1, 2).float() / 255.0, False)
     assert rel(a, b) < TOL
-    with pytest.raises(XcpError):
-        net.features(u8)                    # grad enabled + trainable parameters: the fp32 plan refuses (forward-only)
     with pytest.raises(XcpError):
         net.set_precision("fp16")
     net.set_precision("bf16")
@@ -220,3 +219,134 @@ def test_fp32_lstm_hidden_sizes_vs_torch(H):
         o, (hn, cn) = ours(x)
         ro, (rhn, rcn) = ref(x.double())
     assert rel(o, ro) < 1e-5 and rel(hn, rhn) < 1e-5 and rel(cn, rcn) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- backward
+def _leaf(sd):
+    return {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+            for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("cfg", [(64, 128, 2, 2, False, True, 37), (128, 256, 2, 2, True, True, 22), (728, 728, 3, 1, True, True, 19),
+                                  (728, 1024, 2, 2, True, False, 19), (64, 64, 2, 1, True, True, 12), (32, 48, 1, 1, True, True, 9)])
+@pytest.mark.parametrize("training", [False, True])
+def test_fp32_block_backward_every_tensor_within_1e4(cfg, training):
+    """Block (all flavours of Xception.py:126-140 + a stride-1 skip-conv block) through the plan executor's backward on the fp32
+    kernels: input gradient and EVERY parameter gradient within 1e-4 of the oracle's autograd, frozen and batch statistics."""
+    from multimodal_deepfake_detection_b200 import Block
+    cin, cout, reps, stride, swr, gf, hw = cfg
+    torch.manual_seed(5)
+    blk = Block(cin, cout, reps, stride, start_with_relu=swr, grow_first=gf).to(DEV).train(training).set_precision("fp32")
+    with torch.no_grad():
+        for m_ in blk.modules():
+            if isinstance(m_, torch.nn.BatchNorm2d):
+                m_.running_mean.normal_(0, 0.1); m_.running_var.uniform_(0.5, 1.5); m_.weight.uniform_(0.5, 1.5); m_.bias.normal_(0, 0.1)
+    x = torch.randn(5, cin, hw, hw, device=DEV) * 0.7
+    sd = {"b." + k: v.clone() for k, v in blk.state_dict().items()}
+    leaves = _leaf(sd)
+    xr = x.clone().requires_grad_(True)
+    o = O.block_forward(leaves, "b", ("b", cin, cout, reps, stride, swr, gf), xr, training, {})
+    dout = torch.randn_like(o)
+    o.backward(dout)
+    xo = x.clone().requires_grad_(True)
+    out = blk(xo)
+    out.backward(dout)
+    errs = {"out": rel(out, o), "dx": rel(xo.grad, xr.grad)}
+    errs.update({k: rel(p.grad, leaves["b." + k].grad) for k, p in blk.named_parameters()})
+    worst = max(errs, key=errs.get)
+    print("fp32 block %s training=%s: worst %s %.2e" % (cfg, training, worst, errs[worst]))
+    assert errs[worst] < TOL, (worst, errs[worst])
+
+
+def _xception_grads(sd2, training, n=6, seed=21, dtype64=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 3, 299, 299, generator=g).to(DEV)
+    labels = torch.randint(0, 2, (n,), generator=g).to(DEV)
+    scale = 1.0 if training else 50.0
+    net = _net(sd2, train=training)
+    so = _leaf(sd2)
+    lo = F.cross_entropy(O.xception_logits(so, x, training, {}) * scale, labels); lo.backward()
+    l = F.cross_entropy(net(x) * scale, labels); l.backward()
+    s64 = None
+    if dtype64:
+        s64 = {k: (v.double().clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else
+                   (v.double().clone() if v.dtype.is_floating_point else v.clone())) for k, v in sd2.items()}
+        F.cross_entropy(O.xception_logits(s64, x.double(), training, {}) * scale, labels).backward()
+    return net, so, s64, l.item(), lo.item()
+
+
+def test_fp32_xception_backward_every_tensor_within_1e4(sd2):
+    """Whole backbone + fc, CE loss, 6x3x299x299 frames, frozen BatchNorm statistics: all 156 parameter gradients of the plan's
+    backward within 1e-4 of the fp32 oracle (north_star asks 1e-2 of the bf16 plan; this pins the chain rule itself)."""
+    net, so, _, l, lo = _xception_grads(sd2, False)
+    errs = {k: rel(p.grad, so[k].grad) for k, p in net.named_parameters()}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print("fp32 xception backward (frozen BN): loss %.6f vs %.6f, worst %s, median %.2e" % (
+        l, lo, [(k, "%.2e" % v) for k, v in worst], float(np.median(list(errs.values())))))
+    assert abs(l - lo) < 1e-5 * max(1.0, abs(lo))
+    assert len(errs) == 156 and all(p.grad is not None for p in net.parameters())
+    assert worst[0][1] < TOL, worst
+
+
+def test_fp32_xception_backward_batch_statistics_vs_fp64_truth(sd2):
+    """Train-mode BatchNorm (the mode the reference trains in, train_visual.py:558).  Through 40 stacked batch-statistics BNs the
+    gradient of the seeded random-init network is ill-conditioned in fp32 ITSELF: the fp32 oracle differs from the fp64
+    oracle by 4e-3 ... 8e-3 per tensor (tools/fp32_grad_probe.py; every Block alone, batch statistics included, is at 1e-6
+    above).  So the truth here is the oracle in fp64, and the plan must be as close to it as the fp32 oracle is: per tensor
+    within 2x the oracle's own fp32 error (+1e-4), same median, and the tensors above the first BN backward (fc, bn4.weight)
+    within 1e-4 absolutely."""
+    net, s32, s64, l, lo = _xception_grads(sd2, True, dtype64=True)
+    ours = {k: rel(p.grad, s64[k].grad) for k, p in net.named_parameters()}
+    o32 = {k: rel(s32[k].grad, s64[k].grad) for k in ours}
+    worst = max(ours, key=lambda k: ours[k] / (o32[k] + 1e-4))
+    print("fp32 xception backward (batch statistics) vs fp64 oracle: ours median %.2e max %.2e | fp32 oracle median %.2e max %.2e | "
+          "worst ratio %s %.2e vs %.2e" % (float(np.median(list(ours.values()))), max(ours.values()),
+                                          float(np.median(list(o32.values()))), max(o32.values()), worst, ours[worst], o32[worst]))
+    assert abs(l - lo) < 1e-5
+    for k in ("fc.weight", "fc.bias", "bn4.weight"):
+        assert ours[k] < TOL, (k, ours[k])
+    assert all(ours[k] < 2.0 * o32[k] + 1e-4 for k in ours), (worst, ours[worst], o32[worst])
+    assert np.median(list(ours.values())) < 1.25 * np.median(list(o32.values())) + 1e-5
+
+
+@pytest.mark.parametrize("M,K,N", [(361 * 3 + 5, 768, 768), (5476, 128, 256), (1000, 1536, 2048), (21609, 64, 128)])
+def test_split3_makes_the_tensor_core_gemms_fp32_grade(M, K, N):
+    """The PRODUCTION tcgen05 kernels (xcp_gemm_tn epi=2, xcp_gemm_wgrad) fed 3-way bf16 splits of fp32 operands reproduce the
+    fp64 product to ~1e-6: indexing / accumulation / split-K logic of the kernels that train, checked far below bf16 noise."""
+    from multimodal_deepfake_detection_b200 import ops
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    out, _ = ops.gemm_tn(ops.split3(a, 0, False), ops.split3(b, 1, False), ops.EPI_F32)
+    ref = (a.double() @ b.double().t())
+    e_fwd = relmax(out, ref)
+    plain, _ = ops.gemm_tn(a.to(torch.bfloat16), b.to(torch.bfloat16), ops.EPI_F32)
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    dw = torch.zeros(N, K, device=DEV)
+    ops.gemm_wgrad(ops.split3(dy, 0, True), ops.split3(a, 1, True), dw)
+    ref_w = dy.double().t() @ a.double()
+    e_w = relmax(dw, ref_w)
+    print("split3 M=%d K=%d N=%d: gemm_tn %.2e (plain bf16 %.2e), wgrad %.2e" % (M, K, N, e_fwd, relmax(plain, ref), e_w))
+    assert e_fwd < 2e-5 and e_w < 2e-5, (e_fwd, e_w)
+
+
+def test_fp32_plan_on_split3_tensor_core_gemms(sd2):
+    """Same backward as above with every pointwise / skip GEMM (forward, dgrad, wgrad) routed through the production tcgen05
+    kernels on split operands (XCP_FP32_GEMM=split3)."""
+    from multimodal_deepfake_detection_b200 import ops
+    g = torch.Generator().manual_seed(22)
+    x = torch.rand(3, 3, 299, 299, generator=g).to(DEV)
+    labels = torch.randint(0, 2, (3,), generator=g).to(DEV)
+    net = _net(sd2, train=False)
+    so = _leaf(sd2)
+    lo = F.cross_entropy(O.xception_logits(so, x, False, {}) * 50.0, labels); lo.backward()
+    old = ops.FP32_GEMM[0]
+    ops.FP32_GEMM[0] = "split3"
+    try:
+        l = F.cross_entropy(net(x) * 50.0, labels); l.backward()
+    finally:
+        ops.FP32_GEMM[0] = old
+    errs = {k: rel(p.grad, so[k].grad) for k, p in net.named_parameters()}
+    worst = max(errs, key=errs.get)
+    print("fp32 plan on split3 tcgen05 GEMMs: worst %s %.2e median %.2e" % (worst, errs[worst], float(np.median(list(errs.values())))))
+    assert errs[worst] < 5e-4, (worst, errs[worst])

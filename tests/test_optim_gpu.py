@@ -84,3 +84,46 @@ def test_fused_adam_graph_capture():
     assert int(o.state[ours[0]]["step"]) == 4
     for a, b in zip(ours, ref):
         assert torch.allclose(a, b, rtol=5e-5, atol=5e-6), (a - b).abs().max().item()
+
+
+def test_fused_adam_graph_replay_follows_scheduler_and_state_dict_is_a_copy():
+    """(1) lr / weight_decay live in device memory and a captured step re-reads them, so an LR scheduler keeps
+    working under CUDA-graph replay; (2) state_dict() must not detach the live state from the arenas the graph updates:
+    two exports taken around replays show the step count and the moments advancing."""
+    from multimodal_deepfake_detection_b200 import FusedAdam
+    dev = torch.device("cuda", 0)
+    ours = [torch.nn.Parameter(t.clone()) for t in _params(dev)]
+    ref = [torch.nn.Parameter(t.clone()) for t in _params(dev)]
+    grads = [torch.randn_like(p) for p in ours]
+    for p, q, g in zip(ours, ref, grads):
+        p.grad = g.clone(); q.grad = g.clone()
+    o = FusedAdam(ours, lr=1e-2, weight_decay=1e-3)
+    r = torch.optim.Adam(ref, lr=1e-2, weight_decay=1e-3)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        o.step()
+    torch.cuda.current_stream().wait_stream(s)
+    r.step()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o.step()
+    sd0 = o.state_dict()
+    for lr in (1e-2, 3e-3, 1e-3):                       # what ReduceLROnPlateau / OneCycleLR do between steps
+        for grp in o.param_groups:
+            grp["lr"] = lr
+        for grp in r.param_groups:
+            grp["lr"] = lr
+        o.refresh_hyper()
+        graph.replay(); r.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ours, ref):
+        assert torch.allclose(a, b, rtol=5e-5, atol=5e-6), (a - b).abs().max().item()
+    sd1 = o.state_dict()
+    assert float(sd0["state"][0]["step"]) == 1.0 and float(sd1["state"][0]["step"]) == 4.0
+    assert not torch.equal(sd0["state"][0]["exp_avg"], sd1["state"][0]["exp_avg"])
+    # the live state still aliases the arenas (int32 device counter, views of the flat moment buffers)
+    st = o.state[ours[0]]
+    assert st["step"].dtype == torch.int32 and int(st["step"]) == 4
+    assert torch.equal(st["exp_avg"], sd1["state"][0]["exp_avg"])
+    assert all(not k.startswith("_xcp_") for g in sd1["param_groups"] for k in g)

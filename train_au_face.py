@@ -76,10 +76,12 @@ def main():
         m = binary_metrics(ey, ep)
         thr, fpr, tpr = youden_threshold(ey, ep)
         print(f"Eval: AUC={m['AUC']:.4f}, pAUC={m['pAUC']:.4f}, EER={m['EER']:.4f}, AP={m['AP']:.4f}, thr={thr:.3f}, FPR={fpr:.3f}, TPR={tpr:.3f}")
-        if m["AUC"] > best_auc or epoch == 0:
-            best_auc, early_stop_count = max(best_auc, m["AUC"]), 0
+        if m["AUC"] > best_auc:                          # strict, like train_au_face.py:748
+            best_auc, early_stop_count = m["AUC"], 0
+            # the ArcFace weights that scored this AUC (the evaluation above ran on the EMA head): test_au_face.py must score
+            # with the same ones that picked the checkpoint
             torch.save({"model": ema_model.state_dict(), "embed": ema_head.module.embed_head.state_dict(),
-                        "arcface": head.arcface.state_dict(), "best_auc": best_auc}, os.path.join(CKPT_DIR, CKPT_NAME))
+                        "arcface": ema_head.module.arcface.state_dict(), "best_auc": best_auc}, os.path.join(CKPT_DIR, CKPT_NAME))
             print(f"New best AUC: {m['AUC']:.4f} - Model saved.")
         else:
             early_stop_count += 1

@@ -42,6 +42,9 @@ def _epoch(model, criterion, loader, device, optimizer=None):
 
 def main():
     device = require_b200()
+    from Dataset.synthetic import dataset_missing, synthetic_requested
+    if not synthetic_requested():      # the reference's AU-patch loader is absent: synthetic patch sequences only
+        raise dataset_missing("AUPatchFeatureLoader", None)
     n, steps, n_mels = env_int("XCP_SYNTH_CLIPS", 16), env_int("XCP_PATCH_STEPS", 120), env_int("XCP_N_MELS", 64)
     train_loader = synthetic_loader(SyntheticAudio(n, steps, n_mels, seed=0), 2, True, collate_fn)
     eval_loader = synthetic_loader(SyntheticAudio(max(n // 2, 2), steps, n_mels, seed=1), 2, False, collate_fn)
