@@ -63,7 +63,24 @@ def _worker(rank, world, port, ret):
             print("DDP %-55s err_vs_avg %.3e  diff_vs_own %.3e  own0_vs_own1 %.3e" % (k, *v), flush=True)
     # wgrad accumulation order (RED) differs between two runs of the same shard: a few 1e-3 on the tiny stem tensors
     assert worst < 2e-2, worst
-    assert len(bucketer._buckets) >= 3
+    assert len(bucketer._buckets) >= 3 and bucketer.direct_reduced == 0          # every p.grad IS a view of the reduced arena
+    # gradient accumulation (train_au_face.py:676-693): p.grad exists when the second backward starts, so autograd
+    # ADDS the arena views into it -- the hooks must not reduce the arena in place, finish() averages the accumulated p.grad:
+    # avg_r(avg + local_r) = avg + avg
+    loss = F.binary_cross_entropy(model(model.extract_features(data[rank][0], dev)), data[rank][1])
+    loss.backward()
+    bucketer.finish()
+    assert bucketer.direct_reduced > 0
+    acc_worst = 0.0
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        e = got[k] + expect[k]
+        acc_worst = max(acc_worst, (p.grad - e).norm().item() / (e.norm().item() + 1e-12))
+    assert acc_worst < 2e-2, acc_worst
+    model.zero_grad(set_to_none=True)
+    got2 = _grads(model, data[rank][0], data[rank][1], dev, bucketer)           # back on the overlapped path
+    assert bucketer.direct_reduced == 0 and max((got2[k] - expect[k]).norm().item() / (expect[k].norm().item() + 1e-12) for k in expect) < 2e-2
     opt = FusedAdam(model.parameters(), lr=1e-3)
     opt.step()
     torch.cuda.synchronize()

@@ -109,6 +109,30 @@ def test_xception_gradients_frozen_bn_within_1e2(sd2):
     assert statistics.median(ours.values()) <= 1.1 * statistics.median(bf16.values())
 
 
+def test_xception_gradients_frozen_bn_at_the_c2_batch_within_1e2(sd2):
+    """north_star's bound, no slack, at BASELINE config 2's size (64 x 3 x 299 x 299): EVERY one of the 156 parameter-gradient
+    tensors of the bf16 production plan within 1e-2 relative of the fp32 oracle (measured on B200: worst 0.91e-2, median
+    0.51e-2; the bound is where 36 separable convolutions of bf16 storage end up -- ~7 roundings of 2^-9 per unit, forward
+    before the tensor plus backward after it -- and holds by 9 %).  What makes this meaningful rather than lucky: the chain
+    rule itself is pinned at 1e-6 ... 3e-5 by the fp32 arithmetic of the same plan (tests/test_fp32_plan_gpu.py) and every
+    bf16 kernel is within one ulp of its fp32 twin (tests/test_kernel_twins_gpu.py)."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(64, 3, 299, 299, generator=g).to(DEV)
+    labels = torch.randint(0, 2, (64,), generator=g).to(DEV)
+    net = Xception(num_classes=2).to(DEV).eval()
+    net.load_state_dict(sd2)
+    so = _leaf(sd2)
+    lo = F.cross_entropy(O.xception_logits(so, x, False, {}) * 50.0, labels); lo.backward()
+    l = F.cross_entropy(net(x) * 50.0, labels); l.backward()
+    errs = {k: rel(p.grad, so[k].grad) for k, p in net.named_parameters()}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print("bf16 gradients at 64x3x299x299 (frozen BN): worst %s median %.2e" % ([(k, "%.2e" % v) for k, v in worst],
+                                                                              statistics.median(errs.values())))
+    assert abs(l.item() - lo.item()) < 5e-3 * max(1.0, abs(lo.item()))
+    assert len(errs) == 156 and worst[0][1] < 1e-2, worst
+    assert statistics.median(errs.values()) < 6e-3
+
+
 def test_xception_gradients_batch_stats_like_for_like(sd2):
     g = torch.Generator().manual_seed(2)
     x = torch.rand(12, 3, 299, 299, generator=g).to(DEV)
@@ -386,3 +410,55 @@ def test_200_step_training_curve_within_tolerance():
     cur = m.state_dict()
     for k in ("feature_extractor.bn1.running_mean", "feature_extractor.block8.rep.5.running_var", "feature_extractor.bn4.running_var"):
         assert rel(cur[k], fo[k]) < 2e-2, k
+
+
+def test_200_step_unfrozen_training_curve_at_299():
+    """north_star: "a 200-step training-loss curve within tolerance", on the benchmark's own protocol: backbone UNFROZEN
+    (train_visual.py:551-556, epoch >= 3), train-mode BatchNorm, Adam on every parameter, 4 clips x 4 frames of 3 x 299 x 299
+    per step (two alternating batches), our bf16 plan + fused optimizer against the fp32 oracle + torch.optim.Adam on the GPU.
+    Tolerance: |loss_ours - loss_oracle| <= 1.5e-2 at every one of the 200 steps and <= 5e-3 on average (measured on B200:
+    5.4e-3 / 2.0e-3 while the loss falls from 0.693 to 0.015 in both runs)."""
+    from multimodal_deepfake_detection_b200 import BCELoss, FusedAdam
+    m, full = _lstm_models(128, XceptionLSTMV)
+    g = torch.Generator().manual_seed(12)
+    batches = [(torch.rand(4, 4, 3, 299, 299, generator=g).to(DEV), torch.tensor([[1.0], [0.0], [1.0], [0.0]], device=DEV))
+               for _ in range(2)]
+    m.train()
+    for p in m.feature_extractor.parameters():
+        p.requires_grad = True
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.eval()
+    fo = _leaf(full)
+    opt_o = torch.optim.Adam([v for v in fo.values() if v.requires_grad], lr=1e-5, weight_decay=1e-4)      # train_visual.py:533
+    opt = FusedAdam(m.parameters(), lr=1e-5, weight_decay=1e-4)
+    crit = BCELoss()
+    ours, ref = [], []
+    for step in range(200):
+        clips, y = batches[step & 1]
+        opt_o.zero_grad(set_to_none=True); ns = {}
+        lo = F.binary_cross_entropy(O.xception_lstm_forward(fo, clips, training=True, new_stats=ns), y); lo.backward(); opt_o.step()
+        for k, v in ns.items():
+            fo[k] = v
+        opt.zero_grad(set_to_none=True)
+        l = crit(m(m.extract_features(clips, torch.device(DEV))), y); l.backward(); opt.step()
+        ours.append(l.detach()); ref.append(lo.detach())
+    ours, ref = torch.stack(ours).cpu().numpy(), torch.stack(ref).cpu().numpy()
+    d = np.abs(ours - ref)
+    print("unfrozen 200-step curve @299: max|d| %.3e mean|d| %.3e ours %s ref %s" % (d.max(), d.mean(),
+          np.round(ours[::25], 4).tolist(), np.round(ref[::25], 4).tolist()))
+    assert d.max() < 1.5e-2 and d.mean() < 5e-3, (float(d.max()), float(d.mean()), ours[::25].tolist(), ref[::25].tolist())
+    assert ours[-10:].mean() < 0.1 * ours[:10].mean() and ref[-10:].mean() < 0.1 * ref[:10].mean()       # both actually train
+    cur = m.state_dict()
+    # running statistics after 200 steps of two separately trained networks (the weights themselves have moved apart)
+    for k in ("feature_extractor.bn1.running_mean", "feature_extractor.block8.rep.5.running_var", "feature_extractor.bn4.running_var"):
+        assert rel(cur[k], fo[k]) < 1e-1, (k, rel(cur[k], fo[k]))
+    # every part of the network moved, by a comparable amount and in a correlated direction (Adam steps of 1e-5: compare the
+    # displacement, not the weights; bf16 gradients decide the sign of the small components differently)
+    for k in ("feature_extractor.conv1.weight", "feature_extractor.block6.rep.4.pointwise.weight", "feature_extractor.bn3.weight",
+              "lstm.weight_ih_l0", "fc_out.weight"):
+        d_ours = (cur[k] - full[k]).flatten().double(); d_ref = (fo[k].detach() - full[k]).flatten().double()
+        cos = float(torch.dot(d_ours, d_ref) / (d_ours.norm() * d_ref.norm() + 1e-30))
+        ratio = float(d_ours.norm() / (d_ref.norm() + 1e-30))
+        print("   displacement %-52s |ours|/|ref| %.3f cos %.3f" % (k, ratio, cos))
+        assert d_ref.norm().item() > 0 and 0.5 < ratio < 2.0 and cos > 0.5, (k, ratio, cos)
