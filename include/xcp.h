@@ -87,9 +87,11 @@ int xcp_bn_act(const void* y, const float* scale, const float* shift, int relu, 
 /* input sampling of the stride-2 skip conv (Xception.py:55,93): out[f,ho,wo,:] = act(x[f,2ho,2wo,:]) */
 int xcp_gather_s2(const void* x, const float* scale, const float* shift, int relu, void* out, int F, int H, int W, int C,
                   int device, void* stream);
-/* BN + MaxPool2d(3,2,1) (Xception.py:86) + skip BN + residual add (Xception.py:92-98); idx = arg-max taps (uint8) */
+/* BN + MaxPool2d(3,2,1) (Xception.py:86) + skip BN + residual add (Xception.py:92-98); idx = arg-max taps (uint8);
+ * ymax (optional, bf16 [F,Ho,Wo,C]) = the raw y at the arg-max, consumed by xcp_bn_bwd_sums in backward */
 int xcp_pool_add_fwd(const void* y, const float* scale, const float* shift, const void* ys, const float* scale_s,
-                     const float* shift_s, void* out, void* idx, int F, int H, int W, int C, int device, void* stream);
+                     const float* shift_s, void* out, void* idx, void* ymax, int F, int H, int W, int C, int device,
+                     void* stream);
 /* BN + residual add (blocks 4-11, Xception.py:96-98); scale_s/shift_s != NULL applies the skip BN (stride-1 skip conv) */
 int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const void* skip, const float* scale_s,
                    const float* shift_s, void* out, long long n, int C, int device, void* stream);
@@ -97,6 +99,11 @@ int xcp_bn_add_fwd(const void* y, const float* scale, const float* shift, const 
 int xcp_bn_relu_gap(const void* y, const float* scale, const float* shift, float* feat, int F, int HW, int C, int device,
                     void* stream);
 int xcp_bnbwd_num_parts(void);
+/* pass 1 of the BatchNorm backward alone: sums[2][C] = (sum G, sum G*y) over an [n_pix, C] bf16 pair; workspace = fp32
+ * [xcp_bnbwd_num_parts()][2][C].  For the max-pool blocks it runs on (ymax, G) at pooled resolution (sum dz = sum G,
+ * sum dz*y = sum G*y[arg-max]) and its result is handed to xcp_bn_bwd as `presums`. */
+int xcp_bn_bwd_sums(const void* y, const void* G, float* workspace, float* sums, long long n_pix, int C, int device,
+                    void* stream);
 /* two-pass BatchNorm backward with the ReLU / MaxPool / GAP gradient routing folded into its loads; see elementwise.cu */
 int xcp_bn_bwd(int mode, const void* y, const void* G, const void* idx, const float* dfeat, const float* scale,
                const float* shift, const float* gamma, const float* mean, const float* rstd, int training, const float* presums,
@@ -192,8 +199,10 @@ int xcp_f32_lstm_fwd(const float* xproj, const float* b_ih, const float* b_hh, c
 int xcp_f32_dw3x3_fused(const float* x, const float* w9, const float* scale, const float* shift, int relu, float* out, int F,
                         int H, int W, int C, int device, void* stream);                           /* ~ xcp_dw3x3_fwd */
 int xcp_f32_pool_add_fused(const float* y, const float* scale, const float* shift, const float* ys, const float* scale_s,
-                           const float* shift_s, float* out, void* idx, int F, int H, int W, int C, int device,
+                           const float* shift_s, float* out, void* idx, float* ymax, int F, int H, int W, int C, int device,
                            void* stream);                                                        /* ~ xcp_pool_add_fwd */
+int xcp_f32_bn_bwd_sums(const float* y, const float* G, float* sums, long long n_pix, int C, int device,
+                        void* stream);                                                           /* ~ xcp_bn_bwd_sums */
 int xcp_f32_bn_add(const float* y, const float* scale, const float* shift, const float* skip, const float* scale_s,
                    const float* shift_s, float* out, long long n, int C, int device, void* stream); /* ~ xcp_bn_add_fwd */
 int xcp_f32_bn_relu_gap(const float* y, const float* scale, const float* shift, float* feat, int F, int HW, int C, int device,

@@ -35,7 +35,8 @@ SIGNATURES = {
     "xcp_bn_eval_affine": "ppppfppppiiip",
     "xcp_bn_act": "pppipliip",
     "xcp_gather_s2": "pppipiiiiip",
-    "xcp_pool_add_fwd": "ppppppppiiiiip",
+    "xcp_pool_add_fwd": "pppppppppiiiiip",
+    "xcp_bn_bwd_sums": "ppppliip",
     "xcp_bn_add_fwd": "pppppppliip",
     "xcp_bn_relu_gap": "ppppiiiip",
     "xcp_bnbwd_num_parts": "",
@@ -76,7 +77,8 @@ SIGNATURES = {
     "xcp_f32_gap": "ppiiiip",
     "xcp_f32_lstm_fwd": "pppppppiiiip",
     "xcp_f32_dw3x3_fused": "ppppipiiiiip",
-    "xcp_f32_pool_add_fused": "ppppppppiiiiip",
+    "xcp_f32_pool_add_fused": "pppppppppiiiiip",
+    "xcp_f32_bn_bwd_sums": "pppliip",
     "xcp_f32_bn_add": "pppppppliip",
     "xcp_f32_bn_relu_gap": "ppppiiiip",
     "xcp_f32_bn_bwd": "ipppppppppippppppiiiiiiiip",
@@ -95,7 +97,7 @@ _NO_STATUS = {"xcp_version", "xcp_bnbwd_num_parts", "xcp_gemm_stats_parts", "xcp
 # kernels launched per C-ABI call (for bench.py's `gpu_launches`; 0 = host-only query)
 _LAUNCHES = {"xcp_version": 0, "xcp_check_device": 0, "xcp_bnbwd_num_parts": 0, "xcp_gemm_stats_parts": 0,
              "xcp_stem_conv1_parts": 0, "xcp_stem_conv1_wgrad_ws_bytes": 0, "xcp_f32_bn_stats_parts": 0, "xcp_mfcc_frames": 0, "xcp_mfcc": 2, "xcp_stem_conv1_wgrad": 3, "xcp_bn_bwd": 3,
-             "xcp_arcface_loss": 2, "xcp_adam_multi": 2, "xcp_f32_bn_bwd": 3, "xcp_f32_dw3x3_bwd": 2}
+             "xcp_arcface_loss": 2, "xcp_adam_multi": 2, "xcp_f32_bn_bwd": 3, "xcp_f32_dw3x3_bwd": 2, "xcp_bn_bwd_sums": 2}
 _count = 0
 
 _lock = threading.Lock()

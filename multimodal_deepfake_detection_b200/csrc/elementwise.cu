@@ -225,8 +225,8 @@ __global__ void gather_s2_kernel(const uint4* __restrict__ x, const float* __res
 // idx (uint8 per element) records the arg-max tap (first maximum in row-major window order) for backward.
 __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                     const uint4* __restrict__ ys, const float* __restrict__ scale_s,
-                                    const float* __restrict__ shift_s, uint4* __restrict__ out, uint2* __restrict__ idx, int F,
-                                    int H, int W, int C) {
+                                    const float* __restrict__ shift_s, uint4* __restrict__ out, uint2* __restrict__ idx,
+                                    uint4* __restrict__ ymax, int F, int H, int W, int C) {
     const int ncg = C >> 3, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long n8 = (long long)F * Ho * Wo * ncg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -302,6 +302,9 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
             o.y = (uint32_t)bidx[4] | ((uint32_t)bidx[5] << 8) | ((uint32_t)bidx[6] << 16) | ((uint32_t)bidx[7] << 24);
             idx[i] = o;
         }
+        // the RAW winner y[arg-max]: the BatchNorm backward through the pool needs sum dz*y = sum_windows G * y[arg-max],
+        // which it can then take from this quarter-size tensor instead of re-reading all of y (xcp_bn_bwd_sums)
+        if (ymax != nullptr) ymax[i] = make_uint4(best[0] ^ sgn[0], best[1] ^ sgn[1], best[2] ^ sgn[2], best[3] ^ sgn[3]);
     }
 }
 
@@ -971,13 +974,13 @@ extern "C" int xcp_gather_s2(const void* x, const float* scale, const float* shi
 }
 
 extern "C" int xcp_pool_add_fwd(const void* y, const float* scale, const float* shift, const void* ys, const float* scale_s,
-                                const float* shift_s, void* out, void* idx, int F, int H, int W, int C, int device,
+                                const float* shift_s, void* out, void* idx, void* ymax, int F, int H, int W, int C, int device,
                                 void* stream) {
     XCP_REQUIRE(C % 8 == 0, "xcp_pool_add_fwd: C %% 8");
     XCP_CUDA(cudaSetDevice(device));
     const long long n8 = (long long)F * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 8);
     pool_add_fwd_kernel<<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)ys, scale_s, shift_s,
-                                                          (uint4*)out, (uint2*)idx, F, H, W, C);
+                                                          (uint4*)out, (uint2*)idx, (uint4*)ymax, F, H, W, C);
     return check_cuda(cudaGetLastError(), "pool_add_fwd launch");
 }
 
@@ -1040,6 +1043,34 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
         else bnbwd_apply_kernel<<<ga, 256, 0, ST>>>((const uint4*)y, s, coef, coef + C, coef + 2 * C, (uint4*)dy, n8, grid_w, grid_h);
     }
     return check_cuda(cudaGetLastError(), "bn_bwd launch");
+}
+
+// partials [nparts][2][C] -> sums [2][C]
+__global__ void bnbwd_fold_kernel(const float* __restrict__ partials, int nparts, int C, float* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * C) return;
+    double a = 0.0;
+    for (int p = 0; p < nparts; ++p) a += (double)partials[(long long)p * 2 * C + i];
+    sums[i] = (float)a;
+}
+
+// Pass 1 of the BatchNorm backward on its own: sums[0][c] = sum G, sums[1][c] = sum G*y over an [n_pix, C] pair of tensors.
+// Used for the max-pool blocks (Xception.py:86): with dz routed to the arg-max pixels, sum dz = sum G and
+// sum dz*y = sum_windows G * y[arg-max], so the pass runs over the pooled-resolution pair (y_max from xcp_pool_add_fwd, G)
+// -- a quarter of the bytes of walking y with the routing logic -- and its result goes to xcp_bn_bwd as `presums`.
+extern "C" int xcp_bn_bwd_sums(const void* y, const void* G, float* workspace, float* sums, long long n_pix, int C, int device,
+                               void* stream) {
+    XCP_REQUIRE(C % 8 == 0 && n_pix > 0 && y != nullptr && G != nullptr && workspace != nullptr && sums != nullptr, "xcp_bn_bwd_sums: bad args");
+    XCP_CUDA(cudaSetDevice(device));
+    BnBwdSrc s{SRC_DIRECT, (const __nv_bfloat16*)G, nullptr, nullptr, nullptr, nullptr, 1, 1, 1, C};
+    const long long n8 = n_pix * (C / 8);
+    long long g = (n8 + 255) / 256;
+    int nparts = (int)(g < xcp_bnbwd_num_parts() ? g : xcp_bnbwd_num_parts());
+    if ((long long)nparts * 256 < C / 8) nparts = (C / 8 + 255) / 256;
+    bnbwd_reduce_kernel<<<nparts, 256, 2 * C * sizeof(float), ST>>>((const uint4*)y, s, workspace, n8);
+    XCP_CUDA(cudaGetLastError());
+    bnbwd_fold_kernel<<<(2 * C + 255) / 256, 256, 0, ST>>>(workspace, nparts, C, sums);
+    return check_cuda(cudaGetLastError(), "bn_bwd_sums launch");
 }
 
 extern "C" int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int Cp, int HW, int device, void* stream) {

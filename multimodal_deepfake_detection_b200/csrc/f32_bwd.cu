@@ -58,7 +58,8 @@ f32_dw_fused_kernel(const float* __restrict__ x, const float* __restrict__ w9, c
 __global__ void __launch_bounds__(256)
 f32_pool_add_fused_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ ys, const float* __restrict__ scale_s, const float* __restrict__ shift_s,
-                          float* __restrict__ out, unsigned char* __restrict__ idx, int F, int H, int W, int C, int Ho, int Wo) {
+                          float* __restrict__ out, unsigned char* __restrict__ idx, float* __restrict__ ymax, int F, int H, int W, int C,
+                          int Ho, int Wo) {
     const long long total = (long long)F * Ho * Wo * C;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int c = (int)(i % C);
@@ -66,19 +67,21 @@ f32_pool_add_fused_kernel(const float* __restrict__ y, const float* __restrict__
         const int wo = (int)(p % Wo); p /= Wo;
         const int ho = (int)(p % Ho);
         const long long f = p / Ho;
-        float m = -INFINITY;
+        float m = -INFINITY, raw = 0.f;
         int best = 4;
         for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) {
                 const int hi = 2 * ho + kh - 1, wi = 2 * wo + kw - 1;
                 if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
-                const float v = fmaf(y[((f * H + hi) * W + wi) * C + c], scale[c], shift[c]);
-                if (v > m) { m = v; best = kh * 3 + kw; }
+                const float yv = y[((f * H + hi) * W + wi) * C + c];
+                const float v = fmaf(yv, scale[c], shift[c]);
+                if (v > m) { m = v; best = kh * 3 + kw; raw = yv; }
             }
         float s = ys[i];
         if (scale_s != nullptr) s = fmaf(s, scale_s[c], shift_s[c]);
         out[i] = m + s;
         if (idx != nullptr) idx[i] = (unsigned char)best;
+        if (ymax != nullptr) ymax[i] = raw;
     }
 }
 
@@ -432,13 +435,13 @@ extern "C" int xcp_f32_dw3x3_fused(const float* x, const float* w9, const float*
 }
 
 extern "C" int xcp_f32_pool_add_fused(const float* y, const float* scale, const float* shift, const float* ys, const float* scale_s,
-                                      const float* shift_s, float* out, void* idx, int F, int H, int W, int C, int device,
+                                      const float* shift_s, float* out, void* idx, float* ymax, int F, int H, int W, int C, int device,
                                       void* stream) {
     XCP_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && scale != nullptr && shift != nullptr && ys != nullptr, "xcp_f32_pool_add_fused: bad arguments");
     XCP_CUDA(cudaSetDevice(device));
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     f32_pool_add_fused_kernel<<<grid_for((long long)F * Ho * Wo * C, 256), 256, 0, ST>>>(y, scale, shift, ys, scale_s, shift_s, out,
-                                                                                      (unsigned char*)idx, F, H, W, C, Ho, Wo);
+                                                                                      (unsigned char*)idx, ymax, F, H, W, C, Ho, Wo);
     return check_cuda(cudaGetLastError(), "f32_pool_add_fused launch");
 }
 
@@ -476,6 +479,15 @@ extern "C" int xcp_f32_bn_bwd(int mode, const float* y, const float* G, const vo
     if (dy != nullptr)
         f32_bn_bwd_apply_kernel<<<grid_for((long long)F * H * W * C, 256), 256, 0, ST>>>(y, s, coef, dy, grid_w, grid_h);
     return check_cuda(cudaGetLastError(), "f32_bn_bwd launch");
+}
+
+// ~ xcp_bn_bwd_sums: sums[0][c] = sum G, sums[1][c] = sum G*y over [n_pix, C]
+extern "C" int xcp_f32_bn_bwd_sums(const float* y, const float* G, float* sums, long long n_pix, int C, int device, void* stream) {
+    XCP_REQUIRE(n_pix > 0 && n_pix < (1LL << 31) && C > 0, "xcp_f32_bn_bwd_sums: bad shape");
+    XCP_CUDA(cudaSetDevice(device));
+    BnSrc s{SRC_DIRECT, G, nullptr, nullptr, nullptr, nullptr, 1, 1, (int)n_pix, C};
+    f32_bn_bwd_reduce_kernel<<<(C + 31) / 32, 256, 0, ST>>>(y, s, sums);
+    return check_cuda(cudaGetLastError(), "f32_bn_bwd_sums launch");
 }
 
 extern "C" int xcp_f32_dw3x3_bwd(const float* dD, const float* xin, const float* w9, const float* scale, const float* shift, int relu,

@@ -245,7 +245,7 @@ def sep_forward(cache: PackCache, spec: SepSpec, src: torch.Tensor, src_st, relu
 
 
 class BlockTape:
-    __slots__ = ("spec", "inp", "units", "xs", "ys", "st_s", "idx", "out")
+    __slots__ = ("spec", "inp", "units", "xs", "ys", "st_s", "idx", "ymax", "out")
 
 
 def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: list, save: bool = True) -> BlockTape:
@@ -258,7 +258,7 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
         bt.units.append(t)
         src, src_st = t.y, t.st
     last = bt.units[-1]
-    bt.xs = bt.ys = bt.st_s = bt.idx = None
+    bt.xs = bt.ys = bt.st_s = bt.idx = bt.ymax = None
     F_, H, W, _ = inp.shape
     if spec.skip is not None:
         wb, _ = cache.pw_for(inp, spec.skip.weight)
@@ -277,7 +277,11 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
             nbt.append(spec.skipbn.num_batches_tracked)
         bt.xs, bt.ys, bt.st_s = xs, ys, st_s
         if spec.stride == 2:
-            bt.out, bt.idx = ops.pool_add_fwd(last.y, last.st.scale, last.st.shift, ys, st_s.scale, st_s.shift, want_idx=save)
+            if save:      # + the raw winners y[arg-max]: backward takes the BatchNorm sums from them instead of re-walking y
+                bt.out, bt.idx, bt.ymax = ops.pool_add_fwd(last.y, last.st.scale, last.st.shift, ys, st_s.scale, st_s.shift,
+                                                           want_idx=True, want_ymax=True)
+            else:
+                bt.out, bt.idx = ops.pool_add_fwd(last.y, last.st.scale, last.st.shift, ys, st_s.scale, st_s.shift, want_idx=False)
         else:
             bt.out = ops.bn_add_fwd(last.y, last.st.scale, last.st.shift, ys, st_s.scale, st_s.shift)
     else:
@@ -353,7 +357,10 @@ def block_backward(cache: PackCache, sink: GradSink, bt: BlockTape, G: torch.Ten
         dxs = _pw_backward(cache, sink, spec.skip.weight, dys, bt.xs)
         if spec.stride == 2:
             add_half = dxs
-            dy_last = ops.bn_bwd(ops.SRC_POOL, last.y, last.st, last.spec.bn.weight.detach(), dg, db, G=G, idx=bt.idx)
+            # dz is G routed to the arg-max pixels: sum dz = sum G, sum dz*y = sum G*y[arg-max] -- pass 1 runs on the two
+            # pooled-resolution tensors (a quarter of the bytes of walking y with the routing logic)
+            presums = ops.bn_bwd_sums(bt.ymax, G) if bt.ymax is not None else None
+            dy_last = ops.bn_bwd(ops.SRC_POOL, last.y, last.st, last.spec.bn.weight.detach(), dg, db, G=G, idx=bt.idx, presums=presums)
         else:
             add_full = dxs
             dy_last = ops.bn_bwd(ops.SRC_DIRECT, last.y, last.st, last.spec.bn.weight.detach(), dg, db, G=G)

@@ -149,7 +149,7 @@ def strip_module_prefix(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 def visual_batch(model, arcface, video, labels, seq_lengths, train: bool):
     """One batch of train_visual.py:563-572 / test_visual.py:614-619 -> (loss or None, P(fake) per clip)."""
     feats = model.extract_features(video, seq_lengths)
-    emb = model.lstm(feats)[0][:, -1, :]
+    emb = model.last_step(model.lstm(feats)[0], seq_lengths)        # [:, -1, :] unless model.use_seq_lengths (row f-2)
     if labels is None:
         logits = arcface(emb)
         return None, torch.softmax(logits, dim=1)[:, 1]

@@ -260,6 +260,7 @@ class _XceptionFn(torch.autograd.Function):
         params = net._backbone_params()
         sink = ex.GradSink(params, dfeat.device, scratch_floats=2 * sum(ops.phys(p.numel()) + 4 for p in params if p.dim() == 1))
         hook = net.__dict__.get("_grad_ready_hook")
+        net.__dict__["_last_sink"] = sink      # the arena of the latest backward (every p.grad is a view of it; tools / bench inspect it)
         if hook is not None:
             sink.on_ready = lambda lo, hi: hook(sink, lo, hi)
         ex.xception_backward(net, ctx.tape, dfeat.float(), sink)
@@ -510,11 +511,44 @@ class _XceptionLSTMBase(nn.Module):
             ps += [self.fc_layers[k].weight, self.fc_layers[k].bias]
         return ps + [self.fc_out.weight, self.fc_out.bias]
 
+    # ---- variable-length clips (second half).  The shipped class ignores lengths: zero-padded frames run
+    # through the backbone (and, in train mode, into the BatchNorm statistics) and the head reads the LSTM output at the last,
+    # possibly padded, step (XceptionLSTMV.py:55,68; video_dataloader.py:59-64).  That stays the default (drop-in).  With
+    # ``use_seq_lengths = True`` (or XCP_USE_SEQ_LENGTHS=1) a ``seq_lengths`` tensor handed to extract_features / last_step /
+    # forward is honoured: only the valid frames are packed through the backbone, and the clip embedding is the LSTM output at
+    # step length-1 (a causal LSTM: identical to running the unpadded clip).  Pack / unpack / select are index copies.
+    use_seq_lengths = False
+
+    def _lengths_on(self, seq_lengths) -> bool:
+        on = self.use_seq_lengths or os.environ.get("XCP_USE_SEQ_LENGTHS", "0") == "1"
+        return bool(on) and torch.is_tensor(seq_lengths) and not seq_lengths.dtype.is_floating_point
+
+    def _packed_features(self, frames: torch.Tensor, b: int, t: int, seq_lengths: torch.Tensor) -> torch.Tensor:
+        """frames [b*t, ...] (padded) -> features [b, t, 2048] with zeros at the padded steps; only valid frames are computed."""
+        lens = seq_lengths.detach().to("cpu").long().clamp_(0, t)              # the collate builds them on the host
+        if int(lens.min()) < 1:
+            raise XcpError("seq_lengths: every clip needs at least one valid frame, got %s" % lens.tolist())
+        valid = (torch.arange(t).unsqueeze(0) < lens.unsqueeze(1)).reshape(-1)
+        idx = torch.nonzero(valid).squeeze(1).to(frames.device)
+        feats_v = self.feature_extractor(frames.index_select(0, idx))
+        feats = torch.zeros((b * t, feats_v.shape[-1]), device=frames.device, dtype=feats_v.dtype)
+        return feats.index_copy(0, idx, feats_v).view(b, t, -1)
+
+    def last_step(self, lstm_out: torch.Tensor, seq_lengths=None) -> torch.Tensor:
+        """The clip embedding: lstm_out[:, -1, :] (XceptionLSTMV.py:68; train_visual.py:569), or -- lengths honoured -- the output
+        at each clip's last VALID step."""
+        if not self._lengths_on(seq_lengths):
+            return lstm_out[:, -1, :]
+        b, t, _ = lstm_out.shape
+        last = (seq_lengths.detach().long().clamp(1, t) - 1).to(lstm_out.device)
+        return lstm_out[torch.arange(b, device=lstm_out.device), last]
+
     def forward(self, features, seq_lengths=None):
         """lstm -> last step -> fc_layers -> sigmoid(fc_out) (XceptionLSTMV.py:66-70).  The optional second argument
-        exists because train_visual.py's older variants pass seq_lengths; like the shipped class, lengths are not used."""
+        exists because train_visual.py's older variants pass seq_lengths; like the shipped class, lengths are not used
+        unless ``use_seq_lengths`` is set."""
         lstm_out, _ = self.lstm(features)
-        last = lstm_out[:, -1, :]
+        last = self.last_step(lstm_out, seq_lengths)
         drop = self.fc_layers[2]
         return _HeadFn.apply(last, drop.training, float(drop.p), False, *self._head_params())
 
@@ -541,6 +575,8 @@ class XceptionLSTMV(_XceptionLSTMBase):
         else:
             b, t, c, h, w = video_batch.shape
             frames = video_batch.reshape(b * t, c, h, w)
+        if self._lengths_on(device):                  # honour seq_lengths: padded frames never reach the backbone
+            return self._packed_features(frames, b, t, device)
         feats = self.feature_extractor(frames)
         return feats.view(b, t, -1)
 

@@ -318,18 +318,35 @@ def gather_s2(x, scale=None, shift=None, relu=False):
     return out
 
 
-def pool_add_fwd(y, scale, shift, ys, scale_s, shift_s, want_idx=True):
+def pool_add_fwd(y, scale, shift, ys, scale_s, shift_s, want_idx=True, want_ymax=False):
+    """-> (out, idx) or, with want_ymax, (out, idx, ymax): ymax = the raw y at the arg-max (saved for bn_bwd_sums)."""
     F_, H, W, C = y.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=y.dtype)
     idx = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=torch.uint8) if want_idx else None
+    ymax = torch.empty((F_, Ho, Wo, C), device=y.device, dtype=y.dtype) if want_ymax else None
     if y.dtype == F32:
-        _lib.call("xcp_f32_pool_add_fused", _p(y), _p(scale), _p(shift), _p(ys), _p(scale_s), _p(shift_s), _p(out), _p(idx), F_, H, W,
-                  C, y.device.index, _s())
-        return out, idx
-    _lib.call("xcp_pool_add_fwd", _p(y), _p(scale), _p(shift), _p(ys), _p(scale_s), _p(shift_s), _p(out), _p(idx), F_, H, W, C,
-              y.device.index, _s())
-    return out, idx
+        _lib.call("xcp_f32_pool_add_fused", _p(y), _p(scale), _p(shift), _p(ys), _p(scale_s), _p(shift_s), _p(out), _p(idx), _p(ymax),
+                  F_, H, W, C, y.device.index, _s())
+    else:
+        _lib.call("xcp_pool_add_fwd", _p(y), _p(scale), _p(shift), _p(ys), _p(scale_s), _p(shift_s), _p(out), _p(idx), _p(ymax), F_, H,
+                  W, C, y.device.index, _s())
+    return (out, idx, ymax) if want_ymax else (out, idx)
+
+
+def bn_bwd_sums(y: torch.Tensor, G: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[2, C] fp32 = (sum G, sum G*y) over two same-shape [.., C] activations: pass 1 of the BatchNorm backward on its own."""
+    C = y.shape[-1]
+    n_pix = y.numel() // C
+    assert G.shape == y.shape and G.dtype == y.dtype
+    sums = out if out is not None else torch.empty((2, C), device=y.device, dtype=F32)
+    if y.dtype == F32:
+        _lib.call("xcp_f32_bn_bwd_sums", _p(y), _p(G), _p(sums), n_pix, C, y.device.index, _s())
+        return sums
+    _chk(y, BF16, "bn_bwd_sums.y"); _chk(G, BF16, "bn_bwd_sums.G")
+    ws = torch.empty((_lib.call("xcp_bnbwd_num_parts"), 2, C), device=y.device, dtype=F32)
+    _lib.call("xcp_bn_bwd_sums", _p(y), _p(G), _p(ws), _p(sums), n_pix, C, y.device.index, _s())
+    return sums
 
 
 def bn_add_fwd(y, scale, shift, skip, scale_s=None, shift_s=None):

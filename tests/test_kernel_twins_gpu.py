@@ -182,6 +182,22 @@ def test_pool_add_and_bn_add_and_gap_twins(shape, skipbn):
     # (pad channels have scale = shift = 0: every tap ties there)
     same = (idx_b[..., :Cr] == idx_f[..., :Cr]).float().mean().item()
     assert same > 0.999, same
+    # raw winners saved for the backward sums: the same bf16 value in both arithmetics; sums over (ymax, G) == sums over dz, dz*y
+    _, _, ym_b = ops.pool_add_fwd(yb, sc, sh, sb, sc2, sh2, want_ymax=True)
+    _, _, ym_f = ops.pool_add_fwd(yf, sc, sh, sf, sc2, sh2, want_ymax=True)
+    agree = (ym_b.float()[..., :Cr] == ym_f[..., :Cr]).float().mean().item()
+    assert agree > 0.999, agree
+    Gb, Gf = bfx(F_, Ho, Wo, C, seed=36)
+    s_b, s_f = ops.bn_bwd_sums(ym_b, Gb), ops.bn_bwd_sums(ym_f, Gf)
+    assert relmax(s_b[:, :Cr], s_f[:, :Cr]) < 1e-3 * (2.0 - agree) and s_b.shape == (2, C)          # (a tie may pick another equal winner)
+    st, gamma = _bn_state(C, Cr, 37, True)
+    z = lambda: torch.zeros(Cr, device=DEV)  # noqa: E731
+    dg1, db1, dg2, db2 = z(), z(), z(), z()
+    dy1 = ops.bn_bwd(ops.SRC_POOL, yb, st, gamma, dg1, db1, G=Gb, idx=idx_b)                       # in-kernel routing reduce
+    dy2 = ops.bn_bwd(ops.SRC_POOL, yb, st, gamma, dg2, db2, G=Gb, idx=idx_b, presums=ops.bn_bwd_sums(ym_b, Gb))
+    ref_scale = max(dg1.abs().max().item(), db1.abs().max().item())
+    assert (dg1 - dg2).abs().max().item() < 2e-5 * ref_scale and (db1 - db2).abs().max().item() < 2e-5 * ref_scale
+    assert one_ulp(dy2, dy1.float(), extra=(dy1.float().abs().max().item() + 1.0) * 4e-6) <= 1.01
     fb, ff = bfx(F_, H, W, C, seed=35)
     a = ops.bn_add_fwd(yb, sc, sh, fb); b = ops.bn_add_fwd(yf, sc, sh, ff)
     assert one_ulp(a, b, extra=b.abs().max().item() * 2e-6) <= 1.01

@@ -462,3 +462,47 @@ def test_200_step_unfrozen_training_curve_at_299():
         ratio = float(d_ours.norm() / (d_ref.norm() + 1e-30))
         print("   displacement %-52s |ours|/|ref| %.3f cos %.3f" % (k, ratio, cos))
         assert d_ref.norm().item() > 0 and 0.5 < ratio < 2.0 and cos > 0.5, (k, ratio, cos)
+
+
+def test_seq_lengths_mode_matches_unpadded_clips():
+    """SURVEY §8 row f-2 (second half): with ``use_seq_lengths`` the zero-padded frames never reach the backbone and the clip
+    embedding is the LSTM output at the last VALID step -- identical (eval mode: frames are independent) to running each clip
+    unpadded on its own; the default stays the shipped class's behaviour (lengths ignored, XceptionLSTMV.py:55,68)."""
+    m, full = _lstm_models(32, XceptionLSTMV)
+    m.eval()
+    g = torch.Generator().manual_seed(9)
+    lens = [3, 5, 2, 5]
+    clips = [torch.rand(n, 3, 75, 75, generator=g) for n in lens]
+    padded = torch.zeros(4, 5, 3, 75, 75)
+    for i, c in enumerate(clips):
+        padded[i, :c.shape[0]] = c                                   # video_dataloader.py:59-64
+    padded = padded.to(DEV)
+    seq = torch.tensor(lens)
+    _lib.reset_launch_count()
+    with torch.no_grad():
+        f_def = m.extract_features(padded, seq)                      # default: lengths ignored, 20 frames
+        n_def = _lib.launch_count()
+        p_def = m(f_def, seq)
+        m.use_seq_lengths = True
+        _lib.reset_launch_count()
+        f_len = m.extract_features(padded, seq)                      # 15 valid frames only
+        p_len = m(f_len, seq)
+        e_len = m.last_step(m.lstm(f_len)[0], seq)
+        singles = [m(m.extract_features(c.unsqueeze(0).to(DEV), torch.device(DEV))) for c in clips]
+        e_single = [m.lstm(m.extract_features(c.unsqueeze(0).to(DEV), torch.device(DEV)))[0][:, -1, :] for c in clips]
+    assert n_def > 0
+    for i, n in enumerate(lens):
+        assert torch.equal(f_len[i, :n], f_def[i, :n])               # valid frames: bit-identical features (batch independence)
+        assert (f_len[i, n:] == 0).all()
+        assert (p_len[i] - singles[i][0]).abs().max().item() < 2e-3 and rel(e_len[i:i + 1], e_single[i]) < 2e-2
+    # clips 1 and 3 are full length: both modes agree there; the padded ones differ (the default reads a padded step)
+    assert (p_len[1] - p_def[1]).abs().max().item() < 2e-3
+    # training through the packed path: gradients reach the backbone, LSTM and head
+    m.train()
+    for p in m.feature_extractor.parameters():
+        p.requires_grad = True
+    out = m(m.extract_features(padded, seq), seq)
+    F.binary_cross_entropy(out, torch.tensor([[1.0], [0.0], [1.0], [0.0]], device=DEV)).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    with pytest.raises(Exception):
+        m.extract_features(padded, torch.tensor([0, 5, 2, 5]))
