@@ -81,6 +81,11 @@ int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t row
 
 int make_tmap_4d(CUtensorMap* map, const void* base, const uint64_t dims_[4], const uint64_t strides_bytes[3],
                  const uint32_t box_[4], int swizzle_bytes) {
+    return make_tmap_4d_l2(map, base, dims_, strides_bytes, box_, swizzle_bytes, 256);
+}
+
+int make_tmap_4d_l2(CUtensorMap* map, const void* base, const uint64_t dims_[4], const uint64_t strides_bytes[3],
+                    const uint32_t box_[4], int swizzle_bytes, int l2_promotion_bytes) {
     EncodeTiledFn enc = get_encode();
     XCP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
     cuuint64_t dims[4] = {dims_[0], dims_[1], dims_[2], dims_[3]};
@@ -88,7 +93,10 @@ int make_tmap_4d(CUtensorMap* map, const void* base, const uint64_t dims_[4], co
     cuuint32_t box[4] = {box_[0], box_[1], box_[2], box_[3]};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes),
+                     l2_promotion_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                     : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                     : l2_promotion_bytes >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     XCP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed: CUresult %d", (int)r);
     return 0;

@@ -24,6 +24,10 @@ int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t row
                  uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 int make_tmap_4d(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
                  const uint32_t box[4], int swizzle_bytes);
+// same with an explicit L2 promotion size (256 / 128 / 64 / 0 bytes): a 64-channel (128-byte) box row of a wider tensor promoted
+// to 256 B drags in the neighbouring channel tile, which is wasted DRAM traffic unless that tile is consumed at about the same time
+int make_tmap_4d_l2(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                    const uint32_t box[4], int swizzle_bytes, int l2_promotion_bytes);
 
 // ------------------------------------------------------------------ small device utils
 XCP_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

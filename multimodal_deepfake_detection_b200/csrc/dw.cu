@@ -593,6 +593,9 @@ static int dw_grid(const DwGeom& g, int ctas_per_sm) {
     return (int)(per_ct * g.c_tiles);
 }
 
+int dws_try_fwd(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int H, int W,
+                int C, cudaStream_t st, int* handled);          // dw_stream.cu
+
 }  // namespace xcp
 
 using namespace xcp;
@@ -856,6 +859,11 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
     XCP_REQUIRE((scale == nullptr) == (shift == nullptr), "xcp_dw3x3_fwd: scale/shift must both be given or both null");
     XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_fwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
+    {   // row-stream kernels (dw_stream.cu) for the shapes they are instantiated for
+        int handled = 0;
+        const int r = dws_try_fwd(x, w9, scale, shift, relu, out, F, H, W, C, (cudaStream_t)stream, &handled);
+        if (handled) return r;
+    }
     if (H == W && H <= 8) {
         const char* e = getenv("XCP_DW_NO_SMALL");                                    // A/B hook
         if (!(e && e[0] == '1')) {
