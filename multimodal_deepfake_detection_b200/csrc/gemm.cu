@@ -658,6 +658,9 @@ static int grid_tn(const TnPlan& pl, int units) {
     return pl.cta2 ? gemm_grid<256, EPI, false, fit_stages<256, 64, EPI, true>(), 64, true>(units) : gemm_grid<256, EPI, false, fit_stages<256, 64, EPI, false>(), 64, false>(units);
 }
 
+int conv3x3_wgrad32_try(const void* dy_grid, const void* x, float* gk, int F, int Hg, int Wg, int Cin, int Cout, cudaStream_t st,
+                        int* handled);          // conv_wgrad.cu
+
 }  // namespace xcp
 
 using namespace xcp;
@@ -796,6 +799,15 @@ extern "C" int xcp_conv3x3_gemm(const void* a, const void* b, void* out, float* 
             if (int e = make_tmap_2d(&tmA, a, (uint64_t)Cin, (uint64_t)Mg, (uint64_t)Cin * 2, Cin, box_rows, Cin * 2)) return e;
         }
     }
+    // data gradient: every grid row is an output row (no compaction) -> the epilogue can use the bulk tensor store of the
+    // pointwise GEMMs instead of 64-byte row pieces scattered by the threads (486 -> ? us at 256 frames, tools/kernel_bench.py)
+    if (sign < 0 && Ho == Hg && Wo == Wg && stats == nullptr) {
+        static const char* off = getenv("XCP_CONV_NO_TMA_STORE");    // A/B switch
+        if (off == nullptr) {
+            if (int e = make_tmap_2d(&p.tmC, out, (uint64_t)Cout, (uint64_t)Mg, (uint64_t)Cout * 2, 32, 32, 64)) return e;
+            p.tma_store = 1;
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (Cin == 32) {
         if (stats != nullptr) return launch_gemm<64, EPI_BF16_STATS, false, fit_stages<64, 32, EPI_BF16_STATS, false>(), 32>(tmA, tmB, p, st);
@@ -814,6 +826,11 @@ extern "C" int xcp_conv3x3_wgrad(const void* dy_grid, const void* x, float* gk, 
     XCP_CUDA(cudaSetDevice(device));
     const long long R = (long long)F * Hg * Wg;
     XCP_REQUIRE(R < (1LL << 31) - 65536, "xcp_conv3x3_wgrad: grid too large for 32-bit TMA coordinates");
+    {   // the stem shape (32 -> 64) has its own kernel: all nine taps per CTA, one epilogue (conv_wgrad.cu)
+        int handled = 0;
+        const int r = conv3x3_wgrad32_try(dy_grid, x, gk, F, Hg, Wg, Cin, Cout, (cudaStream_t)stream, &handled);
+        if (handled) return r;
+    }
     CUtensorMap tmA, tmB;
     if (int e = make_tmap_2d(&tmA, dy_grid, (uint64_t)Cout, (uint64_t)R, (uint64_t)Cout * 2, 64, 64, 128)) return e;
     if (int e = make_tmap_2d(&tmB, x, (uint64_t)Cin, (uint64_t)R, (uint64_t)Cin * 2, 64, 64, 128)) return e;
