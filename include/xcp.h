@@ -33,6 +33,12 @@ int xcp_check_device(int device);
  * BatchNorm (Xception.py:67,73,78) | 2 fp32 out (+ optional bias[N]).  lda/ldb/ldo are row pitches in elements. */
 int xcp_gemm_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N, int K,
                 int epi, float* stats, const float* bias, int device, void* stream);
+/* Inference plan (eval-mode BatchNorm folded into the weights; the reference's no_grad evaluation, test_visual.py:609-624):
+ * out[M,N] = relu?( A[M,K] * B[N,K]^T + bias[N] + residual[M,N] ) as bf16.  B = pointwise weights pre-multiplied per output
+ * channel by gamma * rsqrt(running_var + eps) (xcp_pack_weight_scaled), bias = beta - running_mean * that scale; residual
+ * (optional, bf16, row pitch ld_res) is the identity-skip input of a Block (Xception.py:96-98).  N % 32 == 0. */
+int xcp_gemm_tn_bias(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N, int K,
+                     const float* bias, int relu, const void* residual, long long ld_res, int device, void* stream);
 /* rows of `stats` written by xcp_gemm_tn(epi=1) / xcp_conv3x3_gemm for an M x N problem (<= SM count when N fits one tile) */
 int xcp_gemm_stats_parts(long long M, int N, int device);
 /* dW[P,Q] += dY[R,P]^T * X[R,Q] (fp32 accumulate into dW): weight gradient of the layers above. */
@@ -115,6 +121,9 @@ int xcp_nchw_to_nhwc(const float* x, void* out, int F, int C, int Cp, int HW, in
 int xcp_nhwc_to_nchw(const void* x, float* out, int F, int C, int Cp, int HW, int device, void* stream);
 /* fp32 [R,Cc] -> bf16 [Rp,Cp] (zero padded) and optionally its transpose bf16 [Cp,Rp] */
 int xcp_pack_weight(const float* w, void* out, void* out_t, int R, int Cc, int Rp, int Cp, int device, void* stream);
+/* same, every row r multiplied by row_scale[r] before rounding (BatchNorm scale folded into the weights); no transpose */
+int xcp_pack_weight_scaled(const float* w, const float* row_scale, void* out, int R, int Cc, int Rp, int Cp, int device,
+                           void* stream);
 int xcp_pack_dw(const float* w, float* w9, int C, int Cp, int device, void* stream);                      /* w9 = [9][Cp] */
 int xcp_unpack_dw_grad(const float* g9, float* gw, int C, int accumulate, int device, void* stream);
 /* multi-tensor xcp_pack_weight / xcp_pack_dw: `table` = n_tensors x {const float* src; void* out; void* out_t; int R, Cc, Rp,

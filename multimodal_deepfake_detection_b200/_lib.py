@@ -20,6 +20,7 @@ SIGNATURES = {
     "xcp_version": "",
     "xcp_check_device": "i",
     "xcp_gemm_tn": "plplpliiiippip",
+    "xcp_gemm_tn_bias": "plplpliiipiplip",
     "xcp_gemm_stats_parts": "lii",
     "xcp_gemm_wgrad": "plplpliiiip",
     "xcp_gemm_ref": "plplpliiiiip",
@@ -44,6 +45,7 @@ SIGNATURES = {
     "xcp_nchw_to_nhwc": "ppiiiiip",
     "xcp_nhwc_to_nchw": "ppiiiiip",
     "xcp_pack_weight": "pppiiiiip",
+    "xcp_pack_weight_scaled": "pppiiiiip",
     "xcp_pack_dw": "ppiiip",
     "xcp_pack_multi": "piiip",
     "xcp_unpack_dw_grad": "ppiiip",

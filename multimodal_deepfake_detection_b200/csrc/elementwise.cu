@@ -748,13 +748,16 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 }
 
 // fp32 [R, Cc] -> bf16 [Rp, Cp] (zero padded) and (optionally) its transpose bf16 [Cp, Rp]
+// row_scale (optional, [Rp]): every row is multiplied by its entry before rounding -- the inference plan folds the BatchNorm
+// scale gamma * rstd of an output channel into the pointwise weights this way (test_visual.py:609-624)
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_t,
-                                   int R, int Cc, int Rp, int Cp) {
+                                   int R, int Cc, int Rp, int Cp, const float* __restrict__ row_scale = nullptr) {
     __shared__ float t[32][33];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int rr = r0 + r, cc = c0 + threadIdx.x;
-        const float v = (rr < R && cc < Cc) ? w[(long long)rr * Cc + cc] : 0.f;
+        float v = (rr < R && cc < Cc) ? w[(long long)rr * Cc + cc] : 0.f;
+        if (row_scale != nullptr && rr < R) v *= row_scale[rr];
         t[r][threadIdx.x] = v;
         if (rr < Rp && cc < Cp && out != nullptr) out[(long long)rr * Cp + cc] = __float2bfloat16(v);
     }
@@ -1095,6 +1098,15 @@ extern "C" int xcp_pack_weight(const float* w, void* out, void* out_t, int R, in
     dim3 grid((Cp + 31) / 32, (Rp + 31) / 32), block(32, 8);
     pack_weight_kernel<<<grid, block, 0, ST>>>(w, (__nv_bfloat16*)out, (__nv_bfloat16*)out_t, R, Cc, Rp, Cp);
     return check_cuda(cudaGetLastError(), "pack_weight launch");
+}
+
+extern "C" int xcp_pack_weight_scaled(const float* w, const float* row_scale, void* out, int R, int Cc, int Rp, int Cp, int device,
+                                      void* stream) {
+    XCP_REQUIRE(Rp >= R && Cp >= Cc && row_scale != nullptr, "xcp_pack_weight_scaled: bad arguments");
+    XCP_CUDA(cudaSetDevice(device));
+    dim3 grid((Cp + 31) / 32, (Rp + 31) / 32), block(32, 8);
+    pack_weight_kernel<<<grid, block, 0, ST>>>(w, (__nv_bfloat16*)out, nullptr, R, Cc, Rp, Cp, row_scale);
+    return check_cuda(cudaGetLastError(), "pack_weight_scaled launch");
 }
 
 extern "C" int xcp_pack_multi(const void* table, int n_tensors, int n_tiles, int device, void* stream) {

@@ -25,7 +25,9 @@
 
 namespace xcp {
 
-enum { EPI_BF16 = 0, EPI_BF16_STATS = 1, EPI_F32 = 2, EPI_RED_F32 = 3 };
+enum { EPI_BF16 = 0, EPI_BF16_STATS = 1, EPI_F32 = 2, EPI_RED_F32 = 3, EPI_BF16_BIAS = 4 };
+// EPI_BF16_BIAS (inference plan, BatchNorm folded into the weights): out = relu?(acc + bias[n] + residual[m][n]) as bf16
+__host__ __device__ constexpr bool epi_is_bf16(int epi) { return epi == EPI_BF16 || epi == EPI_BF16_STATS || epi == EPI_BF16_BIAS; }
 
 struct GemmParams {
     CUtensorMap tmC;      // EPI_BF16 / EPI_BF16_STATS with tma_store: the bf16 output as [M rows, N cols], box 32 x 32, 64B swizzle
@@ -35,7 +37,10 @@ struct GemmParams {
     long long ldo;
     float* stats;         // EPI_BF16_STATS: [parts][2][N]; parts = gridDim.x if stats_per_cta else num_m_tiles
     int stats_per_cta;    // single N tile: each CTA accumulates its tiles' sums and writes one partial row
-    const float* bias;    // EPI_F32: optional [N]
+    const float* bias;    // EPI_F32: optional [N]; EPI_BF16_BIAS: [N rounded up to 32]
+    const void* residual; // EPI_BF16_BIAS: optional bf16 [M, ld_res] added before the activation
+    long long ld_res;
+    int epi_relu;
     int num_m_tiles, num_n_tiles, num_k_blocks;
     int splits, k_blocks_per_split;   // split over the reduction dim (EPI_RED_F32)
     // implicit-GEMM mode for the dense 3x3 stem conv: K block kb reads A rows shifted by a_row_shift[kb]
@@ -63,11 +68,12 @@ template <int BLOCK_N, int BLOCK_K>
 __host__ __device__ constexpr int b_stage_bytes() { return BLOCK_N * BLOCK_K * 2; }
 
 constexpr int STORE_STAGE_BYTES = 8 * 2 * 2048;   // TMA-store epilogue: 8 warps x 2 buffers x (32 rows x 64 B)
+constexpr int RES_STAGE_BYTES = 8 * 2048;         // EPI_BF16_BIAS: 8 warps x (32 rows x 64 B) residual tile, same swizzle
 template <int BLOCK_N, int BLOCK_K, int EPI, bool CTA2>
 __host__ __device__ constexpr int gemm_fixed_smem() {
     return 1024 /*align slack*/ + 256 /*barriers*/ +
            (EPI == EPI_BF16_STATS ? ((BLOCK_N == 64 ? 8 * 32 * 36 * 4 : 0) + 4 * 2 * BLOCK_N * 4) : 0) +
-           ((EPI == EPI_BF16 || EPI == EPI_BF16_STATS) ? STORE_STAGE_BYTES : 0);
+           (epi_is_bf16(EPI) ? STORE_STAGE_BYTES : 0) + (EPI == EPI_BF16_BIAS ? RES_STAGE_BYTES : 0);
 }
 template <int BLOCK_N, int BLOCK_K, bool CTA2>
 __host__ __device__ constexpr int gemm_stage_bytes() { return BLOCK_M * BLOCK_K * 2 + b_stage_bytes<BLOCK_N, BLOCK_K>() / (CTA2 ? 2 : 1); }
@@ -108,7 +114,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float* s_tr = reinterpret_cast<float*>(after);                       // [8][32][36]  (144-byte rows: conflict-free v4 stores); BLOCK_N == 64 only
     float* s_part = s_tr + ((STATS && BLOCK_N == 64) ? 8 * 32 * 36 : 0);                    // [4][2][BLOCK_N]
     uint8_t* s_store = reinterpret_cast<uint8_t*>(s_part + (STATS ? 4 * 2 * BLOCK_N : 0));      // [8 warps][2][32 rows x 64 B], 64B-swizzled
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_store + ((EPI == EPI_BF16 || EPI == EPI_BF16_STATS) ? STORE_STAGE_BYTES : 0));
+    uint8_t* s_res = s_store + (epi_is_bf16(EPI) ? STORE_STAGE_BYTES : 0);                      // [8 warps][32 rows x 64 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_res + (EPI == EPI_BF16_BIAS ? RES_STAGE_BYTES : 0));
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
@@ -327,6 +334,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int ci = 0; ci < NCW; ++ci) {
                 const int c = c_lo + ci;
                 if (c >= c_hi) break;
+                uint4 resv[4];
+                if (EPI == EPI_BF16_BIAS && p.residual != nullptr) {
+                    // residual tile (32 rows x 32 bf16): coalesced 16-byte loads (4 lanes per 64-byte row piece, 8 rows per
+                    // instruction), issued before the accumulator read so that their latency overlaps it
+                    const long long row0 = (long long)m_blk * BLOCK_M + q * 32;
+                    const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual) + n_blk * BLOCK_N + c * 32 + (lane & 3) * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = (lane >> 2) + 8 * i;
+                        resv[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (row0 + rr < p.M) resv[i] = ldg_nc_v4(rbase + (row0 + rr) * p.ld_res);
+                    }
+                }
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
                 uint32_t fa[16], fb[16];
@@ -343,7 +363,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 // conv weight gradient: tile column c*32 belongs to tap n_blk*(BLOCK_N/64) + c/2, channel offset (c & 1)*32
                 const int wg_tap = n_blk * (BLOCK_N / 64) + (c >> 1);
                 const int gcol = p.wg_taps > 0 ? wg_tap * p.wg_tap_cols + (c & 1) * 32 : n_blk * BLOCK_N + c * 32;
-                if (EPI == EPI_BF16 || EPI == EPI_BF16_STATS) {
+                if (EPI == EPI_BF16_BIAS) {
+                    // folded-BatchNorm epilogue: per-column shift, optional residual tile (bf16, read straight from global: each
+                    // thread owns one row = 64 contiguous bytes per chunk), optional ReLU -- all on the accumulator registers
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + gcol);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 b = __ldg(bp + g);
+                        r[g * 4 + 0] = __float_as_uint(__uint_as_float(r[g * 4 + 0]) + b.x);
+                        r[g * 4 + 1] = __float_as_uint(__uint_as_float(r[g * 4 + 1]) + b.y);
+                        r[g * 4 + 2] = __float_as_uint(__uint_as_float(r[g * 4 + 2]) + b.z);
+                        r[g * 4 + 3] = __float_as_uint(__uint_as_float(r[g * 4 + 3]) + b.w);
+                    }
+                    if (p.residual != nullptr) {
+                        // -> swizzled per-warp staging -> every thread reads back its own accumulator row.  (Reading the row straight
+                        // from global, 64 B per thread at the row pitch, made the GEMM 3x slower: 251 vs 85 us.)
+                        const uint32_t rs = smem_u32(s_res) + (uint32_t)(warp - 2) * 2048u;
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rr = (lane >> 2) + 8 * i;
+                            const uint32_t a = rs + (uint32_t)rr * 64u + (uint32_t)(((lane & 3) ^ ((rr >> 1) & 3)) * 16);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(resv[i].x), "r"(resv[i].y), "r"(resv[i].z), "r"(resv[i].w) : "memory");
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 v;
+                            const uint32_t a = rs + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) * 16);
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+                            float f[8]; unpack8(v, f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) r[g * 8 + j] = __float_as_uint(__uint_as_float(r[g * 8 + j]) + f[j]);
+                        }
+                    }
+                    if (p.epi_relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+                    }
+                }
+                if (epi_is_bf16(EPI)) {
                     if (p.tma_store) {
                         // bf16 rows -> 64B-swizzled staging tile (conflict-free 16 B stores) -> one bulk tensor store of the
                         // 32 x 32 box: full-line coalesced writes issued by the TMA unit instead of 32 row-scattered 16 B
@@ -512,7 +571,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
-        if ((EPI == EPI_BF16 || EPI == EPI_BF16_STATS) && p.tma_store && lane == 0) tma_store_wait_read<0>();
+        if (epi_is_bf16(EPI) && p.tma_store && lane == 0) tma_store_wait_read<0>();
         if (STATS && p.stats_per_cta) {
             if (reg_stats) {
                 // one cross-lane reduction for the whole kernel: full butterfly over the 8 lanes that share a column set
@@ -699,6 +758,34 @@ extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long lon
         case EPI_BF16_STATS: return dispatch_tn<EPI_BF16_STATS>(pl, tmA, tmB, p, st);
         default: return dispatch_tn<EPI_F32>(pl, tmA, tmB, p, st);
     }
+}
+
+// Inference plan: out[M,N] = relu?( A[M,K] * B[N,K]^T + bias[N] + residual[M,N] ) in bf16, where B holds
+// the pointwise weights pre-multiplied by the BatchNorm scale (xcp_fold_bn_weight) and bias the BatchNorm shift.
+extern "C" int xcp_gemm_tn_bias(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N,
+                                int K, const float* bias, int relu, const void* residual, long long ld_res, int device, void* stream) {
+    XCP_REQUIRE(M > 0 && N > 0 && K > 0, "xcp_gemm_tn_bias: empty problem M=%d N=%d K=%d", M, N, K);
+    XCP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "xcp_gemm_tn_bias: K/lda/ldb must be multiples of 8 (16B TMA rows)");
+    XCP_REQUIRE(N % 32 == 0 && ldo % 8 == 0, "xcp_gemm_tn_bias: N must be a multiple of 32 (channel pitch), ldo of 8");
+    XCP_REQUIRE(bias != nullptr, "xcp_gemm_tn_bias: bias missing");
+    XCP_REQUIRE(residual == nullptr || (ld_res % 8 == 0 && (uintptr_t)residual % 16 == 0), "xcp_gemm_tn_bias: residual alignment");
+    XCP_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)bias % 16 == 0),
+                "xcp_gemm_tn_bias: 16B alignment");
+    XCP_CUDA(cudaSetDevice(device));
+    const TnPlan pl = plan_tn(M, N);
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, BLOCK_M, 128)) return e;
+    if (int e = make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, pl.cta2 ? pl.bn / 2 : pl.bn, 128)) return e;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.bias = bias;
+    p.residual = residual; p.ld_res = ld_res; p.epi_relu = relu;
+    p.num_m_tiles = pl.num_m_tiles;
+    p.num_n_tiles = pl.num_n_tiles;
+    p.num_k_blocks = (K + 63) / 64;
+    p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
+    if (int e = make_tmap_2d(&p.tmC, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 32, 32, 64)) return e;
+    p.tma_store = 1;
+    return dispatch_tn<EPI_BF16_BIAS>(pl, tmA, tmB, p, (cudaStream_t)stream);
 }
 
 // Number of partial rows xcp_gemm_tn (epi=1) writes into `stats` for an M x N problem.

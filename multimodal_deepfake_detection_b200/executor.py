@@ -50,6 +50,11 @@ def bump_param_epoch():
     PARAM_EPOCH[0] += 1
 
 
+# Bumped whenever a train-mode BatchNorm forward updates running statistics through raw pointers: the BN-folded weight packs of
+# the inference plan (PackCache.pw_folded) carry it in their tag.
+BN_EPOCH = [0]
+
+
 class PackCache:
     """bf16 / re-laid-out copies of the fp32 master parameters, rebuilt when a parameter changes.
     These are derived caches, never part of state_dict (SURVEY.md §5 checkpoint contract)."""
@@ -135,6 +140,30 @@ class PackCache:
         """[N,K,1,1] fp32 -> (bf16 [Np,Kp], bf16 [Kp,Np]), zero-padded to the physical channel pitches (ops.phys)"""
         return self._get(w, "pw", lambda t: ops.pack_weight(t.view(t.shape[0], t.shape[1]), True, pad=True))
 
+    def pw_folded(self, w: torch.Tensor, bn):
+        """Inference plan: ([N,K,1,1] fp32, eval-mode BatchNorm2d) -> (bf16 [Np,Kp] with row n scaled by
+        gamma_n * rsqrt(running_var_n + eps), fp32 bias [Np] = beta - running_mean * scale); pad rows / entries are zero."""
+        key = (id(w), "pwf")
+        tag = (w.data_ptr(), w._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               bn.running_mean.data_ptr(), float(bn.eps), self.generation, PARAM_EPOCH[0], BN_EPOCH[0], w.device)
+        hit = self._c.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        N, K = w.shape[0], w.shape[1]
+        st = ops.bn_finalize(None, 1, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, False, 0.0, bn.eps,
+                             C=ops.phys(N))
+        val = (ops.pack_weight_scaled(w.detach().view(N, K), st.scale), st.shift)
+        self._c[key] = (tag, val)
+        return val
+
+    def identity_affine(self, C: int, device):
+        """(ones [C], zeros [C]) fp32: the affine of a tensor whose BatchNorm is already folded in"""
+        key = ("ident", C, str(device))
+        hit = self._c.get(key)
+        if hit is None:
+            hit = self._c[key] = (None, (torch.ones(C, device=device, dtype=F32), torch.zeros(C, device=device, dtype=F32)))
+        return hit[1]
+
     def pw32(self, w: torch.Tensor):
         """fp32 validation plan: [N,K,1,1] fp32 -> (fp32 [Np,Kp], fp32 [Kp,Np]) zero-padded to the physical pitches (plain copies:
         layout plumbing, no arithmetic)."""
@@ -204,6 +233,7 @@ def _bn_state(bn, parts, count):
     running stats in eval mode.  The state vectors have the physical channel pitch (pad channels: scale = shift = 0)."""
     training = bn.training or (bn.running_mean is None)
     if training:
+        BN_EPOCH[0] += 1
         rm = bn.running_mean if bn.track_running_stats else None
         rv = bn.running_var if bn.track_running_stats else None
         mom = bn.momentum if bn.momentum is not None else 0.1
@@ -289,6 +319,60 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
             raise ops._lib.XcpError("Block: a strided block without a skip conv cannot occur (Xception.py:54)")
         bt.out = ops.bn_add_fwd(last.y, last.st.scale, last.st.shift, inp)
     return bt
+
+
+# ------------------------------------------------------------------------------------------------ inference plan (row f-3)
+def _sep_folded(cache: PackCache, spec: SepSpec, src: torch.Tensor, relu_in: bool, relu_out: bool, residual=None) -> torch.Tensor:
+    """[ReLU?] -> depthwise -> pointwise with the BatchNorm folded in: relu?(d @ (scale * W)^T + shift [+ residual]).  The ReLU
+    that follows the BatchNorm in the graph runs in the GEMM epilogue, so the next depthwise reads an activated tensor."""
+    F_, H, W, C = src.shape
+    d = ops.dw3x3_fwd(src, cache.dw(spec.sep.conv1.weight), None, None, relu_in)
+    wf, bias = cache.pw_folded(spec.sep.pointwise.weight, spec.bn)
+    M = F_ * H * W
+    y = ops.gemm_tn_bias(d.view(M, C), wf, bias, relu_out, residual.view(M, -1) if residual is not None else None)
+    return y.view(F_, H, W, y.shape[1])
+
+
+def _block_folded(cache: PackCache, spec: BlockSpec, inp: torch.Tensor) -> torch.Tensor:
+    """Block.forward (Xception.py:89-99) in the inference plan: BatchNorms folded into the pointwise / skip weights, the ReLU
+    between units and the identity-skip add in the GEMM epilogues; nothing is saved."""
+    ys = None
+    if spec.skip is not None:
+        xs = ops.gather_s2(inp) if spec.stride == 2 else inp
+        Fs, Hs, Ws, Cs = xs.shape
+        wf, bias = cache.pw_folded(spec.skip.weight, spec.skipbn)
+        ys = ops.gemm_tn_bias(xs.view(Fs * Hs * Ws, Cs), wf, bias, False)
+        ys = ys.view(Fs, Hs, Ws, ys.shape[1])
+    src = inp
+    n = len(spec.units)
+    for i, u in enumerate(spec.units):
+        relu_in = u.relu if i == 0 else False            # later units read a tensor the previous epilogue already activated
+        last = i == n - 1
+        relu_out = (not last) and spec.units[i + 1].relu
+        residual = None
+        if last and spec.stride == 1:
+            residual = ys if ys is not None else inp
+        src = _sep_folded(cache, u, src, relu_in, relu_out, residual)
+    if spec.stride == 1:
+        return src
+    one, zero = cache.identity_affine(src.shape[-1], src.device)
+    out, _ = ops.pool_add_fwd(src, one, zero, ys, one, zero, want_idx=False)
+    return out
+
+
+def _folded_ok(net) -> bool:
+    if __import__("os").environ.get("XCP_NO_FOLD", "0") == "1":          # A/B hook (bench.py, tests)
+        return False
+    for m in net.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and (m.training or m.running_mean is None):
+            return False
+    for spec in net._block_specs:
+        if spec.stride not in (1, 2) or (spec.stride == 2 and spec.skip is None):
+            return False
+        for i, u in enumerate(spec.units):
+            if u.bn is None or (i > 0 and not u.relu):
+                return False
+    return True
 
 
 # ------------------------------------------------------------------------------------------------ backward pieces
@@ -418,6 +502,15 @@ def xception_forward(net, x: torch.Tensor, save: bool = True):
     x2 = ops.bn_act(y2, st2.scale, st2.shift, True)
     tp.y1, tp.st1, tp.x1, tp.y2, tp.st2, tp.x2 = y1, st1, x1, y2, st2, x2
     cur = x2
+    if not save and not fp32 and _folded_ok(net):
+        # inference plan: eval-mode BatchNorm folded into the pointwise weights, ReLU / residual add in the GEMM epilogues
+        for spec in net._block_specs:
+            cur = _block_folded(cache, spec, cur)
+        e3, e4 = net._exit_specs
+        y3 = _sep_folded(cache, e3, cur, e3.relu, True)                      # conv3 -> bn3 -> relu   (Xception.py:189-191)
+        y4 = _sep_folded(cache, e4, y3, False, False)                        # conv4 -> bn4; relu + GAP below (192-198)
+        one, zero = cache.identity_affine(y4.shape[-1], y4.device)
+        return ops.bn_relu_gap(y4, one, zero), None
     tp.blocks = []
     for spec in net._block_specs:                                             # Xception.py:176-187
         bt = block_forward(cache, spec, cur, nbt, save)

@@ -249,7 +249,8 @@ class FusedLinear(nn.Linear):
 class _XceptionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, *params):
-        save = any(ctx.needs_input_grad[2:])
+        # needs_input_grad ignores torch.no_grad(); the caller records the grad mode it was entered with (Xception.features)
+        save = any(ctx.needs_input_grad[2:]) and net.__dict__.get("_want_tape", True)
         feat, tape = ex.xception_forward(net, x if x.dtype == torch.uint8 else x.float(), save=save)
         ctx.net, ctx.tape = net, tape
         return feat
@@ -343,6 +344,7 @@ class Xception(nn.Module):
                 raise XcpError("Xception: uint8 frames must be NHWC [F,H,W,3], got %s" % (tuple(x.shape),))
         elif x.dim() != 4 or x.shape[1] != 3:
             raise XcpError("Xception: expected an input of shape [F,3,H,W], got %s" % (tuple(x.shape),))
+        self.__dict__["_want_tape"] = torch.is_grad_enabled()      # no_grad evaluation: nothing saved, inference plan eligible
         return _XceptionFn.apply(self, x, *self._backbone_params())
 
     def forward(self, x):

@@ -71,6 +71,34 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optiona
     return out, stats
 
 
+def gemm_tn_bias(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Inference plan: out[M,N] = relu?(a[M,K] @ b[N,K]^T + bias[N] + residual[M,N]) in bf16 (b = BN-folded weights)."""
+    _chk(a, BF16, "gemm_tn_bias.a"); _chk(b, BF16, "gemm_tn_bias.b"); _chk(bias, F32, "gemm_tn_bias.bias")
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and bias.numel() >= N
+    if residual is not None:
+        _chk(residual, BF16, "gemm_tn_bias.residual")
+        assert residual.shape == (M, N)
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=BF16)
+    _lib.call("xcp_gemm_tn_bias", _p(a), K, _p(b), K, _p(out), N, M, N, K, _p(bias), int(relu), _p(residual), N,
+              a.device.index, _s())
+    return out
+
+
+def pack_weight_scaled(w: torch.Tensor, row_scale: torch.Tensor) -> torch.Tensor:
+    """fp32 [N,K] -> bf16 [phys(N), phys(K)] with row n multiplied by row_scale[n] (BatchNorm scale folded into the weights)."""
+    _chk(w, F32, "pack_weight_scaled.w"); _chk(row_scale, F32, "pack_weight_scaled.scale")
+    R, Cc = w.shape
+    Rp, Cp = phys(R), phys(Cc)
+    assert row_scale.numel() >= R
+    out = torch.empty((Rp, Cp), device=w.device, dtype=BF16)
+    _lib.call("xcp_pack_weight_scaled", _p(w), _p(row_scale), _p(out), R, Cc, Rp, Cp, w.device.index, _s())
+    return out
+
+
 def _f32_bn_stats(y2d: torch.Tensor) -> torch.Tensor:
     """Per-channel (sum, sum-sq) partials of an fp32 [M,C] matrix in the layout xcp_bn_finalize reads."""
     M, C = y2d.shape

@@ -47,6 +47,35 @@ def test_gemm_tn_bf16_stats(M, N, K):
     assert torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("M,N,K,relu,res", [(2000, 768, 768, True, False), (1444, 768, 768, False, True), (300, 128, 64, True, True),
+                                             (5000, 256, 128, False, False), (100, 2048, 1536, True, False), (77, 1024, 768, False, True)])
+def test_gemm_tn_bias_epilogue(M, N, K, relu, res):
+    """inference-plan epilogue: relu?(A B^T + bias + residual) (BatchNorm folded into B, row f-3)"""
+    a = rnd(M, K, seed=31, dtype=torch.bfloat16)
+    b = rnd(N, K, seed=32, scale=0.05, dtype=torch.bfloat16)
+    bias = rnd(N, seed=33, scale=0.5)
+    r = rnd(M, N, seed=34, dtype=torch.bfloat16) if res else None
+    out = ops.gemm_tn_bias(a, b, bias, relu, r)
+    ref = a.float() @ b.float().t() + bias[None, :]
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = F.relu(ref)
+    assert rel_err(out.float(), ref) < 6e-3
+    if relu:
+        assert float(out.float().min()) >= 0.0
+
+
+def test_pack_weight_scaled():
+    w = rnd(728, 728, seed=35)
+    sc = rnd(768, seed=36) * 0.5 + 1.0
+    out = ops.pack_weight_scaled(w, sc)
+    assert out.shape == (768, 768)
+    ref = torch.zeros(768, 768, device=DEV)
+    ref[:728, :728] = w * sc[:728, None]
+    assert torch.equal(out.float(), ref.bfloat16().float())
+
+
 @pytest.mark.parametrize("M,N,K", [(64, 512, 2048), (300, 2048, 2048), (5, 128, 128)])
 def test_gemm_tn_f32_bias(M, N, K):
     a = rnd(M, K, seed=3, dtype=torch.bfloat16)

@@ -61,6 +61,39 @@ def test_xception_eval_matches_reference_golden(golden, sd2):
     assert rel(logits75, _t(golden["A_eval_logits_75"])) < 2e-2
 
 
+def test_folded_inference_plan_matches_unfolded_plan_and_oracle(sd2, monkeypatch):
+    """eval-mode BatchNorm folded into the pointwise weights, ReLU / identity-skip add in the GEMM epilogue.
+    Same features as the consumer-side-BatchNorm plan (XCP_NO_FOLD=1) and as the fp32 oracle, on running statistics and
+    affine parameters that are far from the identity (bn_jitter); a parameter change must invalidate the folded packs."""
+    from multimodal_deepfake_detection_b200 import executor as ex
+    sd = {k: v.to(DEV) for k, v in O.synth_state_dict(77, num_classes=2, bn_jitter=0.5).items()}
+    net = Xception(num_classes=2).to(DEV).eval()
+    net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(5, 3, 299, 299, generator=g).to(DEV)
+    with torch.no_grad():
+        ref = O.xception_features(sd, x, False, {})
+        folded = net.features(x)
+        assert any(k[1] == "pwf" for k in net._pack_cache._c if isinstance(k, tuple) and len(k) == 2)      # the folded plan ran
+        monkeypatch.setenv("XCP_NO_FOLD", "1")
+        plain = net.features(x)
+        monkeypatch.delenv("XCP_NO_FOLD")
+    assert rel(folded, ref) < 2e-3 and rel(plain, ref) < 2e-3
+    assert rel(folded, plain) < 2e-3
+    # in-place change of a BatchNorm buffer through torch (version counter) and through the train-mode kernels (BN_EPOCH)
+    with torch.no_grad():
+        net.block5.rep[1].pointwise.weight.mul_(1.5)
+        net.bn3.running_var.mul_(2.0)
+        sd_new = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        again = net.features(x)
+        assert rel(again, O.xception_features(sd_new, x, False, {})) < 2e-3
+        e0 = ex.BN_EPOCH[0]
+        net.train(); net.features(x); net.eval()
+        assert ex.BN_EPOCH[0] > e0
+        sd_new = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        assert rel(net.features(x), O.xception_features(sd_new, x, False, {})) < 2e-3
+
+
 def test_xception_train_forward_and_running_stats(sd2):
     g = torch.Generator().manual_seed(0)
     x = torch.rand(12, 3, 299, 299, generator=g).to(DEV)
