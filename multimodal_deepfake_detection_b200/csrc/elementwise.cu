@@ -103,36 +103,41 @@ __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, int C_real, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
                    float* scale, float* shift, float* mean_out, float* rstd_out) {
-    __shared__ double s1[32][33], s2[32][33];
-    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cx;
+    // block = 8 channels x 128 part-lanes (the first version used 32 channels x 32 part-lanes: 24 CTAs for 768 channels, ~23
+    // dependent load batches per thread over the 722 per-tile partial rows of a middle-flow layer, 11.8 us per launch x 40
+    // launches per step, profiles/r2p_launches_B16.md; now 96 CTAs x <= 6 rows per thread)
+    __shared__ double s1[128][9], s2[128][9];
+    const int cx = threadIdx.x & 7, ry = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cx;
     double a = 0.0, b = 0.0;
     if (c < C) {
         int pi = ry;
-        for (; pi + 96 < nparts; pi += 128) {
+        for (; pi + 128 < nparts; pi += 256) {
             const float a0 = partials[((long long)pi * 2 + 0) * C + c], b0 = partials[((long long)pi * 2 + 1) * C + c];
-            const float a1 = partials[((long long)(pi + 32) * 2 + 0) * C + c], b1 = partials[((long long)(pi + 32) * 2 + 1) * C + c];
-            const float a2 = partials[((long long)(pi + 64) * 2 + 0) * C + c], b2 = partials[((long long)(pi + 64) * 2 + 1) * C + c];
-            const float a3 = partials[((long long)(pi + 96) * 2 + 0) * C + c], b3 = partials[((long long)(pi + 96) * 2 + 1) * C + c];
-            a += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
-            b += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+            const float a1 = partials[((long long)(pi + 128) * 2 + 0) * C + c], b1 = partials[((long long)(pi + 128) * 2 + 1) * C + c];
+            a += (double)a0 + (double)a1;
+            b += (double)b0 + (double)b1;
         }
-        for (; pi < nparts; pi += 32) {
+        for (; pi < nparts; pi += 128) {
             a += (double)partials[((long long)pi * 2 + 0) * C + c];
             b += (double)partials[((long long)pi * 2 + 1) * C + c];
         }
     }
     s1[ry][cx] = a; s2[ry][cx] = b;
     __syncthreads();
-    // transpose-reduce: warp w sums channel w's 32 lane partials
-    a = s1[cx][ry]; b = s2[cx][ry];
+    // warp w < 8 sums channel w's 128 lane partials
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (w >= 8) return;
+    a = (s1[ln][w] + s1[ln + 32][w]) + (s1[ln + 64][w] + s1[ln + 96][w]);
+    b = (s2[ln][w] + s2[ln + 32][w]) + (s2[ln + 64][w] + s2[ln + 96][w]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-    const int cc = blockIdx.x * 32 + ry;
-    if (cx == 0 && cc >= C_real && cc < C) {       // zero-padded channels (physical width > logical): stay exactly 0
+    const int cc = blockIdx.x * 8 + w;
+    const int cx0 = ln;     // lane 0 of the warp finalizes
+    if (cx0 == 0 && cc >= C_real && cc < C) {       // zero-padded channels (physical width > logical): stay exactly 0
         scale[cc] = 0.f; shift[cc] = 0.f; mean_out[cc] = 0.f; rstd_out[cc] = 0.f;
     }
-    if (cx == 0 && cc < C_real) {
+    if (cx0 == 0 && cc < C_real) {
         const double mean = a / count;
         double var = b / count - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -945,7 +950,7 @@ extern "C" int xcp_bn_finalize(const float* partials, int nparts, int C, int c_r
                                float* mean_out, float* rstd_out, int device, void* stream) {
     XCP_REQUIRE(nparts > 0 && C > 0 && count > 0 && c_real > 0 && c_real <= C, "xcp_bn_finalize: bad args");
     XCP_CUDA(cudaSetDevice(device));
-    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, ST>>>(partials, nparts, C, c_real, count, gamma, beta, running_mean, running_var,
+    bn_finalize_kernel<<<(C + 7) / 8, 1024, 0, ST>>>(partials, nparts, C, c_real, count, gamma, beta, running_mean, running_var,
                                                       momentum, eps, scale, shift, mean_out, rstd_out);
     return check_cuda(cudaGetLastError(), "bn_finalize launch");
 }
