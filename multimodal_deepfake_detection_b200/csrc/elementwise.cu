@@ -10,90 +10,7 @@
 
 namespace xcp {
 
-// ======================================================================================== stem conv1
-// y[F,H1,W1,32] (bf16 NHWC) = conv3x3 stride 2 pad 0 of the input frames; per-block (sum, sumsq) partials for bn1.
-// Input: U8 = false: fp32 NCHW [F,3,H,W] in [0,1] (what video_dataloader.py:35 hands the reference model);
-//        U8 = true : uint8 NHWC [F,H,W,3], scaled by 1/255 on the fly -- the on-disk frame format (video_dataloader.py:27-35),
-//                    4x fewer bytes over PCIe and HBM and no host-side permute.
-// One thread = one output pixel x 32 channels held as 16 packed f32x2 accumulators (FFMA2); the 27x32 filter sits in shared
-// memory as f32x2 pairs (broadcast LDS.128).  BatchNorm statistics are accumulated per thread in registers over all of its pixels
-// (the stored, bf16-rounded values are NOT used: fp32 accumulators, like the GEMM epilogues) and reduced once per block.
-template <bool U8>
-XCP_DEVINL float stem_tap(const void* x, long long f, int ic, int h, int w, int H, int W) {
-    if (U8) return (float)__ldg(reinterpret_cast<const uint8_t*>(x) + (((long long)f * H + h) * W + w) * 3 + ic) * (1.f / 255.f);
-    return __ldg(reinterpret_cast<const float*>(x) + (((long long)f * 3 + ic) * H + h) * W + w);
-}
-
-template <bool U8>
-__global__ void __launch_bounds__(128)
-stem_conv1_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
-                      float* __restrict__ partials, int F, int H, int W, int H1, int W1) {
-    __shared__ float s_w[27][32];
-    __shared__ float s_t[128][33];
-    for (int i = threadIdx.x; i < 27 * 32; i += 128) {
-        const int oc = i / 27, tap = i % 27;       // w is [oc][ic][kh][kw]
-        s_w[tap][oc] = w[i];
-    }
-    __syncthreads();
-    const long long M = (long long)F * H1 * W1;
-    const long long chunks = (M + 127) / 128;
-    float run1 = 0.f, run2 = 0.f;                  // running (sum, sumsq) of channel tid & 31 over pixel rows tid >> 5 (mod 4)
-    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
-        const long long pix = ch * 128 + threadIdx.x;
-        float acc[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-        if (pix < M) {
-            const int wo = (int)(pix % W1);
-            const int ho = (int)((pix / W1) % H1);
-            const long long f = pix / ((long long)W1 * H1);
-#pragma unroll
-            for (int ic = 0; ic < 3; ++ic)
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const float xv = stem_tap<U8>(x, f, ic, 2 * ho + kh, 2 * wo + kw, H, W);
-                        const int tap = (ic * 3 + kh) * 3 + kw;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = fmaf(xv, s_w[tap][j], acc[j]);
-                    }
-            __nv_bfloat16* yp = y + pix * 32;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float t8[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) t8[j] = acc[g * 8 + j];
-                *reinterpret_cast<uint4*>(yp + g * 8) = pack8(t8);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s_t[threadIdx.x][j] = acc[j];   // zeros for out-of-range pixels
-        __syncthreads();
-        {   // all 128 threads: channel (tid & 31), pixel rows (tid >> 5) * 32 .. + 31
-            const int chn = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * 32;
-            float a = 0.f, b = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                const float v = s_t[r0 + r][chn];
-                a += v;
-                b = fmaf(v, v, b);
-            }
-            run1 += a; run2 += b;
-        }
-    }
-    // fold the 4 row groups: s_t is free again after the barrier
-    __syncthreads();
-    s_t[threadIdx.x >> 5][threadIdx.x & 31] = run1;
-    s_t[4 + (threadIdx.x >> 5)][threadIdx.x & 31] = run2;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        const int st = threadIdx.x >> 5, chn = threadIdx.x & 31;
-        partials[((long long)blockIdx.x * 2 + st) * 32 + chn] =
-            s_t[st * 4 + 0][chn] + s_t[st * 4 + 1][chn] + s_t[st * 4 + 2][chn] + s_t[st * 4 + 3][chn];
-    }
-}
+// (stem conv1: csrc/stem_conv1.cu)
 
 // ======================================================================================== BN finalize
 // partials: [nparts][2][C].  Train mode: batch mean / biased var -> scale, shift, saved mean, rstd; running stats
@@ -861,41 +778,6 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ gk, float* 
     gw[idx] += gk[(long long)o * (9 * I) + tap * I + i];
 }
 
-// Weight gradient of the stem conv1 (3->32, k3 s2 p0; Xception.py:118,168): dW[oc][27] += sum_pix dy[pix][oc] * patch[pix][27].
-// Done on the tensor cores: the 27-tap input patches are materialised once as a bf16 [M, 32] matrix (taps 27..31
-// zero) and the reduction over the M = F*H1*W1 pixels is the MN-major split-K tcgen05 GEMM of gemm.cu
-// (xcp_gemm_wgrad, P = Q = 32), followed by a 864-element scatter-add into the nn.Conv2d layout.
-template <bool U8>
-__global__ void __launch_bounds__(256)
-stem_conv1_im2col_kernel(const void* __restrict__ x, uint4* __restrict__ patches, int F, int H, int W, int H1, int W1) {
-    const long long M = (long long)F * H1 * W1;
-    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < M; pix += (long long)gridDim.x * blockDim.x) {
-        const int wo = (int)(pix % W1);
-        const int ho = (int)((pix / W1) % H1);
-        const long long f = pix / ((long long)W1 * H1);
-        float v[32];
-#pragma unroll
-        for (int ic = 0; ic < 3; ++ic)
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) v[(ic * 3 + kh) * 3 + kw] = stem_tap<U8>(x, f, ic, 2 * ho + kh, 2 * wo + kw, H, W);
-#pragma unroll
-        for (int j = 27; j < 32; ++j) v[j] = 0.f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            float t8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t8[j] = v[g * 8 + j];
-            patches[pix * 4 + g] = pack8(t8);
-        }
-    }
-}
-__global__ void stem_conv1_wgrad_scatter_kernel(const float* __restrict__ gk, float* __restrict__ dW) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 32 * 27) dW[i] += gk[(i / 27) * 32 + (i % 27)];
-}
-
 // bilinear (align_corners=False) upsample of [F,C,n,1] fp32 to [F,C,S,S] fp32 (XceptionLSTMA.py:45-46).
 // With input width 1 every output column equals the row value, so only the vertical lerp is computed.
 __global__ void bilinear_up_kernel(const float* __restrict__ x, float* __restrict__ out, long long planes, int n, int S) {
@@ -924,26 +806,6 @@ static int ew_grid(long long n, int block) {
 using namespace xcp;
 
 #define ST ((cudaStream_t)stream)
-
-// number of partial rows xcp_stem_conv1_fwd writes ( = its grid size)
-extern "C" int xcp_stem_conv1_parts(int F, int H, int W, int device) {
-    if (cudaSetDevice(device) != cudaSuccess) return -1;
-    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
-    const long long chunks = ((long long)F * H1 * W1 + 127) / 128;
-    const long long cap = 4LL * num_sms();
-    return (int)(chunks < cap ? chunks : cap);
-}
-
-extern "C" int xcp_stem_conv1_fwd(const void* x, int x_u8_nhwc, const float* w, void* y, float* partials, int F, int H, int W,
-                                  int device, void* stream) {
-    XCP_REQUIRE(F > 0 && H >= 3 && W >= 3, "xcp_stem_conv1_fwd: bad shape");
-    XCP_CUDA(cudaSetDevice(device));
-    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
-    const int grid = xcp_stem_conv1_parts(F, H, W, device);
-    if (x_u8_nhwc) stem_conv1_fwd_kernel<true><<<grid, 128, 0, ST>>>(x, w, (__nv_bfloat16*)y, partials, F, H, W, H1, W1);
-    else stem_conv1_fwd_kernel<false><<<grid, 128, 0, ST>>>(x, w, (__nv_bfloat16*)y, partials, F, H, W, H1, W1);
-    return check_cuda(cudaGetLastError(), "stem_conv1_fwd launch");
-}
 
 extern "C" int xcp_bn_finalize(const float* partials, int nparts, int C, int c_real, double count, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
@@ -1144,33 +1006,6 @@ extern "C" int xcp_unpack_conv3x3_grad(const float* gk, float* gw, int O, int I,
     XCP_CUDA(cudaSetDevice(device));
     unpack_conv3x3_grad_kernel<<<(O * I * 9 + 255) / 256, 256, 0, ST>>>(gk, gw, O, I);
     return check_cuda(cudaGetLastError(), "unpack_conv3x3_grad launch");
-}
-
-extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, long long ld_x, float* dW, long long ld_dw,
-                              int R, int P, int Q, int device, void* stream);
-
-// bytes of device scratch xcp_stem_conv1_wgrad needs (im2col patches bf16 [M,32] + fp32 [32,32] accumulator)
-extern "C" long long xcp_stem_conv1_wgrad_ws_bytes(int F, int H, int W) {
-    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
-    return (long long)F * H1 * W1 * 64 + 32 * 32 * 4;
-}
-
-extern "C" int xcp_stem_conv1_wgrad(const void* x, int x_u8_nhwc, const void* dy, float* dW, void* workspace, int F, int H, int W,
-                                    int device, void* stream) {
-    XCP_REQUIRE(workspace != nullptr && ((uintptr_t)workspace % 16) == 0, "xcp_stem_conv1_wgrad: workspace missing / unaligned");
-    XCP_CUDA(cudaSetDevice(device));
-    const int H1 = (H - 3) / 2 + 1, W1 = (W - 3) / 2 + 1;
-    const long long M = (long long)F * H1 * W1;
-    XCP_REQUIRE(M < (1LL << 31), "xcp_stem_conv1_wgrad: too many pixels for 32-bit TMA coordinates");
-    float* gk = reinterpret_cast<float*>(workspace);
-    uint4* patches = reinterpret_cast<uint4*>(reinterpret_cast<char*>(workspace) + 32 * 32 * 4);
-    XCP_CUDA(cudaMemsetAsync(gk, 0, 32 * 32 * 4, ST));
-    if (x_u8_nhwc) stem_conv1_im2col_kernel<true><<<ew_grid(M, 256), 256, 0, ST>>>(x, patches, F, H, W, H1, W1);
-    else stem_conv1_im2col_kernel<false><<<ew_grid(M, 256), 256, 0, ST>>>(x, patches, F, H, W, H1, W1);
-    XCP_CUDA(cudaGetLastError());
-    if (int e = xcp_gemm_wgrad(dy, 32, patches, 32, gk, 32, (int)M, 32, 32, device, stream)) return e;
-    stem_conv1_wgrad_scatter_kernel<<<4, 256, 0, ST>>>(gk, dW);
-    return check_cuda(cudaGetLastError(), "stem_conv1_wgrad launch");
 }
 
 extern "C" int xcp_bilinear_up(const float* x, float* out, long long planes, int n, int S, int device, void* stream) {

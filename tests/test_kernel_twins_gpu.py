@@ -269,5 +269,7 @@ def test_stem_backward_twins(F_, Hg):
     w1 = (torch.randn(32, 3, 3, 3, generator=g) * 0.3).to(DEV)
     y1_b, p_b = ops.stem_conv1_fwd(x, w1)
     y1_f, p_f = ops.stem_conv1_fwd(x, w1, F32)
-    assert one_ulp(y1_b, y1_f, extra=y1_f.abs().max().item() * 4e-6) <= 1.01
-    assert relmax(p_b.sum(0), p_f.sum(0)) < 2e-5
+    # the production kernel is a tf32 tensor-core product (frames and weights rounded to 10 mantissa bits, fp32 accumulate; csrc/
+    # stem_conv1.cu): 2^-11 per operand, i.e. ~5e-4 of the output scale instead of fp32's 1e-6
+    assert one_ulp(y1_b, y1_f, extra=y1_f.abs().max().item() * 1e-3) <= 1.01
+    assert relmax(p_b.sum(0), p_f.sum(0)) < 2e-3

@@ -141,8 +141,14 @@ def test_stem_conv1(F_, H):
     y, parts = ops.stem_conv1_fwd(x, w)
     assert rel_err(y.float().permute(0, 3, 1, 2), ref) < 8e-3
     s = parts.sum(0)
-    assert rel_err(s[0], ref.sum((0, 2, 3))) < 1e-4
-    assert rel_err(s[1], (ref * ref).sum((0, 2, 3))) < 1e-4
+    # the kernel runs on tf32 tensor-core MMAs (operands rounded to 10 mantissa bits, fp32 accumulate): the statistics are those
+    # of the fp32 accumulators of exactly that product -> tight against a tf32-rounded reference, 1e-3 against the fp32 one
+    def tf32(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)
+    ref_t = F.conv2d(tf32(x), tf32(w), stride=2)
+    assert rel_err(s[0], ref_t.sum((0, 2, 3))) < 1e-4
+    assert rel_err(s[1], (ref_t * ref_t).sum((0, 2, 3))) < 1e-4
+    assert rel_err(s[0], ref.sum((0, 2, 3))) < 1e-3 and rel_err(s[1], (ref * ref).sum((0, 2, 3))) < 1e-3
     dy = rnd(*y.shape, seed=12, dtype=torch.bfloat16)
     dw = torch.zeros_like(w)
     ops.stem_conv1_wgrad(x, dy, dw)
@@ -566,8 +572,9 @@ def test_stem_conv1_uint8_nhwc_ingest_matches_float_path():
     assert rel_err(y_u, y_f) < 1e-3 and rel_err(p_u.sum(0), p_f.sum(0)) < 1e-5
     ref = F.conv2d(xf, w, stride=2)
     assert rel_err(y_u.float().permute(0, 3, 1, 2), ref) < 4e-3
-    assert rel_err(p_u[:, 0].sum(0), ref.sum((0, 2, 3))) < 1e-4          # BN partial sums come from the fp32 accumulators
-    assert rel_err(p_u[:, 1].sum(0), (ref * ref).sum((0, 2, 3))) < 1e-4
+    # BN partial sums come from the fp32 accumulators of the tf32 tensor-core product (operands rounded to 10 mantissa bits)
+    assert rel_err(p_u[:, 0].sum(0), ref.sum((0, 2, 3))) < 1e-3
+    assert rel_err(p_u[:, 1].sum(0), (ref * ref).sum((0, 2, 3))) < 1e-3
     dy = rnd(*y_f.shape, seed=33, dtype=torch.bfloat16)
     dw_f = torch.zeros_like(w); dw_u = torch.zeros_like(w)
     ops.stem_conv1_wgrad(xf, dy, dw_f)
