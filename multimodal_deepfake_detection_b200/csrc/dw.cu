@@ -382,6 +382,8 @@ struct DwBwdParams {
     float* dw;                    // [C][9]  (the nn.Conv2d weight-gradient layout), accumulated with RED
     float* bnsum;                 // [2][C]  (sum dz, sum dz*y), accumulated with RED (caller zero-fills); AFFINE only
     int c_real;                   // logical channel count (<= C, the physical pitch): dw has c_real rows
+    int add_pre;                  // the residual gradients are added BEFORE the ReLU mask (they are gradients wrt the activated input:
+                                  // block 1 reading relu(bn2(y2)) straight from the stem's raw conv2 output, executor.py)
 };
 
 template <bool AFFINE, bool RELU, int ADDM, int MINB>
@@ -483,6 +485,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
                 const uint32_t xb = sbase + s * stage_bytes + g_bytes + (uint32_t)x0 * 128u + (uint32_t)lane * 4u + (uint32_t)r0 * x_row;
                 const int rmax = min(r1, gH - gh0);
                 const long long e0 = ((long long)f * gH + gh0 + r0) * row_b + (long long)gx0 * pix_b + (long long)c0 * 2;
+                const bool pre = (ADDM != 0) && p.add_pre != 0;
                 auto run = [&](auto edge_tag) {
                     constexpr bool EDGE = decltype(edge_tag)::value;      // partial strip: ncols < SW
                     auto load_g = [&](uint32_t a, u64 (&w)[LW]) {
@@ -522,7 +525,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
                 dwa[3] = fma2(av, WB[px + 2], dwa[3]); dwa[4] = fma2(av, WB[px + 1], dwa[4]); dwa[5] = fma2(av, WB[px], dwa[5]); \
                 dwa[6] = fma2(av, WA[px + 2], dwa[6]); dwa[7] = fma2(av, WA[px + 1], dwa[7]); dwa[8] = fma2(av, WA[px], dwa[8]); \
                 float dl, dh; upk2(da, dl, dh);                                                            \
-                if (RELU) { dl = zl > 0.f ? dl : 0.f; dh = zh > 0.f ? dh : 0.f; }                          \
+                if (RELU && !pre) { dl = zl > 0.f ? dl : 0.f; dh = zh > 0.f ? dh : 0.f; }                  \
                 if (ADDM & 1) {                                                                            \
                     const uint32_t ar = lds32(fa + px * 128);                                              \
                     dl += bf16_lo(ar); dh += bf16_hi(ar);                                                  \
@@ -531,6 +534,7 @@ dw3x3_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant_
                     const uint32_t ar = __ldg(reinterpret_cast<const uint32_t*>(hrow + (px >> 1) * pix_b)); \
                     dl += bf16_lo(ar); dh += bf16_hi(ar);                                                  \
                 }                                                                                          \
+                if (RELU && pre) { dl = zl > 0.f ? dl : 0.f; dh = zh > 0.f ? dh : 0.f; }                   \
                 if (AFFINE) { const u64 dzv = pk2(dl, dh); sdz = add2(sdz, dzv); sdzy = fma2(dzv, yv, sdzy); } \
                 *reinterpret_cast<uint32_t*>(dzp + px * pix_b) = pack_bf16(dl, dh);                        \
             }                                                                                              \
@@ -941,7 +945,8 @@ extern "C" int xcp_dw3x3_fwd(const void* x, const float* w9, const float* scale,
     return check_cuda(cudaGetLastError(), "dw3x3_fwd launch");
 }
 
-// Backward of xcp_dw3x3_fwd.  dz = mask * conv_transpose(dD) [+ add_full] [+ add_half at even pixels];
+// Backward of xcp_dw3x3_fwd.  dz = mask * conv_transpose(dD) [+ add_full] [+ add_half at even pixels]; relu = 2: the adds are
+// gradients wrt the ACTIVATED input and go inside the mask: dz = mask * (conv_transpose(dD) + add_full + add_half);
 // dw[c_real][9] += weight gradient (nn.Conv2d layout); bnsum[2][C] += (sum dz, sum dz*x) per channel when
 // scale/shift are given (the caller zero-fills bnsum).
 extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift,
@@ -968,7 +973,7 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     if (int e = make_dw_tmap(&tmX, xin, g, 0)) return e;
     if (int e = make_dw_tmap(&tmF, add_full != nullptr ? add_full : xin, g, 0)) return e;
     DwBwdParams p{g, w9, scale, shift, (__nv_bfloat16*)dz, (const __nv_bfloat16*)add_full,
-                  (const __nv_bfloat16*)add_half, dw, bnsum, c_real};
+                  (const __nv_bfloat16*)add_half, dw, bnsum, c_real, relu == 2 ? 1 : 0};
     const int smem = g.stages * stage_bytes + 256;
     const int threads = 32 * (g.strips * g.RS + 1);
     const int grid = dw_grid(g, minb);

@@ -275,16 +275,20 @@ def sep_forward(cache: PackCache, spec: SepSpec, src: torch.Tensor, src_st, relu
 
 
 class BlockTape:
-    __slots__ = ("spec", "inp", "units", "xs", "ys", "st_s", "idx", "ymax", "out")
+    __slots__ = ("spec", "inp", "inp_st", "units", "xs", "ys", "st_s", "idx", "ymax", "out")
 
 
-def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: list, save: bool = True) -> BlockTape:
-    """Block.forward (Xception.py:89-99).  inp: materialised bf16 NHWC block input."""
+def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: list, save: bool = True, inp_st=None) -> BlockTape:
+    """Block.forward (Xception.py:89-99).  inp: materialised bf16 NHWC block input -- or, with inp_st, the RAW output of the
+    producer convolution whose pending BatchNorm + ReLU (inp_st) is applied on the fly by the two readers of the block input
+    (depthwise prologue, stride-2 gather): block 1 reads relu(bn2(conv2)) this way, so x2 is never written (Xception.py:172-176)."""
     bt = BlockTape()
-    bt.spec, bt.inp, bt.units = spec, inp, []
-    src, src_st = inp, None
-    for u in spec.units:
-        t = sep_forward(cache, u, src, src_st, u.relu, nbt)
+    bt.spec, bt.inp, bt.inp_st, bt.units = spec, inp, inp_st, []
+    if inp_st is not None and (spec.skip is None or spec.stride != 2):
+        raise ops._lib.XcpError("Block: an unmaterialised input needs a strided skip-conv block (the residual add reads the input)")
+    src, src_st = inp, inp_st
+    for i, u in enumerate(spec.units):
+        t = sep_forward(cache, u, src, src_st, u.relu or (i == 0 and inp_st is not None), nbt)
         bt.units.append(t)
         src, src_st = t.y, t.st
     last = bt.units[-1]
@@ -293,7 +297,7 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
     if spec.skip is not None:
         wb, _ = cache.pw_for(inp, spec.skip.weight)
         if spec.stride == 2:
-            xs = ops.gather_s2(inp)
+            xs = ops.gather_s2(inp) if inp_st is None else ops.gather_s2(inp, inp_st.scale, inp_st.shift, True)
         elif spec.stride == 1:
             xs = inp
         else:
@@ -322,23 +326,29 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
 
 
 # ------------------------------------------------------------------------------------------------ inference plan (row f-3)
-def _sep_folded(cache: PackCache, spec: SepSpec, src: torch.Tensor, relu_in: bool, relu_out: bool, residual=None) -> torch.Tensor:
+def _sep_folded(cache: PackCache, spec: SepSpec, src: torch.Tensor, relu_in: bool, relu_out: bool, residual=None, src_st=None) -> torch.Tensor:
     """[ReLU?] -> depthwise -> pointwise with the BatchNorm folded in: relu?(d @ (scale * W)^T + shift [+ residual]).  The ReLU
     that follows the BatchNorm in the graph runs in the GEMM epilogue, so the next depthwise reads an activated tensor."""
     F_, H, W, C = src.shape
-    d = ops.dw3x3_fwd(src, cache.dw(spec.sep.conv1.weight), None, None, relu_in)
+    if src_st is not None:
+        d = ops.dw3x3_fwd(src, cache.dw(spec.sep.conv1.weight), src_st.scale, src_st.shift, True)
+    else:
+        d = ops.dw3x3_fwd(src, cache.dw(spec.sep.conv1.weight), None, None, relu_in)
     wf, bias = cache.pw_folded(spec.sep.pointwise.weight, spec.bn)
     M = F_ * H * W
     y = ops.gemm_tn_bias(d.view(M, C), wf, bias, relu_out, residual.view(M, -1) if residual is not None else None)
     return y.view(F_, H, W, y.shape[1])
 
 
-def _block_folded(cache: PackCache, spec: BlockSpec, inp: torch.Tensor) -> torch.Tensor:
+def _block_folded(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, inp_st=None) -> torch.Tensor:
     """Block.forward (Xception.py:89-99) in the inference plan: BatchNorms folded into the pointwise / skip weights, the ReLU
     between units and the identity-skip add in the GEMM epilogues; nothing is saved."""
     ys = None
     if spec.skip is not None:
-        xs = ops.gather_s2(inp) if spec.stride == 2 else inp
+        if inp_st is not None:        # unmaterialised input: the producer's BatchNorm + ReLU runs inside the gather
+            xs = ops.gather_s2(inp, inp_st.scale, inp_st.shift, True)
+        else:
+            xs = ops.gather_s2(inp) if spec.stride == 2 else inp
         Fs, Hs, Ws, Cs = xs.shape
         wf, bias = cache.pw_folded(spec.skip.weight, spec.skipbn)
         ys = ops.gemm_tn_bias(xs.view(Fs * Hs * Ws, Cs), wf, bias, False)
@@ -352,7 +362,7 @@ def _block_folded(cache: PackCache, spec: BlockSpec, inp: torch.Tensor) -> torch
         residual = None
         if last and spec.stride == 1:
             residual = ys if ys is not None else inp
-        src = _sep_folded(cache, u, src, relu_in, relu_out, residual)
+        src = _sep_folded(cache, u, src, relu_in, relu_out, residual, src_st=inp_st if i == 0 else None)
     if spec.stride == 1:
         return src
     one, zero = cache.identity_affine(src.shape[-1], src.device)
@@ -392,7 +402,7 @@ def _pw_backward(cache: PackCache, sink: GradSink, weight: torch.Tensor, dy: tor
     return da.view(*a.shape)
 
 
-def _dw_backward(cache: PackCache, sink: GradSink, t: SepTape, dd: torch.Tensor, add_full=None, add_half=None):
+def _dw_backward(cache: PackCache, sink: GradSink, t: SepTape, dd: torch.Tensor, add_full=None, add_half=None, add_pre=False):
     """Backward of the depthwise conv of unit t.  Returns (dz, bnsum): the gradient wrt the DW's pre-activation
     source (raw y of the producer if a BN was pending, else the materialised input)."""
     w = t.spec.sep.conv1.weight
@@ -400,7 +410,9 @@ def _dw_backward(cache: PackCache, sink: GradSink, t: SepTape, dd: torch.Tensor,
     C = t.src.shape[-1]                 # physical pitch
     aff = t.src_st is not None
     bnsum = sink.scratch(2 * C).view(2, C) if aff else None
-    dz, bnsum = ops.dw3x3_bwd(dd, t.src, w9, t.src_st.scale if aff else None, t.src_st.shift if aff else None, t.src_relu,
+    # add_pre: the residual gradients are gradients wrt the ACTIVATED input (unmaterialised block input) -> inside the ReLU mask
+    relu = 2 if (add_pre and t.src_relu) else t.src_relu
+    dz, bnsum = ops.dw3x3_bwd(dd, t.src, w9, t.src_st.scale if aff else None, t.src_st.shift if aff else None, relu,
                               sink.view(w), add_full=add_full, add_half=add_half, bnsum=bnsum)
     sink.done(w)
     return dz, bnsum
@@ -410,16 +422,18 @@ def _bn_param_grads(sink: GradSink, bn):
     return sink.view(bn.weight), sink.view(bn.bias)
 
 
-def units_backward(cache: PackCache, sink: GradSink, units: List[SepTape], dy_last: torch.Tensor, add_full=None, add_half=None):
+def units_backward(cache: PackCache, sink: GradSink, units: List[SepTape], dy_last: torch.Tensor, add_full=None, add_half=None,
+                   want_sums=False):
     """Walk a chain of sep units backwards.  dy_last = gradient wrt the raw PW output of the last unit.
-    Returns the gradient wrt the chain's materialised input."""
+    Returns the gradient wrt the chain's materialised input -- or, for an unmaterialised input (first unit with a pending
+    BatchNorm, want_sums), (gradient wrt that BatchNorm's output, its (sum dz, sum dz*y) for the BatchNorm backward)."""
     dy = dy_last
     for i in range(len(units) - 1, -1, -1):
         t = units[i]
         dd = _pw_backward(cache, sink, t.spec.sep.pointwise.weight, dy, t.d)
         if i == 0:
-            g_in, _ = _dw_backward(cache, sink, t, dd, add_full=add_full, add_half=add_half)
-            return g_in
+            g_in, sums0 = _dw_backward(cache, sink, t, dd, add_full=add_full, add_half=add_half, add_pre=t.src_st is not None)
+            return (g_in, sums0) if want_sums else g_in
         prev = units[i - 1]
         dz, bnsum = _dw_backward(cache, sink, t, dd)
         dg, db = _bn_param_grads(sink, prev.spec.bn)
@@ -428,8 +442,9 @@ def units_backward(cache: PackCache, sink: GradSink, units: List[SepTape], dy_la
     raise AssertionError
 
 
-def block_backward(cache: PackCache, sink: GradSink, bt: BlockTape, G: torch.Tensor) -> torch.Tensor:
-    """G: gradient wrt the block output (bf16 NHWC).  Returns the gradient wrt the block input."""
+def block_backward(cache: PackCache, sink: GradSink, bt: BlockTape, G: torch.Tensor):
+    """G: gradient wrt the block output (bf16 NHWC).  Returns the gradient wrt the block input; for an unmaterialised input
+    (bt.inp_st) the pair (gradient wrt the producer's BatchNorm output, BatchNorm-backward sums)."""
     spec = bt.spec
     last = bt.units[-1]
     dg, db = _bn_param_grads(sink, last.spec.bn)
@@ -452,7 +467,7 @@ def block_backward(cache: PackCache, sink: GradSink, bt: BlockTape, G: torch.Ten
         add_full = G
         dy_last = ops.bn_bwd(ops.SRC_DIRECT, last.y, last.st, last.spec.bn.weight.detach(), dg, db, G=G)
     sink.done(last.spec.bn.weight); sink.done(last.spec.bn.bias)
-    return units_backward(cache, sink, bt.units, dy_last, add_full=add_full, add_half=add_half)
+    return units_backward(cache, sink, bt.units, dy_last, add_full=add_full, add_half=add_half, want_sums=bt.inp_st is not None)
 
 
 # ------------------------------------------------------------------------------------------------ whole backbone
@@ -499,21 +514,27 @@ def xception_forward(net, x: torch.Tensor, save: bool = True):
     st2 = _bn_state(net.bn2, parts2, y2.numel() // 64)
     if need2:
         nbt.append(net.bn2.num_batches_tracked)
-    x2 = ops.bn_act(y2, st2.scale, st2.shift, True)
+    # x2 = relu(bn2(y2)) is the input of block 1 only (Xception.py:172-176): its two readers (the first depthwise and the
+    # stride-2 gather of the skip conv) apply bn2 + ReLU on the fly, so x2 is neither written nor saved -- one 708 MB write and,
+    # in backward, the reduce pass of bn2 (the depthwise backward delivers its sums) per 256 frames.  The fp32 validation plan
+    # keeps the materialised form (its twin kernels implement the round-1 signatures).
+    specs = net._block_specs
+    fuse_x2 = (not fp32) and specs[0].stride == 2 and specs[0].skip is not None and __import__("os").environ.get("XCP_MATERIALISE_X2", "0") != "1"
+    x2 = None if fuse_x2 else ops.bn_act(y2, st2.scale, st2.shift, True)
     tp.y1, tp.st1, tp.x1, tp.y2, tp.st2, tp.x2 = y1, st1, x1, y2, st2, x2
-    cur = x2
+    cur = y2 if fuse_x2 else x2
     if not save and not fp32 and _folded_ok(net):
         # inference plan: eval-mode BatchNorm folded into the pointwise weights, ReLU / residual add in the GEMM epilogues
-        for spec in net._block_specs:
-            cur = _block_folded(cache, spec, cur)
+        for bi, spec in enumerate(specs):
+            cur = _block_folded(cache, spec, cur, st2 if (fuse_x2 and bi == 0) else None)
         e3, e4 = net._exit_specs
         y3 = _sep_folded(cache, e3, cur, e3.relu, True)                      # conv3 -> bn3 -> relu   (Xception.py:189-191)
         y4 = _sep_folded(cache, e4, y3, False, False)                        # conv4 -> bn4; relu + GAP below (192-198)
         one, zero = cache.identity_affine(y4.shape[-1], y4.device)
         return ops.bn_relu_gap(y4, one, zero), None
     tp.blocks = []
-    for spec in net._block_specs:                                             # Xception.py:176-187
-        bt = block_forward(cache, spec, cur, nbt, save)
+    for bi, spec in enumerate(specs):                                         # Xception.py:176-187
+        bt = block_forward(cache, spec, cur, nbt, save, inp_st=st2 if (fuse_x2 and bi == 0) else None)
         cur = bt.out
         tp.blocks.append(bt if save else None)
     # exit flow: conv3 (no ReLU in front) -> bn3 -> relu -> conv4 -> bn4 -> relu -> GAP   (Xception.py:189-198)
@@ -533,8 +554,11 @@ def xception_backward(net, tp: XceptionTape, dfeat: torch.Tensor, sink: GradSink
     dy4 = ops.bn_bwd(ops.SRC_GAP_RELU, u4.y, u4.st, net.bn4.weight.detach(), dg, db, dfeat=dfeat.contiguous())
     sink.done(net.bn4.weight); sink.done(net.bn4.bias)
     G = units_backward(cache, sink, [u3, u4], dy4)
+    presums2 = None
     for bt in reversed(tp.blocks):
         G = block_backward(cache, sink, bt, G)
+        if bt.inp_st is not None:              # block 1 on the unmaterialised x2: (dL/d bn2-output with the ReLU mask applied, sums)
+            G, presums2 = G
     # stem.  G = dL/dx2 with x2 = relu(bn2(y2)); dy2 is written on the zero-padded conv2 input grid
     F_, H1, W1, _ = tp.y1.shape
     dg, db = _bn_param_grads(sink, net.bn2)
@@ -545,7 +569,10 @@ def xception_backward(net, tp: XceptionTape, dfeat: torch.Tensor, sink: GradSink
         sink.done(net.conv2.weight)
         dx1 = ops.conv3x3_gemm_dgrad(dy2, net.conv2.weight.detach())
     else:
-        dy2g = ops.bn_bwd(ops.SRC_RELU, tp.y2, tp.st2, net.bn2.weight.detach(), dg, db, G=G, grid_hw=(H1, W1))
+        if presums2 is not None:
+            dy2g = ops.bn_bwd(ops.SRC_DIRECT, tp.y2, tp.st2, net.bn2.weight.detach(), dg, db, G=G, presums=presums2, grid_hw=(H1, W1))
+        else:
+            dy2g = ops.bn_bwd(ops.SRC_RELU, tp.y2, tp.st2, net.bn2.weight.detach(), dg, db, G=G, grid_hw=(H1, W1))
         sink.done(net.bn2.weight); sink.done(net.bn2.bias)
         gk = torch.zeros((64, 9 * 32), device=G.device, dtype=F32)
         ops.conv3x3_wgrad(dy2g, tp.x1, gk)

@@ -227,6 +227,30 @@ def test_dw3x3_bwd_residual_adds():
     assert rel_err(both, ref) < 8e-3
 
 
+def test_dw3x3_bwd_residual_adds_inside_the_relu_mask():
+    """relu = 2 (unmaterialised block input, executor.block_forward(inp_st=...)): the residual gradients are gradients wrt the
+    ACTIVATED input relu(scale*x + shift), so they go inside the mask: dz = mask * (conv_transpose(dD) + add_half@even)."""
+    F_, H, W, C = 2, 21, 21, 64
+    x = rnd(F_, H, W, C, seed=23, dtype=torch.bfloat16)
+    w9 = ops.pack_dw(rnd(C, 1, 3, 3, seed=24, scale=0.4))
+    scale, shift = rnd(C, seed=25) * 0.5 + 1.0, rnd(C, seed=26, scale=0.3)
+    dD = rnd(F_, H, W, C, seed=27, dtype=torch.bfloat16)
+    half = rnd(F_, 11, 11, C, seed=28, dtype=torch.bfloat16)
+    gw = torch.zeros(C, 1, 3, 3, device=DEV)
+    # reference through autograd: a = relu(scale*x+shift) feeds the depthwise conv AND (at even pixels) a second consumer
+    xt = x.float().permute(0, 3, 1, 2)
+    z = (xt * scale[None, :, None, None] + shift[None, :, None, None]).requires_grad_(True)
+    a = F.relu(z)
+    wt = rnd(C, 1, 3, 3, seed=24, scale=0.4)
+    out = F.conv2d(a, wt, padding=1, groups=C)
+    loss = (out * dD.float().permute(0, 3, 1, 2)).sum() + (a[:, :, ::2, ::2] * half.float().permute(0, 3, 1, 2)).sum()
+    loss.backward()
+    dz, bns = ops.dw3x3_bwd(dD, x, w9, scale, shift, 2, gw, add_half=half)
+    assert rel_err(dz.float().permute(0, 3, 1, 2), z.grad) < 8e-3
+    assert rel_err(bns[0], z.grad.sum((0, 2, 3))) < 2e-2
+    assert rel_err(bns[1], (z.grad * xt).sum((0, 2, 3))) < 2e-2
+
+
 # ------------------------------------------------------------------------------------------------ BN & elementwise
 @pytest.mark.parametrize("shape", [(4, 19, 19, 728), (2, 37, 37, 256), (3, 10, 10, 2048), (1, 149, 149, 32)])
 def test_bn_finalize_and_apply(shape):
