@@ -32,13 +32,16 @@ int xcp_check_device(int device);
  * epi: 0 bf16 out | 1 bf16 out + per-channel (sum, sum-sq) partials stats[ceil(M/128)][2][N] for train-mode
  * BatchNorm (Xception.py:67,73,78) | 2 fp32 out (+ optional bias[N]).  lda/ldb/ldo are row pitches in elements. */
 int xcp_gemm_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N, int K,
-                int epi, float* stats, const float* bias, int device, void* stream);
+                int epi, float* stats, const float* bias, int n_real, int k_real, int device, void* stream);
+/* n_real / k_real (0 = N / K): logical channel counts when N / K are channel pitches whose tail is zero padding (728 in 768):
+ * the tensor-core work that would only multiply padding is skipped, the padded output columns are written as zeros. */
 /* Inference plan (eval-mode BatchNorm folded into the weights; the reference's no_grad evaluation, test_visual.py:609-624):
  * out[M,N] = relu?( A[M,K] * B[N,K]^T + bias[N] + residual[M,N] ) as bf16.  B = pointwise weights pre-multiplied per output
  * channel by gamma * rsqrt(running_var + eps) (xcp_pack_weight_scaled), bias = beta - running_mean * that scale; residual
  * (optional, bf16, row pitch ld_res) is the identity-skip input of a Block (Xception.py:96-98).  N % 32 == 0. */
 int xcp_gemm_tn_bias(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N, int K,
-                     const float* bias, int relu, const void* residual, long long ld_res, int device, void* stream);
+                     const float* bias, int relu, const void* residual, long long ld_res, int n_real, int k_real, int device,
+                     void* stream);
 /* rows of `stats` written by xcp_gemm_tn(epi=1) / xcp_conv3x3_gemm for an M x N problem (<= SM count when N fits one tile) */
 int xcp_gemm_stats_parts(long long M, int N, int device);
 /* dW[P,Q] += dY[R,P]^T * X[R,Q] (fp32 accumulate into dW): weight gradient of the layers above. */

@@ -19,8 +19,8 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctyp
 SIGNATURES = {
     "xcp_version": "",
     "xcp_check_device": "i",
-    "xcp_gemm_tn": "plplpliiiippip",
-    "xcp_gemm_tn_bias": "plplpliiipiplip",
+    "xcp_gemm_tn": "plplpliiiippiiip",
+    "xcp_gemm_tn_bias": "plplpliiipipliiip",
     "xcp_gemm_stats_parts": "lii",
     "xcp_gemm_wgrad": "plplpliiiip",
     "xcp_gemm_ref": "plplpliiiiip",

@@ -42,6 +42,11 @@ struct GemmParams {
     long long ld_res;
     int epi_relu;
     int num_m_tiles, num_n_tiles, num_k_blocks;
+    // Channel-pitch trimming (728 logical channels live in a 768 pitch: the pad is zero).  The MMAs skip what is only padding:
+    // the LAST N tile is issued with n_last (< BLOCK_N, a multiple of 16) columns and -- K-major, one split -- the last K block with
+    // k_steps_last (< BLOCK_K/16) K steps.  0 = no trimming.  At K = N = 728 that is 46 of 48 K steps and 736 of 768 columns: 8 % of
+    // the tensor work of a middle-flow GEMM.  Output columns >= n_last of the last tile are written as zeros.
+    int n_last, k_steps_last;
     int splits, k_blocks_per_split;   // split over the reduction dim (EPI_RED_F32)
     // implicit-GEMM mode for the dense 3x3 stem conv: K block kb reads A rows shifted by a_row_shift[kb]
     int conv_taps;        // 0 = plain GEMM
@@ -198,7 +203,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int t = u - split * tiles_mn;
             const int m_blk = t / p.num_n_tiles, n_blk = t - m_blk * p.num_n_tiles;
             const int m0 = m_blk * m_row0_mul + (int)rank * BLOCK_M;        // first A row (K-major) / M column (MN-major)
-            const int n0 = n_blk * BLOCK_N + (int)rank * B_ROWS;
+            const int n_eff = (p.n_last > 0 && n_blk == p.num_n_tiles - 1) ? p.n_last : BLOCK_N;
+            const int n0 = n_blk * BLOCK_N + (int)rank * (CTA2 ? n_eff / 2 : B_ROWS);
             const int kb0 = split * p.k_blocks_per_split;
             const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -241,11 +247,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
         // ------------------------------------------------ MMA issuer (leader CTA only in pair mode)
-        constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
+        constexpr uint32_t idesc_full = make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
+        const uint32_t idesc_last = p.n_last > 0 ? make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.n_last, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0) : idesc_full;
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         int s = 0; uint32_t ph = 0; uint32_t iter = 0;
         for (int u = worker; u < num_units; u += num_workers, ++iter) {
             const int split = u / tiles_mn;
+            const uint32_t idesc = ((u - split * tiles_mn) % p.num_n_tiles == p.num_n_tiles - 1) ? idesc_last : idesc_full;
             const int kb0 = split * p.k_blocks_per_split;
             const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
             const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
@@ -255,8 +263,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
+                const int ksteps = (p.k_steps_last > 0 && kb == p.num_k_blocks - 1) ? p.k_steps_last : BLOCK_K / UMMA_K;
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    if (k >= ksteps) break;
                     uint64_t adesc, bdesc;
                     if (!MN_MAJOR) {
                         adesc = make_smem_desc(a_base + s * A_BYTES + k * (UMMA_K * 2), 0, SBO, LAYOUT);
@@ -348,9 +358,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
+                const bool trimmed = p.n_last > 0 && n_blk == p.num_n_tiles - 1 && c * 32 >= p.n_last;   // pure padding: never computed
+                if (!trimmed) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
                 uint32_t fa[16], fb[16];
-                if (STATS && p.conv_taps == 0) {
+                if (STATS && p.conv_taps == 0 && trimmed) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { fa[j] = 0u; fb[j] = 0u; }
+                } else if (STATS && p.conv_taps == 0) {
                     // The accumulator chunk is read a second time in the mma-fragment shape (16x256b: a thread holds
                     // 4 rows x 4 column pairs) for the column statistics.  The shared-memory crossbar carries the UMMA
                     // operand reads (~96 of 128 B/clk), so the epilogue must stay off it: the first version transposed
@@ -698,6 +716,26 @@ static TnPlan plan_tn(long long M, int N) {
     return pl;
 }
 
+// pad trimming of a K-major problem whose operands carry n_real <= N / k_real <= K logical channels (the rest of the pitch is zero)
+static void set_trim(GemmParams& p, int bn, int N, int K, int n_real, int k_real) {
+    const char* off = getenv("XCP_GEMM_NO_TRIM");                       // A/B hook
+    if (off != nullptr && off[0] == '1') return;
+    if (n_real > 0 && n_real < N) {
+        const int last = n_real - bn * (p.num_n_tiles - 1);
+        if (last > 0) {
+            const int nl = (last + 15) / 16 * 16;
+            if (nl < bn) p.n_last = nl;
+        }
+    }
+    if (k_real > 0 && k_real < K && p.splits == 1) {
+        const int last = k_real - 64 * (p.num_k_blocks - 1);
+        if (last > 0) {
+            const int ks = (last + 15) / 16;
+            if (ks < 4) p.k_steps_last = ks;
+        }
+    }
+}
+
 template <int EPI>
 static int dispatch_tn(const TnPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
     if (pl.bn == 64) return launch_gemm<64, EPI, false, fit_stages<64, 64, EPI, false>(), 64>(a, b, p, st);
@@ -729,7 +767,8 @@ static int pick_block_n(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
 // D[M,N] = A[M,K] * B[N,K]^T  (bf16 in, fp32 accumulate).  epi: 0 bf16 out, 1 bf16 out + per-column
 // (sum, sum-sq) partials per 128-row tile into stats[ceil(M/128)][2][N], 2 fp32 out (+ optional bias[N]).
 extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo,
-                           int M, int N, int K, int epi, float* stats, const float* bias, int device, void* stream) {
+                           int M, int N, int K, int epi, float* stats, const float* bias, int n_real, int k_real, int device,
+                           void* stream) {
     XCP_REQUIRE(M > 0 && N > 0 && K > 0, "xcp_gemm_tn: empty problem M=%d N=%d K=%d", M, N, K);
     XCP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "xcp_gemm_tn: K/lda/ldb must be multiples of 8 (16B TMA rows)");
     XCP_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "xcp_gemm_tn: N/ldo must be multiples of 8");
@@ -748,6 +787,7 @@ extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long lon
     p.num_k_blocks = (K + 63) / 64;
     p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
     p.stats_per_cta = (p.num_n_tiles == 1) ? 1 : 0;
+    if (epi != EPI_F32) set_trim(p, pl.bn, N, K, n_real, k_real);
     if (epi != EPI_F32) {
         if (int e = make_tmap_2d(&p.tmC, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 32, 32, 64)) return e;
         p.tma_store = 1;
@@ -763,7 +803,8 @@ extern "C" int xcp_gemm_tn(const void* A, long long lda, const void* B, long lon
 // Inference plan: out[M,N] = relu?( A[M,K] * B[N,K]^T + bias[N] + residual[M,N] ) in bf16, where B holds
 // the pointwise weights pre-multiplied by the BatchNorm scale (xcp_fold_bn_weight) and bias the BatchNorm shift.
 extern "C" int xcp_gemm_tn_bias(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N,
-                                int K, const float* bias, int relu, const void* residual, long long ld_res, int device, void* stream) {
+                                int K, const float* bias, int relu, const void* residual, long long ld_res, int n_real, int k_real,
+                                int device, void* stream) {
     XCP_REQUIRE(M > 0 && N > 0 && K > 0, "xcp_gemm_tn_bias: empty problem M=%d N=%d K=%d", M, N, K);
     XCP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "xcp_gemm_tn_bias: K/lda/ldb must be multiples of 8 (16B TMA rows)");
     XCP_REQUIRE(N % 32 == 0 && ldo % 8 == 0, "xcp_gemm_tn_bias: N must be a multiple of 32 (channel pitch), ldo of 8");
@@ -785,6 +826,7 @@ extern "C" int xcp_gemm_tn_bias(const void* A, long long lda, const void* B, lon
     p.splits = 1; p.k_blocks_per_split = p.num_k_blocks;
     if (int e = make_tmap_2d(&p.tmC, out, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 32, 32, 64)) return e;
     p.tma_store = 1;
+    set_trim(p, pl.bn, N, K, n_real, k_real);
     return dispatch_tn<EPI_BF16_BIAS>(pl, tmA, tmB, p, (cudaStream_t)stream);
 }
 
@@ -822,6 +864,12 @@ extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, lo
     if (splits < 1) splits = 1;
     p.k_blocks_per_split = (p.num_k_blocks + splits - 1) / splits;
     p.splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+    {   // the last N tile only covers Q - bn * (tiles - 1) real columns (728 -> 216 of 256): issue the MMAs that wide
+        const char* off = getenv("XCP_GEMM_NO_TRIM");
+        const int last = Q - bn * (p.num_n_tiles - 1);
+        const int nl = (last + 15) / 16 * 16;
+        if (!(off != nullptr && off[0] == '1') && last > 0 && nl < bn) p.n_last = nl;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {
         case 64: return launch_gemm<64, EPI_RED_F32, true, fit_stages<64, 64, EPI_RED_F32, false>(), 64>(tmA, tmB, p, st);

@@ -262,11 +262,11 @@ def sep_forward(cache: PackCache, spec: SepSpec, src: torch.Tensor, src_st, relu
     t = SepTape()
     t.spec, t.src, t.src_st, t.src_relu, t.d = spec, src, src_st, relu, d
     if spec.bn is None:
-        y, _ = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16)
+        y, _ = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16, n_real=spec.cout, k_real=spec.cin)
         t.y, t.st = y.view(F_, H, W, y.shape[1]), None
         return t
     need = _bn_needs_stats(spec.bn)
-    y, parts = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16)
+    y, parts = ops.gemm_tn(d.view(M, C), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16, n_real=spec.cout, k_real=spec.cin)
     t.y = y.view(F_, H, W, y.shape[1])
     t.st = _bn_state(spec.bn, parts, M)
     if need and spec.bn.track_running_stats:
@@ -304,7 +304,8 @@ def block_forward(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, nbt: lis
             raise ops._lib.XcpError("Block: only strides 1 and 2 are implemented on the sm_100a path (Xception uses 1, 2)")
         Fs, Hs, Ws, Cs = xs.shape
         need = _bn_needs_stats(spec.skipbn)
-        ys, parts = ops.gemm_tn(xs.view(Fs * Hs * Ws, Cs), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16)
+        ys, parts = ops.gemm_tn(xs.view(Fs * Hs * Ws, Cs), wb, ops.EPI_BF16_STATS if need else ops.EPI_BF16,
+                                n_real=spec.cout, k_real=spec.cin)
         ys = ys.view(Fs, Hs, Ws, ys.shape[1])
         st_s = _bn_state(spec.skipbn, parts, Fs * Hs * Ws)
         if need and spec.skipbn.track_running_stats:
@@ -336,7 +337,8 @@ def _sep_folded(cache: PackCache, spec: SepSpec, src: torch.Tensor, relu_in: boo
         d = ops.dw3x3_fwd(src, cache.dw(spec.sep.conv1.weight), None, None, relu_in)
     wf, bias = cache.pw_folded(spec.sep.pointwise.weight, spec.bn)
     M = F_ * H * W
-    y = ops.gemm_tn_bias(d.view(M, C), wf, bias, relu_out, residual.view(M, -1) if residual is not None else None)
+    y = ops.gemm_tn_bias(d.view(M, C), wf, bias, relu_out, residual.view(M, -1) if residual is not None else None,
+                         n_real=spec.cout, k_real=spec.cin)
     return y.view(F_, H, W, y.shape[1])
 
 
@@ -351,7 +353,7 @@ def _block_folded(cache: PackCache, spec: BlockSpec, inp: torch.Tensor, inp_st=N
             xs = ops.gather_s2(inp) if spec.stride == 2 else inp
         Fs, Hs, Ws, Cs = xs.shape
         wf, bias = cache.pw_folded(spec.skip.weight, spec.skipbn)
-        ys = ops.gemm_tn_bias(xs.view(Fs * Hs * Ws, Cs), wf, bias, False)
+        ys = ops.gemm_tn_bias(xs.view(Fs * Hs * Ws, Cs), wf, bias, False, n_real=spec.cout, k_real=spec.cin)
         ys = ys.view(Fs, Hs, Ws, ys.shape[1])
     src = inp
     n = len(spec.units)
@@ -398,7 +400,7 @@ def _pw_backward(cache: PackCache, sink: GradSink, weight: torch.Tensor, dy: tor
     if not need_dgrad:
         return None
     _, wt = cache.pw_for(dy, weight)
-    da, _ = ops.gemm_tn(dy.view(M, Np), wt, ops.EPI_BF16)
+    da, _ = ops.gemm_tn(dy.view(M, Np), wt, ops.EPI_BF16, n_real=K, k_real=N)
     return da.view(*a.shape)
 
 

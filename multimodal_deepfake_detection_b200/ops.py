@@ -54,8 +54,9 @@ def check_device(device: torch.device):
 
 # ------------------------------------------------------------------------------------------------ GEMMs
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optional[torch.Tensor] = None,
-            out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """out[M,N] = a[M,K] @ b[N,K]^T.  Returns (out, stats_partials or None)."""
+            out: Optional[torch.Tensor] = None, n_real: int = 0, k_real: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """out[M,N] = a[M,K] @ b[N,K]^T.  Returns (out, stats_partials or None).  n_real / k_real: logical channel counts when N / K
+    are zero-padded channel pitches (728 in 768): the MMAs skip the padding, the padded output columns come out as zeros."""
     if a.dtype == F32:
         return _gemm_tn_f32(a, b, epi)
     _chk(a, BF16, "gemm_tn.a"); _chk(b, BF16, "gemm_tn.b")
@@ -67,12 +68,13 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, epi: int = EPI_BF16, bias: Optiona
     stats = None
     if epi == EPI_BF16_STATS:
         stats = torch.empty((_lib.call("xcp_gemm_stats_parts", M, N, a.device.index), 2, N), device=a.device, dtype=F32)
-    _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), a.device.index, _s())
+    _lib.call("xcp_gemm_tn", _p(a), K, _p(b), K, _p(out), N, M, N, K, epi, _p(stats), _p(bias), int(n_real), int(k_real),
+              a.device.index, _s())
     return out, stats
 
 
 def gemm_tn_bias(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor, relu: bool, residual: Optional[torch.Tensor] = None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, n_real: int = 0, k_real: int = 0) -> torch.Tensor:
     """Inference plan: out[M,N] = relu?(a[M,K] @ b[N,K]^T + bias[N] + residual[M,N]) in bf16 (b = BN-folded weights)."""
     _chk(a, BF16, "gemm_tn_bias.a"); _chk(b, BF16, "gemm_tn_bias.b"); _chk(bias, F32, "gemm_tn_bias.bias")
     M, K = a.shape
@@ -84,7 +86,7 @@ def gemm_tn_bias(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor, relu: boo
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=BF16)
     _lib.call("xcp_gemm_tn_bias", _p(a), K, _p(b), K, _p(out), N, M, N, K, _p(bias), int(relu), _p(residual), N,
-              a.device.index, _s())
+              int(n_real), int(k_real), a.device.index, _s())
     return out
 
 

@@ -76,6 +76,34 @@ def test_pack_weight_scaled():
     assert torch.equal(out.float(), ref.bfloat16().float())
 
 
+@pytest.mark.parametrize("M,epi", [(2000, 0), (2000, 1), (700, 1), (100, 0)])
+def test_gemm_tn_pad_trimming(M, epi, monkeypatch):
+    """K = N = 768 pitches holding 728 logical channels (zero pad): with n_real / k_real the MMAs skip the padding (46 of 48 K
+    steps, 736 of 768 columns, CTA pairs re-split the trimmed N) -- same result as the untrimmed launch, padded output columns
+    exactly zero, same BatchNorm partial sums."""
+    a = torch.zeros(M, 768, device=DEV, dtype=torch.bfloat16); a[:, :728] = rnd(M, 728, seed=41, dtype=torch.bfloat16)
+    b = torch.zeros(768, 768, device=DEV, dtype=torch.bfloat16); b[:728, :728] = rnd(728, 728, seed=42, scale=0.05, dtype=torch.bfloat16)
+    out_t, st_t = ops.gemm_tn(a, b, epi, n_real=728, k_real=728)
+    monkeypatch.setenv("XCP_GEMM_NO_TRIM", "1")
+    out_f, st_f = ops.gemm_tn(a, b, epi, n_real=728, k_real=728)
+    monkeypatch.delenv("XCP_GEMM_NO_TRIM")
+    assert torch.equal(out_t, out_f)
+    assert float(out_t[:, 728:].abs().max()) == 0.0
+    ref = a.float() @ b.float().t()
+    assert rel_err(out_t.float(), ref) < 6e-3
+    if epi == 1:
+        assert rel_err(st_t.sum(0), st_f.sum(0)) < 1e-6
+        assert rel_err(st_t.sum(0)[0], ref.sum(0)) < 2e-3
+    # weight gradient with the logical (728, 728) shape: the last N tile is issued 224 wide
+    dy = a; x = torch.zeros(M, 768, device=DEV, dtype=torch.bfloat16); x[:, :728] = rnd(M, 728, seed=43, dtype=torch.bfloat16)
+    dw_t = torch.zeros(728, 728, device=DEV); dw_f = torch.zeros(728, 728, device=DEV)
+    ops.gemm_wgrad(dy, x, dw_t)
+    monkeypatch.setenv("XCP_GEMM_NO_TRIM", "1")
+    ops.gemm_wgrad(dy, x, dw_f)
+    monkeypatch.delenv("XCP_GEMM_NO_TRIM")
+    assert rel_err(dw_t, dw_f) < 1e-5 and rel_err(dw_t, dy.float()[:, :728].t() @ x.float()[:, :728]) < 1e-4
+
+
 @pytest.mark.parametrize("M,N,K", [(64, 512, 2048), (300, 2048, 2048), (5, 128, 128)])
 def test_gemm_tn_f32_bias(M, N, K):
     a = rnd(M, K, seed=3, dtype=torch.bfloat16)
