@@ -36,6 +36,8 @@ class GradBucketer:
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        import os
+        bucket_mb = float(os.environ.get("XCP_DDP_BUCKET_MB", bucket_mb))      # tuning hook
         self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
         self.backbone = backbone
         self._avg_supported = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
