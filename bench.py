@@ -494,7 +494,8 @@ def build_workload(cfg: str, B: int, dev, rank: int, world: int):
                     for _ in range(2)]
 
             def fwd_loss(clips, y):
-                return crit(model(model.extract_features(clips, dev)), y)       # train_audio.py:20,39 criterion on the sigmoid output
+                # train_audio.py:20,39: BCELoss on the sigmoid output -- head + criterion as one launch (north_star (3))
+                return model.forward_loss(model.extract_features(clips, dev), y)[0]
             w.update(modules=[model], params=list(model.parameters()), backbones=[(model.feature_extractor, None)], units=B,
                      desc="XceptionLSTMV(128) train step, backbone unfrozen, train-mode BN, BCE, fused Adam(1e-5, wd 1e-4)",
                      shape={"clips_per_gpu": B, "frames_per_clip": T_FRAMES, "frame": "3x299x299"}, model=model)
@@ -518,7 +519,7 @@ def build_workload(cfg: str, B: int, dev, rank: int, world: int):
                     for _ in range(2)]
 
             def fwd_loss(patches, y):
-                return crit(model.forward_logits(model.extract_features(patches, dev)), y)
+                return model.forward_loss(model.extract_features(patches, dev), y, smoothing=crit.smoothing)[0]
             w.update(modules=[model], params=list(model.parameters()), backbones=[(model.feature_extractor, None)], units=B,
                      desc="XceptionLSTMA(128) train step on log-mel patch sequences (train_au_patch.py protocol): backbone unfrozen, "
                           "label-smoothing BCE-with-logits, fused Adam(1e-4, wd 1e-4)",

@@ -157,6 +157,25 @@ int xcp_sigmoid_fwd(const float* z, float* p, int n, int device, void* stream);
 int xcp_sigmoid_bwd(const float* p, const float* dp, float* dz, int n, int device, void* stream);
 int xcp_bce_fwd_bwd(const float* z, const float* y, float smoothing, float* probs, float* loss, float* dz, int B, int device,
                     void* stream);
+/* The whole classifier head + loss in ONE launch per direction (BASELINE north_star (3); XceptionLSTMV.py:25-44,66-70,
+ * train_audio.py:20,39, train_au_patch.py:203-211).  Input row b = x + b*row_stride + (row_index ? row_index[b]*H : 0): the
+ * lstm_out[:, -1, :] select (or the per-clip last valid step) is an address, not a copy.  wb / dwb: HOST arrays of 10 device
+ * pointers {W0,b0,...,W4,b4} (fc_layers[0,3,6,9], fc_out) and their gradient slots (accumulated into; entries may be NULL).
+ * Dropout: `mask` = optional uint8 keep masks [4][B][Wd]; else, with p_drop > 0 and `rng` = device {u64 seed, u64 launch
+ * counter}, the kernel draws the masks itself and advances the counter (CUDA-graph replays draw fresh masks); both NULL =
+ * no dropout.  acts = [4][B][Wd] layer outputs saved for the backward.  loss_mode 0: none; 1: nn.BCELoss on the sigmoid
+ * output (loss, dz = dL/dz); 2: BCE-with-logits on y(1-smoothing)+smoothing/2.  bar = 2 x u32, zero before the first
+ * launch (every launch leaves it zero).  B <= 32, H % 4 == 0, Wd % 16 == 0, both <= 1024.
+ * Backward: dz[b] = dsrc[b] * (prob ? p(1-p) : 1) * (gscale ? *gscale : 1); dacts = [4][B][Wd] scratch; dx (nullable) = gradient
+ * wrt the LSTM output with the same row addressing as x; the kernel first zeroes dx_zero_n floats from dx_base (the whole
+ * [B,T,H] gradient), then adds the selected rows. */
+int xcp_head_mlp_fwd(const float* x, long long row_stride, const long long* row_index, const void* const* wb, const void* mask,
+                     void* rng, float p_drop, float* acts, float* z, float* prob, int loss_mode, const float* y, float smoothing,
+                     float* loss, float* dz, void* bar, int B, int H, int Wd, int device, void* stream);
+int xcp_head_mlp_bwd(const float* dsrc, const float* prob, const float* gscale, const float* x, long long row_stride,
+                     const long long* row_index, const float* acts, float drop_scale, const void* const* wb, void* const* dwb,
+                     float* dacts, float* dx, float* dx_base, long long dx_zero_n, void* bar, int B, int H, int Wd, int device,
+                     void* stream);
 /* nn.BCELoss() (mean) on probabilities + its gradient wrt p in one launch (train_audio.py:20,39); dp may be NULL */
 int xcp_bce_prob_fwd_bwd(const float* p, const float* y, float* loss, float* dp, int n, int device, void* stream);
 int xcp_arcface_loss(const float* x, const float* w, const long long* labels, float s, float m, int loss_mode,

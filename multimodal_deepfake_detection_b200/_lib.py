@@ -61,6 +61,8 @@ SIGNATURES = {
     "xcp_sigmoid_bwd": "pppiip",
     "xcp_bce_fwd_bwd": "ppfpppiip",
     "xcp_bce_prob_fwd_bwd": "ppppiip",
+    "xcp_head_mlp_fwd": "plppppfpppipfpppiiiip",
+    "xcp_head_mlp_bwd": "pppplppfppppplpiiiip",
     "xcp_arcface_loss": "pppffipfppppppiifip",
     "xcp_fusion_pool_reg": "ppppppiiifffip",
     "xcp_fusion_pool_bwd": "pppiiiip",

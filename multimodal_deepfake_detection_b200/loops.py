@@ -194,8 +194,6 @@ def audio_epoch(model, loader, device, optimizer=None, frontend=None, frames: in
     """train_audio.py:33-46 / 55-67: BCELoss on the sigmoid output; returns (mean loss, accuracy).
     With `frontend` (audio_frontend.MFCC) a 2-D batch is taken as raw waveforms (B, samples) and turned into the
     (B, frames, 3, 13) MFCC tensor on the device (row f-4) instead of coming from the offline librosa files."""
-    from .modules import BCELoss
-    criterion = BCELoss()
     train = optimizer is not None
     total = torch.zeros((), device=device)
     hits = torch.zeros((), device=device)
@@ -209,8 +207,8 @@ def audio_epoch(model, loader, device, optimizer=None, frontend=None, frames: in
                     raise XcpError("audio_epoch: got raw waveforms %s but no MFCC front-end" % (tuple(audio.shape),))
                 audio = frontend.clips(audio, frames=frames)
             feats = model.extract_features(audio, device)
-            out = model(feats)
-            loss = criterion(out, labels)
+            # head + nn.BCELoss in one launch: same values and gradients as criterion(model(feats), labels)
+            loss, out = model.forward_loss(feats, labels.float().view(-1, 1))
             if train:
                 optimizer.zero_grad(set_to_none=True)
                 loss.backward()

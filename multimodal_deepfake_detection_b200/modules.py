@@ -446,41 +446,72 @@ class FusedLSTM(nn.LSTM):
 
 
 # ================================================================================================ MLP head
+def _head_forward(ctx, lstm_out, row_index, training, p_drop, want_logits, labels, smoothing, masks, wb):
+    """fc_layers (4 x Linear+ReLU+Dropout(0.3)) + fc_out (+ sigmoid) (+ criterion) of XceptionLSTMV.py:25-44,66-70 as ONE
+    launch (csrc/head_fused.cu): the last-step select is an address into the LSTM output, dropout masks are drawn in the
+    kernel, the loss and dL/dz come out of the same launch when ``labels`` is given."""
+    x = lstm_out if lstm_out.dim() == 3 else lstm_out.unsqueeze(1)
+    x = x.float().contiguous()
+    B = x.shape[0]
+    if B > 32:
+        raise XcpError("classifier head: at most 32 clips per call (got %d)" % B)
+    ctx.set_materialize_grads(False)
+    p = float(p_drop) if training else 0.0
+    loss_mode = 0 if labels is None else (2 if want_logits else 1)
+    y = labels.detach().float().contiguous() if labels is not None else None
+    acts, z, prob, loss, dz = ops.head_mlp_fwd(x, row_index, [t.detach() for t in wb], p, masks, loss_mode, y,
+                                               float(smoothing or 0.0))
+    ctx.x, ctx.row_index, ctx.acts, ctx.dz, ctx.wb = x, row_index, acts, dz, wb
+    ctx.prob = None if want_logits else prob.detach()        # detached: no output -> grad_fn -> ctx cycle
+    ctx.scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+    ctx.in_shape = lstm_out.shape
+    return (z if want_logits else prob), loss
+
+
+def _head_backward(ctx, dout, dloss):
+    wb = ctx.wb
+    n_fixed = 8
+    if dout is None and dloss is None:
+        return (None,) * (n_fixed + len(wb))
+    if dout is None:                       # the fused criterion: dz was formed by the forward launch, scaled by dloss in the kernel
+        dsrc, prob, gscale = ctx.dz, None, dloss.detach().float().contiguous()
+    elif dloss is None:                    # an external criterion on the sigmoid output / the logits
+        dsrc, prob, gscale = dout.detach().float().contiguous(), ctx.prob, None
+    else:
+        d2 = dout.detach().float()
+        if ctx.prob is not None:
+            d2 = d2 * ctx.prob * (1.0 - ctx.prob)
+        dsrc, prob, gscale = (ctx.dz * dloss.detach().float() + d2).contiguous(), None, None
+    sink = ex.GradSink(list(wb), ctx.x.device)
+    dx = ops.head_mlp_bwd(dsrc, prob, gscale, ctx.x, ctx.row_index, ctx.acts, ctx.scale, [t.detach() for t in wb],
+                          [sink.view(t) for t in wb], want_dx=ctx.needs_input_grad[0])
+    if dx is not None:
+        dx = dx.view(ctx.in_shape)
+    return (dx,) + (None,) * (n_fixed - 1) + tuple(sink.view(t) for t in wb)
+
+
 class _HeadFn(torch.autograd.Function):
-    """fc_layers (4 x Linear+ReLU+Dropout(0.3)) + fc_out + sigmoid (XceptionLSTMV.py:25-44,68-70)."""
+    """Head without a criterion: -> probabilities (or fc_out logits)."""
 
     @staticmethod
-    def forward(ctx, h_last, training, p_drop, want_logits, *wb):
-        x = h_last.float().contiguous()
-        B = x.shape[0]
-        if B > 32:
-            raise XcpError("classifier head: at most 32 clips per call (got %d)" % B)
-        acts = [x]
-        scale = 1.0 / (1.0 - p_drop) if (training and p_drop > 0) else 1.0
-        for li in range(4):
-            W, b = wb[2 * li].detach(), wb[2 * li + 1].detach()
-            mask = None
-            if training and p_drop > 0:
-                mask = (torch.rand((B, W.shape[0]), device=x.device) >= p_drop).to(torch.uint8)
-            acts.append(ops.linear_small_fwd(acts[-1], W, b, 1, mask, scale))
-        z = ops.linear_small_fwd(acts[-1], wb[8].detach(), wb[9].detach(), 0)
-        if want_logits:                          # fc_out without the sigmoid (criteria that take logits, train_au_patch.py:203-214)
-            ctx.acts, ctx.prob, ctx.scale, ctx.wb = acts, None, scale, wb
-            return z
-        prob = ops.sigmoid_fwd(z)
-        ctx.acts, ctx.prob, ctx.scale, ctx.wb = acts, prob.detach(), scale, wb     # detached: no output -> grad_fn -> ctx cycle
-        return prob
+    def forward(ctx, lstm_out, row_index, training, p_drop, want_logits, labels, smoothing, masks, *wb):
+        return _head_forward(ctx, lstm_out, row_index, training, p_drop, want_logits, None, None, masks, wb)[0]
 
     @staticmethod
-    def backward(ctx, dprob):
-        acts, wb, scale = ctx.acts, ctx.wb, ctx.scale
-        sink = ex.GradSink(list(wb), dprob.device)
-        dz = dprob.float().contiguous() if ctx.prob is None else ops.sigmoid_bwd(ctx.prob, dprob.float().contiguous())
-        delta = ops.linear_small_bwd(dz, None, 1.0, acts[4], wb[8].detach(), sink.view(wb[8]), sink.view(wb[9]))
-        for li in range(3, -1, -1):
-            delta = ops.linear_small_bwd(delta, acts[li + 1], scale, acts[li], wb[2 * li].detach(), sink.view(wb[2 * li]),
-                                         sink.view(wb[2 * li + 1]), want_din=(li > 0 or ctx.needs_input_grad[0]))
-        return (delta if ctx.needs_input_grad[0] else None, None, None, None) + tuple(sink.view(p) for p in wb)
+    def backward(ctx, dout):
+        return _head_backward(ctx, dout, None)
+
+
+class _HeadLossFn(torch.autograd.Function):
+    """Head + criterion in one launch: -> (probabilities or logits, loss)."""
+
+    @staticmethod
+    def forward(ctx, lstm_out, row_index, training, p_drop, want_logits, labels, smoothing, masks, *wb):
+        return _head_forward(ctx, lstm_out, row_index, training, p_drop, want_logits, labels, smoothing, masks, wb)
+
+    @staticmethod
+    def backward(ctx, dout, dloss):
+        return _head_backward(ctx, dout, dloss)
 
 
 class _XceptionLSTMBase(nn.Module):
@@ -545,21 +576,39 @@ class _XceptionLSTMBase(nn.Module):
         last = (seq_lengths.detach().long().clamp(1, t) - 1).to(lstm_out.device)
         return lstm_out[torch.arange(b, device=lstm_out.device), last]
 
+    def _row_index(self, lstm_out, seq_lengths):
+        if not self._lengths_on(seq_lengths):
+            return None
+        t = lstm_out.shape[1]
+        return (seq_lengths.detach().long().clamp(1, t) - 1).to(lstm_out.device).contiguous()
+
     def forward(self, features, seq_lengths=None):
-        """lstm -> last step -> fc_layers -> sigmoid(fc_out) (XceptionLSTMV.py:66-70).  The optional second argument
-        exists because train_visual.py's older variants pass seq_lengths; like the shipped class, lengths are not used
-        unless ``use_seq_lengths`` is set."""
+        """lstm -> last step -> fc_layers -> sigmoid(fc_out) (XceptionLSTMV.py:66-70); the head is one launch.  The optional
+        second argument exists because train_visual.py's older variants pass seq_lengths; like the shipped class, lengths
+        are not used unless ``use_seq_lengths`` is set."""
         lstm_out, _ = self.lstm(features)
-        last = self.last_step(lstm_out, seq_lengths)
         drop = self.fc_layers[2]
-        return _HeadFn.apply(last, drop.training, float(drop.p), False, *self._head_params())
+        return _HeadFn.apply(lstm_out, self._row_index(lstm_out, seq_lengths), drop.training, float(drop.p), False, None, None,
+                             None, *self._head_params())
 
     def forward_logits(self, features):
         """Same path as forward() without the final sigmoid: fc_out logits (B,1) for logit-space criteria such as
         LabelSmoothingBCEWithLogitsLoss (train_au_patch.py:203-214)."""
         lstm_out, _ = self.lstm(features)
         drop = self.fc_layers[2]
-        return _HeadFn.apply(lstm_out[:, -1, :], drop.training, float(drop.p), True, *self._head_params())
+        return _HeadFn.apply(lstm_out, None, drop.training, float(drop.p), True, None, None, None, *self._head_params())
+
+    def forward_loss(self, features, labels, seq_lengths=None, smoothing=None):
+        """forward() and its criterion as ONE kernel (BASELINE north_star (3)): ``smoothing=None`` -> (nn.BCELoss()(probabilities,
+        labels), probabilities) as train_audio.py:20,39 computes them; a float -> (LabelSmoothingBCEWithLogitsLoss(smoothing)
+        (logits, labels), logits) as train_au_patch.py:203-214 does.  Same values and gradients as the two-call form."""
+        lstm_out, _ = self.lstm(features)
+        drop = self.fc_layers[2]
+        if labels.numel() != lstm_out.shape[0]:
+            raise XcpError("forward_loss: %d labels for %d clips" % (labels.numel(), lstm_out.shape[0]))
+        out, loss = _HeadLossFn.apply(lstm_out, self._row_index(lstm_out, seq_lengths), drop.training, float(drop.p),
+                                      smoothing is not None, labels, smoothing, None, *self._head_params())
+        return loss, out
 
 
 class XceptionLSTMV(_XceptionLSTMBase):

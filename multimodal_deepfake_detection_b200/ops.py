@@ -561,6 +561,89 @@ def linear_small_bwd(delta_raw, out_act, drop_scale, a, W, dW, db, want_din=True
     return din
 
 
+_HEAD_STATE = {}
+
+
+def head_state(device: torch.device):
+    """Per-device state of the fused head kernels: the grid-barrier counters of the forward and the backward launch
+    (zero at rest) and the dropout generator {seed, launch counter} -- device resident, so CUDA-graph replays draw
+    fresh masks.  The seed is torch's at first use (torch.manual_seed makes the masks reproducible)."""
+    st = _HEAD_STATE.get(device.index)
+    if st is None:
+        bars = torch.zeros((8,), device=device, dtype=torch.int32)
+        rng = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64).to(device)
+        st = _HEAD_STATE[device.index] = (bars, rng)
+    return st
+
+
+def head_reseed(device: torch.device, seed: int):
+    bars, rng = head_state(device)
+    rng.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else 0 for t in tensors])
+
+
+def _head_rows(x, row_index):
+    """x [B,T,H] fp32 contiguous -> (pointer to row 0 of the selected rows, row stride): step T-1 of every clip, or step
+    row_index[b] when an int64 device tensor of per-clip steps is given."""
+    B, T, H = x.shape
+    base = x.data_ptr() + (0 if row_index is not None else (T - 1) * H * 4)
+    return ctypes.c_void_p(base), T * H
+
+
+def head_mlp_fwd(x, row_index, wb, p_drop: float = 0.0, masks=None, loss_mode: int = 0, y=None, smoothing: float = 0.0):
+    """Whole classifier head (+ loss) in one launch.  x: LSTM output [B,T,H] fp32 (the last step, or step row_index[b], is
+    read in place).  wb: [W0,b0,...,W4,b4].  -> (acts [4,B,Wd], z [B,1], prob [B,1], loss or None, dz or None)."""
+    _chk(x, F32, "head_mlp_fwd.x")
+    dev = x.device
+    B, T, H = x.shape
+    xp, row_stride = _head_rows(x, row_index)
+    Wd = wb[0].shape[0]
+    for t in wb:
+        _chk(t, F32, "head_mlp_fwd.weights")
+    bars, rng = head_state(dev)
+    acts = torch.empty((4, B, Wd), device=dev, dtype=F32)
+    z = torch.empty((B, 1), device=dev, dtype=F32)
+    prob = torch.empty((B, 1), device=dev, dtype=F32)
+    loss = dz = None
+    if loss_mode:
+        _chk(y, F32, "head_mlp_fwd.y")
+        if y.numel() != B:
+            raise _lib.XcpError("head loss: %d targets for %d rows" % (y.numel(), B))
+        loss = torch.empty((), device=dev, dtype=F32)
+        dz = torch.empty((B, 1), device=dev, dtype=F32)
+    if masks is not None:
+        _chk(masks, torch.uint8, "head_mlp_fwd.masks")
+        if tuple(masks.shape) != (4, B, Wd):
+            raise _lib.XcpError("head_mlp_fwd: masks must be [4, %d, %d]" % (B, Wd))
+    ptrs = _ptr_array(wb)
+    _lib.call("xcp_head_mlp_fwd", xp, int(row_stride), _p(row_index), ctypes.c_void_p(ctypes.addressof(ptrs)), _p(masks),
+              _p(rng) if (masks is None and p_drop > 0) else ctypes.c_void_p(0), float(p_drop), _p(acts), _p(z), _p(prob),
+              int(loss_mode), _p(y), float(smoothing), _p(loss), _p(dz), _p(bars), B, H, Wd, dev.index, _s())
+    return acts, z, prob, loss, dz
+
+
+def head_mlp_bwd(dsrc, prob, gscale, x, row_index, acts, drop_scale: float, wb, dwb, want_dx: bool = True):
+    """Backward of head_mlp_fwd in one launch: accumulates into the gradient slots dwb (entries may be None) and returns the
+    gradient wrt the whole LSTM output [B,T,H] (zero-filled by the kernel, the selected rows added) or None."""
+    _chk(dsrc, F32, "head_mlp_bwd.dsrc"); _chk(x, F32, "head_mlp_bwd.x")
+    dev = x.device
+    B, T, H = x.shape
+    xp, row_stride = _head_rows(x, row_index)
+    dx = torch.empty_like(x) if want_dx else None
+    dxp = ctypes.c_void_p(dx.data_ptr() + (xp.value - x.data_ptr())) if want_dx else ctypes.c_void_p(0)
+    Wd = wb[0].shape[0]
+    bars, _ = head_state(dev)
+    dacts = torch.empty((4, B, Wd), device=dev, dtype=F32)
+    wp, gp = _ptr_array(wb), _ptr_array(dwb)
+    _lib.call("xcp_head_mlp_bwd", _p(dsrc), _p(prob), _p(gscale), xp, int(row_stride), _p(row_index), _p(acts),
+              float(drop_scale), ctypes.c_void_p(ctypes.addressof(wp)), ctypes.c_void_p(ctypes.addressof(gp)), _p(dacts), dxp, _p(dx),
+              int(dx.numel()) if dx is not None else 0, ctypes.c_void_p(bars.data_ptr() + 16), B, H, Wd, dev.index, _s())
+    return dx
+
+
 def sigmoid_fwd(z):
     p = torch.empty_like(z)
     _lib.call("xcp_sigmoid_fwd", _p(z), _p(p), z.numel(), z.device.index, _s())

@@ -27,8 +27,8 @@ def _epoch(model, criterion, loader, device, optimizer=None):
     with torch.set_grad_enabled(train):
         for patches, labels in loader:
             patches, labels = patches.to(device, non_blocking=True), labels.to(device, non_blocking=True).float().view(-1, 1)
-            logits = model.forward_logits(model.extract_features(patches, device))
-            loss = criterion(logits, labels)              # loss and dL/dlogits in one kernel
+            # head + criterion (train_au_patch.py:203-214) in one launch: same loss / gradients as criterion(forward_logits(.), labels)
+            loss, logits = model.forward_loss(model.extract_features(patches, device), labels, smoothing=criterion.smoothing)
             if train:
                 optimizer.zero_grad(set_to_none=True)
                 loss.backward()
