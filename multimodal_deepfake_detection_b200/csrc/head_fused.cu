@@ -19,9 +19,9 @@ namespace xcp {
 
 constexpr int HEAD_MAXB = 32;
 constexpr int HEAD_BCH = 8;      // batch rows per accumulator chunk
-constexpr int HEAD_NS = 16;      // neurons per backward block
+constexpr int HEAD_NS = 8;       // neurons per backward block
 constexpr int HEAD_FWD_CTAS = 128;
-constexpr int HEAD_BWD_CTAS = 64;
+constexpr int HEAD_BWD_CTAS = 128;
 
 struct HeadFwdArgs {
     const float* x; long long row_stride; const long long* row_index;   // input row b = x + b*row_stride + row_index[b]*H
@@ -90,10 +90,13 @@ XCP_DEVINL bool drop_keep(unsigned long long seed, unsigned long long counter, i
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// Hidden layers: warp per output neuron, the weight row (K <= 1024 floats) held in registers as 8 float4 per lane and
-// reused for all B rows; activations written by other CTAs are read with ld.global.cg (L2) after the grid barrier.
+// Hidden layers: warp per output neuron.  After the grid barrier every CTA stages the layer's whole input [B][K] (<= 128 KB,
+// written by other CTAs: ld.global.cg) into shared memory once; the weight row (K <= 1024 floats) sits in registers as
+// 8 float4 per lane and is reused for all B rows; the NEXT layer's weight row is requested before the barrier so the HBM
+// latency of the weights hides behind the barrier wait.
 __global__ void __launch_bounds__(256)
 head_mlp_fwd_kernel(const HeadFwdArgs p) {
+    extern __shared__ float4 s_act[];            // [B][K/4]
     __shared__ float s_loss[HEAD_MAXB];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * 8 + wib, nw = gridDim.x * 8;
@@ -102,22 +105,36 @@ head_mlp_fwd_kernel(const HeadFwdArgs p) {
     const bool draw = p.mask == nullptr && p.rng != nullptr && p.p_drop > 0.f;
     if (p.rng) { seed = p.rng[0]; counter = p.rng[1]; }
 
+    float4 wv[8];
+    auto load_row = [&](int l, int n) {
+        const int K = l == 0 ? p.H : Wd;
+        const float4* wrow = reinterpret_cast<const float4*>(p.W[l] + (long long)n * K);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = j * 32 + lane;
+            wv[j] = c < (K >> 2) ? __ldg(wrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    bool have = false;
+    if (gw < Wd) { load_row(0, gw); have = true; }
+
     for (int l = 0; l < 4; ++l) {
         const int K = l == 0 ? p.H : Wd;
         const int K4 = K >> 2;
-        const float* __restrict__ W = p.W[l];
         const float* __restrict__ bias = p.bias[l];
         float* out = p.acts + (long long)l * B * Wd;
         const float* in = l == 0 ? nullptr : p.acts + (long long)(l - 1) * B * Wd;
         const uint8_t* mask = p.mask ? p.mask + (long long)l * B * Wd : nullptr;
+        for (int i = threadIdx.x; i < B * K4; i += 256) {       // all copies in flight at once (cp.async.cg: L2, never L1)
+            const int b = i / K4, c = i - b * K4;
+            const float* arow = l == 0 ? p.x + (long long)b * p.row_stride + (p.row_index ? p.row_index[b] * p.H : 0) : in + (long long)b * Wd;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_act + i)), "l"(reinterpret_cast<const float4*>(arow) + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
         for (int n = gw; n < Wd; n += nw) {
-            float4 wv[8];
-            const float4* wrow = reinterpret_cast<const float4*>(W + (long long)n * K);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = j * 32 + lane;
-                wv[j] = c < K4 ? __ldg(wrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            if (!(have && n == gw)) load_row(l, n);
+            have = false;
             const float bn = bias ? bias[n] : 0.f;
             for (int b0 = 0; b0 < B; b0 += HEAD_BCH) {
                 float acc[HEAD_BCH];
@@ -125,14 +142,12 @@ head_mlp_fwd_kernel(const HeadFwdArgs p) {
                 for (int b = 0; b < HEAD_BCH; ++b) {
                     acc[b] = 0.f;
                     if (b0 + b < B) {
-                        const float* arow = l == 0 ? p.x + (long long)(b0 + b) * p.row_stride + (p.row_index ? p.row_index[b0 + b] * p.H : 0)
-                                                   : in + (long long)(b0 + b) * Wd;
-                        const float4* ar = reinterpret_cast<const float4*>(arow);
+                        const float4* ar = s_act + (b0 + b) * K4;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int c = j * 32 + lane;
                             if (c < K4) {
-                                const float4 av = __ldcg(ar + c);
+                                const float4 av = ar[c];
                                 acc[b] = fmaf(wv[j].x, av.x, acc[b]); acc[b] = fmaf(wv[j].y, av.y, acc[b]);
                                 acc[b] = fmaf(wv[j].z, av.z, acc[b]); acc[b] = fmaf(wv[j].w, av.w, acc[b]);
                             }
@@ -153,6 +168,7 @@ head_mlp_fwd_kernel(const HeadFwdArgs p) {
                 }
             }
         }
+        if (l < 3 && gw < Wd) { load_row(l + 1, gw); have = true; }
         grid_sync(p.bar, (unsigned)(l + 1) * gridDim.x);
     }
 
@@ -334,9 +350,10 @@ head_mlp_bwd_kernel(const HeadBwdArgs p) {
     grid_exit(p.bar, nullptr, 0);
 }
 
-static int head_grid(const void* kernel, int want, int device, int* grid) {
+static int head_grid(const void* kernel, int want, size_t smem, int device, int* grid) {
     int per_sm = 0, sms = 0;
-    XCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
+    if (smem > 48 * 1024) XCP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem));
     XCP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int cap = per_sm * sms;
     XCP_REQUIRE(cap >= 8, "head kernel: the device cannot hold 8 co-resident CTAs (%d)", cap);
@@ -375,8 +392,9 @@ extern "C" int xcp_head_mlp_fwd(const float* x, long long row_stride, const long
     a.acts = acts; a.z = z; a.prob = prob; a.loss_mode = loss_mode; a.y = y; a.smoothing = smoothing; a.loss = loss; a.dz = dz;
     a.bar = (unsigned*)bar; a.B = B; a.H = H; a.Wd = Wd;
     int grid = 0;
-    if (int rc = head_grid((const void*)head_mlp_fwd_kernel, HEAD_FWD_CTAS, device, &grid)) return rc;
-    head_mlp_fwd_kernel<<<grid, 256, 0, ST>>>(a);
+    const size_t smem = (size_t)B * (H > Wd ? H : Wd) * sizeof(float);
+    if (int rc = head_grid((const void*)head_mlp_fwd_kernel, HEAD_FWD_CTAS, smem, device, &grid)) return rc;
+    head_mlp_fwd_kernel<<<grid, 256, smem, ST>>>(a);
     return check_cuda(cudaGetLastError(), "head_mlp_fwd launch");
 }
 
@@ -398,7 +416,7 @@ extern "C" int xcp_head_mlp_bwd(const float* dsrc, const float* prob, const floa
     }
     a.dacts = dacts; a.dx = dx; a.dx_base = dx_base; a.dx_zero_n = dx ? dx_zero_n : 0; a.bar = (unsigned*)bar; a.B = B; a.H = H; a.Wd = Wd;
     int grid = 0;
-    if (int rc = head_grid((const void*)head_mlp_bwd_kernel, HEAD_BWD_CTAS, device, &grid)) return rc;
+    if (int rc = head_grid((const void*)head_mlp_bwd_kernel, HEAD_BWD_CTAS, 0, device, &grid)) return rc;
     head_mlp_bwd_kernel<<<grid, 256, 0, ST>>>(a);
     return check_cuda(cudaGetLastError(), "head_mlp_bwd launch");
 }
