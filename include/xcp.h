@@ -65,6 +65,9 @@ int xcp_conv3x3_wgrad(const void* dy_grid, const void* x, float* gk, int F, int 
 int xcp_stem_conv1_parts(int F, int H, int W, int device);
 int xcp_stem_conv1_fwd(const void* x, int x_u8_nhwc, const float* w, void* y, float* partials, int F, int H, int W, int device,
                        void* stream);
+/* inference form (row f-3): out = relu(scale*conv1(x) + shift), eval-mode bn1 folded (Xception.py:168-170 in one pass) */
+int xcp_stem_conv1_fwd_affine(const void* x, int x_u8_nhwc, const float* w, const float* scale, const float* shift, void* out, int F,
+                              int H, int W, int device, void* stream);
 /* weight gradient: im2col (bf16 [M,32]) + MN-major tcgen05 split-K GEMM; `workspace` = xcp_stem_conv1_wgrad_ws_bytes() bytes */
 long long xcp_stem_conv1_wgrad_ws_bytes(int F, int H, int W);
 int xcp_stem_conv1_wgrad(const void* x, int x_u8_nhwc, const void* dy, float* dW, void* workspace, int F, int H, int W, int device,

@@ -28,6 +28,7 @@ SIGNATURES = {
     "xcp_conv3x3_wgrad": "pppiiiiiip",
     "xcp_stem_conv1_parts": "iiii",
     "xcp_stem_conv1_fwd": "pipppiiiip",
+    "xcp_stem_conv1_fwd_affine": "pippppiiiip",
     "xcp_stem_conv1_wgrad_ws_bytes": "iii",
     "xcp_stem_conv1_wgrad": "pipppiiiip",
     "xcp_dw3x3_fwd": "ppppipiiiiip",

@@ -145,10 +145,12 @@ __global__ void gather_s2_kernel(const uint4* __restrict__ x, const float* __res
 
 // out[f,ho,wo,:] = maxpool3x3s2p1( scale*y + shift )[f,ho,wo,:] + (scale_s*ys + shift_s)[f,ho,wo,:]
 // idx (uint8 per element) records the arg-max tap (first maximum in row-major window order) for backward.
-__global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+// IDX = false (inference: no arg-max, no y[arg-max]) drops the index bookkeeping from the instruction stream.
+template <bool IDX>
+__global__ void __launch_bounds__(256, 4) pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                     const uint4* __restrict__ ys, const float* __restrict__ scale_s,
                                     const float* __restrict__ shift_s, uint4* __restrict__ out, uint2* __restrict__ idx,
-                                    uint4* __restrict__ ymax, int F, int H, int W, int C) {
+                                    uint4* __restrict__ ymax, int F, int H, int W, int C, int fast) {
     const int ncg = C >> 3, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long n8 = (long long)F * Ho * Wo * ncg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -167,13 +169,13 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp) {
             sgn[pp] = (sc[2 * pp] < 0.f ? 0x8000u : 0u) | (sc[2 * pp + 1] < 0.f ? 0x80000000u : 0u);
-            best[pp] = 0xff80ff80u;                       // (-inf, -inf)
             bi[pp] = 0u;
         }
         // all 9 taps are loaded up front from clamped (always valid) addresses and masked afterwards: nine independent
         // 16-byte loads in flight per thread instead of a chain of bounds-checked ones
         uint4 raw[9];
         bool ok[9];
+        const bool interior = fast && ho > 0 && wo > 0 && 2 * ho + 1 < H && 2 * wo + 1 < W;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
             const int h = 2 * ho - 1 + kh;
@@ -186,31 +188,53 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
                 raw[kh * 3 + kw] = __ldg(y + (((long long)f * H + hc) * W + wc) * ncg + cg);
             }
         }
+        if (interior && (sgn[0] | sgn[1] | sgn[2] | sgn[3]) == 0u) {
+            // whole window inside the image, no negative scale in this channel group (all but a few per cent of the threads):
+            // no border select, no sign flip -- compare-mask, max and index merge are the only per-tap instructions (3 of 5)
+            best[0] = raw[0].x; best[1] = raw[0].y; best[2] = raw[0].z; best[3] = raw[0].w;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const uint32_t wv[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
-            const uint32_t kk = (uint32_t)k * 0x00010001u;
+            for (int k = 1; k < 9; ++k) {
+                const uint32_t wv[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+                const uint32_t kk = (uint32_t)k * 0x00010001u;
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-                const uint32_t v = ok[k] ? (wv[pp] ^ sgn[pp]) : 0xff80ff80u;
-                __nv_bfloat162 vb, bb;
-                *reinterpret_cast<uint32_t*>(&vb) = v;
-                *reinterpret_cast<uint32_t*>(&bb) = best[pp];
-                const uint32_t m = __hgt2_mask(vb, bb);                    // 0xffff per half where v > best (first maximum wins ties)
-                const __nv_bfloat162 mx = __hmax2(vb, bb);
-                best[pp] = *reinterpret_cast<const uint32_t*>(&mx);
-                bi[pp] = (bi[pp] & ~m) | (kk & m);
+                for (int pp = 0; pp < 4; ++pp) {
+                    __nv_bfloat162 vb, bb;
+                    *reinterpret_cast<uint32_t*>(&vb) = wv[pp];
+                    *reinterpret_cast<uint32_t*>(&bb) = best[pp];
+                    if (IDX) {
+                        const uint32_t m = __hgt2_mask(vb, bb);                // 0xffff per half where v > best (first maximum wins ties)
+                        bi[pp] = (bi[pp] & ~m) | (kk & m);
+                    }
+                    const __nv_bfloat162 mx = __hmax2(vb, bb);
+                    best[pp] = *reinterpret_cast<const uint32_t*>(&mx);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) best[pp] = 0xff80ff80u;         // (-inf, -inf)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const uint32_t wv[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+                const uint32_t kk = (uint32_t)k * 0x00010001u;
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    const uint32_t v = ok[k] ? (wv[pp] ^ sgn[pp]) : 0xff80ff80u;
+                    __nv_bfloat162 vb, bb;
+                    *reinterpret_cast<uint32_t*>(&vb) = v;
+                    *reinterpret_cast<uint32_t*>(&bb) = best[pp];
+                    const uint32_t m = __hgt2_mask(vb, bb);                    // 0xffff per half where v > best (first maximum wins ties)
+                    const __nv_bfloat162 mx = __hmax2(vb, bb);
+                    best[pp] = *reinterpret_cast<const uint32_t*>(&mx);
+                    bi[pp] = (bi[pp] & ~m) | (kk & m);
+                }
             }
         }
         float bestf[8];
-        int bidx[8];
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp) {
             const uint32_t yv = best[pp] ^ sgn[pp];
             bestf[2 * pp] = fmaf(bf16_lo(yv), sc[2 * pp], sh[2 * pp]);
             bestf[2 * pp + 1] = fmaf(bf16_hi(yv), sc[2 * pp + 1], sh[2 * pp + 1]);
-            bidx[2 * pp] = (int)(bi[pp] & 0xffffu);
-            bidx[2 * pp + 1] = (int)(bi[pp] >> 16);
         }
         float s[8];
         unpack8(ldg_nc_v4(ys + i), s);
@@ -218,15 +242,17 @@ __global__ void pool_add_fwd_kernel(const uint4* __restrict__ y, const float* __
 #pragma unroll
         for (int j = 0; j < 8; ++j) bestf[j] += fmaf(s[j], sc[j], sh[j]);
         out[i] = pack8(bestf);
-        if (idx != nullptr) {
-            uint2 o;
-            o.x = (uint32_t)bidx[0] | ((uint32_t)bidx[1] << 8) | ((uint32_t)bidx[2] << 16) | ((uint32_t)bidx[3] << 24);
-            o.y = (uint32_t)bidx[4] | ((uint32_t)bidx[5] << 8) | ((uint32_t)bidx[6] << 16) | ((uint32_t)bidx[7] << 24);
-            idx[i] = o;
+        if (IDX) {
+            if (idx != nullptr) {       // bi[pp] = (tap of channel 2pp) | (tap of channel 2pp+1) << 16  ->  one byte per channel
+                uint2 o;
+                o.x = __byte_perm(bi[0], bi[1], 0x6420);
+                o.y = __byte_perm(bi[2], bi[3], 0x6420);
+                idx[i] = o;
+            }
+            // the RAW winner y[arg-max]: the BatchNorm backward through the pool needs sum dz*y = sum_windows G * y[arg-max],
+            // which it can then take from this quarter-size tensor instead of re-reading all of y (xcp_bn_bwd_sums)
+            if (ymax != nullptr) ymax[i] = make_uint4(best[0] ^ sgn[0], best[1] ^ sgn[1], best[2] ^ sgn[2], best[3] ^ sgn[3]);
         }
-        // the RAW winner y[arg-max]: the BatchNorm backward through the pool needs sum dz*y = sum_windows G * y[arg-max],
-        // which it can then take from this quarter-size tensor instead of re-reading all of y (xcp_bn_bwd_sums)
-        if (ymax != nullptr) ymax[i] = make_uint4(best[0] ^ sgn[0], best[1] ^ sgn[1], best[2] ^ sgn[2], best[3] ^ sgn[3]);
     }
 }
 
@@ -849,8 +875,14 @@ extern "C" int xcp_pool_add_fwd(const void* y, const float* scale, const float* 
     XCP_REQUIRE(C % 8 == 0, "xcp_pool_add_fwd: C %% 8");
     XCP_CUDA(cudaSetDevice(device));
     const long long n8 = (long long)F * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 8);
-    pool_add_fwd_kernel<<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)ys, scale_s, shift_s,
-                                                          (uint4*)out, (uint2*)idx, (uint4*)ymax, F, H, W, C);
+    static int slow_env = -1;                                      // A/B hook: XCP_POOL_SLOW=1 = the round-1 instruction stream
+    if (slow_env < 0) { const char* e = getenv("XCP_POOL_SLOW"); slow_env = e ? atoi(e) : 0; }
+    if (idx != nullptr || ymax != nullptr || slow_env)
+        pool_add_fwd_kernel<true><<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)ys, scale_s, shift_s,
+                                                                    (uint4*)out, (uint2*)idx, (uint4*)ymax, F, H, W, C, !slow_env);
+    else
+        pool_add_fwd_kernel<false><<<ew_grid(n8, 256), 256, 0, ST>>>((const uint4*)y, scale, shift, (const uint4*)ys, scale_s, shift_s,
+                                                                     (uint4*)out, nullptr, nullptr, F, H, W, C, 1);
     return check_cuda(cudaGetLastError(), "pool_add_fwd launch");
 }
 

@@ -93,7 +93,8 @@ XCP_DEVINL int stem_tap_off(int k, int pitch) {
 template <bool U8>
 __global__ void __launch_bounds__(256, 2)
 stem_conv1_fwd_mma_kernel(const void* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
-                          float* __restrict__ partials, const StemGeom g) {
+                          float* __restrict__ partials, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const StemGeom g) {
     extern __shared__ float s_dyn[];
     float* s_in = s_dyn;                                                  // [3][S1_NIN][pitch]
     uint8_t* s_out = reinterpret_cast<uint8_t*>(s_in + (U8 ? 1 : 2) * 3 * S1_NIN * g.pitch);   // [8 warps][16 rows x 80 B]
@@ -108,9 +109,13 @@ stem_conv1_fwd_mma_kernel(const void* __restrict__ x, const float* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = 8 * j + gq, k0 = 8 * s + t, k1 = k0 + 4;
-            b0[s][j] = f32_to_tf32(k0 < 27 ? w[n * 27 + k0] : 0.f);
-            b1[s][j] = f32_to_tf32(k1 < 27 ? w[n * 27 + k1] : 0.f);
+            const float fold = scale ? scale[n] : 1.f;     // inference: eval-mode bn1 scale folded into the filter rows
+            b0[s][j] = f32_to_tf32(k0 < 27 ? w[n * 27 + k0] * fold : 0.f);
+            b1[s][j] = f32_to_tf32(k1 < 27 ? w[n * 27 + k1] * fold : 0.f);
         }
+    float bsh[4][2];                                  // inference epilogue: + bn1 shift, ReLU (channels 8j + 2t + {0,1})
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { bsh[j][0] = shift ? shift[8 * j + 2 * t] : 0.f; bsh[j][1] = shift ? shift[8 * j + 2 * t + 1] : 0.f; }
     int off0[4], off1[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) { off0[s] = 4 * stem_tap_off(8 * s + t, g.pitch); off1[s] = 4 * stem_tap_off(8 * s + t + 4, g.pitch); }   // bytes
@@ -179,6 +184,10 @@ stem_conv1_fwd_mma_kernel(const void* __restrict__ x, const float* __restrict__ 
             // statistics on the fp32 accumulators (rows past the group: masked), bf16 rows through a padded staging tile
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                if (shift != nullptr) {               // y = relu(bn1(conv1(x))) written directly, no statistics
+                    c[j][0] = fmaxf(c[j][0] + bsh[j][0], 0.f); c[j][1] = fmaxf(c[j][1] + bsh[j][1], 0.f);
+                    c[j][2] = fmaxf(c[j][2] + bsh[j][0], 0.f); c[j][3] = fmaxf(c[j][3] + bsh[j][1], 0.f);
+                }
                 if (v0) { st1[j][0] += c[j][0]; st1[j][1] += c[j][1]; st2[j][0] = fmaf(c[j][0], c[j][0], st2[j][0]); st2[j][1] = fmaf(c[j][1], c[j][1], st2[j][1]); }
                 if (v1) { st1[j][0] += c[j][2]; st1[j][1] += c[j][3]; st2[j][0] = fmaf(c[j][2], c[j][2], st2[j][0]); st2[j][1] = fmaf(c[j][3], c[j][3], st2[j][1]); }
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(stg + gq * 80 + j * 16 + t * 4), "r"(pack_bf16(c[j][0], c[j][1])) : "memory");
@@ -208,7 +217,7 @@ stem_conv1_fwd_mma_kernel(const void* __restrict__ x, const float* __restrict__ 
             if (gq == 0) { s_stat[warp][0][8 * j + 2 * t + e] = a; s_stat[warp][1][8 * j + 2 * t + e] = b; }
         }
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < 64 && partials != nullptr) {
         const int st = threadIdx.x >> 5, chn = threadIdx.x & 31;
         float a = 0.f;
 #pragma unroll
@@ -349,8 +358,8 @@ extern "C" int xcp_stem_conv1_parts(int F, int H, int W, int device) {
     return stem_grid(stem_geom(F, H, W));
 }
 
-extern "C" int xcp_stem_conv1_fwd(const void* x, int x_u8_nhwc, const float* w, void* y, float* partials, int F, int H, int W,
-                                  int device, void* stream) {
+static int stem_conv1_launch(const void* x, int x_u8_nhwc, const float* w, void* y, float* partials, const float* scale,
+                             const float* shift, int F, int H, int W, int device, void* stream) {
     XCP_REQUIRE(F > 0 && H >= 3 && W >= 3, "xcp_stem_conv1_fwd: bad shape");
     XCP_CUDA(cudaSetDevice(device));
     const StemGeom g = stem_geom(F, H, W);
@@ -359,12 +368,26 @@ extern "C" int xcp_stem_conv1_fwd(const void* x, int x_u8_nhwc, const float* w, 
     const int grid = stem_grid(g);
     if (x_u8_nhwc) {
         XCP_CUDA(cudaFuncSetAttribute(stem_conv1_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        stem_conv1_fwd_mma_kernel<true><<<grid, 256, smem, ST>>>(x, w, (__nv_bfloat16*)y, partials, g);
+        stem_conv1_fwd_mma_kernel<true><<<grid, 256, smem, ST>>>(x, w, (__nv_bfloat16*)y, partials, scale, shift, g);
     } else {
         XCP_CUDA(cudaFuncSetAttribute(stem_conv1_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        stem_conv1_fwd_mma_kernel<false><<<grid, 256, smem, ST>>>(x, w, (__nv_bfloat16*)y, partials, g);
+        stem_conv1_fwd_mma_kernel<false><<<grid, 256, smem, ST>>>(x, w, (__nv_bfloat16*)y, partials, scale, shift, g);
     }
     return check_cuda(cudaGetLastError(), "stem_conv1_fwd launch");
+}
+
+extern "C" int xcp_stem_conv1_fwd(const void* x, int x_u8_nhwc, const float* w, void* y, float* partials, int F, int H, int W,
+                                  int device, void* stream) {
+    XCP_REQUIRE(partials != nullptr, "xcp_stem_conv1_fwd: partials");
+    return stem_conv1_launch(x, x_u8_nhwc, w, y, partials, nullptr, nullptr, F, H, W, device, stream);
+}
+
+// inference form: out = relu(scale * conv1(x) + shift) with eval-mode bn1 folded (scale into the filter rows, shift + ReLU in the
+// epilogue): relu(bn1(conv1(x))) of Xception.py:168-170 in one pass, no raw conv output, no statistics
+extern "C" int xcp_stem_conv1_fwd_affine(const void* x, int x_u8_nhwc, const float* w, const float* scale, const float* shift, void* out,
+                                         int F, int H, int W, int device, void* stream) {
+    XCP_REQUIRE(scale != nullptr && shift != nullptr, "xcp_stem_conv1_fwd_affine: scale / shift");
+    return stem_conv1_launch(x, x_u8_nhwc, w, out, nullptr, scale, shift, F, H, W, device, stream);
 }
 
 // (the first version needed an im2col scratch matrix; kept in the ABI, a token size is enough now)

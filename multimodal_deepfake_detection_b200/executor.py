@@ -505,11 +505,18 @@ def xception_forward(net, x: torch.Tensor, save: bool = True):
     x = x.contiguous()
     tp.x = x
     # stem: conv1 -> bn1 -> relu -> conv2 -> bn2 -> relu                      (Xception.py:168-174)
-    y1, parts1 = ops.stem_conv1_fwd(x, net.conv1.weight.detach(), F32 if fp32 else BF16)
-    st1 = _bn_state(net.bn1, parts1, y1.numel() // 32)
-    if _bn_needs_stats(net.bn1):
-        nbt.append(net.bn1.num_batches_tracked)
-    x1 = ops.bn_act(y1, st1.scale, st1.shift, True)
+    folded = (not save) and (not fp32) and _folded_ok(net)
+    if folded:
+        # inference plan: eval-mode bn1 folded into the conv1 filter rows, shift + ReLU in its epilogue -- relu(bn1(conv1(x))) in one pass
+        st1 = _bn_state(net.bn1, None, 1)
+        y1 = None
+        x1 = ops.stem_conv1_fwd_affine(x, net.conv1.weight.detach(), st1.scale, st1.shift)
+    else:
+        y1, parts1 = ops.stem_conv1_fwd(x, net.conv1.weight.detach(), F32 if fp32 else BF16)
+        st1 = _bn_state(net.bn1, parts1, y1.numel() // 32)
+        if _bn_needs_stats(net.bn1):
+            nbt.append(net.bn1.num_batches_tracked)
+        x1 = ops.bn_act(y1, st1.scale, st1.shift, True)
     wk = net.conv2.weight.detach() if fp32 else cache.conv3x3(net.conv2.weight)[0]
     need2 = _bn_needs_stats(net.bn2)
     y2, parts2 = ops.conv3x3_gemm_fwd(x1, wk, want_stats=need2)
@@ -525,7 +532,7 @@ def xception_forward(net, x: torch.Tensor, save: bool = True):
     x2 = None if fuse_x2 else ops.bn_act(y2, st2.scale, st2.shift, True)
     tp.y1, tp.st1, tp.x1, tp.y2, tp.st2, tp.x2 = y1, st1, x1, y2, st2, x2
     cur = y2 if fuse_x2 else x2
-    if not save and not fp32 and _folded_ok(net):
+    if folded:
         # inference plan: eval-mode BatchNorm folded into the pointwise weights, ReLU / residual add in the GEMM epilogues
         for bi, spec in enumerate(specs):
             cur = _block_folded(cache, spec, cur, st2 if (fuse_x2 and bi == 0) else None)

@@ -257,6 +257,15 @@ def stem_conv1_fwd(x: torch.Tensor, w: torch.Tensor, act_dtype=BF16):
     return y, parts
 
 
+def stem_conv1_fwd_affine(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+    """Inference form of the stem: relu(scale * conv1(x) + shift) in one pass (eval-mode bn1 folded), bf16 NHWC."""
+    _chk(w, F32, "stem_conv1.w"); _chk(scale, F32, "stem_conv1.scale"); _chk(shift, F32, "stem_conv1.shift")
+    u8, F_, H, W = _stem_input(x, "stem_conv1.x")
+    out = torch.empty((F_, (H - 3) // 2 + 1, (W - 3) // 2 + 1, 32), device=x.device, dtype=BF16)
+    _lib.call("xcp_stem_conv1_fwd_affine", _p(x), int(u8), _p(w), _p(scale), _p(shift), _p(out), F_, H, W, x.device.index, _s())
+    return out
+
+
 def stem_conv1_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor):
     u8, F_, H, W = _stem_input(x, "stem_conv1_wgrad.x")
     if dy.dtype == F32:

@@ -647,3 +647,51 @@ def test_model_accepts_uint8_clips():
         a = m.extract_features(u8)
         b = m.extract_features(xf)
     assert a.shape == (2, 3, 2048) and rel_err(a, b) < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 147, 147, 128), (3, 37, 37, 768), (2, 19, 19, 1024), (1, 6, 5, 16), (2, 8, 8, 64), (1, 3, 3, 8)])
+def test_pool_add_fwd_interior_fast_path_ties_and_no_index_variant(shape):
+    """All-positive BatchNorm scales take the interior fast path (no border select, no sign flip).  Inputs drawn from seven
+    values so that nearly every window has ties: the arg-max must be the FIRST maximum in row-major window order, exactly
+    like F.max_pool2d(return_indices=True) (Xception.py:86 MaxPool2d(3, 2, 1)); y[arg-max] is the raw winner; the inference
+    variant without index bookkeeping writes bit-identical sums."""
+    F_, H, W, C = shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    g = torch.Generator().manual_seed(H * 131 + C)
+    y = (torch.randint(-3, 4, shape, generator=g).float() * 0.5).to(DEV).bfloat16()
+    ys = rnd(F_, Ho, Wo, C, seed=61, dtype=torch.bfloat16)
+    sc = (torch.rand(C, generator=g) + 0.5).to(DEV); sh = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    scs = (torch.rand(C, generator=g) + 0.5).to(DEV); shs = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    out, idx, ymax = ops.pool_add_fwd(y, sc, sh, ys, scs, shs, True, True)
+    out_noidx, none_idx = ops.pool_add_fwd(y, sc, sh, ys, scs, shs, False, False)
+    assert none_idx is None and torch.equal(out, out_noidx)
+    z = y.float().permute(0, 3, 1, 2) * sc[None, :, None, None] + sh[None, :, None, None]
+    ref, ind = F.max_pool2d(z, 3, 2, 1, return_indices=True)
+    zs = ys.float().permute(0, 3, 1, 2) * scs[None, :, None, None] + shs[None, :, None, None]
+    assert rel_err(out.float().permute(0, 3, 1, 2), ref + zs) < 8e-3
+    ho = torch.arange(Ho, device=DEV)[None, None, :, None]; wo = torch.arange(Wo, device=DEV)[None, None, None, :]
+    tap = (ind // W - (2 * ho - 1)) * 3 + (ind % W - (2 * wo - 1))
+    assert torch.equal(idx.permute(0, 3, 1, 2).long(), tap)
+    y_at = torch.gather(y.float().permute(0, 3, 1, 2).reshape(F_, C, H * W), 2, ind.reshape(F_, C, Ho * Wo)).reshape(F_, C, Ho, Wo)
+    assert torch.equal(ymax.float().permute(0, 3, 1, 2), y_at)
+
+
+@pytest.mark.parametrize("F_,H", [(2, 299), (3, 64), (1, 75)])
+def test_stem_conv1_affine_inference_form(F_, H):
+    """Inference stem (row f-3): relu(bn1(conv1(x))) of Xception.py:168-170 in ONE pass -- eval-mode bn1 scale folded into the
+    filter rows, shift + ReLU in the epilogue -- against torch and against the two-pass path (conv1, then BN + ReLU)."""
+    x = torch.rand(F_, 3, H, H, device=DEV)
+    w = rnd(32, 3, 3, 3, seed=11, scale=0.3)
+    scale = rnd(32, seed=12) * 0.3 + 1.0
+    scale[::5] *= -1
+    shift = rnd(32, seed=13, scale=0.3)
+    out = ops.stem_conv1_fwd_affine(x, w, scale, shift)
+    ref = F.relu(F.conv2d(x, w, stride=2) * scale[None, :, None, None] + shift[None, :, None, None])
+    assert rel_err(out.float().permute(0, 3, 1, 2), ref) < 8e-3
+    y, _ = ops.stem_conv1_fwd(x, w)
+    two_pass = ops.bn_act(y, scale, shift, True)
+    assert rel_err(out, two_pass) < 8e-3          # the two-pass path rounds the raw conv output to bf16 before the affine
+    u8 = (x * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    out_u8 = ops.stem_conv1_fwd_affine(u8, w, scale, shift)
+    ref_u8 = F.relu(F.conv2d(u8.permute(0, 3, 1, 2).float() / 255.0, w, stride=2) * scale[None, :, None, None] + shift[None, :, None, None])
+    assert rel_err(out_u8.float().permute(0, 3, 1, 2), ref_u8) < 8e-3
