@@ -33,8 +33,9 @@ int xcp_check_device(int device);
  * BatchNorm (Xception.py:67,73,78) | 2 fp32 out (+ optional bias[N]).  lda/ldb/ldo are row pitches in elements. */
 int xcp_gemm_tn(const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo, int M, int N, int K,
                 int epi, float* stats, const float* bias, int n_real, int k_real, int device, void* stream);
-/* n_real / k_real (0 = N / K): logical channel counts when N / K are channel pitches whose tail is zero padding (728 in 768):
- * the tensor-core work that would only multiply padding is skipped, the padded output columns are written as zeros. */
+/* n_real / k_real (0 = N / K): logical channel counts when N / K are channel pitches whose tail is zero padding (728 in 768).
+ * With XCP_GEMM_TRIM=1 in the environment the tensor-core work that would only multiply padding is skipped (the padded output
+ * columns are written as zeros either way).  Off by default: measured slower in the training step (csrc/gemm.cu, set_trim). */
 /* Inference plan (eval-mode BatchNorm folded into the weights; the reference's no_grad evaluation, test_visual.py:609-624):
  * out[M,N] = relu?( A[M,K] * B[N,K]^T + bias[N] + residual[M,N] ) as bf16.  B = pointwise weights pre-multiplied per output
  * channel by gamma * rsqrt(running_var + eps) (xcp_pack_weight_scaled), bias = beta - running_mean * that scale; residual

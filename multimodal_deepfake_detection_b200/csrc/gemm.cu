@@ -96,7 +96,9 @@ __host__ __device__ constexpr int fit_stages() {
 // MN_MAJOR=false: A is [M,K] row-major, B is [N,K] row-major (both K-major):      D = A * B^T
 // MN_MAJOR=true : A is [K,M] row-major, B is [K,N] row-major (both MN-major):     D = A^T * B
 // BLOCK_K=64 -> 128B swizzle; BLOCK_K=32 -> 64B swizzle (K-major only; used by the stem implicit GEMM)
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2>
+// TRIM: pad-trimming instantiation (GemmParams::n_last / k_steps_last).  A template parameter, not a run-time test: the untrimmed
+// kernels must keep exactly the code (and register allocation) they have without the feature.
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
     static_assert(BLOCK_K == 64 || (BLOCK_K == 32 && !MN_MAJOR), "unsupported BLOCK_K");
@@ -203,7 +205,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int t = u - split * tiles_mn;
             const int m_blk = t / p.num_n_tiles, n_blk = t - m_blk * p.num_n_tiles;
             const int m0 = m_blk * m_row0_mul + (int)rank * BLOCK_M;        // first A row (K-major) / M column (MN-major)
-            const int n_eff = (p.n_last > 0 && n_blk == p.num_n_tiles - 1) ? p.n_last : BLOCK_N;
+            const int n_eff = (TRIM && p.n_last > 0 && n_blk == p.num_n_tiles - 1) ? p.n_last : BLOCK_N;
             const int n0 = n_blk * BLOCK_N + (int)rank * (CTA2 ? n_eff / 2 : B_ROWS);
             const int kb0 = split * p.k_blocks_per_split;
             const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
@@ -248,12 +250,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp == 1 && lane == 0 && rank == 0) {
         // ------------------------------------------------ MMA issuer (leader CTA only in pair mode)
         constexpr uint32_t idesc_full = make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
-        const uint32_t idesc_last = p.n_last > 0 ? make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.n_last, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0) : idesc_full;
+        const uint32_t idesc_last = (TRIM && p.n_last > 0) ? make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, (uint32_t)p.n_last, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0) : idesc_full;
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
         int s = 0; uint32_t ph = 0; uint32_t iter = 0;
         for (int u = worker; u < num_units; u += num_workers, ++iter) {
             const int split = u / tiles_mn;
-            const uint32_t idesc = ((u - split * tiles_mn) % p.num_n_tiles == p.num_n_tiles - 1) ? idesc_last : idesc_full;
+            const uint32_t idesc = (TRIM && (u - split * tiles_mn) % p.num_n_tiles == p.num_n_tiles - 1) ? idesc_last : idesc_full;
             const int kb0 = split * p.k_blocks_per_split;
             const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
             const uint32_t as = iter & 1, aph = (iter >> 1) & 1;
@@ -263,10 +265,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const int ksteps = (p.k_steps_last > 0 && kb == p.num_k_blocks - 1) ? p.k_steps_last : BLOCK_K / UMMA_K;
+                const int ksteps = (TRIM && p.k_steps_last > 0 && kb == p.num_k_blocks - 1) ? p.k_steps_last : BLOCK_K / UMMA_K;
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    if (k >= ksteps) break;
+                    if (TRIM && k >= ksteps) break;
                     uint64_t adesc, bdesc;
                     if (!MN_MAJOR) {
                         adesc = make_smem_desc(a_base + s * A_BYTES + k * (UMMA_K * 2), 0, SBO, LAYOUT);
@@ -344,6 +346,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int ci = 0; ci < NCW; ++ci) {
                 const int c = c_lo + ci;
                 if (c >= c_hi) break;
+                if (TRIM && p.n_last > 0 && n_blk == p.num_n_tiles - 1 && c * 32 >= p.n_last) {
+                    // pure padding (channel pitch past the trimmed last N tile): the MMAs never produced these accumulator columns.
+                    // Written as zeros on a path of its own, ahead of the real one, so that the hot path keeps the register
+                    // allocation it has without trimming (merged into it, the statistics variant spilled 100 bytes per thread
+                    // and the forward GEMM lost 12 %).
+                    if (epi_is_bf16(EPI)) {
+                        if (p.tma_store) {
+                            const uint32_t stg = smem_u32(s_store) + (uint32_t)(((warp - 2) * 2 + (int)(n_store & 1)) * 2048);
+                            if (n_store >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(stg + (uint32_t)lane * 64u + (uint32_t)(g * 16)), "r"(0u) : "memory");
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&p.tmC),
+                                             "r"(stg), "r"(n_blk * BLOCK_N + c * 32), "r"(m_blk * BLOCK_M + q * 32) : "memory");
+                                tma_store_commit();
+                            }
+                            ++n_store;
+                        } else if (row_ok) {
+                            __nv_bfloat16* zrow = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n_blk * BLOCK_N + c * 32;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                if (n_blk * BLOCK_N + c * 32 + g * 8 + 8 <= p.N) *reinterpret_cast<uint4*>(zrow + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        if (STATS && p.conv_taps == 0 && !reg_stats) {
+                            s_part[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = 0.f;
+                            s_part[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = 0.f;
+                        }
+                    }
+                    continue;
+                }
                 uint4 resv[4];
                 if (EPI == EPI_BF16_BIAS && p.residual != nullptr) {
                     // residual tile (32 rows x 32 bf16): coalesced 16-byte loads (4 lanes per 64-byte row piece, 8 rows per
@@ -358,17 +393,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 uint32_t r[32];
-                const bool trimmed = p.n_last > 0 && n_blk == p.num_n_tiles - 1 && c * 32 >= p.n_last;   // pure padding: never computed
-                if (!trimmed) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
-                else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0u;
-                }
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
                 uint32_t fa[16], fb[16];
-                if (STATS && p.conv_taps == 0 && trimmed) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { fa[j] = 0u; fb[j] = 0u; }
-                } else if (STATS && p.conv_taps == 0) {
+                if (STATS && p.conv_taps == 0) {
                     // The accumulator chunk is read a second time in the mma-fragment shape (16x256b: a thread holds
                     // 4 rows x 4 column pairs) for the column statistics.  The shared-memory crossbar carries the UMMA
                     // operand reads (~96 of 128 B/clk), so the epilogue must stay off it: the first version transposed
@@ -653,7 +680,7 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __n
 
 // ----------------------------------------------------------------------------------------------------
 // Persistent grid size: one CTA (or CTA pair) per SM (pair), capped by the number of work units.
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2>
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false>
 static int gemm_grid(int units) {
     if (!CTA2) return units < num_sms() ? units : num_sms();
     static int max_clusters[64] = {0};
@@ -662,7 +689,7 @@ static int gemm_grid(int units) {
     if (dev < 0 || dev >= 64) dev = 0;
     if (max_clusters[dev] == 0) {
         constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI, CTA2>(STAGES);
-        auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>;
+        auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() & ~1); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem;
@@ -679,18 +706,18 @@ static int gemm_grid(int units) {
     return 2 * c;
 }
 
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2 = false>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM>
+static int launch_gemm_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI, CTA2>(STAGES);
     static_assert(smem <= 232448, "smem budget");
-    auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>;
+    auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM>;
     static bool attr_set = false;   // per-instantiation; benign race (idempotent)
     if (!attr_set) {
         XCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
-    const int grid = gemm_grid<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2>(units);
+    const int grid = gemm_grid<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM>(units);
     if (!CTA2) {
         kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
         return check_cuda(cudaGetLastError(), "gemm_kernel launch");
@@ -702,6 +729,20 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p), "gemm_kernel (CTA pair) launch");
+}
+
+// The trimming instantiation exists where the 728-in-768 layers land (256-wide N tiles, 64-wide K blocks, bf16 / RED epilogues);
+// a trimming request on any other shape is dropped (trimming is an optimisation: the untrimmed product is the same numbers).
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2 = false>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    constexpr bool CAN_TRIM = BLOCK_N == 256 && BLOCK_K == 64 && EPI != EPI_F32;
+    if (p.n_last > 0 || p.k_steps_last > 0) {
+        if constexpr (CAN_TRIM) return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, true>(tmA, tmB, p, stream);
+        GemmParams q = p;
+        q.n_last = 0; q.k_steps_last = 0;
+        return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false>(tmA, tmB, q, stream);
+    }
+    return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false>(tmA, tmB, p, stream);
 }
 
 // K-major ("TN") problem plan shared by the launcher and xcp_gemm_stats_parts.
@@ -718,8 +759,11 @@ static TnPlan plan_tn(long long M, int N) {
 
 // pad trimming of a K-major problem whose operands carry n_real <= N / k_real <= K logical channels (the rest of the pitch is zero)
 static void set_trim(GemmParams& p, int bn, int N, int K, int n_real, int k_real) {
-    const char* off = getenv("XCP_GEMM_NO_TRIM");                       // A/B hook
-    if (off != nullptr && off[0] == '1') return;
+    // OFF by default.  Measured on one box (gpurun r4l, bench.py step, ms): untrimmed 35.11 / 35.13, trimmed 35.35 / 35.36 -- the
+    // narrower last N tile (224 of 256 columns) and the shortened last K block cost more in MMA / pipeline efficiency than the 8 % of
+    // skipped tensor work returns, in all three GEMM families.  XCP_GEMM_TRIM=1 turns it on (A/B hook; tests cover both).
+    const char* on = getenv("XCP_GEMM_TRIM");
+    if (!(on != nullptr && on[0] == '1')) return;
     if (n_real > 0 && n_real < N) {
         const int last = n_real - bn * (p.num_n_tiles - 1);
         if (last > 0) {
@@ -865,10 +909,10 @@ extern "C" int xcp_gemm_wgrad(const void* dY, long long ld_dy, const void* X, lo
     p.k_blocks_per_split = (p.num_k_blocks + splits - 1) / splits;
     p.splits = (p.num_k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
     {   // the last N tile only covers Q - bn * (tiles - 1) real columns (728 -> 216 of 256): issue the MMAs that wide
-        const char* off = getenv("XCP_GEMM_NO_TRIM");
+        const char* on = getenv("XCP_GEMM_TRIM");                      // off by default: see set_trim
         const int last = Q - bn * (p.num_n_tiles - 1);
         const int nl = (last + 15) / 16 * 16;
-        if (!(off != nullptr && off[0] == '1') && last > 0 && nl < bn) p.n_last = nl;
+        if (on != nullptr && on[0] == '1' && last > 0 && nl < bn) p.n_last = nl;
     }
     cudaStream_t st = (cudaStream_t)stream;
     switch (bn) {

@@ -571,18 +571,27 @@ def linear_small_bwd(delta_raw, out_act, drop_scale, a, W, dW, db, want_din=True
 
 
 _HEAD_STATE = {}
+_HEAD_BARS = {}
 
 
 def head_state(device: torch.device):
-    """Per-device state of the fused head kernels: the grid-barrier counters of the forward and the backward launch
-    (zero at rest) and the dropout generator {seed, launch counter} -- device resident, so CUDA-graph replays draw
-    fresh masks.  The seed is torch's at first use (torch.manual_seed makes the masks reproducible)."""
-    st = _HEAD_STATE.get(device.index)
-    if st is None:
-        bars = torch.zeros((8,), device=device, dtype=torch.int32)
-        rng = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64).to(device)
-        st = _HEAD_STATE[device.index] = (bars, rng)
-    return st
+    """Per-device state of the fused head kernels -> (barrier counters, dropout generator).  The grid-barrier counters of the
+    forward and the backward launch (zero at rest) are per (device, stream): launches on different streams may overlap and must
+    not share a counter (a CUDA graph keeps the counters of the stream it was captured on).  The dropout generator {seed,
+    launch counter} is device resident, so CUDA-graph replays draw fresh masks; the seed is torch's at first use
+    (torch.manual_seed makes the masks reproducible), decorrelated across data-parallel ranks."""
+    rng = _HEAD_STATE.get(device.index)
+    if rng is None:
+        import os
+        rank = int(os.environ.get("RANK", device.index or 0))
+        seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF
+        rng = _HEAD_STATE[device.index] = torch.tensor([seed, 0], dtype=torch.int64).to(device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    bars = _HEAD_BARS.get(key)
+    if bars is None:
+        with torch.cuda.device(device):
+            bars = _HEAD_BARS[key] = torch.zeros((8,), device=device, dtype=torch.int32)
+    return bars, rng
 
 
 def head_reseed(device: torch.device, seed: int):

@@ -83,10 +83,10 @@ def test_gemm_tn_pad_trimming(M, epi, monkeypatch):
     exactly zero, same BatchNorm partial sums."""
     a = torch.zeros(M, 768, device=DEV, dtype=torch.bfloat16); a[:, :728] = rnd(M, 728, seed=41, dtype=torch.bfloat16)
     b = torch.zeros(768, 768, device=DEV, dtype=torch.bfloat16); b[:728, :728] = rnd(728, 728, seed=42, scale=0.05, dtype=torch.bfloat16)
+    monkeypatch.setenv("XCP_GEMM_TRIM", "1")         # off by default (measured slower in the step, csrc/gemm.cu set_trim): A/B hook
     out_t, st_t = ops.gemm_tn(a, b, epi, n_real=728, k_real=728)
-    monkeypatch.setenv("XCP_GEMM_NO_TRIM", "1")
+    monkeypatch.delenv("XCP_GEMM_TRIM")
     out_f, st_f = ops.gemm_tn(a, b, epi, n_real=728, k_real=728)
-    monkeypatch.delenv("XCP_GEMM_NO_TRIM")
     assert torch.equal(out_t, out_f)
     assert float(out_t[:, 728:].abs().max()) == 0.0
     ref = a.float() @ b.float().t()
@@ -97,10 +97,10 @@ def test_gemm_tn_pad_trimming(M, epi, monkeypatch):
     # weight gradient with the logical (728, 728) shape: the last N tile is issued 224 wide
     dy = a; x = torch.zeros(M, 768, device=DEV, dtype=torch.bfloat16); x[:, :728] = rnd(M, 728, seed=43, dtype=torch.bfloat16)
     dw_t = torch.zeros(728, 728, device=DEV); dw_f = torch.zeros(728, 728, device=DEV)
+    monkeypatch.setenv("XCP_GEMM_TRIM", "1")
     ops.gemm_wgrad(dy, x, dw_t)
-    monkeypatch.setenv("XCP_GEMM_NO_TRIM", "1")
+    monkeypatch.delenv("XCP_GEMM_TRIM")
     ops.gemm_wgrad(dy, x, dw_f)
-    monkeypatch.delenv("XCP_GEMM_NO_TRIM")
     assert rel_err(dw_t, dw_f) < 1e-5 and rel_err(dw_t, dy.float()[:, :728].t() @ x.float()[:, :728]) < 1e-4
 
 

@@ -34,12 +34,12 @@ for M, N, K in ((92416, 768, 768), (256 * 147 * 147 // 4, 128, 128), (256 * 74 *
         import os
         res = {}
         dw = torch.zeros(728, 728, device="cuda")
-        for tag, env in (("trim", "0"), ("full", "1")):
-            os.environ["XCP_GEMM_NO_TRIM"] = env
+        for tag, env in (("trim", "1"), ("full", "0")):
+            os.environ["XCP_GEMM_TRIM"] = env
             res[tag] = (timeit(lambda: ops.gemm_tn(a, b, ops.EPI_BF16, out=out, n_real=728, k_real=728)),
                         timeit(lambda: ops.gemm_tn(a, b, ops.EPI_BF16_STATS, out=out, n_real=728, k_real=728)),
                         timeit(lambda: ops.gemm_wgrad(a, res_like, dw)))
-        os.environ["XCP_GEMM_NO_TRIM"] = "0"
+        os.environ["XCP_GEMM_TRIM"] = "0"
         print("   pad trimming (728 of 768): plain %.1f -> %.1f us | stats %.1f -> %.1f | wgrad %.1f -> %.1f" % (
             res["full"][0], res["trim"][0], res["full"][1], res["trim"][1], res["full"][2], res["trim"][2]), flush=True)
     print("M=%6d N=%4d K=%4d  plain %7.1f us | bias+relu %7.1f | bias+residual %7.1f | stats %7.1f" % (M, N, K, t0, t1, t2, t3), flush=True)
