@@ -188,7 +188,14 @@ def call(name: str, *args):
         _timer.append((name, tuple(a if isinstance(a, (int, float)) else (getattr(a, "value", None) is not None) for a in args), e0, e1))
     else:
         rc = getattr(lib, name)(*args)
-    _count += _LAUNCHES.get(name, 1)
+    if name == "xcp_bn_bwd":
+        # reduce pass (unless the sums are given) + finalize (folded into the apply kernel when the sums are complete and the
+        # source is not the max-pool routing) + apply pass (when dy is wanted): include/xcp.h argument order
+        presums, dy = bool(args[11].value), bool(args[16].value)
+        fused = presums and dy and not (args[0] == 2 and args[22] <= 0)
+        _count += (0 if presums else 1) + (0 if fused else 1) + (1 if dy else 0)
+    else:
+        _count += _LAUNCHES.get(name, 1)
     if name in _NO_STATUS:
         return rc
     if rc != 0:

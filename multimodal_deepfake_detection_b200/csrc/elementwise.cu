@@ -602,10 +602,20 @@ bnbwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, int
 
 // pass 2: dy = A*dz + B*y + Cc  (bf16).  conv_grid_w > 0: scatter rows onto a zero-initialised
 // (conv_grid_h x conv_grid_w) "input grid" layout used by the stem implicit-GEMM backward.
+// When the per-channel sums are already complete (one [2][C] row: produced by the depthwise backward or xcp_bn_bwd_sums), the
+// finalize step -- a few flops per channel -- runs inside the apply kernel: every thread derives the coefficients of its own 8
+// channels, the first thread of each channel group adds dgamma / dbeta.  One launch (and its ~7 us) less per BatchNorm.
+struct BnBwdFin {
+    const float* sums;            // [2][C] or null (= read the coefficients the finalize kernel wrote)
+    const float* gamma; const float* mean; const float* rstd;
+    float* dgamma; float* dbeta;
+    double count; int training, c_real;
+};
+
 __global__ void __launch_bounds__(256, 2)
 bnbwd_apply_kernel(const uint4* __restrict__ y, const BnBwdSrc s, const float* __restrict__ coefA,
                    const float* __restrict__ coefB, const float* __restrict__ coefC, uint4* __restrict__ dy, long long n8,
-                   int grid_w, int grid_h) {
+                   int grid_w, int grid_h, const BnBwdFin fin) {
     const int ncg = s.C >> 3;
     const long long T = (long long)gridDim.x * blockDim.x;
     const long long S = T - (T % ncg);                 // a thread stays on one channel group: coefficients live in registers
@@ -613,10 +623,31 @@ bnbwd_apply_kernel(const uint4* __restrict__ y, const BnBwdSrc s, const float* _
     if (gid >= S) return;
     const int cg = (int)(gid % ncg);
     float A[8], B[8], Cc[8];
+    if (fin.sums != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            A[j] = 0.f; B[j] = 0.f; Cc[j] = 0.f;
+            if (c < fin.c_real) {                      // same arithmetic as bnbwd_finalize_kernel (fp64 on a handful of values)
+                const double s1 = fin.sums[c], s2 = fin.sums[s.C + c];
+                const double m = fin.mean[c], r = fin.rstd[c], g = fin.gamma[c];
+                const double dg = r * (s2 - m * s1);
+                const double a = g * r;
+                double b = 0.0, cc = 0.0;
+                if (fin.training) { b = -g * r * r * dg / fin.count; cc = -b * m - a * s1 / fin.count; }
+                A[j] = (float)a; B[j] = (float)b; Cc[j] = (float)cc;
+                if (gid < ncg) {                       // one thread per channel group owns the parameter gradients
+                    if (fin.dgamma != nullptr) fin.dgamma[c] += (float)dg;
+                    if (fin.dbeta != nullptr) fin.dbeta[c] += (float)s1;
+                }
+            }
+        }
+    } else {
     load_affine8(coefA, coefB, cg * 8, A, B);
     {
         const float4 c0 = *reinterpret_cast<const float4*>(coefC + cg * 8), c1 = *reinterpret_cast<const float4*>(coefC + cg * 8 + 4);
         Cc[0] = c0.x; Cc[1] = c0.y; Cc[2] = c0.z; Cc[3] = c0.w; Cc[4] = c1.x; Cc[5] = c1.y; Cc[6] = c1.z; Cc[7] = c1.w;
+    }
     }
     const bool paired = (s.mode == SRC_DIRECT || s.mode == SRC_RELU);
     const uint4* Gv = reinterpret_cast<const uint4*>(s.G);
@@ -932,9 +963,16 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
         XCP_CUDA(cudaGetLastError());
         sums = workspace;
     }
-    bnbwd_finalize_kernel<<<(C + 31) / 32, 256, 0, ST>>>(sums, nparts, C, c_real, count, gamma, mean, rstd, training, coef, coef + C,
-                                                           coef + 2 * C, dgamma, dbeta);
-    XCP_CUDA(cudaGetLastError());
+    // complete sums + a plain apply pass: the finalize arithmetic runs inside the apply kernel (no finalize launch)
+    static int nofuse_env = -1;                                    // A/B hook: XCP_BN_FIN_SEPARATE=1 keeps the separate finalize launch
+    if (nofuse_env < 0) { const char* e = getenv("XCP_BN_FIN_SEPARATE"); nofuse_env = e ? atoi(e) : 0; }
+    const bool fused_fin = presums != nullptr && dy != nullptr && !pool && !nofuse_env;
+    BnBwdFin fin{fused_fin ? presums : nullptr, gamma, mean, rstd, dgamma, dbeta, count, training, c_real};
+    if (!fused_fin) {
+        bnbwd_finalize_kernel<<<(C + 31) / 32, 256, 0, ST>>>(sums, nparts, C, c_real, count, gamma, mean, rstd, training, coef, coef + C,
+                                                               coef + 2 * C, dgamma, dbeta);
+        XCP_CUDA(cudaGetLastError());
+    }
     if (dy != nullptr) {
         // grid-stride with a channel-group preserving stride: the grid must hold at least one thread per channel group
         const long long work = pool ? nq8 : (n8 + BNBWD_U - 1) / BNBWD_U;
@@ -942,7 +980,7 @@ extern "C" int xcp_bn_bwd(int mode, const void* y, const void* G, const void* id
         int ga = (int)(ga_ < 2LL * num_sms() ? (ga_ > 0 ? ga_ : 1) : 2LL * num_sms());      // persistent: 2 resident CTAs per SM
         if ((long long)ga * 256 < C / 8) ga = (C / 8 + 255) / 256;
         if (pool) bnbwd_pool_kernel<true><<<ga, 256, 0, ST>>>((const uint4*)y, s, nullptr, coef, coef + C, coef + 2 * C, (uint4*)dy, nq8);
-        else bnbwd_apply_kernel<<<ga, 256, 0, ST>>>((const uint4*)y, s, coef, coef + C, coef + 2 * C, (uint4*)dy, n8, grid_w, grid_h);
+        else bnbwd_apply_kernel<<<ga, 256, 0, ST>>>((const uint4*)y, s, coef, coef + C, coef + 2 * C, (uint4*)dy, n8, grid_w, grid_h, fin);
     }
     return check_cuda(cudaGetLastError(), "bn_bwd launch");
 }
