@@ -311,7 +311,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         //                          CTA in the mma-fragment layout, one cross-lane reduction at the very end;
         //                   TILE = several N tiles -> per-tile reduction (recursive halving) and per-tile partial rows;
         //                   CONV = stem implicit GEMM (row masks) -> shared-memory transpose per chunk.
-        const bool reg_stats = STATS && p.stats_per_cta && p.conv_taps == 0;
+        // CONV_REG: the stem conv2 forward (the only BLOCK_K = 32 user) takes the REG path too -- the rows outside the valid output
+        // window are masked in the fragment layout with a ballot of the per-row validity, so its epilogue needs neither the
+        // shared-memory transpose nor the two 256-thread barriers per tile (ncu r4q: 567 us, tensor pipe 18 % active, 3400 clk per
+        // 128-row tile against an 860 clk MMA floor -- the epilogue was the kernel).
+        constexpr bool CONV_REG = STATS && BLOCK_K == 32;
+        const bool reg_stats = STATS && p.stats_per_cta && (p.conv_taps == 0 || CONV_REG);
         u64 acc1[NCW][4], acc2[NCW][4];
 #pragma unroll
         for (int i = 0; i < NCW; ++i)
@@ -395,7 +400,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
                 uint32_t fa[16], fb[16];
-                if (STATS && p.conv_taps == 0) {
+                if (STATS && (p.conv_taps == 0 || CONV_REG)) {
                     // The accumulator chunk is read a second time in the mma-fragment shape (16x256b: a thread holds
                     // 4 rows x 4 column pairs) for the column statistics.  The shared-memory crossbar carries the UMMA
                     // operand reads (~96 of 128 B/clk), so the epilogue must stay off it: the first version transposed
@@ -487,14 +492,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                     }
-                    if (STATS && p.conv_taps == 0) {
+                    if (STATS && (p.conv_taps == 0 || CONV_REG)) {
                         u64 s1[4], s2[4];
+                        uint32_t okm = 0xffffffffu;               // CONV_REG: bit l = row q*32 + l lies inside the valid output window
+                        if (CONV_REG) okm = __ballot_sync(0xffffffffu, row_ok);
+                        const int fr = lane >> 2;                 // fragment rows of this thread: fr, fr + 8 (fa), fr + 16, fr + 24 (fb)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const u64 v0 = pk2(__uint_as_float(fa[4 * j + 0]), __uint_as_float(fa[4 * j + 1]));
-                            const u64 v1 = pk2(__uint_as_float(fa[4 * j + 2]), __uint_as_float(fa[4 * j + 3]));
-                            const u64 v2 = pk2(__uint_as_float(fb[4 * j + 0]), __uint_as_float(fb[4 * j + 1]));
-                            const u64 v3 = pk2(__uint_as_float(fb[4 * j + 2]), __uint_as_float(fb[4 * j + 3]));
+                            u64 v0 = pk2(__uint_as_float(fa[4 * j + 0]), __uint_as_float(fa[4 * j + 1]));
+                            u64 v1 = pk2(__uint_as_float(fa[4 * j + 2]), __uint_as_float(fa[4 * j + 3]));
+                            u64 v2 = pk2(__uint_as_float(fb[4 * j + 0]), __uint_as_float(fb[4 * j + 1]));
+                            u64 v3 = pk2(__uint_as_float(fb[4 * j + 2]), __uint_as_float(fb[4 * j + 3]));
+                            if (CONV_REG) {
+                                if (!((okm >> fr) & 1u)) v0 = 0ull;
+                                if (!((okm >> (fr + 8)) & 1u)) v1 = 0ull;
+                                if (!((okm >> (fr + 16)) & 1u)) v2 = 0ull;
+                                if (!((okm >> (fr + 24)) & 1u)) v3 = 0ull;
+                            }
                             s1[j] = add2(add2(v0, v1), add2(v2, v3));
                             s2[j] = fma2(v0, v0, fma2(v1, v1, fma2(v2, v2, mul2(v3, v3))));
                         }
