@@ -180,6 +180,23 @@ int xcp_head_mlp_bwd(const float* dsrc, const float* prob, const float* gscale, 
                      const long long* row_index, const float* acts, float drop_scale, const void* const* wb, void* const* dwb,
                      float* dacts, float* dx, float* dx_base, long long dx_zero_n, void* bar, int B, int H, int Wd, int device,
                      void* stream);
+/* The fused region of train_au_face.py:659-674 in ONE launch per direction: mean-pool both token streams ([B,Tv,D], [B,Ta,D]), concat,
+ * embed_head (Linear(2D,N0) -> ReLU -> Dropout -> Linear(N0,N3)), ArcFace margin logits on N3-wide embeddings (2 classes), loss_mode 0:
+ * cross entropy / 1: class-balanced focal (class_w[2], gamma), + lambda_align * mse(v_pool, a_pool) + lambda_temp * 0.5 * (temporal
+ * smoothness of both streams).  labels NULL: inference logits s*cos only.  Forward outputs: pooled [B,2D], h [B,N0], e [B,N3],
+ * logits [B,2], loss, and the unit-loss gradients de [B,N3], darc_scratch (first 2*N3 floats = d loss / d arc_w; size B*2*N3);
+ * rows = 2*B floats of scratch; mask / rng / bar as for xcp_head_mlp_fwd (mask = uint8 [B,N0]).
+ * Backward: everything scaled by *gscale (NULL = 1): dW0, db0, dW3, db3, darc accumulated into; dv / da (nullable) written;
+ * dh [B,N0], dpooled [B,2D] scratch. */
+int xcp_fusion_head_fwd(const float* v, const float* a, int B, int Tv, int Ta, int D, const float* W0, const float* b0, const float* W3,
+                        const float* b3, int N0, int N3, const float* arc_w, const long long* labels, float s, float m, int loss_mode,
+                        const float* class_w, float gamma, float lambda_align, float lambda_temp, const void* mask, void* rng,
+                        float p_drop, float* pooled, float* h, float* e, float* logits, float* loss, float* de, float* darc_scratch,
+                        float* rows, void* bar, int device, void* stream);
+int xcp_fusion_head_bwd(const float* gscale, const float* v, const float* a, int B, int Tv, int Ta, int D, const float* W0,
+                        const float* W3, int N0, int N3, const float* pooled, const float* h, const float* de, const float* darc_unit,
+                        float drop_scale, float lambda_align, float lambda_temp, float* dW0, float* db0, float* dW3, float* db3,
+                        float* darc, float* dh, float* dpooled, float* dv, float* da, void* bar, int device, void* stream);
 /* nn.BCELoss() (mean) on probabilities + its gradient wrt p in one launch (train_audio.py:20,39); dp may be NULL */
 int xcp_bce_prob_fwd_bwd(const float* p, const float* y, float* loss, float* dp, int n, int device, void* stream);
 int xcp_arcface_loss(const float* x, const float* w, const long long* labels, float s, float m, int loss_mode,

@@ -62,6 +62,8 @@ SIGNATURES = {
     "xcp_sigmoid_bwd": "pppiip",
     "xcp_bce_fwd_bwd": "ppfpppiip",
     "xcp_bce_prob_fwd_bwd": "ppppiip",
+    "xcp_fusion_head_fwd": "ppiiiippppiippffipfffppfpppppppppip",
+    "xcp_fusion_head_bwd": "pppiiiippiippppfffppppppppppip",
     "xcp_head_mlp_fwd": "plppppfpppipfpppiiiip",
     "xcp_head_mlp_bwd": "pppplppfppppplpiiiip",
     "xcp_arcface_loss": "pppffipfppppppiifip",

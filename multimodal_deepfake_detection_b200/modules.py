@@ -782,35 +782,35 @@ class LabelSmoothingBCEWithLogitsLoss(nn.Module):
 # ================================================================================================ fusion head (train_au_face)
 class _FusionHeadFn(torch.autograd.Function):
     """The fused region of train_au_face.py:659-674: token mean-pooling, concat, embed_head (Linear-ReLU-Dropout-
-    Linear), ArcFace margin logits, CB-focal loss, alignment MSE and temporal smoothness -- loss and every gradient
-    (tokens, embed_head, ArcFace weight) in one pass of C-ABI kernels."""
+    Linear), ArcFace margin logits, CB-focal loss, alignment MSE and temporal smoothness -- ONE launch for the forward and
+    the loss, ONE for every gradient (tokens, embed_head, ArcFace weight), csrc/head_fused.cu."""
 
     @staticmethod
-    def forward(ctx, v_tok, a_tok, labels, W0, b0, W3, b3, arc_w, class_w, cfg):
+    def forward(ctx, v_tok, a_tok, labels, W0, b0, W3, b3, arc_w, class_w, cfg, mask=None):
         s, m, gamma, la, lt, training, p_drop = cfg
         v = v_tok.float().contiguous(); a = a_tok.float().contiguous()
-        B = v.shape[0]
-        pooled, loss_reg, dv, da = ops.fusion_pool_reg(v, a, la, lt)
-        scale = 1.0 / (1.0 - p_drop) if (training and p_drop > 0) else 1.0
-        mask = (torch.rand((B, W0.shape[0]), device=v.device) >= p_drop).to(torch.uint8) if scale != 1.0 else None
-        h = ops.linear_small_fwd(pooled, W0.detach(), b0.detach(), 1, mask, scale)
-        e = ops.linear_small_fwd(h, W3.detach(), b3.detach(), 0)
-        darc = torch.zeros_like(arc_w)
-        logits, loss_cls, de = ops.arcface_loss(e, arc_w.detach(), labels, s, m, 1 if class_w is not None else 0, class_w, gamma,
-                                                dw=darc)
-        dW3 = torch.zeros_like(W3); db3 = torch.zeros_like(b3)
-        dh = ops.linear_small_bwd(de, None, 1.0, h, W3.detach(), dW3, db3)
-        dW0 = torch.zeros_like(W0); db0 = torch.zeros_like(b0)
-        dpooled = ops.linear_small_bwd(dh, h, scale, pooled, W0.detach(), dW0, db0)
-        ops.fusion_pool_bwd(dpooled, dv, da)
-        ctx.save_for_backward(dv, da, dW0, db0, dW3, db3, darc)
-        ctx.mark_non_differentiable(logits)
-        return loss_cls + loss_reg, logits
+        p = float(p_drop) if training else 0.0
+        out = ops.fusion_head_fwd(v, a, labels, W0.detach(), b0.detach(), W3.detach(), b3.detach(), arc_w.detach(), class_w,
+                                  s, m, gamma, la, lt, p, mask)
+        ctx.v, ctx.a, ctx.saved, ctx.params = v, a, out, (W0, b0, W3, b3, arc_w)
+        ctx.cfg = (1.0 / (1.0 - p) if p > 0 else 1.0, la, lt)
+        ctx.shapes = (v_tok.shape, a_tok.shape)
+        ctx.mark_non_differentiable(out["logits"])
+        return out["loss"], out["logits"]
 
     @staticmethod
     def backward(ctx, dloss, _dlogits):
-        dv, da, dW0, db0, dW3, db3, darc = ctx.saved_tensors
-        return (dv * dloss, da * dloss, None, dW0 * dloss, db0 * dloss, dW3 * dloss, db3 * dloss, darc * dloss, None, None)
+        W0, b0, W3, b3, arc_w = ctx.params
+        scale, la, lt = ctx.cfg
+        sink = ex.GradSink([W0, b0, W3, b3, arc_w], ctx.v.device)
+        dv, da = ops.fusion_head_bwd(dloss.detach().float().contiguous(), ctx.v, ctx.a, W0.detach(), W3.detach(), ctx.saved, scale, la, lt,
+                                     sink.view(W0), sink.view(b0), sink.view(W3), sink.view(b3), sink.view(arc_w),
+                                     want_dv=ctx.needs_input_grad[0], want_da=ctx.needs_input_grad[1])
+        if dv is not None:
+            dv = dv.view(ctx.shapes[0])
+        if da is not None:
+            da = da.view(ctx.shapes[1])
+        return (dv, da, None, sink.view(W0), sink.view(b0), sink.view(W3), sink.view(b3), sink.view(arc_w), None, None, None)
 
 
 class FusionHead(nn.Module):
@@ -831,16 +831,15 @@ class FusionHead(nn.Module):
         e = self.embed_head
         cfg = (self.arcface.s, self.arcface.m, self.cbfocal.gamma, self.lambda_align, self.lambda_temp, self.training, float(e[2].p))
         return _FusionHeadFn.apply(v_tokens, au_tokens, labels.long().contiguous(), e[0].weight, e[0].bias, e[3].weight, e[3].bias,
-                                   self.arcface.weight, self.cbfocal.class_weights, cfg)
+                                   self.arcface.weight, self.cbfocal.class_weights, cfg, None)
 
     @torch.no_grad()
     def predict_logits(self, v_tokens, au_tokens):
-        """Inference logits s*cos (labels=None path of ArcFaceHead, train_au_face.py:715-716)."""
-        pooled, _, _, _ = ops.fusion_pool_reg(v_tokens.float().contiguous(), au_tokens.float().contiguous(), 0.0, 0.0, want_grad=False)
+        """Inference logits s*cos (labels=None path of ArcFaceHead, train_au_face.py:715-716): the same single launch without labels."""
         e = self.embed_head
-        h = ops.linear_small_fwd(pooled, e[0].weight, e[0].bias, 1)
-        emb = ops.linear_small_fwd(h, e[3].weight, e[3].bias, 0)
-        return self.arcface(emb)
+        out = ops.fusion_head_fwd(v_tokens.float().contiguous(), au_tokens.float().contiguous(), None, e[0].weight, e[0].bias,
+                                  e[3].weight, e[3].bias, self.arcface.weight, None, self.arcface.s, self.arcface.m, 0.0, 0.0, 0.0)
+        return out["logits"]
 
 
 class AUFaceCrossDetector(nn.Module):

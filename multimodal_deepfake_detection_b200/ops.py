@@ -662,6 +662,58 @@ def head_mlp_bwd(dsrc, prob, gscale, x, row_index, acts, drop_scale: float, wb, 
     return dx
 
 
+def fusion_head_fwd(v, a, labels, W0, b0, W3, b3, arc_w, class_w, s: float, m: float, gamma: float, lambda_align: float,
+                    lambda_temp: float, p_drop: float = 0.0, mask=None):
+    """train_au_face.py:659-674 in one launch: token pooling, embed_head, ArcFace logits, CE / CB-focal (class_w given) + the
+    regularisers.  labels None: inference logits only.  -> dict(pooled, h, e, logits, loss, de, darc) (de / darc: unit-loss
+    gradients wrt the embedding / the ArcFace weight, consumed by fusion_head_bwd)."""
+    _chk(v, F32, "fusion_head.v"); _chk(a, F32, "fusion_head.a")
+    B, Tv, D = v.shape
+    Ta = a.shape[1]
+    if a.shape[0] != B or a.shape[2] != D:
+        raise _lib.XcpError("fusion head: token streams %s and %s differ in batch / width" % (tuple(v.shape), tuple(a.shape)))
+    N0, N3 = W0.shape[0], W3.shape[0]
+    if W0.shape[1] != 2 * D or W3.shape[1] != N0 or tuple(arc_w.shape) != (2, N3):
+        raise _lib.XcpError("fusion head: embed_head / ArcFace shapes do not match the tokens")
+    dev = v.device
+    bars, rng = head_state(dev)
+    out = {"pooled": torch.empty((B, 2 * D), device=dev, dtype=F32), "h": torch.empty((B, N0), device=dev, dtype=F32),
+           "e": torch.empty((B, N3), device=dev, dtype=F32), "logits": torch.empty((B, 2), device=dev, dtype=F32),
+           "loss": None, "de": None, "darc": None}
+    rows = torch.empty((2 * B,), device=dev, dtype=F32)
+    if labels is not None:
+        _chk(labels, torch.int64, "fusion_head.labels")
+        out["loss"] = torch.empty((), device=dev, dtype=F32)
+        out["de"] = torch.empty((B, N3), device=dev, dtype=F32)
+        out["darc"] = torch.empty((B, 2, N3), device=dev, dtype=F32)
+    if mask is not None:
+        _chk(mask, torch.uint8, "fusion_head.mask")
+    _lib.call("xcp_fusion_head_fwd", _p(v), _p(a), B, Tv, Ta, D, _p(W0), _p(b0), _p(W3), _p(b3), N0, N3, _p(arc_w), _p(labels),
+              float(s), float(m), 1 if class_w is not None else 0, _p(class_w), float(gamma), float(lambda_align), float(lambda_temp),
+              _p(mask), _p(rng) if (mask is None and p_drop > 0) else ctypes.c_void_p(0), float(p_drop), _p(out["pooled"]),
+              _p(out["h"]), _p(out["e"]), _p(out["logits"]), _p(out["loss"]), _p(out["de"]), _p(out["darc"]), _p(rows),
+              ctypes.c_void_p(bars.data_ptr() + 8), dev.index, _s())
+    return out
+
+
+def fusion_head_bwd(gscale, v, a, W0, W3, saved, drop_scale: float, lambda_align: float, lambda_temp: float, dW0, db0, dW3, db3,
+                    darc, want_dv: bool = True, want_da: bool = True):
+    """Backward of fusion_head_fwd in one launch; parameter gradients are accumulated into the given slots."""
+    B, Tv, D = v.shape
+    Ta = a.shape[1]
+    N0, N3 = W0.shape[0], W3.shape[0]
+    dev = v.device
+    bars, _ = head_state(dev)
+    dh = torch.empty((B, N0), device=dev, dtype=F32)
+    dpooled = torch.empty((B, 2 * D), device=dev, dtype=F32)
+    dv = torch.empty_like(v) if want_dv else None
+    da = torch.empty_like(a) if want_da else None
+    _lib.call("xcp_fusion_head_bwd", _p(gscale), _p(v), _p(a), B, Tv, Ta, D, _p(W0), _p(W3), N0, N3, _p(saved["pooled"]), _p(saved["h"]),
+              _p(saved["de"]), _p(saved["darc"]), float(drop_scale), float(lambda_align), float(lambda_temp), _p(dW0), _p(db0), _p(dW3),
+              _p(db3), _p(darc), _p(dh), _p(dpooled), _p(dv), _p(da), ctypes.c_void_p(bars.data_ptr() + 24), dev.index, _s())
+    return dv, da
+
+
 def sigmoid_fwd(z):
     p = torch.empty_like(z)
     _lib.call("xcp_sigmoid_fwd", _p(z), _p(p), z.numel(), z.device.index, _s())

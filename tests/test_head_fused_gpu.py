@@ -12,9 +12,6 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pytestmark = pytest.mark.gpu
 
-if not torch.cuda.is_available():
-    pytest.skip("needs a B200", allow_module_level=True)
-
 from multimodal_deepfake_detection_b200 import ops  # noqa: E402
 from multimodal_deepfake_detection_b200 import modules as M  # noqa: E402
 from oracle import xception_oracle as orc  # noqa: E402
@@ -210,3 +207,68 @@ def test_model_forward_loss_equals_forward_plus_criterion():
         assert rel_err(a, b) < 1e-4
     # against the reference's own criterion on the same probabilities
     assert abs(l1.item() - torch.nn.BCELoss()(o1, y).item()) < 1e-6
+
+
+@pytest.mark.parametrize("B,Tv,Ta,D,focal", [(4, 16, 16, 256, True), (9, 16, 120, 256, True), (32, 5, 7, 128, False), (1, 1, 3, 64, True),
+                                             (6, 2, 1, 512, False)])
+def test_fused_fusion_head_matches_oracle(B, Tv, Ta, D, focal):
+    """train_au_face.py:659-674 as one launch per direction against oracle/xception_oracle.py::fusion_head_loss under torch
+    autograd: loss, logits and every gradient (both token streams of different lengths, embed_head, ArcFace weight), with an
+    injected dropout mask and a non-unit upstream gradient."""
+    g = torch.Generator().manual_seed(B * 17 + D)
+    v = torch.randn(B, Tv, D, generator=g).to(DEV); a = torch.randn(B, Ta, D, generator=g).to(DEV)
+    W0 = (torch.randn(256, 2 * D, generator=g) * (1.0 / D) ** 0.5).to(DEV); b0 = (torch.randn(256, generator=g) * 0.1).to(DEV)
+    W3 = (torch.randn(128, 256, generator=g) * (2.0 / 256) ** 0.5).to(DEV); b3 = (torch.randn(128, generator=g) * 0.1).to(DEV)
+    arc = torch.randn(2, 128, generator=g).to(DEV)
+    labels = torch.randint(0, 2, (B,), generator=g).to(DEV)
+    keep = (torch.rand(B, 256, generator=g) >= 0.2).to(DEV)
+    cw = orc.cb_focal_weights([500, 10000]).to(DEV) if focal else None
+
+    leaves = [t.clone().requires_grad_(True) for t in (v, a, W0, b0, W3, b3, arc)]
+    rv, ra, rW0, rb0, rW3, rb3, rarc = leaves
+    if focal:
+        loss_ref, logits_ref = orc.fusion_head_loss({"0.weight": rW0, "0.bias": rb0, "3.weight": rW3, "3.bias": rb3}, rarc, rv, ra, labels, cw,
+                                                    s=30.0, m=0.30, gamma=2.0, lambda_align=0.2, lambda_temp=0.1, drop_mask=keep.float() / 0.8)
+    else:       # plain cross entropy on the margin logits (train_visual.py:455-474,532) + the same regularisers
+        vp, ap = rv.mean(1), ra.mean(1)
+        hdn = F.relu(F.linear(torch.cat([vp, ap], 1), rW0, rb0)) * keep.float() / 0.8
+        logits_ref = orc.arcface_logits(rarc, F.linear(hdn, rW3, rb3), labels, 30.0, 0.30)
+        ltv = (rv[:, 1:] - rv[:, :-1]).pow(2).mean() if Tv > 1 else 0.0
+        lta = (ra[:, 1:] - ra[:, :-1]).pow(2).mean() if Ta > 1 else 0.0
+        loss_ref = F.cross_entropy(logits_ref, labels) + 0.2 * F.mse_loss(vp, ap) + 0.1 * 0.5 * (ltv + lta)
+    (loss_ref * 1.3).backward()
+
+    mine = [t.clone().requires_grad_(True) for t in (v, a, W0, b0, W3, b3, arc)]
+    cfg = (30.0, 0.30, 2.0, 0.2, 0.1, True, 0.2)
+    loss, logits = M._FusionHeadFn.apply(mine[0], mine[1], labels, mine[2], mine[3], mine[4], mine[5], mine[6], cw, cfg,
+                                         keep.to(torch.uint8).contiguous())
+    (loss * 1.3).backward()
+    assert abs(loss.item() - loss_ref.item()) < 2e-5 * max(1.0, abs(loss_ref.item()))
+    assert rel_err(logits, logits_ref.detach()) < 1e-5
+    names = ("v_tokens", "au_tokens", "embed.0.weight", "embed.0.bias", "embed.3.weight", "embed.3.bias", "arcface.weight")
+    for n, x, r in zip(names, mine, leaves):
+        assert rel_err(x.grad, r.grad) < 2e-4, (n, rel_err(x.grad, r.grad))
+    bars, _ = ops.head_state(DEV)
+    assert int(bars.abs().sum()) == 0
+
+
+def test_fusion_head_module_inference_logits_and_dropout_draw():
+    """FusionHead.predict_logits == s * cos of the embedding (labels=None path, train_au_face.py:715-716); train-mode dropout is drawn
+    in the kernel (two calls differ, keep rate ~0.8)."""
+    torch.manual_seed(5)
+    head = M.FusionHead(256, samples_per_cls=(500, 10000)).to(DEV)
+    g = torch.Generator().manual_seed(9)
+    v = torch.randn(8, 16, 256, generator=g).to(DEV); a = torch.randn(8, 16, 256, generator=g).to(DEV)
+    y = torch.randint(0, 2, (8,), generator=g).to(DEV)
+    head.eval()
+    lg = head.predict_logits(v, a)
+    e = head.embed_head
+    emb = F.linear(F.relu(F.linear(torch.cat([v.mean(1), a.mean(1)], 1), e[0].weight, e[0].bias)), e[3].weight, e[3].bias)
+    ref = orc.arcface_logits(head.arcface.weight, emb, None, head.arcface.s, head.arcface.m)
+    assert rel_err(lg, ref.detach()) < 1e-5
+    head.train()
+    l1, _ = head(v, a, y)
+    l2, _ = head(v, a, y)
+    assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() != l2.item()
+    l1.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in head.parameters())
