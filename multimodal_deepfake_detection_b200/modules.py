@@ -792,7 +792,11 @@ class _FusionHeadFn(torch.autograd.Function):
         p = float(p_drop) if training else 0.0
         out = ops.fusion_head_fwd(v, a, labels, W0.detach(), b0.detach(), W3.detach(), b3.detach(), arc_w.detach(), class_w,
                                   s, m, gamma, la, lt, p, mask)
-        ctx.v, ctx.a, ctx.saved, ctx.params = v, a, out, (W0, b0, W3, b3, arc_w)
+        # only what the backward launch reads -- NOT the returned loss / logits: an output kept on ctx closes a cycle
+        # (output -> grad_fn -> ctx -> output) that keeps the step's autograd graph, and with it the parameters' AccumulateGrad
+        # nodes of an eager warm-up step on the default stream, alive into a later CUDA-graph capture (which then fails)
+        ctx.saved = {k: out[k] for k in ("pooled", "h", "de", "darc")}
+        ctx.v, ctx.a, ctx.params = v, a, (W0, b0, W3, b3, arc_w)
         ctx.cfg = (1.0 / (1.0 - p) if p > 0 else 1.0, la, lt)
         ctx.shapes = (v_tok.shape, a_tok.shape)
         ctx.mark_non_differentiable(out["logits"])
