@@ -116,3 +116,35 @@ def test_graphed_inference_matches_eager_eval():
         e8 = fn(u8).clone()
     infer8 = GraphedInference(fn, (u8,), modules=[m])
     assert torch.equal(infer8(u8), e8)
+
+
+def test_fusion_head_step_captures_after_eager_steps():
+    """The audio-face fusion step (train_au_face.py:659-693 protocol: token streams -> FusionHead -> backward -> AdamW) captured
+    after eager steps on the default stream, as bench.py --config c5 does.  Regression: an output tensor kept on the autograd ctx
+    closed a reference cycle that kept the eager steps' graph (and the parameters' AccumulateGrad nodes on the default stream)
+    alive, and the capture failed with cudaErrorStreamCaptureImplicit."""
+    from multimodal_deepfake_detection_b200 import FusedAdam, FusionHead
+    torch.manual_seed(3)
+    head = FusionHead(64, samples_per_cls=(500, 10000), p_drop=0.0).to(DEV).train()
+    proj_v = torch.nn.Linear(32, 64).to(DEV); proj_a = torch.nn.Linear(32, 64).to(DEV)      # stand-ins for the two token streams
+    params = list(head.parameters()) + list(proj_v.parameters()) + list(proj_a.parameters())
+    opt = FusedAdam(params, lr=1e-3, weight_decay=1e-2, decoupled=True, max_norm=1.0)
+    g = torch.Generator().manual_seed(1)
+    batches = [(torch.randn(4, 6, 32, generator=g).to(DEV), torch.randn(4, 9, 32, generator=g).to(DEV),
+                torch.randint(0, 2, (4,), generator=g).to(DEV)) for _ in range(3)]
+
+    def step(xv, xa, y):
+        opt.zero_grad(set_to_none=True)
+        loss, _ = head(proj_v(xv), proj_a(xa), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step(*batches[0])
+    graphed = GraphedTrainStep(step, batches[0], modules=[head], warmup=1, optimizers=[opt])
+    w_before = head.embed_head[0].weight.detach().clone()
+    losses = [float(graphed(*b).detach()) for b in batches for _ in range(2)]
+    assert all(torch.isfinite(torch.tensor(losses))) and graphed.replays == 6
+    assert (head.embed_head[0].weight.detach() - w_before).abs().max().item() > 0        # the replayed steps trained
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
