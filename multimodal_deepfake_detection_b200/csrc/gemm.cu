@@ -98,9 +98,16 @@ __host__ __device__ constexpr int fit_stages() {
 // BLOCK_K=64 -> 128B swizzle; BLOCK_K=32 -> 64B swizzle (K-major only; used by the stem implicit GEMM)
 // TRIM: pad-trimming instantiation (GemmParams::n_last / k_steps_last).  A template parameter, not a run-time test: the untrimmed
 // kernels must keep exactly the code (and register allocation) they have without the feature.
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false>
+// PLAIN: the pointwise / weight-gradient GEMMs proper -- no implicit-convolution taps, no halo mode, bf16 epilogues through the bulk
+// tensor store.  Those run-time switches become compile-time constants, so the kernels that carry 37 % of the training step do
+// not pay (registers, predicated instructions) for the stem's modes.
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false, bool PLAIN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    const int x_conv_taps = PLAIN ? 0 : p.conv_taps;
+    const int x_wg_taps = PLAIN ? 0 : p.wg_taps;
+    const int x_tma_store = PLAIN ? (epi_is_bf16(EPI) ? 1 : 0) : p.tma_store;
+    const int x_conv_halo = PLAIN ? 0 : p.conv_halo;
     static_assert(BLOCK_K == 64 || (BLOCK_K == 32 && !MN_MAJOR), "unsupported BLOCK_K");
     static_assert(!CTA2 || (BLOCK_K == 64 && BLOCK_N >= 128), "CTA-pair mode: BLOCK_K 64, BLOCK_N 128/256");
     constexpr bool STATS = (EPI == EPI_BF16_STATS);
@@ -117,7 +124,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = sA + STAGES * A_BYTES;
-    uint8_t* after = (!MN_MAJOR && !CTA2 && p.conv_halo) ? smem + 2 * p.halo_bytes + 9 * B_BYTES : sB + STAGES * B_BYTES;
+    uint8_t* after = (!MN_MAJOR && !CTA2 && x_conv_halo) ? smem + 2 * p.halo_bytes + 9 * B_BYTES : sB + STAGES * B_BYTES;
     float* s_tr = reinterpret_cast<float*>(after);                       // [8][32][36]  (144-byte rows: conflict-free v4 stores); BLOCK_N == 64 only
     float* s_part = s_tr + ((STATS && BLOCK_N == 64) ? 8 * 32 * 36 : 0);                    // [4][2][BLOCK_N]
     uint8_t* s_store = reinterpret_cast<uint8_t*>(s_part + (STATS ? 4 * 2 * BLOCK_N : 0));      // [8 warps][2][32 rows x 64 B], 64B-swizzled
@@ -154,7 +161,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int num_units = tiles_mn * p.splits;
     const int m_row0_mul = CTA2 ? 2 * BLOCK_M : BLOCK_M;
 
-    if (!MN_MAJOR && !CTA2 && p.conv_halo && warp < 2) {
+    if (!MN_MAJOR && !CTA2 && x_conv_halo && warp < 2) {
         // ================================================ implicit GEMM, halo mode (see GemmParams): producer + MMA issuer
         uint8_t* sH = smem;                               // [2][halo_bytes]
         uint8_t* sW = smem + 2 * p.halo_bytes;            // [9][B_BYTES] resident weights (barrier full[2])
@@ -218,7 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tma_load_2d_cg2(sA + s * A_BYTES, &tmA, (full0_leader + 8u * (uint32_t)s), kb * BLOCK_K, m0);
                         tma_load_2d_cg2(sB + s * B_BYTES, &tmB, (full0_leader + 8u * (uint32_t)s), kb * BLOCK_K, n0);
                     } else {
-                        if (p.conv_taps > 0) {
+                        if (x_conv_taps > 0) {
                             tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], 0, m0 + p.a_row_shift[kb]);
                         } else {
                             tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BLOCK_K, m0);
@@ -234,11 +241,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                     for (int a = 0; a < B_ROWS / 64; ++a) {
                         if (CTA2) tma_load_2d_cg2(sB + s * B_BYTES + a * (64 * 128), &tmB, (full0_leader + 8u * (uint32_t)s), n0 + a * 64, kb * 64);
-                        else if (p.wg_taps > 0) {
+                        else if (x_wg_taps > 0) {
                             // N tile = B_ROWS/64 filter taps; 64-column box `a` is tap n_blk*(B_ROWS/64)+a: the activation rows shifted
                             // by that tap's offset (taps past the last one: a box entirely past the last row -> zero fill)
                             const int tap = n_blk * (B_ROWS / 64) + a;
-                            const int row = tap < p.wg_taps ? kb * 64 + p.a_row_shift[tap] : p.K + 64;
+                            const int row = tap < x_wg_taps ? kb * 64 + p.a_row_shift[tap] : p.K + 64;
                             tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], 0, row);
                         }
                         else tma_load_2d(sB + s * B_BYTES + a * (64 * 128), &tmB, &full[s], n0 + a * 64, kb * 64);
@@ -316,7 +323,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // shared-memory transpose nor the two 256-thread barriers per tile (ncu r4q: 567 us, tensor pipe 18 % active, 3400 clk per
         // 128-row tile against an 860 clk MMA floor -- the epilogue was the kernel).
         constexpr bool CONV_REG = STATS && BLOCK_K == 32;
-        const bool reg_stats = STATS && p.stats_per_cta && (p.conv_taps == 0 || CONV_REG);
+        const bool reg_stats = STATS && p.stats_per_cta && (x_conv_taps == 0 || CONV_REG);
         u64 acc1[NCW][4], acc2[NCW][4];
 #pragma unroll
         for (int i = 0; i < NCW; ++i)
@@ -339,7 +346,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // (h, w) fall inside the valid output window and compact them.
             bool row_ok = grow < p.M;
             long long orow = grow;
-            if (p.conv_taps > 0) {          // (the host guarantees M < 2^31: 32-bit divisions)
+            if (x_conv_taps > 0) {          // (the host guarantees M < 2^31: 32-bit divisions)
                 const uint32_t gw = (uint32_t)p.conv_grid_w, gh = (uint32_t)p.conv_grid_h, g32 = (uint32_t)grow;
                 const uint32_t f = g32 / (gw * gh);
                 const uint32_t rem = g32 - f * gw * gh;
@@ -357,7 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     // allocation it has without trimming (merged into it, the statistics variant spilled 100 bytes per thread
                     // and the forward GEMM lost 12 %).
                     if (epi_is_bf16(EPI)) {
-                        if (p.tma_store) {
+                        if (x_tma_store) {
                             const uint32_t stg = smem_u32(s_store) + (uint32_t)(((warp - 2) * 2 + (int)(n_store & 1)) * 2048);
                             if (n_store >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
 #pragma unroll
@@ -377,7 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             for (int g = 0; g < 4; ++g)
                                 if (n_blk * BLOCK_N + c * 32 + g * 8 + 8 <= p.N) *reinterpret_cast<uint4*>(zrow + g * 8) = make_uint4(0u, 0u, 0u, 0u);
                         }
-                        if (STATS && p.conv_taps == 0 && !reg_stats) {
+                        if (STATS && x_conv_taps == 0 && !reg_stats) {
                             s_part[(q * 2 + 0) * BLOCK_N + c * 32 + lane] = 0.f;
                             s_part[(q * 2 + 1) * BLOCK_N + c * 32 + lane] = 0.f;
                         }
@@ -400,7 +407,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, r);
                 uint32_t fa[16], fb[16];
-                if (STATS && (p.conv_taps == 0 || CONV_REG)) {
+                if (STATS && (x_conv_taps == 0 || CONV_REG)) {
                     // The accumulator chunk is read a second time in the mma-fragment shape (16x256b: a thread holds
                     // 4 rows x 4 column pairs) for the column statistics.  The shared-memory crossbar carries the UMMA
                     // operand reads (~96 of 128 B/clk), so the epilogue must stay off it: the first version transposed
@@ -412,7 +419,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tmem_ld_wait();
                 // conv weight gradient: tile column c*32 belongs to tap n_blk*(BLOCK_N/64) + c/2, channel offset (c & 1)*32
                 const int wg_tap = n_blk * (BLOCK_N / 64) + (c >> 1);
-                const int gcol = p.wg_taps > 0 ? wg_tap * p.wg_tap_cols + (c & 1) * 32 : n_blk * BLOCK_N + c * 32;
+                const int gcol = x_wg_taps > 0 ? wg_tap * p.wg_tap_cols + (c & 1) * 32 : n_blk * BLOCK_N + c * 32;
                 if (EPI == EPI_BF16_BIAS) {
                     // folded-BatchNorm epilogue: per-column shift, optional residual tile (bf16, read straight from global: each
                     // thread owns one row = 64 contiguous bytes per chunk), optional ReLU -- all on the accumulator registers
@@ -453,7 +460,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
                 if (epi_is_bf16(EPI)) {
-                    if (p.tma_store) {
+                    if (x_tma_store) {
                         // bf16 rows -> 64B-swizzled staging tile (conflict-free 16 B stores) -> one bulk tensor store of the
                         // 32 x 32 box: full-line coalesced writes issued by the TMA unit instead of 32 row-scattered 16 B
                         // pieces per warp instruction; rows / columns past M / N are clipped by the tensor map.
@@ -492,7 +499,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                     }
-                    if (STATS && (p.conv_taps == 0 || CONV_REG)) {
+                    if (STATS && (x_conv_taps == 0 || CONV_REG)) {
                         u64 s1[4], s2[4];
                         uint32_t okm = 0xffffffffu;               // CONV_REG: bit l = row q*32 + l lies inside the valid output window
                         if (CONV_REG) okm = __ballot_sync(0xffffffffu, row_ok);
@@ -590,10 +597,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 } else {  // EPI_RED_F32: accumulate the split-K partial tile into fp32 memory
                     float* orow_p = reinterpret_cast<float*>(p.out) + orow * p.ldo + gcol;
-                    if (row_ok && (p.wg_taps == 0 || (wg_tap < p.wg_taps && (c & 1) * 32 < p.wg_tap_cols))) {
+                    if (row_ok && (x_wg_taps == 0 || (wg_tap < x_wg_taps && (c & 1) * 32 < p.wg_tap_cols))) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
-                            if (gcol + g * 4 + 4 <= p.N && (p.wg_taps == 0 || (c & 1) * 32 + g * 4 + 4 <= p.wg_tap_cols)) {
+                            if (gcol + g * 4 + 4 <= p.N && (x_wg_taps == 0 || (c & 1) * 32 + g * 4 + 4 <= p.wg_tap_cols)) {
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow_p + g * 4),
                                              "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
                                              "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
@@ -630,7 +637,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
-        if (epi_is_bf16(EPI) && p.tma_store && lane == 0) tma_store_wait_read<0>();
+        if (epi_is_bf16(EPI) && x_tma_store && lane == 0) tma_store_wait_read<0>();
         if (STATS && p.stats_per_cta) {
             if (reg_stats) {
                 // one cross-lane reduction for the whole kernel: full butterfly over the 8 lanes that share a column set
@@ -694,7 +701,7 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __n
 
 // ----------------------------------------------------------------------------------------------------
 // Persistent grid size: one CTA (or CTA pair) per SM (pair), capped by the number of work units.
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false>
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false, bool PLAIN = false>
 static int gemm_grid(int units) {
     if (!CTA2) return units < num_sms() ? units : num_sms();
     static int max_clusters[64] = {0};
@@ -703,7 +710,7 @@ static int gemm_grid(int units) {
     if (dev < 0 || dev >= 64) dev = 0;
     if (max_clusters[dev] == 0) {
         constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI, CTA2>(STAGES);
-        auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM>;
+        auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM, PLAIN>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() & ~1); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem;
@@ -720,18 +727,18 @@ static int gemm_grid(int units) {
     return 2 * c;
 }
 
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM>
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM, bool PLAIN = false>
 static int launch_gemm_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI, CTA2>(STAGES);
     static_assert(smem <= 232448, "smem budget");
-    auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM>;
+    auto kern = gemm_kernel<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM, PLAIN>;
     static bool attr_set = false;   // per-instantiation; benign race (idempotent)
     if (!attr_set) {
         XCP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
-    const int grid = gemm_grid<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM>(units);
+    const int grid = gemm_grid<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, TRIM, PLAIN>(units);
     if (!CTA2) {
         kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
         return check_cuda(cudaGetLastError(), "gemm_kernel launch");
@@ -756,6 +763,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
         q.n_last = 0; q.k_steps_last = 0;
         return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false>(tmA, tmB, q, stream);
     }
+    // plain pointwise / weight-gradient problems (BLOCK_K = 64, no taps, no halo, bulk-store bf16 epilogue): the specialised kernel
+    static int generic_env = -1;                                   // A/B hook: XCP_GEMM_GENERIC=1 keeps the all-modes kernel
+    if (generic_env < 0) { const char* e = getenv("XCP_GEMM_GENERIC"); generic_env = e ? atoi(e) : 0; }
+    if constexpr (BLOCK_K == 64) {
+        if (!generic_env && p.conv_taps == 0 && p.wg_taps == 0 && p.conv_halo == 0 && p.tma_store == (epi_is_bf16(EPI) ? 1 : 0))
+            return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, true>(tmA, tmB, p, stream);
+    }
     return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false>(tmA, tmB, p, stream);
 }
 
@@ -776,16 +790,17 @@ static void set_trim(GemmParams& p, int bn, int N, int K, int n_real, int k_real
     // OFF by default.  Measured on one box (gpurun r4l, bench.py step, ms): untrimmed 35.11 / 35.13, trimmed 35.35 / 35.36 -- the
     // narrower last N tile (224 of 256 columns) and the shortened last K block cost more in MMA / pipeline efficiency than the 8 % of
     // skipped tensor work returns, in all three GEMM families.  XCP_GEMM_TRIM=1 turns it on (A/B hook; tests cover both).
-    const char* on = getenv("XCP_GEMM_TRIM");
-    if (!(on != nullptr && on[0] == '1')) return;
-    if (n_real > 0 && n_real < N) {
+    const char* on = getenv("XCP_GEMM_TRIM");                            // "1": N and K, "n": N only, "k": K only
+    if (!(on != nullptr && (on[0] == '1' || on[0] == 'n' || on[0] == 'k'))) return;
+    const bool trim_n = on[0] != 'k', trim_k = on[0] != 'n';
+    if (trim_n && n_real > 0 && n_real < N) {
         const int last = n_real - bn * (p.num_n_tiles - 1);
         if (last > 0) {
             const int nl = (last + 15) / 16 * 16;
             if (nl < bn) p.n_last = nl;
         }
     }
-    if (k_real > 0 && k_real < K && p.splits == 1) {
+    if (trim_k && k_real > 0 && k_real < K && p.splits == 1) {
         const int last = k_real - 64 * (p.num_k_blocks - 1);
         if (last > 0) {
             const int ks = (last + 15) / 16;
