@@ -101,9 +101,12 @@ __host__ __device__ constexpr int fit_stages() {
 // PLAIN: the pointwise / weight-gradient GEMMs proper -- no implicit-convolution taps, no halo mode, bf16 epilogues through the bulk
 // tensor store.  Those run-time switches become compile-time constants, so the kernels that carry 37 % of the training step do
 // not pay (registers, predicated instructions) for the stem's modes.
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false, bool PLAIN = false>
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false, int PLAIN = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ GemmParams p) {
+    // PLAIN: 0 = every mode at run time, 1 = plain, 2 / 3 = plain with the statistics mode fixed as well (2: one N tile per CTA,
+    // register accumulators over all tiles; 3: several N tiles, per-tile partial rows): the other mode's accumulators and code go away.
+    const int x_stats_per_cta = PLAIN == 2 ? 1 : (PLAIN == 3 ? 0 : p.stats_per_cta);
     const int x_conv_taps = PLAIN ? 0 : p.conv_taps;
     const int x_wg_taps = PLAIN ? 0 : p.wg_taps;
     const int x_tma_store = PLAIN ? (epi_is_bf16(EPI) ? 1 : 0) : p.tma_store;
@@ -323,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // shared-memory transpose nor the two 256-thread barriers per tile (ncu r4q: 567 us, tensor pipe 18 % active, 3400 clk per
         // 128-row tile against an 860 clk MMA floor -- the epilogue was the kernel).
         constexpr bool CONV_REG = STATS && BLOCK_K == 32;
-        const bool reg_stats = STATS && p.stats_per_cta && (x_conv_taps == 0 || CONV_REG);
+        const bool reg_stats = STATS && x_stats_per_cta && (x_conv_taps == 0 || CONV_REG);
         u64 acc1[NCW][4], acc2[NCW][4];
 #pragma unroll
         for (int i = 0; i < NCW; ++i)
@@ -626,7 +629,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             s1 += s_part[(qq * 2 + 0) * BLOCK_N + c];
                             s2 += s_part[(qq * 2 + 1) * BLOCK_N + c];
                         }
-                        if (p.stats_per_cta) {
+                        if (x_stats_per_cta) {
                             racc1 += s1; racc2 += s2;
                         } else if ((long long)m_blk * BLOCK_M < p.M) {   // (pair mode: the odd tail block has no rows)
                             p.stats[((long long)m_blk * 2 + 0) * p.N + gcol] = s1;
@@ -638,7 +641,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
         if (epi_is_bf16(EPI) && x_tma_store && lane == 0) tma_store_wait_read<0>();
-        if (STATS && p.stats_per_cta) {
+        if (STATS && x_stats_per_cta) {
             if (reg_stats) {
                 // one cross-lane reduction for the whole kernel: full butterfly over the 8 lanes that share a column set
                 // (xor 4, 8, 16), lanes 0..3 of each warp publish their 8 column pairs per chunk, then the 4 lane quarters
@@ -701,7 +704,7 @@ __global__ void gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __n
 
 // ----------------------------------------------------------------------------------------------------
 // Persistent grid size: one CTA (or CTA pair) per SM (pair), capped by the number of work units.
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false, bool PLAIN = false>
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM = false, int PLAIN = 0>
 static int gemm_grid(int units) {
     if (!CTA2) return units < num_sms() ? units : num_sms();
     static int max_clusters[64] = {0};
@@ -727,7 +730,7 @@ static int gemm_grid(int units) {
     return 2 * c;
 }
 
-template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM, bool PLAIN = false>
+template <int BLOCK_N, int EPI, bool MN_MAJOR, int STAGES, int BLOCK_K, bool CTA2, bool TRIM, int PLAIN = 0>
 static int launch_gemm_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     constexpr int smem = gemm_smem_bytes<BLOCK_N, BLOCK_K, EPI, CTA2>(STAGES);
     static_assert(smem <= 232448, "smem budget");
@@ -767,8 +770,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     static int generic_env = -1;                                   // A/B hook: XCP_GEMM_GENERIC=1 keeps the all-modes kernel
     if (generic_env < 0) { const char* e = getenv("XCP_GEMM_GENERIC"); generic_env = e ? atoi(e) : 0; }
     if constexpr (BLOCK_K == 64) {
-        if (!generic_env && p.conv_taps == 0 && p.wg_taps == 0 && p.conv_halo == 0 && p.tma_store == (epi_is_bf16(EPI) ? 1 : 0))
-            return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, true>(tmA, tmB, p, stream);
+        if (!generic_env && p.conv_taps == 0 && p.wg_taps == 0 && p.conv_halo == 0 && p.tma_store == (epi_is_bf16(EPI) ? 1 : 0)) {
+            if constexpr (EPI == EPI_BF16_STATS) {
+                if (p.stats_per_cta) return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, 2>(tmA, tmB, p, stream);
+                return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, 3>(tmA, tmB, p, stream);
+            }
+            return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, 1>(tmA, tmB, p, stream);
+        }
     }
     return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false>(tmA, tmB, p, stream);
 }
