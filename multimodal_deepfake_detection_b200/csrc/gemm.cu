@@ -107,6 +107,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // PLAIN: 0 = every mode at run time, 1 = plain, 2 / 3 = plain with the statistics mode fixed as well (2: one N tile per CTA,
     // register accumulators over all tiles; 3: several N tiles, per-tile partial rows): the other mode's accumulators and code go away.
     const int x_stats_per_cta = PLAIN == 2 ? 1 : (PLAIN == 3 ? 0 : p.stats_per_cta);
+    // folded-BatchNorm epilogue (EPI_BF16_BIAS): PLAIN 2 = no residual tile (its prefetch registers and staging code go away), 3 = residual
+    const void* const x_residual = (EPI == EPI_BF16_BIAS && PLAIN == 2) ? nullptr : p.residual;
     const int x_conv_taps = PLAIN ? 0 : p.conv_taps;
     const int x_wg_taps = PLAIN ? 0 : p.wg_taps;
     const int x_tma_store = PLAIN ? (epi_is_bf16(EPI) ? 1 : 0) : p.tma_store;
@@ -395,11 +397,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     continue;
                 }
                 uint4 resv[4];
-                if (EPI == EPI_BF16_BIAS && p.residual != nullptr) {
+                if (EPI == EPI_BF16_BIAS && x_residual != nullptr) {
                     // residual tile (32 rows x 32 bf16): coalesced 16-byte loads (4 lanes per 64-byte row piece, 8 rows per
                     // instruction), issued before the accumulator read so that their latency overlaps it
                     const long long row0 = (long long)m_blk * BLOCK_M + q * 32;
-                    const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual) + n_blk * BLOCK_N + c * 32 + (lane & 3) * 8;
+                    const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(x_residual) + n_blk * BLOCK_N + c * 32 + (lane & 3) * 8;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = (lane >> 2) + 8 * i;
@@ -435,7 +437,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         r[g * 4 + 2] = __float_as_uint(__uint_as_float(r[g * 4 + 2]) + b.z);
                         r[g * 4 + 3] = __float_as_uint(__uint_as_float(r[g * 4 + 3]) + b.w);
                     }
-                    if (p.residual != nullptr) {
+                    if (x_residual != nullptr) {
                         // -> swizzled per-warp staging -> every thread reads back its own accumulator row.  (Reading the row straight
                         // from global, 64 B per thread at the row pitch, made the GEMM 3x slower: 251 vs 85 us.)
                         const uint32_t rs = smem_u32(s_res) + (uint32_t)(warp - 2) * 2048u;
@@ -771,6 +773,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     if (generic_env < 0) { const char* e = getenv("XCP_GEMM_GENERIC"); generic_env = e ? atoi(e) : 0; }
     if constexpr (BLOCK_K == 64) {
         if (!generic_env && p.conv_taps == 0 && p.wg_taps == 0 && p.conv_halo == 0 && p.tma_store == (epi_is_bf16(EPI) ? 1 : 0)) {
+            if constexpr (EPI == EPI_BF16_BIAS) {
+                if (p.residual == nullptr) return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, 2>(tmA, tmB, p, stream);
+                return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, 3>(tmA, tmB, p, stream);
+            }
             if constexpr (EPI == EPI_BF16_STATS) {
                 if (p.stats_per_cta) return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, 2>(tmA, tmB, p, stream);
                 return launch_gemm_inst<BLOCK_N, EPI, MN_MAJOR, STAGES, BLOCK_K, CTA2, false, 3>(tmA, tmB, p, stream);
