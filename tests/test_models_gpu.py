@@ -374,7 +374,7 @@ def test_arcface_module_both_call_styles(golden):
 
 
 def test_short_training_curve_tracks_oracle():
-    """30 Adam steps on a fixed tiny batch: our loss curve against the fp32 oracle driven by the same optimizer."""
+    """45 Adam steps on a fixed tiny batch: our loss curve against the fp32 oracle driven by the same optimizer."""
     m, full = _lstm_models(32, XceptionLSTMV)
     g = torch.Generator().manual_seed(4)
     clips = torch.rand(8, 2, 3, 139, 139, generator=g).to(DEV)
@@ -388,7 +388,7 @@ def test_short_training_curve_tracks_oracle():
     opt_o = torch.optim.Adam([fo[k] for k in trainable], lr=1e-3)
     opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-3)
     ours, ref = [], []
-    for _ in range(30):
+    for _ in range(45):
         opt_o.zero_grad(); ns = {}
         lo = F.binary_cross_entropy(O.xception_lstm_forward(fo, clips, training=True, new_stats=ns), y); lo.backward(); opt_o.step()
         for k, v in ns.items():
@@ -406,7 +406,9 @@ def test_short_training_curve_tracks_oracle():
     assert np.abs(ours[:2] - ref[:2]).max() < 5e-3 and np.abs(ours[2:4] - ref[2:4]).max() < 2e-2 and abs(ours[4] - ref[4]) < 6e-2, \
         (ours[:5].tolist(), ref[:5].tolist())
     # both over-fit the batch; how fast the tail falls depends on bf16 round-off (summation order of the BN statistics)
-    # (no monotonicity claim on the tail: once the loss is ~1e-3 it wiggles by its own size from step to step)
+    # (no monotonicity claim on the tail: once the loss is ~1e-3 it wiggles by its own size from step to step).  lr = 1e-3 makes
+    # the path chaotic: five numerically equivalent kernel variants (env A/B hooks) put steps 25-30 anywhere between 0.0 and a
+    # 0.2-0.35 bump, and all of them are at ~1e-3 by step 40 -- so the tail is judged after 45 steps, not 30.
     assert ours[-5:].mean() < 0.25 and ours[-5:].mean() < 0.5 * ours[:5].mean() and ref[-5:].mean() < 0.25, \
         (ours[:5].tolist(), ours[-5:].tolist(), ref[-5:].tolist())
 
