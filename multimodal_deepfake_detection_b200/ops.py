@@ -572,6 +572,7 @@ def linear_small_bwd(delta_raw, out_act, drop_scale, a, W, dW, db, want_din=True
 
 _HEAD_STATE = {}
 _HEAD_BARS = {}
+_HEAD_POOL = {}
 
 
 def head_state(device: torch.device):
@@ -589,8 +590,14 @@ def head_state(device: torch.device):
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     bars = _HEAD_BARS.get(key)
     if bars is None:
-        with torch.cuda.device(device):
-            bars = _HEAD_BARS[key] = torch.zeros((8,), device=device, dtype=torch.int32)
+        # slots come out of one zeroed pool per device made at the first (eager) call, so that a stream first seen DURING a CUDA-graph
+        # capture needs no allocation (which would live in that graph's private memory pool) and no captured fill kernel
+        pool = _HEAD_POOL.get(device.index)
+        if pool is None or pool[1] >= pool[0].shape[0]:
+            with torch.cuda.device(device):
+                pool = _HEAD_POOL[device.index] = [torch.zeros((16, 8), device=device, dtype=torch.int32), 0]
+        bars = _HEAD_BARS[key] = pool[0][pool[1]]
+        pool[1] += 1
     return bars, rng
 
 
