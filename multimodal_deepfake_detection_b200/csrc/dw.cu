@@ -597,6 +597,9 @@ static int dw_grid(const DwGeom& g, int ctas_per_sm) {
     return (int)(per_ct * g.c_tiles);
 }
 
+int dw_small_try_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift, int relu, void* dz,
+                     const void* add_full, const void* add_half, float* dw, float* bnsum, int F, int H, int W, int C, int c_real,
+                     cudaStream_t st, int* handled);
 int dws_try_fwd(const void* x, const float* w9, const float* scale, const float* shift, int relu, void* out, int F, int H, int W,
                 int C, cudaStream_t st, int* handled);          // dw_stream.cu
 
@@ -957,6 +960,12 @@ extern "C" int xcp_dw3x3_bwd(const void* dD, const void* xin, const float* w9, c
     XCP_REQUIRE(dw != nullptr && (scale == nullptr || bnsum != nullptr), "xcp_dw3x3_bwd: dw / bnsum missing");
     XCP_REQUIRE((long long)F * H * W < (1LL << 30), "xcp_dw3x3_bwd: too many pixels for 32-bit tile indices");
     XCP_CUDA(cudaSetDevice(device));
+    {   // 2x2 / 4x4 maps (audio model): register-resident whole-image kernel (dw_small_bwd.cu)
+        int handled = 0;
+        const int r = dw_small_try_bwd(dD, xin, w9, scale, shift, relu, dz, add_full, add_half, dw, bnsum, F, H, W, C, c_real,
+                                       (cudaStream_t)stream, &handled);
+        if (handled) return r;
+    }
     // one 512-thread CTA per SM (15 compute warps) measured faster than two 256-thread CTAs on every shape (477 vs 623 us at
     // 147x147x128, 213 vs 309 us at 37x37x728, 65 vs 76 us at 19x19x728; gpurun r2e) except with the staged identity-skip tile
     int dbg_minb = 0;

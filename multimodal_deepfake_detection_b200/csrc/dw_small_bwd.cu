@@ -1,0 +1,139 @@
+// Depthwise 3x3 backward on tiny maps (S x S, S = 2 / 4: the middle and exit flow of the audio model's 64x64 patches,
+// XceptionLSTMA.py:46 -> 4x4x728 x26 layers and 2x2x1024/1536).  Same fused contract as dw3x3_bwd_kernel (dw.cu): dgrad,
+// 9-tap weight gradient, BN-affine / ReLU prologue and mask, identity-skip / stride-2-skip gradient adds, BatchNorm-backward sums.
+//
+// The TMA halo-tile kernel stages (S+2)^2 pixels per S^2 image in 6x6 boxes and ran these layers at 12 % of HBM (92 us per launch
+// at 960 patches: 19 % of the audio model's training step, bench.py --config c4).  Here a thread owns one channel pair of `fpt`
+// whole images: the S^2 gradient pixels of an image sit in registers (coalesced 4-byte loads: a warp reads 128 contiguous bytes
+// per pixel), every operand byte is read once, dz is written once, and the weight-gradient / BatchNorm sums stay in registers
+// across the thread's images before one atomic per (tap, channel).
+#include "common.cuh"
+
+namespace xcp {
+
+template <int S, bool AFFINE, bool RELU, int ADDM>
+__global__ void __launch_bounds__(128)
+dw3x3_small_bwd_kernel(const __nv_bfloat162* __restrict__ dD, const __nv_bfloat162* __restrict__ xin, const float* __restrict__ w9,
+                       const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat162* __restrict__ dz,
+                       const __nv_bfloat162* __restrict__ add_full, const __nv_bfloat162* __restrict__ add_half,
+                       float* __restrict__ dw, float* __restrict__ bnsum, int F, int C, int c_real, int add_pre, int fpt) {
+    constexpr int SH = (S + 1) / 2;                                   // stride-2 skip gradient: [F, SH, SH, C]
+    const int C2 = C >> 1;
+    const long long idx = blockIdx.x * 128LL + threadIdx.x;
+    const int c2 = (int)(idx % C2);
+    const long long f0 = (idx / C2) * fpt;
+    if (f0 >= F) return;
+    const long long f1 = f0 + fpt < F ? f0 + fpt : F;
+    float2 wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[k] = *reinterpret_cast<const float2*>(w9 + (long long)k * C + 2 * c2);
+    float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+    if (AFFINE) { sc = *reinterpret_cast<const float2*>(scale + 2 * c2); sh = *reinterpret_cast<const float2*>(shift + 2 * c2); }
+    float2 dwa[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dwa[k] = make_float2(0.f, 0.f);
+    float2 sdz = make_float2(0.f, 0.f), sdzy = make_float2(0.f, 0.f);
+    const bool pre = (ADDM != 0) && add_pre != 0;
+
+    for (long long f = f0; f < f1; ++f) {
+        const long long base = f * (S * S) * C2 + c2;
+        float2 g[S][S], yv[S][S];
+#pragma unroll
+        for (int y = 0; y < S; ++y)
+#pragma unroll
+            for (int x = 0; x < S; ++x) {
+                g[y][x] = __bfloat1622float2(dD[base + (long long)(y * S + x) * C2]);
+                yv[y][x] = __bfloat1622float2(xin[base + (long long)(y * S + x) * C2]);
+            }
+#pragma unroll
+        for (int y = 0; y < S; ++y)
+#pragma unroll
+            for (int x = 0; x < S; ++x) {
+                const float2 v = yv[y][x];
+                float2 z = v;
+                if (AFFINE) { z.x = fmaf(v.x, sc.x, sh.x); z.y = fmaf(v.y, sc.y, sh.y); }
+                float2 av = z;
+                if (RELU) { av.x = fmaxf(z.x, 0.f); av.y = fmaxf(z.y, 0.f); }
+                float2 d = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int yy = y + 1 - kh, xx = x + 1 - kw;            // the output pixel that read (y, x) through tap (kh, kw)
+                        if (yy >= 0 && yy < S && xx >= 0 && xx < S) {
+                            const float2 gg = g[yy][xx];
+                            d.x = fmaf(wk[kh * 3 + kw].x, gg.x, d.x); d.y = fmaf(wk[kh * 3 + kw].y, gg.y, d.y);
+                            dwa[kh * 3 + kw].x = fmaf(av.x, gg.x, dwa[kh * 3 + kw].x); dwa[kh * 3 + kw].y = fmaf(av.y, gg.y, dwa[kh * 3 + kw].y);
+                        }
+                    }
+                if (RELU && !pre) { d.x = z.x > 0.f ? d.x : 0.f; d.y = z.y > 0.f ? d.y : 0.f; }
+                if (ADDM & 1) {
+                    const float2 a = __bfloat1622float2(add_full[base + (long long)(y * S + x) * C2]);
+                    d.x += a.x; d.y += a.y;
+                }
+                if ((ADDM & 2) && (y & 1) == 0 && (x & 1) == 0) {
+                    const float2 a = __bfloat1622float2(add_half[(f * (SH * SH) + (y >> 1) * SH + (x >> 1)) * C2 + c2]);
+                    d.x += a.x; d.y += a.y;
+                }
+                if (RELU && pre) { d.x = z.x > 0.f ? d.x : 0.f; d.y = z.y > 0.f ? d.y : 0.f; }
+                if (AFFINE) { sdz.x += d.x; sdz.y += d.y; sdzy.x = fmaf(d.x, v.x, sdzy.x); sdzy.y = fmaf(d.y, v.y, sdzy.y); }
+                dz[base + (long long)(y * S + x) * C2] = __floats2bfloat162_rn(d.x, d.y);
+            }
+    }
+    const int c = 2 * c2;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (c < c_real) atomicAdd(dw + (long long)c * 9 + k, dwa[k].x);
+        if (c + 1 < c_real) atomicAdd(dw + (long long)(c + 1) * 9 + k, dwa[k].y);
+    }
+    if (AFFINE) {
+        atomicAdd(bnsum + c, sdz.x); atomicAdd(bnsum + c + 1, sdz.y);
+        atomicAdd(bnsum + C + c, sdzy.x); atomicAdd(bnsum + C + c + 1, sdzy.y);
+    }
+}
+
+template <int S>
+static int launch_small_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift, int relu, void* dz,
+                            const void* add_full, const void* add_half, float* dw, float* bnsum, int F, int C, int c_real,
+                            cudaStream_t st) {
+    const int C2 = C / 2;
+    // enough threads to fill the machine, few enough images per thread to keep the atomics down: ~64 K threads
+    long long fpt = ((long long)F * C2) / 65536;
+    if (fpt < 1) fpt = 1;
+    if (fpt > 16) fpt = 16;
+    const long long groups = (F + fpt - 1) / fpt;
+    const long long n = groups * C2;
+    const int grid = (int)((n + 127) / 128);
+    const int addm = (add_full != nullptr ? 1 : 0) | (add_half != nullptr ? 2 : 0);
+    const int variant = ((scale != nullptr) ? 8 : 0) | (relu ? 4 : 0) | addm;
+    const int add_pre = relu == 2 ? 1 : 0;
+#define SMALL_BWD(A, R, M)                                                                                                            \
+    case ((A ? 8 : 0) | (R ? 4 : 0) | M):                                                                                             \
+        dw3x3_small_bwd_kernel<S, A, R, M><<<grid, 128, 0, st>>>((const __nv_bfloat162*)dD, (const __nv_bfloat162*)xin, w9, scale, shift, \
+            (__nv_bfloat162*)dz, (const __nv_bfloat162*)add_full, (const __nv_bfloat162*)add_half, dw, bnsum, F, C, c_real, add_pre, (int)fpt); \
+        break;
+    switch (variant) {
+        SMALL_BWD(false, false, 0) SMALL_BWD(false, false, 1) SMALL_BWD(false, false, 2) SMALL_BWD(false, false, 3)
+        SMALL_BWD(false, true, 0) SMALL_BWD(false, true, 1) SMALL_BWD(false, true, 2) SMALL_BWD(false, true, 3)
+        SMALL_BWD(true, false, 0) SMALL_BWD(true, false, 1) SMALL_BWD(true, false, 2) SMALL_BWD(true, false, 3)
+        SMALL_BWD(true, true, 0) SMALL_BWD(true, true, 1) SMALL_BWD(true, true, 2) SMALL_BWD(true, true, 3)
+        default: break;
+    }
+#undef SMALL_BWD
+    return check_cuda(cudaGetLastError(), "dw3x3_small_bwd launch");
+}
+
+// -> handled = 1 and the launch status when the shape is one of the register-resident ones; handled = 0 otherwise
+int dw_small_try_bwd(const void* dD, const void* xin, const float* w9, const float* scale, const float* shift, int relu, void* dz,
+                     const void* add_full, const void* add_half, float* dw, float* bnsum, int F, int H, int W, int C, int c_real,
+                     cudaStream_t st, int* handled) {
+    *handled = 0;
+    if (H != W || (H != 2 && H != 4)) return 0;
+    const char* e = getenv("XCP_DW_NO_SMALL_BWD");                                    // A/B hook
+    if (e != nullptr && e[0] == '1') return 0;
+    *handled = 1;
+    if (H == 2) return launch_small_bwd<2>(dD, xin, w9, scale, shift, relu, dz, add_full, add_half, dw, bnsum, F, C, c_real, st);
+    return launch_small_bwd<4>(dD, xin, w9, scale, shift, relu, dz, add_full, add_half, dw, bnsum, F, C, c_real, st);
+}
+
+}  // namespace xcp

@@ -695,3 +695,56 @@ def test_stem_conv1_affine_inference_form(F_, H):
     out_u8 = ops.stem_conv1_fwd_affine(u8, w, scale, shift)
     ref_u8 = F.relu(F.conv2d(u8.permute(0, 3, 1, 2).float() / 255.0, w, stride=2) * scale[None, :, None, None] + shift[None, :, None, None])
     assert rel_err(out_u8.float().permute(0, 3, 1, 2), ref_u8) < 8e-3
+
+
+@pytest.mark.parametrize("F_,S,C", [(5, 4, 768), (1100, 4, 768), (3, 2, 1536), (700, 2, 1024), (9, 4, 64)])
+@pytest.mark.parametrize("mode", ["plain", "relu", "affine_relu", "full", "half", "both", "pre_half"])
+def test_dw3x3_small_bwd_tiny_maps(F_, S, C, mode):
+    """The register-resident depthwise backward of the audio model's 4x4 / 2x2 maps (csrc/dw_small_bwd.cu) in every fused mode
+    against torch autograd: dgrad, 9-tap weight gradient (logical channels of a padded pitch), BN-affine / ReLU mask,
+    identity-skip and stride-2-skip gradient adds (outside and inside the mask), BatchNorm-backward sums; enough frames for
+    several images per thread and a ragged last frame group."""
+    Cr = 728 if C == 768 else C
+    x = rnd(F_, S, S, C, seed=71, dtype=torch.bfloat16)
+    wt = rnd(Cr, 1, 3, 3, seed=72, scale=0.4)
+    dD = rnd(F_, S, S, C, seed=73, dtype=torch.bfloat16)
+    if Cr < C:
+        x[..., Cr:] = 0; dD[..., Cr:] = 0
+    w9 = ops.pack_dw(wt, pad=True)                  # [9][768]: zero taps in the pad channels
+    affine = mode in ("affine_relu", "pre_half")
+    relu = mode != "plain"
+    scale = shift = None
+    if affine:
+        scale = torch.zeros(C, device=DEV); shift = torch.zeros(C, device=DEV)
+        scale[:Cr] = rnd(Cr, seed=74) * 0.5 + 1.0; shift[:Cr] = rnd(Cr, seed=75, scale=0.3)
+    Sh = (S + 1) // 2
+    full = rnd(F_, S, S, C, seed=76, dtype=torch.bfloat16) if mode in ("full", "both") else None
+    half = rnd(F_, Sh, Sh, C, seed=77, dtype=torch.bfloat16) if mode in ("half", "both", "pre_half") else None
+    gw = torch.zeros(Cr, 1, 3, 3, device=DEV)
+    dz, bns = ops.dw3x3_bwd(dD, x, w9, scale, shift, 2 if mode == "pre_half" else relu, gw, add_full=full, add_half=half)
+
+    xt = x.float().permute(0, 3, 1, 2)[:, :Cr]
+    z = xt.clone()
+    if affine:
+        z = z * scale[None, :Cr, None, None] + shift[None, :Cr, None, None]
+    z.requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    a = F.relu(z) if relu else z
+    out = F.conv2d(a, wr, padding=1, groups=Cr)
+    loss = (out * dD.float().permute(0, 3, 1, 2)[:, :Cr]).sum()
+    if mode == "pre_half":              # the stride-2 consumer reads the ACTIVATED input: its gradient goes inside the mask
+        loss = loss + (a[:, :, ::2, ::2] * half.float().permute(0, 3, 1, 2)[:, :Cr]).sum()
+    loss.backward()
+    ref = z.grad.clone()
+    if full is not None:
+        ref = ref + full.float().permute(0, 3, 1, 2)[:, :Cr]
+    if half is not None and mode != "pre_half":
+        ref[:, :, ::2, ::2] += half.float().permute(0, 3, 1, 2)[:, :Cr]
+    got = dz.float().permute(0, 3, 1, 2)
+    assert rel_err(got[:, :Cr], ref) < 8e-3
+    if Cr < C:
+        assert float(got[:, Cr:].abs().max()) == 0.0 or full is not None or half is not None
+    assert rel_err(gw, wr.grad) < 2e-3
+    if affine:
+        assert rel_err(bns[0][:Cr], ref.sum((0, 2, 3))) < 2e-2
+        assert rel_err(bns[1][:Cr], (ref * xt).sum((0, 2, 3))) < 2e-2
