@@ -12,23 +12,28 @@
 namespace xcp {
 
 template <int S, bool AFFINE, bool RELU, int ADDM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 dw3x3_small_bwd_kernel(const __nv_bfloat162* __restrict__ dD, const __nv_bfloat162* __restrict__ xin, const float* __restrict__ w9,
                        const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat162* __restrict__ dz,
                        const __nv_bfloat162* __restrict__ add_full, const __nv_bfloat162* __restrict__ add_half,
                        float* __restrict__ dw, float* __restrict__ bnsum, int F, int C, int c_real, int add_pre, int fpt) {
     constexpr int SH = (S + 1) / 2;                                   // stride-2 skip gradient: [F, SH, SH, C]
+    // block = 32 channel pairs (lanes: 128 contiguous bytes per pixel) x 8 frame groups (warps): the eight warps' weight-gradient
+    // and BatchNorm sums of the same channels are added in shared memory before the atomics (an eighth of them reaches L2; one
+    // atomic per thread and (tap, channel) made the first version atomic bound: 61 us per launch at 960 patches, now 31 -> see DESIGN)
+    __shared__ float s_red[8][22][32];
     const int C2 = C >> 1;
-    const long long idx = blockIdx.x * 128LL + threadIdx.x;
-    const int c2 = (int)(idx % C2);
-    const long long f0 = (idx / C2) * fpt;
-    if (f0 >= F) return;
-    const long long f1 = f0 + fpt < F ? f0 + fpt : F;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int ctiles = (C2 + 31) / 32;
+    const int c2 = (int)(blockIdx.x % ctiles) * 32 + lane;
+    const long long f0 = ((long long)(blockIdx.x / ctiles) * 8 + wrp) * fpt;
+    const bool live = c2 < C2 && f0 < F;
+    const long long f1 = live ? (f0 + fpt < F ? f0 + fpt : F) : f0;
     float2 wk[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wk[k] = *reinterpret_cast<const float2*>(w9 + (long long)k * C + 2 * c2);
+    for (int k = 0; k < 9; ++k) wk[k] = live ? *reinterpret_cast<const float2*>(w9 + (long long)k * C + 2 * c2) : make_float2(0.f, 0.f);
     float2 sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
-    if (AFFINE) { sc = *reinterpret_cast<const float2*>(scale + 2 * c2); sh = *reinterpret_cast<const float2*>(shift + 2 * c2); }
+    if (AFFINE && live) { sc = *reinterpret_cast<const float2*>(scale + 2 * c2); sh = *reinterpret_cast<const float2*>(shift + 2 * c2); }
     float2 dwa[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) dwa[k] = make_float2(0.f, 0.f);
@@ -80,15 +85,18 @@ dw3x3_small_bwd_kernel(const __nv_bfloat162* __restrict__ dD, const __nv_bfloat1
                 dz[base + (long long)(y * S + x) * C2] = __floats2bfloat162_rn(d.x, d.y);
             }
     }
-    const int c = 2 * c2;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        if (c < c_real) atomicAdd(dw + (long long)c * 9 + k, dwa[k].x);
-        if (c + 1 < c_real) atomicAdd(dw + (long long)(c + 1) * 9 + k, dwa[k].y);
-    }
-    if (AFFINE) {
-        atomicAdd(bnsum + c, sdz.x); atomicAdd(bnsum + c + 1, sdz.y);
-        atomicAdd(bnsum + C + c, sdzy.x); atomicAdd(bnsum + C + c + 1, sdzy.y);
+    for (int k = 0; k < 9; ++k) { s_red[wrp][2 * k][lane] = dwa[k].x; s_red[wrp][2 * k + 1][lane] = dwa[k].y; }
+    s_red[wrp][18][lane] = sdz.x; s_red[wrp][19][lane] = sdz.y; s_red[wrp][20][lane] = sdzy.x; s_red[wrp][21][lane] = sdzy.y;
+    __syncthreads();
+    const int c = 2 * c2;
+    for (int j = wrp; j < (AFFINE ? 22 : 18); j += 8) {              // warp w adds rows w, w+8, ...: lanes = channel pairs
+        const float v = ((s_red[0][j][lane] + s_red[1][j][lane]) + (s_red[2][j][lane] + s_red[3][j][lane])) +
+                        ((s_red[4][j][lane] + s_red[5][j][lane]) + (s_red[6][j][lane] + s_red[7][j][lane]));
+        if (c2 >= C2) continue;
+        const int ch = c + (j & 1);
+        if (j < 18) { if (ch < c_real) atomicAdd(dw + (long long)ch * 9 + (j >> 1), v); }
+        else atomicAdd(bnsum + (long long)((j - 18) >> 1) * C + ch, v);
     }
 }
 
@@ -102,14 +110,13 @@ static int launch_small_bwd(const void* dD, const void* xin, const float* w9, co
     if (fpt < 1) fpt = 1;
     if (fpt > 16) fpt = 16;
     const long long groups = (F + fpt - 1) / fpt;
-    const long long n = groups * C2;
-    const int grid = (int)((n + 127) / 128);
+    const int grid = (int)(((groups + 7) / 8) * ((C2 + 31) / 32));
     const int addm = (add_full != nullptr ? 1 : 0) | (add_half != nullptr ? 2 : 0);
     const int variant = ((scale != nullptr) ? 8 : 0) | (relu ? 4 : 0) | addm;
     const int add_pre = relu == 2 ? 1 : 0;
 #define SMALL_BWD(A, R, M)                                                                                                            \
     case ((A ? 8 : 0) | (R ? 4 : 0) | M):                                                                                             \
-        dw3x3_small_bwd_kernel<S, A, R, M><<<grid, 128, 0, st>>>((const __nv_bfloat162*)dD, (const __nv_bfloat162*)xin, w9, scale, shift, \
+        dw3x3_small_bwd_kernel<S, A, R, M><<<grid, 256, 0, st>>>((const __nv_bfloat162*)dD, (const __nv_bfloat162*)xin, w9, scale, shift, \
             (__nv_bfloat162*)dz, (const __nv_bfloat162*)add_full, (const __nv_bfloat162*)add_half, dw, bnsum, F, C, c_real, add_pre, (int)fpt); \
         break;
     switch (variant) {
