@@ -326,10 +326,11 @@ bool cluster_disabled() {
 // Returns 0 = launched, LSTM_CLUSTER_NA = not applicable (caller falls back to the single-CTA kernel), else a CUDA error.
 int lstm_fwd_cluster(const float* xproj, const float* b_ih, const float* b_hh, const void* w_hh_t, float* h_out, float* gates,
                      float* cstate, float* hn, float* cn, int B, int T, int H, cudaStream_t st) {
-    if (cluster_disabled() || (H != 256 && H != 512)) return LSTM_CLUSTER_NA;
+    if (cluster_disabled() || (H != 128 && H != 256 && H != 512)) return LSTM_CLUSTER_NA;
     void* args[] = {&xproj, &b_ih, &b_hh, &w_hh_t, &h_out, &gates, &cstate, &hn, &cn, &B, &T};
     const size_t smem = (size_t)2 * 2 * LC_NB * (H + 8) * 2 + (size_t)LC_NB * 132 * 4 + 2 * LC_NB * 32 * 2;
-    static int st512[64] = {0}, st256[64] = {0};
+    static int st512[64] = {0}, st256[64] = {0}, st128[64] = {0};
+    if (H == 128) return launch_cluster(lstm_fwd_cluster_kernel<128>, st128, 4, B, smem, st, args, "lstm_fwd_cluster launch");
     if (H == 512) return launch_cluster(lstm_fwd_cluster_kernel<512>, st512, 16, B, smem, st, args, "lstm_fwd_cluster launch");
     return launch_cluster(lstm_fwd_cluster_kernel<256>, st256, 8, B, smem, st, args, "lstm_fwd_cluster launch");
 }
@@ -337,10 +338,11 @@ int lstm_fwd_cluster(const float* xproj, const float* b_ih, const float* b_hh, c
 int lstm_bwd_cluster(const float* dout, const float* dhn, const float* dcn, const float* gates, const float* cstate,
                      const float* hstate, const void* w_hh, void* dgates, void* hprev, float* dbias_ih, float* dbias_hh, int B,
                      int T, int H, cudaStream_t st) {
-    if (cluster_disabled() || (H != 256 && H != 512)) return LSTM_CLUSTER_NA;
+    if (cluster_disabled() || (H != 128 && H != 256 && H != 512)) return LSTM_CLUSTER_NA;
     void* args[] = {&dout, &dhn, &dcn, &gates, &cstate, &hstate, &w_hh, &dgates, &hprev, &dbias_ih, &dbias_hh, &B, &T};
     const size_t smem = (size_t)2 * (H / LC_U) * LC_NB * 32 * 4 + (size_t)LC_NB * (H + 4) * 4 + (size_t)2 * LC_NB * (128 + 8) * 2;
-    static int st512[64] = {0}, st256[64] = {0};
+    static int st512[64] = {0}, st256[64] = {0}, st128[64] = {0};
+    if (H == 128) return launch_cluster(lstm_bwd_cluster_kernel<128>, st128, 4, B, smem, st, args, "lstm_bwd_cluster launch");
     if (H == 512) return launch_cluster(lstm_bwd_cluster_kernel<512>, st512, 16, B, smem, st, args, "lstm_bwd_cluster launch");
     return launch_cluster(lstm_bwd_cluster_kernel<256>, st256, 8, B, smem, st, args, "lstm_bwd_cluster launch");
 }

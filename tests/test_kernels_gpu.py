@@ -413,7 +413,7 @@ def test_layout_and_packing():
 
 # ------------------------------------------------------------------------------------------------ LSTM / head
 @pytest.mark.parametrize("B,T,H", [(4, 16, 128), (2, 5, 32), (3, 7, 512), (8, 120, 512), (11, 9, 512), (1, 1, 512), (5, 6, 256),
-                                   (16, 33, 256)])
+                                   (16, 33, 256), (16, 16, 128), (8, 120, 128), (9, 3, 128), (1, 1, 128)])
 def test_lstm_fwd_bwd(B, T, H):
     lstm = torch.nn.LSTM(2048, H, 1, batch_first=True).to(DEV)
     with torch.no_grad():   # the recurrent weights are held in bf16 by the kernel
