@@ -582,30 +582,44 @@ class _XceptionLSTMBase(nn.Module):
         t = lstm_out.shape[1]
         return (seq_lengths.detach().long().clamp(1, t) - 1).to(lstm_out.device).contiguous()
 
+    def _head(self, lstm_out, row_index, want_logits: bool):
+        """The head on every clip of the batch: one launch per 32 clips (the kernels hold 32 rows)."""
+        drop = self.fc_layers[2]
+        args = (drop.training, float(drop.p), want_logits, None, None, None)
+        B = lstm_out.shape[0]
+        if B <= 32:
+            return _HeadFn.apply(lstm_out, row_index, *args, *self._head_params())
+        outs = [_HeadFn.apply(lstm_out[i:i + 32], None if row_index is None else row_index[i:i + 32].contiguous(), *args,
+                              *self._head_params()) for i in range(0, B, 32)]
+        return torch.cat(outs, 0)
+
     def forward(self, features, seq_lengths=None):
         """lstm -> last step -> fc_layers -> sigmoid(fc_out) (XceptionLSTMV.py:66-70); the head is one launch.  The optional
         second argument exists because train_visual.py's older variants pass seq_lengths; like the shipped class, lengths
         are not used unless ``use_seq_lengths`` is set."""
         lstm_out, _ = self.lstm(features)
-        drop = self.fc_layers[2]
-        return _HeadFn.apply(lstm_out, self._row_index(lstm_out, seq_lengths), drop.training, float(drop.p), False, None, None,
-                             None, *self._head_params())
+        return self._head(lstm_out, self._row_index(lstm_out, seq_lengths), False)
 
     def forward_logits(self, features):
         """Same path as forward() without the final sigmoid: fc_out logits (B,1) for logit-space criteria such as
         LabelSmoothingBCEWithLogitsLoss (train_au_patch.py:203-214)."""
         lstm_out, _ = self.lstm(features)
-        drop = self.fc_layers[2]
-        return _HeadFn.apply(lstm_out, None, drop.training, float(drop.p), True, None, None, None, *self._head_params())
+        return self._head(lstm_out, None, True)
 
     def forward_loss(self, features, labels, seq_lengths=None, smoothing=None):
         """forward() and its criterion as ONE kernel (BASELINE north_star (3)): ``smoothing=None`` -> (nn.BCELoss()(probabilities,
         labels), probabilities) as train_audio.py:20,39 computes them; a float -> (LabelSmoothingBCEWithLogitsLoss(smoothing)
-        (logits, labels), logits) as train_au_patch.py:203-214 does.  Same values and gradients as the two-call form."""
+        (logits, labels), logits) as train_au_patch.py:203-214 does.  Same values and gradients as the two-call form (which is
+        what runs for more than 32 clips: the mean over the batch spans several head launches)."""
         lstm_out, _ = self.lstm(features)
-        drop = self.fc_layers[2]
         if labels.numel() != lstm_out.shape[0]:
             raise XcpError("forward_loss: %d labels for %d clips" % (labels.numel(), lstm_out.shape[0]))
+        if lstm_out.shape[0] > 32:
+            out = self._head(lstm_out, self._row_index(lstm_out, seq_lengths), smoothing is not None)
+            y = labels.float().view(-1, 1)
+            crit = LabelSmoothingBCEWithLogitsLoss(smoothing) if smoothing is not None else BCELoss()
+            return crit(out, y), out
+        drop = self.fc_layers[2]
         out, loss = _HeadLossFn.apply(lstm_out, self._row_index(lstm_out, seq_lengths), drop.training, float(drop.p),
                                       smoothing is not None, labels, smoothing, None, *self._head_params())
         return loss, out

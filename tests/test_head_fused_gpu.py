@@ -272,3 +272,32 @@ def test_fusion_head_module_inference_logits_and_dropout_draw():
     assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() != l2.item()
     l1.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in head.parameters())
+
+
+def test_head_on_more_than_32_clips_runs_in_chunks():
+    """More clips than one head launch holds (32): forward / forward_logits / forward_loss split the batch over several launches;
+    values and gradients equal the oracle's head on the whole batch."""
+    torch.manual_seed(11)
+    model = M.XceptionLSTMV(128).to(DEV).train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    g = torch.Generator().manual_seed(2)
+    feats = torch.randn(45, 4, 2048, generator=g).to(DEV)
+    y = torch.randint(0, 2, (45, 1), generator=g).float().to(DEV)
+    params = [p for n, p in model.named_parameters() if n.startswith("fc_")]
+    loss, probs = model.forward_loss(feats, y)
+    for p in params:
+        p.grad = None
+    loss.backward()
+    got = [p.grad.clone() for p in params]
+    with torch.no_grad():
+        lstm_out, _ = model.lstm(feats)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items() if k.startswith("fc_")}
+    p_ref = orc.head_forward(sd, lstm_out[:, -1].float())
+    loss_ref = torch.nn.BCELoss()(p_ref, y)
+    loss_ref.backward()
+    assert probs.shape == (45, 1) and rel_err(probs, p_ref.detach()) < 1e-5 and abs(loss.item() - loss_ref.item()) < 1e-5
+    for (n, _), a in zip([(n, p) for n, p in model.named_parameters() if n.startswith("fc_")], got):
+        assert rel_err(a, sd[n].grad) < 1e-4, n
+    assert rel_err(model.forward_logits(feats), orc.head_forward(sd, lstm_out[:, -1].float(), return_logit=True).detach()) < 1e-5
