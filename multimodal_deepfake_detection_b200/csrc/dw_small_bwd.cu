@@ -1,4 +1,4 @@
-// Depthwise 3x3 backward on tiny maps (S x S, S = 2 / 4: the middle and exit flow of the audio model's 64x64 patches,
+// Depthwise 3x3 backward on tiny maps (S x S, S = 2 / 4 / 8: the middle and exit flow of the audio model's 64x64 patches,
 // XceptionLSTMA.py:46 -> 4x4x728 x26 layers and 2x2x1024/1536).  Same fused contract as dw3x3_bwd_kernel (dw.cu): dgrad,
 // 9-tap weight gradient, BN-affine / ReLU prologue and mask, identity-skip / stride-2-skip gradient adds, BatchNorm-backward sums.
 //
@@ -42,12 +42,17 @@ dw3x3_small_bwd_kernel(const __nv_bfloat162* __restrict__ dD, const __nv_bfloat1
 
     for (long long f = f0; f < f1; ++f) {
         const long long base = f * (S * S) * C2 + c2;
-        float2 g[S][S], yv[S][S];
+        // the image's gradient pixels: fp32 pairs up to 4x4, packed bf16 pairs (unpacked at use) at 8x8 to stay inside the register file
+        constexpr bool PACKED = S > 4;
+        float2 g[PACKED ? 1 : S][PACKED ? 1 : S];
+        uint32_t gp[PACKED ? S : 1][PACKED ? S : 1];
+        float2 yv[S][S];
 #pragma unroll
         for (int y = 0; y < S; ++y)
 #pragma unroll
             for (int x = 0; x < S; ++x) {
-                g[y][x] = __bfloat1622float2(dD[base + (long long)(y * S + x) * C2]);
+                if (PACKED) gp[PACKED ? y : 0][PACKED ? x : 0] = *reinterpret_cast<const uint32_t*>(dD + base + (long long)(y * S + x) * C2);
+                else g[PACKED ? 0 : y][PACKED ? 0 : x] = __bfloat1622float2(dD[base + (long long)(y * S + x) * C2]);
                 yv[y][x] = __bfloat1622float2(xin[base + (long long)(y * S + x) * C2]);
             }
 #pragma unroll
@@ -66,7 +71,9 @@ dw3x3_small_bwd_kernel(const __nv_bfloat162* __restrict__ dD, const __nv_bfloat1
                     for (int kw = 0; kw < 3; ++kw) {
                         const int yy = y + 1 - kh, xx = x + 1 - kw;            // the output pixel that read (y, x) through tap (kh, kw)
                         if (yy >= 0 && yy < S && xx >= 0 && xx < S) {
-                            const float2 gg = g[yy][xx];
+                            float2 gg;
+                            if (PACKED) { const uint32_t q = gp[PACKED ? yy : 0][PACKED ? xx : 0]; gg = make_float2(bf16_lo(q), bf16_hi(q)); }
+                            else gg = g[PACKED ? 0 : yy][PACKED ? 0 : xx];
                             d.x = fmaf(wk[kh * 3 + kw].x, gg.x, d.x); d.y = fmaf(wk[kh * 3 + kw].y, gg.y, d.y);
                             dwa[kh * 3 + kw].x = fmaf(av.x, gg.x, dwa[kh * 3 + kw].x); dwa[kh * 3 + kw].y = fmaf(av.y, gg.y, dwa[kh * 3 + kw].y);
                         }
@@ -135,10 +142,11 @@ int dw_small_try_bwd(const void* dD, const void* xin, const float* w9, const flo
                      const void* add_full, const void* add_half, float* dw, float* bnsum, int F, int H, int W, int C, int c_real,
                      cudaStream_t st, int* handled) {
     *handled = 0;
-    if (H != W || (H != 2 && H != 4)) return 0;
+    if (H != W || (H != 2 && H != 4 && H != 8)) return 0;
     const char* e = getenv("XCP_DW_NO_SMALL_BWD");                                    // A/B hook
     if (e != nullptr && e[0] == '1') return 0;
     *handled = 1;
+    if (H == 8) return launch_small_bwd<8>(dD, xin, w9, scale, shift, relu, dz, add_full, add_half, dw, bnsum, F, C, c_real, st);
     if (H == 2) return launch_small_bwd<2>(dD, xin, w9, scale, shift, relu, dz, add_full, add_half, dw, bnsum, F, C, c_real, st);
     return launch_small_bwd<4>(dD, xin, w9, scale, shift, relu, dz, add_full, add_half, dw, bnsum, F, C, c_real, st);
 }

@@ -697,10 +697,10 @@ def test_stem_conv1_affine_inference_form(F_, H):
     assert rel_err(out_u8.float().permute(0, 3, 1, 2), ref_u8) < 8e-3
 
 
-@pytest.mark.parametrize("F_,S,C", [(5, 4, 768), (1100, 4, 768), (3, 2, 1536), (700, 2, 1024), (9, 4, 64)])
+@pytest.mark.parametrize("F_,S,C", [(5, 4, 768), (1100, 4, 768), (3, 2, 1536), (700, 2, 1024), (9, 4, 64), (5, 8, 768), (300, 8, 256)])
 @pytest.mark.parametrize("mode", ["plain", "relu", "affine_relu", "full", "half", "both", "pre_half"])
 def test_dw3x3_small_bwd_tiny_maps(F_, S, C, mode):
-    """The register-resident depthwise backward of the audio model's 4x4 / 2x2 maps (csrc/dw_small_bwd.cu) in every fused mode
+    """The register-resident depthwise backward of the audio model's 8x8 / 4x4 / 2x2 maps (csrc/dw_small_bwd.cu) in every fused mode
     against torch autograd: dgrad, 9-tap weight gradient (logical channels of a padded pitch), BN-affine / ReLU mask,
     identity-skip and stride-2-skip gradient adds (outside and inside the mask), BatchNorm-backward sums; enough frames for
     several images per thread and a ragged last frame group."""
